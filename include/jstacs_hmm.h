@@ -1,0 +1,212 @@
+/*
+ * jstacs_hmm.h — C ABI of the B200-native HMM engine (libjstacs_hmm_b200.so).
+ *
+ * This is the drop-in boundary for the Jstacs HMM hot path.  Every entry point
+ * names the Jstacs (reference) method it replaces; paths are relative to the
+ * reference root and abbreviated
+ *   HMM/ = de/jstacs/sequenceScores/statisticalModels/trainable/hmm/
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; all buffers are caller-owned HOST memory
+ *     unless the name says `_device`;
+ *   - every function returns 0 on success, a negative jh_status otherwise;
+ *     jh_last_error() returns a thread-local message for the last failure
+ *     (the Java shim turns it into the exception type the reference throws);
+ *   - a handle is used by one caller thread at a time (the reference model
+ *     instance is not thread-safe either, HMM/models/HigherOrderHMM.java:1189);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with JH_ERR_CUDA.
+ */
+#ifndef JSTACS_HMM_H
+#define JSTACS_HMM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JH_ABI_VERSION 1
+
+typedef enum jh_status {
+  JH_OK = 0,
+  JH_ERR_INVALID = -1,      /* IllegalArgumentException in the reference            */
+  JH_ERR_UNSUPPORTED = -2,  /* feature outside the native path (filters, reverse
+                               strand states, position dependent elements, ...)     */
+  JH_ERR_CUDA = -3,         /* no device / CUDA runtime failure                      */
+  JH_ERR_ALPHABET = -4,     /* WrongAlphabetException (AbstractHMM.java:991)         */
+  JH_ERR_NOMEM = -5,
+  JH_ERR_IMPOSSIBLE = -6,   /* "Impossible path": no state path has prob > 0         */
+  JH_ERR_COMM = -7          /* NCCL failure                                          */
+} jh_status;
+
+/*
+ * Flattened model ("context graph" IR).
+ *
+ * It is exactly what the public Transition interface exposes
+ * (HMM/transitions/Transition.java:63-199) plus the emission tables
+ * (HMM/states/emissions/discrete/AbstractConditionalDiscreteEmission.java:100-135):
+ *
+ *   layer class lc = min(layer, max_order)         BasicHigherOrderTransition.java:558-560
+ *   contexts of lc, in lookup[0][lc] order          BasicHigherOrderTransition.java:259-266
+ *   element of a context  = lookup[0][lc][ctx]      :571-573
+ *   child c of an element = {state, descendant}     :547-555 (fillTransitionInformation)
+ *   next context          = lookup[1][min(layer+adv,m)][descendant], adv = silent?0:1
+ *   log transition score  = parameters[c] - logNorm :1116-1118
+ *   log emission score    = (0 - logNorm[cond]) + params[cond][sym], or -log(a)
+ *                           if the condition is not available (pos < order)
+ *                           AbstractConditionalDiscreteEmission.java:431-457
+ *   cond                  = sum_i a^i * x[pos-1-i]  HigherOrderDiscreteEmission.java:138-146
+ */
+typedef struct jh_model_desc {
+  int32_t abi_version;          /* JH_ABI_VERSION */
+  int32_t n_states;             /* S */
+  int32_t alphabet;             /* a (4 for DNA, DNAAlphabet.java:72) */
+  int32_t max_order;            /* m = Transition.getMaximalMarkovOrder() */
+
+  /* contexts, grouped by layer class 0..m */
+  const int32_t *lc_ctx_ptr;    /* [m+2]  contexts of class lc are lc_ctx_ptr[lc] .. lc_ctx_ptr[lc+1]-1 */
+  const int32_t *ctx_elem;      /* [n_ctx_total] transition element of each context */
+  const int32_t *ctx_last_state;/* [n_ctx_total] Transition.getLastContextState, -1 for the start context */
+
+  /* transition elements */
+  int32_t n_elem;
+  const int32_t *elem_child_ptr;/* [n_elem+1] */
+  const int32_t *child_state;   /* [n_child_total] */
+  const int32_t *child_desc;    /* [n_child_total] descendant element index */
+  const int32_t *elem_ctx;      /* [(m+1)*n_elem] lookup[1][lc][elem]: local context index in class lc, or -1 */
+  const int32_t *trans_index;   /* [n_elem] parameter tying, transIndex[t] <= t (BasicHigherOrderTransition.java:81-101) */
+  const double *trans_param;    /* [n_child_total] AbstractTransitionElement.parameters */
+  const double *trans_lognorm;  /* [n_elem]        AbstractTransitionElement.logNorm    */
+  const double *trans_hyper;    /* [n_child_total] AbstractTransitionElement.hyperParameters */
+
+  /* emissions */
+  int32_t n_emis;
+  const int32_t *state_emis;    /* [S] emissionIdx (AbstractHMM.java:273-283) */
+  const int32_t *emis_order;    /* [n_emis] Markov order of the emission, -1 = SilentEmission */
+  const int32_t *emis_cond_ptr; /* [n_emis+1] first condition row of each emission */
+  const double *emis_param;     /* [n_cond_total*a] params[cond][sym]  */
+  const double *emis_lognorm;   /* [n_cond_total]   logNorm[cond]      */
+  const double *emis_hyper;     /* [n_cond_total*a] hyperParams        */
+
+  const uint8_t *state_silent;  /* [S] State.isSilent (SimpleState.java:71-82) */
+  const uint8_t *state_final;   /* [S] AbstractHMM.finalState (AbstractHMM.java:1101-1113) */
+} jh_model_desc;
+
+typedef struct jh_model jh_model;
+typedef struct jh_dataset jh_dataset;
+
+/* ---- library ----------------------------------------------------------- */
+int jh_abi_version(void);
+/* Thread-local message of the last failing call (never NULL). */
+const char *jh_last_error(void);
+/* Number of visible CUDA devices; <0 on failure. */
+int jh_device_count(void);
+/* Select the device used by handles created afterwards (default 0). */
+int jh_set_device(int device);
+/* Counts kernels launched by this library since load (bench.py: gpu_launches). */
+int64_t jh_kernel_launches(void);
+/* Use an existing CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = library stream. */
+int jh_set_stream(void *cuda_stream);
+int jh_synchronize(void);
+
+/* ---- model ------------------------------------------------------------- */
+/* Replaces the object graph built by HigherOrderHMM(...) / HMMFactory.createErgodicHMM
+ * (HMM/models/HigherOrderHMM.java:156-187, HMM/HMMFactory.java:156-181): the shim reads the
+ * model through the public Transition/Emission interfaces and hands the flattened copy over. */
+int jh_model_create(const jh_model_desc *desc, jh_model **out);
+void jh_model_destroy(jh_model *m);
+/* DifferentiableHigherOrderHMM.setParameters(double[],int) (:339-344) — all arrays in jh_model_desc layout.
+ * NULL lognorm pointers mean "recompute like precompute()" (TransitionElement.java:119-126,
+ * AbstractConditionalDiscreteEmission.java:466-480). */
+int jh_model_set_params(jh_model *m, const double *trans_param, const double *trans_lognorm,
+                        const double *emis_param, const double *emis_lognorm);
+/* getCurrentParameterValues (:316-329) + the logNorm fields. Any pointer may be NULL. */
+int jh_model_get_params(jh_model *m, double *trans_param, double *trans_lognorm,
+                        double *emis_param, double *emis_lognorm);
+/* sizes: n_child_total, n_elem, n_cond_total*a, n_cond_total */
+int jh_model_sizes(const jh_model *m, int64_t sizes[4]);
+/* HigherOrderHMM.getLogPriorTerm (:253-259). */
+int jh_model_log_prior(jh_model *m, double *out);
+
+/* ---- data -------------------------------------------------------------- */
+/* Replaces per-symbol DataSet.getElementAt(n).discreteVal(p) (DataSet.java:1001-1012,
+ * Sequence.java:102): sequences are packed ONCE into uint8 codes with int64 offsets
+ * (offsets[n]..offsets[n+1]) and copied to the device; weights may be NULL (all 1,
+ * HigherOrderHMM.java:808-810). Sequences are length-bucketed internally; all outputs
+ * are in caller order. */
+int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_seq,
+                      const double *weights, int32_t alphabet, jh_dataset **out);
+void jh_dataset_destroy(jh_dataset *d);
+int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_residues, int64_t *max_len);
+
+/* ---- compute entry points ---------------------------------------------- */
+/* HigherOrderHMM.getLogScoreFor(DataSet,double[]) (:927-941) == AbstractHMM.logProb per sequence
+ * (AbstractHMM.java:1049-1070): backward recursion, result bwd[0][0]. out[n_seq]. */
+int jh_loglik(jh_model *m, jh_dataset *d, double *out);
+
+/* AbstractHMM.getViterbiPathsFor(DataSet) (AbstractHMM.java:894-900) ==
+ * HigherOrderHMM.viterbi (:617-708) per sequence.  paths: int32, CSR by the dataset offsets
+ * (models without silent states emit exactly one state per residue); scores[n_seq]. */
+int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores);
+
+/* AbstractHMM.getLogStatePosteriorMatrixFor(start,end,seq) (AbstractHMM.java:776-797):
+ * out[S][L] row-major for sequence seq_index. */
+int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out);
+/* AbstractHMM.decodeStatePosterior (:1125-1139) fused with the posterior: paths CSR like
+ * jh_viterbi, loglik[n_seq] (may be NULL). */
+int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik);
+
+/* One E-step == Compute.oneIteration (HigherOrderHMM.java:1250-1261): resets the statistics,
+ * runs baumWelch (mode 1, :723-726) or viterbi(null,...) (mode 0, :617-708) over every sequence,
+ * returns sum_n w_n*score_n in *score. Statistics stay on the device; the optional host
+ * pointers receive copies (trans_stat[n_child_total] per element/child with tying applied,
+ * emis_stat[n_cond_total*a]). */
+#define JH_MODE_VITERBI 0
+#define JH_MODE_BAUM_WELCH 1
+int jh_estep(jh_model *m, jh_dataset *d, int mode, double *trans_stat, double *emis_stat, double *score);
+/* Compute.estimateFromStatistics (:1263-1279) == M-step on the device from the statistics
+ * of the last jh_estep (BasicHigherOrderTransition.java:1242-1262,
+ * AbstractConditionalDiscreteEmission.java:682-699). */
+int jh_mstep(jh_model *m);
+
+/* Termination conditions (de/jstacs/algorithms/optimization/termination/):
+ * IterationCondition.java:83-86, SmallDifferenceOfFunctionEvaluationsCondition.java:86-89. */
+#define JH_TERM_ITERATIONS 0
+#define JH_TERM_SMALL_DIFFERENCE 1
+typedef struct jh_train_opts {
+  int32_t mode;        /* JH_MODE_* */
+  int32_t term_kind;   /* JH_TERM_* */
+  int32_t max_iter;    /* IterationCondition(maxIter); also a hard cap for SMALL_DIFFERENCE (<=0: none) */
+  double eps;          /* SmallDifferenceOfFunctionEvaluationsCondition(eps) */
+} jh_train_opts;
+/* HigherOrderHMM.train inner do-while (:760-770) for one start with skipInit: N E-steps and
+ * N-1 M-steps for IterationCondition(N). objective[cap] receives prior + sum_n w_n*logP_n per
+ * iteration; *n_iter the number of E-steps run. When a communicator is attached
+ * (jh_comm_*) the statistics and the score are all-reduced over the ranks each iteration. */
+int jh_baum_welch(jh_model *m, jh_dataset *d, const jh_train_opts *opts,
+                  double *objective, int32_t cap, int32_t *n_iter);
+
+/* ---- multi-GPU: one process per GPU, shards of the DataSet per rank ------ */
+/* The reference's joinStatistics + setParameters (HigherOrderHMM.java:1263-1288) is a sum over
+ * workers followed by a broadcast; here it is ONE ncclAllReduce(sum, fp64) of
+ * [transition statistics | emission statistics | score] per EM iteration, the M-step is then
+ * run redundantly on every rank. id is the 128 byte ncclUniqueId made by rank 0. */
+#define JH_COMM_ID_BYTES 128
+int jh_comm_unique_id(uint8_t id[JH_COMM_ID_BYTES]);
+int jh_comm_init(jh_model *m, const uint8_t id[JH_COMM_ID_BYTES], int32_t n_ranks, int32_t rank);
+int jh_comm_destroy(jh_model *m);
+/* Device pointer and length (doubles) of the contiguous [trans|emis|score] statistics block,
+ * for callers that run their own collective (e.g. torch.distributed) between jh_estep and jh_mstep. */
+int jh_stats_device(jh_model *m, void **dev_ptr, int64_t *n_doubles);
+
+/* ---- measurement helpers (bench.py) ------------------------------------- */
+/* Sustained FP64 FMA rate of this device in TFLOP/s (2 flops per DFMA), a register-resident DFMA chain. */
+int jh_measure_fp64_peak(double *tflops);
+/* Device time in ms of the kernels of the last compute call (CUDA events on the library stream). */
+int jh_last_kernel_ms(jh_model *m, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JSTACS_HMM_H */
