@@ -109,6 +109,9 @@ int64_t jh_kernel_launches(void);
 /* Use an existing CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = library stream. */
 int jh_set_stream(void *cuda_stream);
 int jh_synchronize(void);
+/* Tuning / test switches: "fast" (1: scaled linear-space kernels where the model allows, 0: reference-order
+ * log-space kernels only), "scratch_mb" (DP scratch budget), "blocks_per_sm", "fast_variant". */
+int jh_set_option(const char *name, int64_t value);
 
 /* ---- model ------------------------------------------------------------- */
 /* Replaces the object graph built by HigherOrderHMM(...) / HMMFactory.createErgodicHMM
@@ -138,6 +141,8 @@ int jh_model_log_prior(jh_model *m, double *out);
 int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_seq,
                       const double *weights, int32_t alphabet, jh_dataset **out);
 void jh_dataset_destroy(jh_dataset *d);
+/* Sequence weights of train(DataSet,double[]) (TrainableStatisticalModel.java:61-88); NULL = all 1. */
+int jh_dataset_set_weights(jh_dataset *d, const double *weights);
 int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_residues, int64_t *max_len);
 
 /* ---- compute entry points ---------------------------------------------- */

@@ -222,14 +222,10 @@ class NativeModel:
         check(lib().jh_viterbi(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(scores)))
         return paths[:data.n_res], scores[:data.n_seq]
 
-    def posterior(self, data: NativeData, index: int, length: int | None = None) -> np.ndarray:
-        n, r, mx = C.c_int64(), C.c_int64(), C.c_int64()
-        check(lib().jh_dataset_info(data.h, C.byref(n), C.byref(r), C.byref(mx)))
-        S = self._n_states
-        out = np.zeros(S * max(mx.value, 1))
+    def posterior(self, data: NativeData, index: int, n_states: int, length: int) -> np.ndarray:
+        out = np.zeros(max(n_states * length, 1))
         check(lib().jh_posterior(self.h, data.h, int(index), _f64(out)))
-        L = self._seq_len(data, index) if length is None else length
-        return out[:S * L].reshape(S, L)
+        return out[:n_states * length].reshape(n_states, length)
 
     def posterior_decode(self, data: NativeData):
         paths = np.zeros(max(data.n_res, 1), dtype=np.int32)
@@ -268,8 +264,3 @@ class NativeModel:
         check(lib().jh_last_kernel_ms(self.h, C.byref(v)))
         return v.value
 
-    # set by hmm.HigherOrderHMM through ir
-    _n_states = 0
-
-    def _seq_len(self, data, index):
-        raise NotImplementedError

@@ -1,0 +1,928 @@
+// jstacs_hmm.cu — C ABI (include/jstacs_hmm.h) of the B200-native HMM engine: handles, dispatch, EM driver.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see __graft_entry__.py).
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+#include "kernels_aux.cuh"
+#include "kernels_exact.cuh"
+#include "kernels_fast.cuh"
+
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+int64_t g_kernel_launches = 0;
+static int g_device = 0;
+static cudaStream_t g_user_stream = nullptr;
+static bool g_have_user_stream = false;
+
+struct Options {
+  int64_t fast = 1;            // use the scaled linear-space kernels where the model allows it
+  int64_t scratch_mb = 24576;  // upper bound of DP scratch memory
+  int64_t blocks_per_sm = 0;   // 0 = occupancy API
+  int64_t fast_variant = 0;
+};
+static Options g_opt;
+
+void jh_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      jh_set_error("out of device memory allocating %zu bytes", count * sizeof(T));
+      return JH_ERR_NOMEM;
+    }
+    n = count;
+    return JH_OK;
+  }
+  int reserve(size_t count) { return count <= n ? (int)JH_OK : alloc(count); }
+  int upload(const std::vector<T> &h, cudaStream_t s) {
+    int r = alloc(h.size());
+    if (r) return r;
+    if (!h.empty()) JH_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return JH_OK;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+struct Id128 {  // ncclUniqueId (128 bytes, passed by value)
+  char b[128];
+};
+struct NcclApi {
+  void *lib = nullptr;
+  int (*GetUniqueId)(void *) = nullptr;
+  int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return JH_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    jh_set_error("libnccl.so.2 not found: %s", dlerror());
+    return JH_ERR_COMM;
+  }
+  g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
+    jh_set_error("libnccl.so.2 lacks a required symbol");
+    g_nccl.lib = nullptr;
+    return JH_ERR_COMM;
+  }
+  return JH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct jh_model {
+  // host IR
+  int S = 0, a = 0, m = 0, Cmax = 0, n_elem = 0, n_child = 0, n_ctx_total = 0, n_cond = 0, n_emis = 0, Kmax = 0;
+  bool has_silent = false;
+  int max_children = 0;
+  std::vector<int> lc_ctx_ptr, ctx_elem, ctx_last, elem_child_ptr, child_state, child_desc, elem_ctx, trans_index;
+  std::vector<int> state_emis, emis_order, emis_cond_ptr;
+  std::vector<uint8_t> state_silent, state_final;
+  std::vector<int> child_elem, child_next, child_stat, in_ptr, in_src, in_p, state_order, state_tab, state_mod, row_flag;
+  // device
+  DevBuf<int> d_lc_ctx_ptr, d_ctx_elem, d_ctx_last, d_elem_child_ptr, d_child_state, d_child_next, d_child_stat, d_in_ptr,
+      d_in_src, d_in_p, d_state_order, d_state_tab, d_state_mod, d_child_elem, d_trans_index, d_row_flag;
+  DevBuf<unsigned char> d_is_final;
+  DevBuf<double> d_trans_param, d_trans_lognorm, d_trans_hyper, d_emis_param, d_emis_lognorm, d_emis_hyper, d_tscore, d_escore;
+  DevBuf<double> d_stats;      // [n_child | n_cond*a | score | pad]
+  DevBuf<double> d_objective;  // per-iteration objective
+  DevBuf<double> d_fwd;        // forward scratch
+  DevBuf<uint8_t> d_choice;    // Viterbi choice scratch
+  DevBuf<unsigned long long> d_counter;
+  DevBuf<int32_t> d_fallback;  // [1 + n] list of sequences the fast path handed to the exact kernels
+  jhf::FastTables fast;        // linear-space tables of the fast path
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  int sm_count = 148;
+  void *comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  int64_t n_stats() const { return (int64_t)n_child + (int64_t)n_cond * a; }
+  cudaStream_t st() const { return g_have_user_stream ? g_user_stream : stream; }
+  DevModel dev() const {
+    DevModel M;
+    M.S = S; M.a = a; M.m = m; M.Cmax = Cmax; M.n_elem = n_elem; M.n_child = n_child; M.n_ctx_total = n_ctx_total; M.n_cond = n_cond;
+    M.Kmax = Kmax;
+    int pw = 1;
+    for (int i = 0; i < Kmax; i++) pw *= a;
+    M.hpow = pw; M.hmod = pw * a;
+    M.a_pow2 = (a & (a - 1)) == 0;
+    M.log_uniform = -log((double)a);
+    M.lc_ctx_ptr = d_lc_ctx_ptr.p; M.ctx_elem = d_ctx_elem.p; M.ctx_last = d_ctx_last.p; M.elem_child_ptr = d_elem_child_ptr.p;
+    M.child_state = d_child_state.p; M.child_next = d_child_next.p; M.child_stat = d_child_stat.p; M.tscore = d_tscore.p;
+    M.in_ptr = d_in_ptr.p; M.in_src = d_in_src.p; M.in_p = d_in_p.p; M.state_order = d_state_order.p; M.state_tab = d_state_tab.p;
+    M.state_mod = d_state_mod.p; M.escore = d_escore.p; M.is_final = d_is_final.p;
+    return M;
+  }
+  jha::DevParams params() const {
+    jha::DevParams P;
+    P.n_elem = n_elem; P.n_child = n_child; P.n_cond = n_cond; P.a = a; P.S = S;
+    P.elem_child_ptr = d_elem_child_ptr.p; P.child_elem = d_child_elem.p; P.trans_index = d_trans_index.p; P.row_emitting = d_row_flag.p;
+    P.trans_param = d_trans_param.p; P.trans_lognorm = d_trans_lognorm.p; P.emis_param = d_emis_param.p; P.emis_lognorm = d_emis_lognorm.p;
+    P.trans_hyper = d_trans_hyper.p; P.emis_hyper = d_emis_hyper.p; P.tscore = d_tscore.p; P.escore = d_escore.p;
+    return P;
+  }
+};
+
+struct jh_dataset {
+  int64_t n_seq = 0, n_res = 0, max_len = 0, min_len = 0;
+  int alphabet = 0;
+  std::vector<int64_t> offsets;
+  std::vector<int32_t> order;
+  // length buckets over `order` (decreasing length): [bucket_ptr[b], bucket_ptr[b+1]) with max length bucket_len[b]
+  std::vector<int64_t> bucket_ptr, bucket_len;
+  DevBuf<uint8_t> d_codes;
+  DevBuf<int64_t> d_offsets;
+  DevBuf<int32_t> d_order;
+  DevBuf<double> d_weights;
+  bool has_weights = false;
+  DevData dev(int64_t first = 0, int64_t count = -1) const {
+    DevData D;
+    D.codes = d_codes.p; D.offsets = d_offsets.p; D.weights = has_weights ? d_weights.p : nullptr;
+    D.order = d_order.p + first; D.n_seq = count < 0 ? n_seq : count;
+    return D;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int jh_abi_version(void) { return JH_ABI_VERSION; }
+extern "C" const char *jh_last_error(void) { return g_err; }
+extern "C" int jh_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    jh_set_error("no CUDA device: %s (there is no CPU fallback)", cudaGetErrorString(cudaGetLastError()));
+    return JH_ERR_CUDA;
+  }
+  return n;
+}
+extern "C" int jh_set_device(int device) {
+  JH_CUDA(cudaSetDevice(device));
+  g_device = device;
+  return JH_OK;
+}
+extern "C" int64_t jh_kernel_launches(void) { return g_kernel_launches; }
+extern "C" int jh_set_stream(void *s) {
+  g_user_stream = (cudaStream_t)s;
+  g_have_user_stream = s != nullptr;
+  return JH_OK;
+}
+extern "C" int jh_synchronize(void) {
+  JH_CUDA(cudaDeviceSynchronize());
+  return JH_OK;
+}
+extern "C" int jh_set_option(const char *name, int64_t value) {
+  std::string n(name ? name : "");
+  if (n == "fast") g_opt.fast = value;
+  else if (n == "scratch_mb") g_opt.scratch_mb = value;
+  else if (n == "blocks_per_sm") g_opt.blocks_per_sm = value;
+  else if (n == "fast_variant") g_opt.fast_variant = value;
+  else {
+    jh_set_error("unknown option '%s'", n.c_str());
+    return JH_ERR_INVALID;
+  }
+  return JH_OK;
+}
+
+static int ensure_device() {
+  int n = jh_device_count();
+  if (n <= 0) {
+    if (n == 0) jh_set_error("no CUDA device visible (there is no CPU fallback)");
+    return JH_ERR_CUDA;
+  }
+  JH_CUDA(cudaSetDevice(g_device));
+  return JH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int prep_scores(jh_model *m) {
+  int n = std::max(m->n_child, m->n_cond * m->a);
+  jha::k_prep_scores<<<(n + 255) / 256, 256, 0, m->st()>>>(m->params());
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return jhf::prepare(m->fast, m->dev(), m->st());
+}
+
+extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
+  if (!d || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  if (d->abi_version != JH_ABI_VERSION) { jh_set_error("jh_model_desc.abi_version %d != %d", d->abi_version, JH_ABI_VERSION); return JH_ERR_INVALID; }
+  if (d->n_states < 1 || d->alphabet < 2 || d->alphabet > 255 || d->max_order < 0 || d->n_elem < 1 || d->n_emis < 1) {
+    jh_set_error("invalid model sizes");
+    return JH_ERR_INVALID;
+  }
+  int r = ensure_device();
+  if (r) return r;
+  jh_model *m = new jh_model();
+  m->S = d->n_states; m->a = d->alphabet; m->m = d->max_order; m->n_elem = d->n_elem; m->n_emis = d->n_emis;
+  m->lc_ctx_ptr.assign(d->lc_ctx_ptr, d->lc_ctx_ptr + m->m + 2);
+  m->n_ctx_total = m->lc_ctx_ptr[m->m + 1];
+  for (int lc = 0; lc <= m->m; lc++) m->Cmax = std::max(m->Cmax, m->lc_ctx_ptr[lc + 1] - m->lc_ctx_ptr[lc]);
+  m->ctx_elem.assign(d->ctx_elem, d->ctx_elem + m->n_ctx_total);
+  m->ctx_last.assign(d->ctx_last_state, d->ctx_last_state + m->n_ctx_total);
+  m->elem_child_ptr.assign(d->elem_child_ptr, d->elem_child_ptr + m->n_elem + 1);
+  m->n_child = m->elem_child_ptr[m->n_elem];
+  m->child_state.assign(d->child_state, d->child_state + m->n_child);
+  m->child_desc.assign(d->child_desc, d->child_desc + m->n_child);
+  m->elem_ctx.assign(d->elem_ctx, d->elem_ctx + (size_t)(m->m + 1) * m->n_elem);
+  m->trans_index.assign(d->trans_index, d->trans_index + m->n_elem);
+  m->state_emis.assign(d->state_emis, d->state_emis + m->S);
+  m->emis_order.assign(d->emis_order, d->emis_order + m->n_emis);
+  m->emis_cond_ptr.assign(d->emis_cond_ptr, d->emis_cond_ptr + m->n_emis + 1);
+  m->n_cond = m->emis_cond_ptr[m->n_emis];
+  m->state_silent.assign(d->state_silent, d->state_silent + m->S);
+  m->state_final.assign(d->state_final, d->state_final + m->S);
+  auto fail = [&](int code, const char *msg) {
+    jh_set_error("%s", msg);
+    delete m;
+    return code;
+  };
+  // validation (the reference checks these in BasicHigherOrderTransition.init and the AbstractHMM constructor)
+  for (int t = 0; t < m->n_elem; t++) {
+    if (m->trans_index[t] < 0 || m->trans_index[t] > t) return fail(JH_ERR_INVALID, "transIndex constraint 0<=transIndex[i]<=i violated");
+    int n = m->elem_child_ptr[t + 1] - m->elem_child_ptr[t];
+    if (n < 0) return fail(JH_ERR_INVALID, "elem_child_ptr must be non-decreasing");
+    int rn = m->elem_child_ptr[m->trans_index[t] + 1] - m->elem_child_ptr[m->trans_index[t]];
+    if (rn != n) return fail(JH_ERR_INVALID, "tied TransitionElements don't have the same number of children");
+    m->max_children = std::max(m->max_children, n);
+  }
+  for (int p = 0; p < m->n_child; p++) {
+    if (m->child_state[p] < 0 || m->child_state[p] >= m->S) return fail(JH_ERR_INVALID, "child state out of range");
+    if (m->child_desc[p] < 0 || m->child_desc[p] >= m->n_elem) return fail(JH_ERR_INVALID, "descendant element out of range");
+  }
+  for (int s = 0; s < m->S; s++) {
+    if (m->state_emis[s] < 0 || m->state_emis[s] >= m->n_emis) return fail(JH_ERR_INVALID, "emission index out of range");
+    if (m->state_silent[s]) m->has_silent = true;
+    if ((m->emis_order[m->state_emis[s]] < 0) != (m->state_silent[s] != 0)) return fail(JH_ERR_INVALID, "state_silent does not match the emission");
+  }
+  // derived tables -----------------------------------------------------------------------------
+  m->child_elem.resize(m->n_child);
+  m->child_stat.resize(m->n_child);
+  for (int t = 0; t < m->n_elem; t++)
+    for (int p = m->elem_child_ptr[t]; p < m->elem_child_ptr[t + 1]; p++) {
+      m->child_elem[p] = t;
+      m->child_stat[p] = m->elem_child_ptr[m->trans_index[t]] + (p - m->elem_child_ptr[t]);
+    }
+  m->child_next.assign((size_t)(m->m + 1) * m->n_child, -1);
+  for (int lc = 0; lc <= m->m; lc++) {
+    int lct = std::min(lc + 1, m->m);
+    for (int p = 0; p < m->n_child; p++) {
+      int adv = m->state_silent[m->child_state[p]] ? 0 : 1;
+      m->child_next[(size_t)lc * m->n_child + p] = m->elem_ctx[(size_t)(adv ? lct : lc) * m->n_elem + m->child_desc[p]];
+    }
+  }
+  // in-edge CSR per source layer class (forward recursion in pull form; order = source context, then child)
+  m->in_ptr.assign((size_t)(m->m + 1) * (m->Cmax + 1), 0);
+  m->in_src.assign((size_t)(m->m + 1) * std::max(m->n_child, 1), 0);
+  m->in_p.assign((size_t)(m->m + 1) * std::max(m->n_child, 1), 0);
+  for (int lc = 0; lc <= m->m; lc++) {
+    int lct = std::min(lc + 1, m->m);
+    int nc = m->lc_ctx_ptr[lc + 1] - m->lc_ctx_ptr[lc], nct = m->lc_ctx_ptr[lct + 1] - m->lc_ctx_ptr[lct];
+    std::vector<std::vector<std::pair<int, int>>> in(nct);
+    for (int c = 0; c < nc; c++) {
+      int e = m->ctx_elem[m->lc_ctx_ptr[lc] + c];
+      if (e < 0 || e >= m->n_elem) return fail(JH_ERR_INVALID, "context element out of range");
+      for (int p = m->elem_child_ptr[e]; p < m->elem_child_ptr[e + 1]; p++) {
+        if (m->state_silent[m->child_state[p]]) continue;
+        int t = m->child_next[(size_t)lc * m->n_child + p];
+        if (t < 0 || t >= nct) return fail(JH_ERR_INVALID, "a child leads to a context that does not exist in the next layer");
+        in[t].push_back({c, p});
+      }
+    }
+    int *ip = m->in_ptr.data() + (size_t)lc * (m->Cmax + 1);
+    int q = 0;
+    for (int t = 0; t < nct; t++) {
+      ip[t] = q;
+      for (auto &sp : in[t]) {
+        m->in_src[(size_t)lc * m->n_child + q] = sp.first;
+        m->in_p[(size_t)lc * m->n_child + q] = sp.second;
+        q++;
+      }
+    }
+    for (int t = nct; t <= m->Cmax; t++) ip[t] = q;
+  }
+  m->state_order.resize(m->S); m->state_tab.resize(m->S); m->state_mod.resize(m->S);
+  m->row_flag.assign(std::max(m->n_cond, 1), 1);
+  for (int e = 0; e < m->n_emis; e++)
+    if (m->emis_order[e] >= 0 && m->emis_cond_ptr[e + 1] > m->emis_cond_ptr[e]) m->row_flag[m->emis_cond_ptr[e]] = 2;
+  for (int s = 0; s < m->S; s++) {
+    int e = m->state_emis[s], k = m->emis_order[e];
+    m->state_order[s] = k;
+    m->state_tab[s] = m->emis_cond_ptr[e] * m->a;
+    int64_t mod = m->a;
+    for (int i = 0; i < k; i++) mod *= m->a;
+    if (k >= 0) {
+      if (mod * m->a > (int64_t)1 << 30) return fail(JH_ERR_UNSUPPORTED, "emission order too large for the context hash");
+      if (m->emis_cond_ptr[e + 1] - m->emis_cond_ptr[e] != mod / m->a) return fail(JH_ERR_INVALID, "emission table does not have alphabet^order conditions");
+      m->Kmax = std::max(m->Kmax, k);
+    }
+    m->state_mod[s] = k >= 0 ? (int)mod : 1;
+  }
+  // device ---------------------------------------------------------------------------------------
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, g_device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(JH_ERR_CUDA, "cudaStreamCreate failed");
+  cudaEventCreate(&m->ev0);
+  cudaEventCreate(&m->ev1);
+  cudaStream_t s = m->st();
+  std::vector<unsigned char> fin(m->state_final.begin(), m->state_final.end());
+  std::vector<double> tp(d->trans_param, d->trans_param + m->n_child), tl(d->trans_lognorm, d->trans_lognorm + m->n_elem),
+      th(d->trans_hyper, d->trans_hyper + m->n_child), ep(d->emis_param, d->emis_param + (size_t)m->n_cond * m->a),
+      el(d->emis_lognorm, d->emis_lognorm + m->n_cond), eh(d->emis_hyper, d->emis_hyper + (size_t)m->n_cond * m->a);
+#define UP(buf, vec) if ((r = m->buf.upload(vec, s)) != 0) { delete m; return r; }
+  UP(d_lc_ctx_ptr, m->lc_ctx_ptr) UP(d_ctx_elem, m->ctx_elem) UP(d_ctx_last, m->ctx_last) UP(d_elem_child_ptr, m->elem_child_ptr)
+  UP(d_child_state, m->child_state) UP(d_child_next, m->child_next) UP(d_child_stat, m->child_stat) UP(d_in_ptr, m->in_ptr)
+  UP(d_in_src, m->in_src) UP(d_in_p, m->in_p) UP(d_state_order, m->state_order) UP(d_state_tab, m->state_tab)
+  UP(d_state_mod, m->state_mod) UP(d_child_elem, m->child_elem) UP(d_trans_index, m->trans_index) UP(d_row_flag, m->row_flag)
+  UP(d_is_final, fin) UP(d_trans_param, tp) UP(d_trans_lognorm, tl) UP(d_trans_hyper, th) UP(d_emis_param, ep)
+  UP(d_emis_lognorm, el) UP(d_emis_hyper, eh)
+#undef UP
+  if ((r = m->d_tscore.alloc(m->n_child)) || (r = m->d_escore.alloc((size_t)m->n_cond * m->a)) ||
+      (r = m->d_stats.alloc(m->n_stats() + 8)) || (r = m->d_counter.alloc(8)) || (r = m->d_objective.alloc(4096))) {
+    delete m;
+    return r;
+  }
+  if ((r = jhf::build(m->fast, m->S, m->a, m->m, m->has_silent, m->Kmax, m->lc_ctx_ptr, m->ctx_elem, m->ctx_last, m->elem_child_ptr,
+                      m->child_state, m->child_stat, m->state_order, m->state_tab, m->state_mod, m->state_final, m->n_child, m->n_cond, s)) != 0) {
+    delete m;
+    return r;
+  }
+  if ((r = prep_scores(m)) != 0) { delete m; return r; }
+  if (cudaStreamSynchronize(s) != cudaSuccess) return fail(JH_ERR_CUDA, "model upload failed");
+  *out = m;
+  return JH_OK;
+}
+
+extern "C" void jh_model_destroy(jh_model *m) {
+  if (!m) return;
+  cudaSetDevice(g_device);
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  jhf::destroy(m->fast);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+extern "C" int jh_model_sizes(const jh_model *m, int64_t sizes[4]) {
+  if (!m || !sizes) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  sizes[0] = m->n_child; sizes[1] = m->n_elem; sizes[2] = (int64_t)m->n_cond * m->a; sizes[3] = m->n_cond;
+  return JH_OK;
+}
+
+extern "C" int jh_model_set_params(jh_model *m, const double *tp, const double *tl, const double *ep, const double *el) {
+  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  cudaStream_t s = m->st();
+  if (tp) JH_CUDA(cudaMemcpyAsync(m->d_trans_param.p, tp, sizeof(double) * m->n_child, cudaMemcpyHostToDevice, s));
+  if (tl) JH_CUDA(cudaMemcpyAsync(m->d_trans_lognorm.p, tl, sizeof(double) * m->n_elem, cudaMemcpyHostToDevice, s));
+  if (ep) JH_CUDA(cudaMemcpyAsync(m->d_emis_param.p, ep, sizeof(double) * m->n_cond * m->a, cudaMemcpyHostToDevice, s));
+  if (el) JH_CUDA(cudaMemcpyAsync(m->d_emis_lognorm.p, el, sizeof(double) * m->n_cond, cudaMemcpyHostToDevice, s));
+  int do_t = tp && !tl, do_e = ep && !el;
+  if (do_t || do_e) {
+    int n = std::max(m->n_elem, m->n_cond);
+    jha::k_precompute_lognorm<<<(n + 127) / 128, 128, 0, s>>>(m->params(), do_t, do_e);
+    JH_LAUNCHED();
+  }
+  int r = prep_scores(m);
+  if (r) return r;
+  JH_CUDA(cudaStreamSynchronize(s));  // the host buffers are borrowed for the call only
+  return JH_OK;
+}
+
+extern "C" int jh_model_get_params(jh_model *m, double *tp, double *tl, double *ep, double *el) {
+  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  cudaStream_t s = m->st();
+  if (tp) JH_CUDA(cudaMemcpyAsync(tp, m->d_trans_param.p, sizeof(double) * m->n_child, cudaMemcpyDeviceToHost, s));
+  if (tl) JH_CUDA(cudaMemcpyAsync(tl, m->d_trans_lognorm.p, sizeof(double) * m->n_elem, cudaMemcpyDeviceToHost, s));
+  if (ep) JH_CUDA(cudaMemcpyAsync(ep, m->d_emis_param.p, sizeof(double) * m->n_cond * m->a, cudaMemcpyDeviceToHost, s));
+  if (el) JH_CUDA(cudaMemcpyAsync(el, m->d_emis_lognorm.p, sizeof(double) * m->n_cond, cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+
+extern "C" int jh_model_log_prior(jh_model *m, double *out) {
+  if (!m || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  jha::k_log_prior<<<1, 32, 0, m->st()>>>(m->params(), nullptr, m->d_objective.p + 4095);
+  JH_LAUNCHED();
+  JH_CUDA(cudaMemcpyAsync(out, m->d_objective.p + 4095, sizeof(double), cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_seq, const double *weights,
+                                 int32_t alphabet, jh_dataset **out) {
+  if (!offsets || !out || n_seq < 0 || (n_seq > 0 && !codes)) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  if (n_seq > 0x7fffffff) { jh_set_error("more than 2^31-1 sequences"); return JH_ERR_UNSUPPORTED; }
+  int r = ensure_device();
+  if (r) return r;
+  if (offsets[0] != 0) { jh_set_error("offsets[0] must be 0"); return JH_ERR_INVALID; }
+  jh_dataset *d = new jh_dataset();
+  d->n_seq = n_seq; d->alphabet = alphabet;
+  d->offsets.assign(offsets, offsets + n_seq + 1);
+  d->n_res = offsets[n_seq];
+  d->min_len = n_seq ? INT64_MAX : 0;
+  bool sorted = true;
+  for (int64_t i = 0; i < n_seq; i++) {
+    int64_t L = offsets[i + 1] - offsets[i];
+    if (L <= 0) {  // the reference fails on an empty sequence too (finalState[-1], HigherOrderHMM.java:498)
+      jh_set_error("sequence %lld is empty", (long long)i);
+      delete d;
+      return JH_ERR_INVALID;
+    }
+    if (i > 0 && L > offsets[i] - offsets[i - 1]) sorted = false;
+    d->max_len = std::max(d->max_len, L);
+    d->min_len = std::min(d->min_len, L);
+  }
+  d->order.resize(n_seq);
+  std::iota(d->order.begin(), d->order.end(), 0);
+  if (!sorted)  // length bucketing: decreasing length, stable
+    std::stable_sort(d->order.begin(), d->order.end(), [&](int32_t x, int32_t y) {
+      return offsets[x + 1] - offsets[x] > offsets[y + 1] - offsets[y];
+    });
+  // buckets: consecutive runs whose length is within a factor 2 of the run's first (longest) sequence
+  d->bucket_ptr.push_back(0);
+  for (int64_t i = 0; i < n_seq;) {
+    int64_t L0 = offsets[d->order[i] + 1] - offsets[d->order[i]];
+    int64_t j = i;
+    while (j < n_seq && 2 * (offsets[d->order[j] + 1] - offsets[d->order[j]]) > L0) j++;
+    d->bucket_len.push_back(L0);
+    d->bucket_ptr.push_back(j);
+    i = j;
+  }
+  cudaStream_t s = g_have_user_stream ? g_user_stream : (cudaStream_t)0;
+  if ((r = d->d_codes.alloc((size_t)d->n_res + 64)) || (r = d->d_offsets.alloc(n_seq + 1)) || (r = d->d_order.alloc(n_seq)) ||
+      (r = d->d_weights.alloc(n_seq))) {
+    delete d;
+    return r;
+  }
+  cudaMemsetAsync(d->d_codes.p + d->n_res, 0, 64, s);
+  if (d->n_res) JH_CUDA(cudaMemcpyAsync(d->d_codes.p, codes, d->n_res, cudaMemcpyHostToDevice, s));
+  JH_CUDA(cudaMemcpyAsync(d->d_offsets.p, offsets, sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, s));
+  if (n_seq) JH_CUDA(cudaMemcpyAsync(d->d_order.p, d->order.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, s));
+  if (weights && n_seq) {
+    JH_CUDA(cudaMemcpyAsync(d->d_weights.p, weights, sizeof(double) * n_seq, cudaMemcpyHostToDevice, s));
+    d->has_weights = true;
+  }
+  // alphabet check on the device (WrongAlphabetException, AbstractHMM.java:991-993)
+  unsigned int *d_mx = nullptr, h_mx = 0;
+  JH_CUDA(cudaMalloc(&d_mx, sizeof(unsigned int)));
+  cudaMemsetAsync(d_mx, 0, sizeof(unsigned int), s);
+  if (d->n_res) {
+    jha::k_max_code<<<592, 256, 0, s>>>(d->d_codes.p, d->n_res, d_mx);
+    JH_LAUNCHED();
+  }
+  cudaMemcpyAsync(&h_mx, d_mx, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(d_mx);
+  if (e != cudaSuccess) {
+    jh_set_error("CUDA error %s while uploading the data set", cudaGetErrorString(e));
+    delete d;
+    return JH_ERR_CUDA;
+  }
+  if ((int)h_mx >= alphabet) {
+    jh_set_error("The AlphabetContainer of the data set and the model do not match (code %u >= alphabet size %d).", h_mx, alphabet);
+    delete d;
+    return JH_ERR_ALPHABET;
+  }
+  *out = d;
+  return JH_OK;
+}
+
+extern "C" int jh_dataset_set_weights(jh_dataset *d, const double *weights) {
+  if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
+  if (!weights) { d->has_weights = false; return JH_OK; }
+  if (d->n_seq) JH_CUDA(cudaMemcpy(d->d_weights.p, weights, sizeof(double) * d->n_seq, cudaMemcpyHostToDevice));
+  d->has_weights = true;
+  return JH_OK;
+}
+
+extern "C" void jh_dataset_destroy(jh_dataset *d) { delete d; }
+
+extern "C" int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_res, int64_t *max_len) {
+  if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
+  if (n_seq) *n_seq = d->n_seq;
+  if (n_res) *n_res = d->n_res;
+  if (max_len) *max_len = d->max_len;
+  return JH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_pair(jh_model *m, jh_dataset *d) {
+  if (!m || !d) { jh_set_error("null handle"); return JH_ERR_INVALID; }
+  if (d->alphabet != m->a) { jh_set_error("The AlphabetContainer of the data set and the model do not match."); return JH_ERR_ALPHABET; }
+  if (m->has_silent) { jh_set_error("silent states are not on the native path yet"); return JH_ERR_UNSUPPORTED; }
+  if (m->m < 1) { jh_set_error("transition order 0 is not on the native path yet"); return JH_ERR_UNSUPPORTED; }
+  return JH_OK;
+}
+
+static int group_size(const jh_model *m) {
+  int g = 2;
+  while (g < 32 && g < m->Cmax) g *= 2;
+  return g;
+}
+
+struct LaunchPlan {
+  int G, threads, grid, groups_per_cta;
+  size_t smem;
+  int64_t slots;
+};
+
+// grid = resident CTAs (multiple of the SM count) bounded by the work and by the scratch budget
+template <typename K>
+static int plan_launch(const jh_model *m, K kernel, int G, size_t extra_smem_doubles, int64_t work, size_t scratch_bytes_per_slot,
+                       LaunchPlan *pl) {
+  pl->G = G; pl->threads = 256; pl->groups_per_cta = 256 / G;
+  pl->smem = ((size_t)pl->groups_per_cta * (2 * m->Cmax + m->S) + extra_smem_doubles) * sizeof(double);
+  if (pl->smem > 200 * 1024) { jh_set_error("model too large for the shared-memory layout (%zu bytes)", pl->smem); return JH_ERR_UNSUPPORTED; }
+  if (pl->smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, pl->threads, pl->smem));
+  if (per_sm < 1) { jh_set_error("kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  int64_t grid = (int64_t)m->sm_count * per_sm;
+  int64_t need = (work + pl->groups_per_cta - 1) / pl->groups_per_cta;
+  grid = std::max<int64_t>(1, std::min(grid, need));
+  if (scratch_bytes_per_slot) {
+    int64_t budget = g_opt.scratch_mb * 1024 * 1024;
+    int64_t max_slots = budget / (int64_t)scratch_bytes_per_slot;
+    if (max_slots < pl->groups_per_cta) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+    grid = std::min<int64_t>(grid, max_slots / pl->groups_per_cta);
+  }
+  pl->grid = (int)grid;
+  pl->slots = grid * pl->groups_per_cta;
+  return JH_OK;
+}
+
+static void timing_begin(jh_model *m) { cudaEventRecord(m->ev0, m->st()); }
+static void timing_end(jh_model *m) { cudaEventRecord(m->ev1, m->st()); m->timed = true; }
+
+extern "C" int jh_last_kernel_ms(jh_model *m, double *ms) {
+  if (!m || !ms || !m->timed) { jh_set_error("no timed call yet"); return JH_ERR_INVALID; }
+  JH_CUDA(cudaEventSynchronize(m->ev1));
+  float f = 0;
+  JH_CUDA(cudaEventElapsedTime(&f, m->ev0, m->ev1));
+  *ms = f;
+  return JH_OK;
+}
+
+#define DISPATCH_G(G, ...)                                  \
+  switch (G) {                                              \
+    case 2: { constexpr int GG = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int GG = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int GG = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int GG = 16; __VA_ARGS__; } break; \
+    default: { constexpr int GG = 32; __VA_ARGS__; } break; \
+  }
+
+// ---- log-likelihood --------------------------------------------------------------------------
+static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out) {
+  int G = group_size(m), r = JH_OK;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  DISPATCH_G(G, {
+    LaunchPlan pl;
+    r = plan_launch(m, jhx::k_exact_loglik<GG>, GG, 0, d->n_seq, 0, &pl);
+    if (!r) {
+      jhx::k_exact_loglik<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(), m->d_counter.p, d_out);
+      JH_LAUNCHED();
+    }
+  });
+  if (r) return r;
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (d->n_seq == 0) return JH_OK;
+  if (!out) { jh_set_error("null output"); return JH_ERR_INVALID; }
+  DevBuf<double> d_out;
+  if ((r = d_out.alloc(d->n_seq))) return r;
+  timing_begin(m);
+  if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
+  else r = run_loglik_exact(m, d, d_out.p);
+  timing_end(m);
+  if (r) return r;
+  JH_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+// ---- Viterbi ------------------------------------------------------------------------------------
+// One launch per length bucket so that the per-slot scratch follows the bucket's longest sequence.
+static int run_viterbi(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_scores, double *d_stats) {
+  if (m->max_children > 254) { jh_set_error("more than 254 children per context"); return JH_ERR_UNSUPPORTED; }
+  int G = group_size(m), r = JH_OK;
+  cudaStream_t s = m->st();
+  for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
+    int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b];
+    JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+    DISPATCH_G(G, {
+      LaunchPlan pl;
+      r = plan_launch(m, jhx::k_exact_viterbi<GG>, GG, 0, count, (size_t)rows * m->Cmax, &pl);
+      if (!r) r = m->d_choice.reserve((size_t)pl.slots * rows * m->Cmax);
+      if (!r) {
+        jhx::k_exact_viterbi<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(first, count), m->d_counter.p, m->d_choice.p, rows,
+                                                                    d_paths, d_scores, d_stats);
+        JH_LAUNCHED();
+      }
+    });
+  }
+  if (r) return r;
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+extern "C" int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (d->n_seq == 0) return JH_OK;
+  DevBuf<int32_t> d_paths;
+  DevBuf<double> d_scores;
+  if ((r = d_paths.alloc(d->n_res)) || (r = d_scores.alloc(d->n_seq))) return r;
+  timing_begin(m);
+  r = run_viterbi(m, d, d_paths.p, d_scores.p, nullptr);
+  timing_end(m);
+  if (r) return r;
+  if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, m->st()));
+  if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+// ---- forward-backward family (exact) ----------------------------------------------------------
+static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, double *d_loglik, double *d_post,
+                        const int32_t *d_list, int64_t n_list) {
+  int G = group_size(m), r = JH_OK;
+  cudaStream_t s = m->st();
+  int64_t n_stats = m->n_stats();
+  int stats_in_smem = mode == JHX_MODE_COUNTS && n_stats * 8 <= 96 * 1024;
+  size_t nb = d_list ? 1 : d->bucket_ptr.size() - 1;
+  for (size_t b = 0; b < nb && !r; b++) {
+    int64_t first = d_list ? 0 : d->bucket_ptr[b], count = d_list ? n_list : d->bucket_ptr[b + 1] - first;
+    int64_t rows = (d_list ? d->max_len : d->bucket_len[b]) + 1;
+    JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+    DISPATCH_G(G, {
+      LaunchPlan pl;
+      r = plan_launch(m, jhx::k_exact_fb<GG>, GG, stats_in_smem ? n_stats : 0, count, (size_t)rows * m->Cmax * sizeof(double), &pl);
+      if (!r) r = m->d_fwd.reserve((size_t)pl.slots * rows * m->Cmax);
+      if (!r) {
+        jhx::k_exact_fb<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(first, count), m->d_counter.p, m->d_fwd.p, rows, mode,
+                                                               m->d_stats.p, stats_in_smem, d_paths, d_loglik, d_post, d_list, n_list);
+        JH_LAUNCHED();
+      }
+    });
+  }
+  if (r) return r;
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (seq_index < 0 || seq_index >= d->n_seq || !out) { jh_set_error("sequence index out of range"); return JH_ERR_INVALID; }
+  int64_t L = d->offsets[seq_index + 1] - d->offsets[seq_index];
+  DevBuf<double> d_post;
+  DevBuf<int32_t> d_list;
+  if ((r = d_post.alloc((size_t)m->S * L)) || (r = d_list.alloc(1))) return r;
+  int32_t sid = (int32_t)seq_index;
+  JH_CUDA(cudaMemcpyAsync(d_list.p, &sid, sizeof(int32_t), cudaMemcpyHostToDevice, m->st()));
+  // scratch sized for this sequence only
+  int64_t saved = d->max_len;
+  d->max_len = L;
+  r = run_fb_exact(m, d, JHX_MODE_POSTERIOR, nullptr, nullptr, d_post.p, d_list.p, 1);
+  d->max_len = saved;
+  if (r) return r;
+  JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (d->n_seq == 0) return JH_OK;
+  DevBuf<int32_t> d_paths;
+  DevBuf<double> d_ll;
+  if ((r = d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
+  timing_begin(m);
+  r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
+  timing_end(m);
+  if (r) return r;
+  if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, m->st()));
+  if (loglik) JH_CUDA(cudaMemcpyAsync(loglik, d_ll.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+// ---- E-step / M-step / EM ------------------------------------------------------------------------
+static int estep_device(jh_model *m, jh_dataset *d, int mode) {
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));  // resetStatistics (HOH:890-895)
+  if (d->n_seq == 0) return JH_OK;
+  if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, nullptr, nullptr, m->d_stats.p);
+  if (g_opt.fast && m->fast.usable) {
+    int r = m->d_fallback.reserve(d->n_seq + 2);
+    if (r) return r;
+    JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+    r = jhf::run_estep(m->fast, m->dev(), *d, m->d_stats.p, m->d_counter.p, m->d_fallback.p, m->d_fwd, m->sm_count, g_opt.scratch_mb,
+                       (int)g_opt.fast_variant, s);
+    if (r) return r;
+    // sequences whose scaled recursion lost all mass are re-run by the reference-order kernels (still on the GPU)
+    int32_t n_fb = 0;
+    JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    JH_CUDA(cudaStreamSynchronize(s));
+    if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, m->d_fallback.p + 1, n_fb);
+    return JH_OK;
+  }
+  return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, nullptr, 0);
+}
+
+static int allreduce_stats(jh_model *m) {
+  if (!m->comm || m->n_ranks <= 1) return JH_OK;
+  int rc = g_nccl.AllReduce(m->d_stats.p, m->d_stats.p, (size_t)m->n_stats() + 1, /*ncclDouble*/ 8, /*ncclSum*/ 0, m->comm, m->st());
+  if (rc != 0) {
+    jh_set_error("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return JH_ERR_COMM;
+  }
+  return JH_OK;
+}
+
+static int mstep_device(jh_model *m) {
+  jha::k_mstep<<<1, 256, 0, m->st()>>>(m->params(), m->d_stats.p, m->d_stats.p + m->n_child);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return prep_scores(m);
+}
+
+extern "C" int jh_estep(jh_model *m, jh_dataset *d, int mode, double *trans_stat, double *emis_stat, double *score) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (mode != JH_MODE_VITERBI && mode != JH_MODE_BAUM_WELCH) { jh_set_error("Training mode not available."); return JH_ERR_INVALID; }
+  timing_begin(m);
+  r = estep_device(m, d, mode);
+  if (!r) r = allreduce_stats(m);
+  timing_end(m);
+  if (r) return r;
+  cudaStream_t s = m->st();
+  if (trans_stat) JH_CUDA(cudaMemcpyAsync(trans_stat, m->d_stats.p, sizeof(double) * m->n_child, cudaMemcpyDeviceToHost, s));
+  if (emis_stat) JH_CUDA(cudaMemcpyAsync(emis_stat, m->d_stats.p + m->n_child, sizeof(double) * m->n_cond * m->a, cudaMemcpyDeviceToHost, s));
+  if (score) JH_CUDA(cudaMemcpyAsync(score, m->d_stats.p + m->n_stats(), sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (trans_stat || emis_stat || score) JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+
+extern "C" int jh_mstep(jh_model *m) {
+  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  return mstep_device(m);
+}
+
+extern "C" int jh_stats_device(jh_model *m, void **dev_ptr, int64_t *n_doubles) {
+  if (!m || !dev_ptr || !n_doubles) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  *dev_ptr = m->d_stats.p;
+  *n_doubles = m->n_stats() + 1;
+  return JH_OK;
+}
+
+extern "C" int jh_baum_welch(jh_model *m, jh_dataset *d, const jh_train_opts *o, double *objective, int32_t cap, int32_t *n_iter) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (!o || !n_iter) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  if (o->term_kind != JH_TERM_ITERATIONS && o->term_kind != JH_TERM_SMALL_DIFFERENCE) { jh_set_error("unknown termination condition"); return JH_ERR_INVALID; }
+  cudaStream_t s = m->st();
+  const int obj_cap = 4000;
+  double old_value, new_value = JH_NEG_INF;
+  int it = 0;
+  timing_begin(m);
+  for (;;) {
+    old_value = new_value;
+    if ((r = estep_device(m, d, o->mode))) return r;
+    if ((r = allreduce_stats(m))) return r;
+    // objective = getLogPriorTerm() + oneIteration()   (HigherOrderHMM.java:762)
+    jha::k_log_prior<<<1, 32, 0, s>>>(m->params(), m->d_stats.p + m->n_stats(), m->d_objective.p + (it % obj_cap));
+    JH_LAUNCHED();
+    bool go_on;
+    if (o->term_kind == JH_TERM_ITERATIONS) {
+      it++;
+      go_on = it < o->max_iter;  // IterationCondition.java:83-86, no host round trip
+      if (it % obj_cap == 0 || !go_on) {
+        int base = ((it - 1) / obj_cap) * obj_cap, cnt = it - base;
+        if (objective && base < cap)
+          JH_CUDA(cudaMemcpyAsync(objective + base, m->d_objective.p, sizeof(double) * std::min(cnt, cap - base), cudaMemcpyDeviceToHost, s));
+        JH_CUDA(cudaStreamSynchronize(s));
+      }
+    } else {
+      JH_CUDA(cudaMemcpyAsync(&new_value, m->d_objective.p + (it % obj_cap), sizeof(double), cudaMemcpyDeviceToHost, s));
+      JH_CUDA(cudaStreamSynchronize(s));
+      if (objective && it < cap) objective[it] = new_value;
+      it++;
+      go_on = o->eps <= fabs(old_value - new_value) && (o->max_iter <= 0 || it < o->max_iter);  // SmallDifference...java:86-89
+    }
+    if (go_on) {
+      if ((r = mstep_device(m))) return r;
+    } else {
+      break;
+    }
+  }
+  timing_end(m);
+  JH_CUDA(cudaStreamSynchronize(s));
+  *n_iter = it;
+  return JH_OK;
+}
+
+// ---- communicator ---------------------------------------------------------------------------------
+extern "C" int jh_comm_unique_id(uint8_t id[JH_COMM_ID_BYTES]) {
+  int r = nccl_load();
+  if (r) return r;
+  Id128 u;
+  memset(&u, 0, sizeof(u));
+  int rc = g_nccl.GetUniqueId(&u);
+  if (rc != 0) { jh_set_error("ncclGetUniqueId failed (%d)", rc); return JH_ERR_COMM; }
+  memcpy(id, &u, JH_COMM_ID_BYTES);
+  return JH_OK;
+}
+
+extern "C" int jh_comm_init(jh_model *m, const uint8_t id[JH_COMM_ID_BYTES], int32_t n_ranks, int32_t rank) {
+  if (!m || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) { jh_set_error("invalid communicator arguments"); return JH_ERR_INVALID; }
+  int r = nccl_load();
+  if (r) return r;
+  JH_CUDA(cudaSetDevice(g_device));
+  Id128 u;
+  memcpy(&u, id, JH_COMM_ID_BYTES);
+  void *comm = nullptr;
+  int rc = g_nccl.CommInitRank(&comm, n_ranks, u, rank);
+  if (rc != 0) { jh_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return JH_ERR_COMM; }
+  m->comm = comm; m->n_ranks = n_ranks; m->rank = rank;
+  return JH_OK;
+}
+
+extern "C" int jh_comm_destroy(jh_model *m) {
+  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  m->comm = nullptr; m->n_ranks = 1; m->rank = 0;
+  return JH_OK;
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+extern "C" int jh_measure_fp64_peak(double *tflops) {
+  int r = ensure_device();
+  if (r) return r;
+  cudaDeviceProp prop;
+  JH_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  double *d_out;
+  JH_CUDA(cudaMalloc(&d_out, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 1 << 16, threads = 512, blocks = prop.multiProcessorCount * 4;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    jha::k_fp64_peak<<<blocks, threads>>>(d_out, iters, 1.0 + rep);
+    JH_LAUNCHED();
+    cudaEventRecord(e1);
+    JH_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = 2.0 * 8.0 * iters * (double)threads * blocks / (best * 1e-3) / 1e12;
+  return JH_OK;
+}

@@ -1,0 +1,168 @@
+// kernels_aux.cuh — parameter preparation, M-step, prior, data checks, FP64 peak probe.
+#pragma once
+#include "common.cuh"
+
+namespace jha {
+
+struct DevParams {
+  int n_elem, n_child, n_cond, a, S;
+  const int *elem_child_ptr;  // [n_elem+1]
+  const int *child_elem;      // [n_child]
+  const int *trans_index;     // [n_elem]
+  const int *row_emitting;    // [n_cond] 1 (all rows belong to emitting emissions)
+  double *trans_param, *trans_lognorm, *emis_param, *emis_lognorm;
+  const double *trans_hyper, *emis_hyper;
+  double *tscore, *escore;  // log-space score tables of the exact kernels
+};
+
+// Normalisation.getLogSum(0,n,v) (Normalisation.java:65-99)
+__device__ inline double log_sum_n(const double *v, int n) {
+  double off = JH_NEG_INF, sum = 0;
+  for (int i = 0; i < n; i++)
+    if (v[i] > off) off = v[i];
+  if (isinf(off)) return JH_NEG_INF;
+  for (int i = 0; i < n; i++) sum = __dadd_rn(sum, exp(__dsub_rn(v[i], off)));
+  return __dadd_rn(off, log(sum));
+}
+
+// score tables: parameters[c] - logNorm (BasicHigherOrderTransition.java:1116-1118) and
+// (0 - logNorm[cond]) + params[cond][sym] (AbstractConditionalDiscreteEmission.java:445-456)
+__global__ void k_prep_scores(DevParams P) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n_child) P.tscore[i] = __dsub_rn(P.trans_param[i], P.trans_lognorm[P.child_elem[i]]);
+  if (i < P.n_cond * P.a) P.escore[i] = __dadd_rn(__dsub_rn(0.0, P.emis_lognorm[i / P.a]), P.emis_param[i]);
+}
+
+// precompute() of both parameter families: logNorm = logSumNormalisation(parameters)
+// (TransitionElement.java:119-126, AbstractConditionalDiscreteEmission.java:466-480)
+__global__ void k_precompute_lognorm(DevParams P, int do_trans, int do_emis) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (do_trans && i < P.n_elem) {
+    int p0 = P.elem_child_ptr[i], n = P.elem_child_ptr[i + 1] - p0;
+    P.trans_lognorm[i] = log_sum_n(P.trans_param + p0, n);
+  }
+  if (do_emis && i < P.n_cond) P.emis_lognorm[i] = log_sum_n(P.emis_param + (size_t)i * P.a, P.a);
+}
+
+// M-step == estimateFromStatistic of every transition element and emission
+// (BasicHigherOrderTransition.java:458-466 + :1242-1262, AbstractConditionalDiscreteEmission.java:682-699).
+// One block; the statistics are modified in place (hyper-parameters added) like in the reference.
+__global__ void k_mstep(DevParams P, double *trans_stat, double *emis_stat) {
+  for (int t = threadIdx.x; t < P.n_elem; t += blockDim.x) {
+    if (P.trans_index[t] != t) continue;
+    int p0 = P.elem_child_ptr[t], n = P.elem_child_ptr[t + 1] - p0;
+    if (n <= 0) continue;
+    double ln = 0;
+    for (int i = 0; i < n; i++) {
+      double s = __dadd_rn(trans_stat[p0 + i], P.trans_hyper[p0 + i]);
+      trans_stat[p0 + i] = s;
+      ln = __dadd_rn(ln, s);
+      P.trans_param[p0 + i] = log(s);
+    }
+    if (ln == 0) {
+      for (int i = 0; i < n; i++) P.trans_param[p0 + i] = 0;
+      ln = n;
+    }
+    ln = log(ln);
+    for (int i = 0; i < n; i++) P.trans_param[p0 + i] = __dsub_rn(P.trans_param[p0 + i], ln);
+    P.trans_lognorm[t] = log_sum_n(P.trans_param + p0, n);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < P.n_elem; t += blockDim.x) {  // tied elements: setParameters + precompute
+    int r = P.trans_index[t];
+    if (r == t) continue;
+    int p0 = P.elem_child_ptr[t], q0 = P.elem_child_ptr[r], n = P.elem_child_ptr[t + 1] - p0;
+    for (int i = 0; i < n; i++) P.trans_param[p0 + i] = P.trans_param[q0 + i];
+    P.trans_lognorm[t] = log_sum_n(P.trans_param + p0, n);
+  }
+  for (int r = threadIdx.x; r < P.n_cond; r += blockDim.x) {
+    double *st = emis_stat + (size_t)r * P.a;
+    const double *hy = P.emis_hyper + (size_t)r * P.a;
+    double sum = 0;
+    for (int i = 0; i < P.a; i++) {
+      st[i] = __dadd_rn(st[i], hy[i]);
+      sum = __dadd_rn(sum, st[i]);
+    }
+    if (sum == 0) {
+      for (int i = 0; i < P.a; i++) st[i] = 1;
+      sum = P.a;
+    }
+    for (int i = 0; i < P.a; i++) P.emis_param[(size_t)r * P.a + i] = log(st[i] / sum);
+    P.emis_lognorm[r] = 0;
+  }
+}
+
+// HigherOrderHMM.getLogPriorTerm (:253-259): sequential, reference order. out[0] = prior (+ add[0] if add != nullptr).
+__global__ void k_log_prior(DevParams P, const double *add, double *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double pt = 0;
+  for (int t = 0; t < P.n_elem; t++) {
+    if (P.trans_index[t] != t) continue;
+    int p0 = P.elem_child_ptr[t], n = P.elem_child_ptr[t + 1] - p0;
+    double term = 0;
+    if (n > 1) {
+      double r = 0, sh = 0;
+      for (int d = 0; d < n; d++) {
+        sh = __dadd_rn(sh, P.trans_hyper[p0 + d]);
+        r = __dadd_rn(r, __dmul_rn(P.trans_hyper[p0 + d], P.trans_param[p0 + d]));
+      }
+      term = sh == 0 ? 0 : __dsub_rn(r, __dmul_rn(sh, P.trans_lognorm[t]));
+    }
+    pt = __dadd_rn(pt, term);
+  }
+  double res = pt, r = 0;
+  int a = P.a;
+  // rows are grouped by emission; the reference sums per emission and then adds to the total. Rows of one emission
+  // are contiguous, emission boundaries are not needed for the value except for the association order, which
+  // is restored with row_emitting[] == 2 marking the first row of each emission.
+  bool open = false;
+  for (int row = 0; row < P.n_cond; row++) {
+    if (P.row_emitting[row] == 2) {
+      if (open) res = __dadd_rn(res, r);
+      r = 0;
+      open = true;
+    }
+    double ess = 0;
+    for (int j = 0; j < a; j++) ess = __dadd_rn(ess, P.emis_hyper[(size_t)row * a + j]);
+    if (ess > 0) {
+      r = __dadd_rn(r, __dmul_rn(-ess, P.emis_lognorm[row]));
+      for (int j = 0; j < a; j++) r = __dadd_rn(r, __dmul_rn(P.emis_hyper[(size_t)row * a + j], P.emis_param[(size_t)row * a + j]));
+    }
+  }
+  if (open) res = __dadd_rn(res, r);
+  out[0] = add ? __dadd_rn(res, add[0]) : res;
+}
+
+// largest residue code of the packed data (alphabet check of AbstractHMM.java:991-993 done once per data set)
+__global__ void k_max_code(const uint8_t *codes, int64_t n, unsigned int *out) {
+  unsigned int mx = 0;
+  int64_t i = (int64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 16, stride = (int64_t)gridDim.x * blockDim.x * 16;
+  for (; i + 16 <= n; i += stride) {
+    uint4 v = *reinterpret_cast<const uint4 *>(codes + i);
+    unsigned int w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      unsigned int x = w[k];
+      unsigned int m = max(max(x & 0xff, (x >> 8) & 0xff), max((x >> 16) & 0xff, x >> 24));
+      mx = max(mx, m);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t j = n - (n % 16); j < n; j++) mx = max(mx, (unsigned int)codes[j]);
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if ((threadIdx.x & 31) == 0 && mx) atomicMax(out, mx);
+}
+
+// FP64 FMA peak probe: 8 independent register-resident DFMA chains per thread.
+__global__ void k_fp64_peak(double *out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.9999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace jha

@@ -805,14 +805,15 @@ class HigherOrderHMM:
         self._push_params()
         if isinstance(seq_or_data, DataSet):
             nd = self._data(seq_or_data)
-            return [eng.posterior(nd, i) for i in range(seq_or_data.getNumberOfElements())]
+            lens = np.diff(seq_or_data.offsets)
+            return [eng.posterior(nd, i, self.getNumberOfStates(), int(lens[i])) for i in range(seq_or_data.getNumberOfElements())]
         seq = seq_or_data
         if endPos is None:
             endPos = seq.getLength() - 1
         if startPos != 0 and any(e.order > 0 for e in self.emission):
             raise NotImplementedError("window posterior with higher-order emissions is not on the native path yet")
         ds = DataSet("", Sequence(self.alphabets, seq.codes[startPos:endPos + 1]), con=self.alphabets)
-        return eng.posterior(self._data(ds), 0)
+        return eng.posterior(self._data(ds), 0, self.getNumberOfStates(), ds.getNumberOfResidues())
 
     def getStatePosteriorMatrixFor(self, seq_or_data):
         """AbstractHMM.getStatePosteriorMatrixFor (:811-820)."""

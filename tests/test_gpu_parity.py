@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Gates (BASELINE.json north_star): Viterbi paths bit-exact; per-sequence log-likelihood <= 1e-9 relative (fp64);
+trained parameters after N EM iterations <= 1e-6; expected counts checked at 1e-9.
+Every test runs the reference-order kernels (fast=0) and, where the model allows, the scaled fast kernels (fast=1).
+"""
+import numpy as np
+import pytest
+
+from helpers import dataset_of, ergodic_hmm, order2_hmm, random_dna, sparse_hmm
+from jstacs_b200 import (DNA, BaumWelchParameterSet, DataSet, DiscreteEmission, HigherOrderHMM, IterationCondition,
+                         Sequence, SmallDifferenceOfFunctionEvaluationsCondition, TransitionElement, ViterbiParameterSet,
+                         WrongAlphabetException)
+from jstacs_b200.workloads import banded_hmm, make_data, planted_dna, ragged_lengths
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9      # north_star: per-sequence log-likelihood within 1e-9 relative
+COUNT_TOL = 1e-9    # expected counts (absolute on O(1..L) values, relative otherwise)
+PARAM_TOL = 1e-6    # north_star: trained parameters within 1e-6
+
+
+@pytest.fixture(scope="module")
+def nat():
+    import __graft_entry__ as g
+
+    g.build()
+    from jstacs_b200 import _native
+
+    if _native.lib().jh_device_count() <= 0:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return _native
+
+
+@pytest.fixture(params=[0, 1], ids=["exact", "fast"])
+def fast(request, nat):
+    nat.check(nat.lib().jh_set_option(b"fast", request.param))
+    yield request.param
+    nat.check(nat.lib().jh_set_option(b"fast", 1))
+
+
+def ragged_data(seed, n, lo=1, hi=120):
+    rng = np.random.default_rng(seed)
+    return dataset_of([random_dna(rng, int(L)) for L in rng.integers(lo, hi, n)])
+
+
+MODELS = {
+    "erg_s2_k1": lambda: ergodic_hmm(2, 1),
+    "erg_s3_k0_map": lambda: ergodic_hmm(3, 0, ess=4.0),
+    "erg_s5_k2": lambda: ergodic_hmm(5, 2),
+    "erg_s8_k2": lambda: ergodic_hmm(8, 2),
+    "erg_s16_k1": lambda: ergodic_hmm(16, 1),
+    "erg_s32_k3": lambda: ergodic_hmm(32, 3, ess=4.0),
+    "sparse": lambda: sparse_hmm(),
+    "order2_s3": lambda: order2_hmm(3, 1),
+    "banded_s40": lambda: banded_hmm(40, 4, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_loglik_matches_oracle(nat, oracle_lib, fast, name):
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(1, 67)
+    got = hmm.getLogScoreFor(data)
+    ref = om.loglik(data.codes, data.offsets)
+    np.testing.assert_allclose(got, ref, rtol=LL_RTOL, atol=0)
+    assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max() + 1e-13  # in practice ~1 ulp of the DP
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_viterbi_paths_bit_exact(nat, oracle_lib, name):
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(2, 61)
+    res = hmm.getViterbiPathsFor(data)
+    rp, rs, _ = om.viterbi(data.codes, data.offsets)
+    for (p, s), p_ref, s_ref in zip(res, rp, rs):
+        assert np.array_equal(p, p_ref)
+        assert s == s_ref  # bit-exact score: only adds and compares
+
+
+def test_viterbi_tie_rule_first_child_in_user_order(nat, oracle_lib):
+    pars = BaumWelchParameterSet(1, IterationCondition(1), 1)
+    for order in ([0, 1, 2], [2, 0, 1], [1, 2, 0]):
+        em = [DiscreteEmission(DNA, 0.0) for _ in range(3)]
+        te = [TransitionElement(None, order, None)] + [TransitionElement([s], order, None) for s in range(3)]
+        hmm = HigherOrderHMM(pars, ["a", "b", "c"], em, *te)
+        seq = Sequence.create(DNA, "ACGTTGCAAC")
+        path, score = hmm.getViterbiPathFor(seq)
+        assert list(path) == [order[0]] * 10
+        om = oracle_lib.OracleModel(hmm.ir())
+        rp, rs, _ = om.viterbi(seq.codes, np.array([0, 10]))
+        assert score == rs[0] and np.array_equal(path, rp[0])
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_estep_counts_match_oracle(nat, oracle_lib, fast, name):
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(3, 53)
+    rng = np.random.default_rng(0)
+    w = rng.random(data.getNumberOfElements()) + 0.5
+    eng, nd = hmm._engine(), hmm._data(data)
+    for weights in (None, w):
+        nd.set_weights(weights)
+        ts, es, sc = eng.estep(nd)
+        rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+        np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+        np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+        assert sc == pytest.approx(rsc, rel=LL_RTOL)
+
+
+@pytest.mark.parametrize("name,ess", [("erg_s2_k1", 0.0), ("erg_s3_k0_map", 4.0), ("erg_s8_k2", 0.0), ("sparse", 0.0),
+                                      ("order2_s3", 0.0), ("erg_s32_k3", 4.0)])
+def test_baum_welch_training_matches_oracle(nat, oracle_lib, fast, name, ess):
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = planted_dna(60, 80, n_states=2, seed=5)
+    n_iter = 6
+    hmm.trainingParameter = BaumWelchParameterSet(1, IterationCondition(n_iter), 1)
+    best = hmm.train(data)
+    robj = om.train(data.codes, data.offsets, max_iter=n_iter)
+    obj = np.array(hmm.last_objectives[0])
+    assert len(obj) == n_iter  # N E-steps, N-1 M-steps (HigherOrderHMM.java:760-770)
+    np.testing.assert_allclose(obj, robj, rtol=LL_RTOL)
+    assert best == obj[-1]
+    got = hmm._engine().get_params()
+    ref = om.get_params()
+    for g, r in zip(got, ref):
+        fin = np.isfinite(r)
+        assert np.array_equal(np.isfinite(g), fin)
+        np.testing.assert_allclose(g[fin], r[fin], rtol=0, atol=PARAM_TOL)
+    # the host mirror received the trained parameters (toXML / getCurrentParameterValues keep working)
+    ir = hmm.ir()
+    np.testing.assert_array_equal(ir.trans_param, got[0])
+    np.testing.assert_array_equal(ir.emis_param, got[2])
+
+
+def test_small_difference_termination(nat, oracle_lib, fast):
+    hmm = ergodic_hmm(3, 1)
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = planted_dna(50, 60, n_states=3, seed=9)
+    hmm.trainingParameter = BaumWelchParameterSet(1, SmallDifferenceOfFunctionEvaluationsCondition(1e-2), 1)
+    hmm.train(data)
+    robj = om.train(data.codes, data.offsets, term_kind=1, eps=1e-2, max_iter=0)
+    obj = np.array(hmm.last_objectives[0])
+    assert len(obj) == len(robj)
+    np.testing.assert_allclose(obj, robj, rtol=LL_RTOL)
+
+
+def test_viterbi_training_matches_oracle(nat, oracle_lib):
+    hmm = ergodic_hmm(3, 1)
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = planted_dna(40, 50, n_states=3, seed=2)
+    eng, nd = hmm._engine(), hmm._data(data)
+    ts, es, sc = eng.estep(nd, mode=nat.MODE_VITERBI)
+    rts, res, rsc = om.estep(data.codes, data.offsets, mode=0)
+    np.testing.assert_array_equal(ts, rts)  # integer counts
+    np.testing.assert_array_equal(es, res)
+    assert sc == pytest.approx(rsc, rel=1e-13)
+    hmm.trainingParameter = ViterbiParameterSet(1, IterationCondition(4), 1)
+    hmm.train(data)
+    robj = om.train(data.codes, data.offsets, mode=0, max_iter=4)
+    np.testing.assert_allclose(hmm.last_objectives[0], robj, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["erg_s2_k1", "erg_s5_k2", "sparse", "order2_s3", "erg_s32_k3"])
+def test_posterior_matrix_and_decoding(nat, oracle_lib, name):
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(4, 12, lo=3, hi=90)
+    mats = hmm.getLogStatePosteriorMatrixFor(data)
+    dec = hmm.decodePosteriorPathsFor(data)
+    ll_ref = om.loglik(data.codes, data.offsets)
+    for i in range(data.getNumberOfElements()):
+        x = data.getElementAt(i).codes
+        ref = om.posterior(x)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(mats[i]), fin)
+        np.testing.assert_allclose(mats[i][fin], ref[fin], rtol=0, atol=1e-10)
+        ref_path = om.decode_posterior(ref)
+        path, ll = dec[i]
+        assert ll == pytest.approx(ll_ref[i], rel=LL_RTOL)
+        # index work is bit-exact wherever the oracle's own top-2 gap is above rounding noise
+        srt = np.sort(ref, axis=0)
+        clear = (srt[-1] - srt[-2] > 1e-9) if ref.shape[0] > 1 else np.ones(ref.shape[1], bool)
+        assert np.array_equal(path[clear], ref_path[clear])
+        assert np.array_equal(HigherOrderHMM.decodeStatePosterior(mats[i])[0][clear], ref_path[clear])
+
+
+def test_edge_cases(nat, oracle_lib):
+    hmm = ergodic_hmm(3, 2)
+    om = oracle_lib.OracleModel(hmm.ir())
+    # empty data set
+    empty = DataSet.from_packed(np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert hmm.getLogScoreFor(empty).size == 0
+    assert hmm.getViterbiPathsFor(empty) == []
+    # single residues and lengths below the emission order
+    data = dataset_of([[0], [3], [1, 2], [2, 2, 2], [0, 1, 2, 3]])
+    np.testing.assert_allclose(hmm.getLogScoreFor(data), om.loglik(data.codes, data.offsets), rtol=LL_RTOL)
+    rp, rs, _ = om.viterbi(data.codes, data.offsets)
+    for (p, s), pr, sr in zip(hmm.getViterbiPathsFor(data), rp, rs):
+        assert np.array_equal(p, pr) and s == sr
+    # an empty sequence is rejected like in the reference
+    with pytest.raises(nat.NativeError) as ei:
+        hmm.getLogScoreFor(DataSet.from_packed(np.array([1, 2], np.uint8), np.array([0, 0, 2], np.int64)))
+    assert ei.value.status == -1
+    # wrong alphabet
+    bad = DataSet.from_packed(np.array([0, 1, 2, 3], np.uint8), np.array([0, 4], np.int64))
+    bad.codes = np.array([0, 1, 7, 3], np.uint8)
+    with pytest.raises(nat.NativeError) as ei:
+        hmm.getLogScoreFor(bad)
+    assert ei.value.status == -4
+    assert isinstance(WrongAlphabetException("x"), Exception)
+
+
+def test_zero_probability_parameters(nat, oracle_lib, fast):
+    """-inf parameters (an M-step with a zero count and no prior yields log(0)): impossible paths are handled and an
+    impossible sequence scores -inf on both sides."""
+    hmm = sparse_hmm()
+    e = hmm.emission[0]
+    lp = e.params.copy()
+    lp[:, 0] = -np.inf  # state a never emits A
+    lp = lp - np.log(np.exp(lp).sum(1, keepdims=True))
+    e.setLogProbabilities(lp)
+    hmm._push_params()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(6, 40, lo=2, hi=50)
+    ref = om.loglik(data.codes, data.offsets)
+    got = hmm.getLogScoreFor(data)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin) and fin.any()
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=LL_RTOL)
+    ts, es, sc = hmm._engine().estep(hmm._data(dataset_of([data.getElementAt(i).codes for i in np.nonzero(fin)[0]])))
+    keep = dataset_of([data.getElementAt(i).codes for i in np.nonzero(fin)[0]])
+    rts, res, rsc = om.estep(keep.codes, keep.offsets)
+    np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+    np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+
+
+def test_java_random_workload_and_ragged_buckets(nat, oracle_lib, fast):
+    """cfg4-style ragged lengths on the java.util.Random stream; length buckets must not change results or order."""
+    lens = ragged_lengths(48, seed=42, lo=20.0, decades=2.0)
+    data = make_data(48, lens)
+    hmm = ergodic_hmm(16, 1)
+    om = oracle_lib.OracleModel(hmm.ir())
+    np.testing.assert_allclose(hmm.getLogScoreFor(data), om.loglik(data.codes, data.offsets), rtol=LL_RTOL)
+    ts, es, sc = hmm._engine().estep(hmm._data(data))
+    rts, res, rsc = om.estep(data.codes, data.offsets)
+    np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+    np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+    assert sc == pytest.approx(rsc, rel=LL_RTOL)
+
+
+def test_full_size_properties_cfg1(nat, fast):
+    """BASELINE cfg1 at full size (10k x 1 kb): size-independent properties instead of an oracle run:
+    counts add up (transitions = sum L_n, emissions = sum (L_n - k)), score == sum of per-sequence log-likelihoods,
+    Viterbi score <= log-likelihood, EM objective is monotone."""
+    hmm = ergodic_hmm(2, 1, n_iter=4)
+    data = make_data(10_000, 1000)
+    eng, nd = hmm._engine(), hmm._data(data)
+    ts, es, sc = eng.estep(nd)
+    assert ts.sum() == pytest.approx(1e7, rel=1e-10)
+    assert es.sum() == pytest.approx(1e7 - 1e4, rel=1e-10)
+    ll = eng.loglik(nd)
+    assert sc == pytest.approx(ll.sum(), rel=1e-11)
+    paths, vs = eng.viterbi(nd)
+    assert (vs <= ll + 1e-9).all() and paths.min() >= 0 and paths.max() <= 1
+    hmm.train(data)
+    assert (np.diff(hmm.last_objectives[0]) >= -1e-6).all()
