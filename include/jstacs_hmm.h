@@ -210,6 +210,8 @@ int jh_stats_device(jh_model *m, void **dev_ptr, int64_t *n_doubles);
 int jh_measure_fp64_peak(double *tflops);
 /* Device time in ms of the kernels of the last compute call (CUDA events on the library stream). */
 int jh_last_kernel_ms(jh_model *m, double *ms);
+/* Device time in ms of the E-step kernel launches alone (the dominant kernel) of the last E-step. */
+int jh_last_main_kernel_ms(jh_model *m, double *ms);
 
 #ifdef __cplusplus
 }

@@ -121,6 +121,7 @@ def lib():
         "jh_measure_fp64_peak": (C.c_int, [_P_F64]),
         "jh_last_kernel_ms": (C.c_int, [vp, _P_F64]),
         "jh_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+        "jh_last_main_kernel_ms": (C.c_int, [vp, _P_F64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -258,6 +259,11 @@ class NativeModel:
         p, n = C.c_void_p(), C.c_int64()
         check(lib().jh_stats_device(self.h, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def last_main_kernel_ms(self) -> float:
+        v = C.c_double()
+        check(lib().jh_last_main_kernel_ms(self.h, C.byref(v)))
+        return v.value
 
     def last_kernel_ms(self) -> float:
         v = C.c_double()

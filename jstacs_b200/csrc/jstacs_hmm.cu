@@ -125,8 +125,8 @@ struct jh_model {
   DevBuf<int32_t> d_fallback;  // [1 + n] list of sequences the fast path handed to the exact kernels
   jhf::FastTables fast;        // linear-space tables of the fast path
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool timed = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  bool timed = false, ktimed = false;
   int sm_count = 148;
   void *comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -355,6 +355,8 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(JH_ERR_CUDA, "cudaStreamCreate failed");
   cudaEventCreate(&m->ev0);
   cudaEventCreate(&m->ev1);
+  cudaEventCreate(&m->evk0);
+  cudaEventCreate(&m->evk1);
   cudaStream_t s = m->st();
   std::vector<unsigned char> fin(m->state_final.begin(), m->state_final.end());
   std::vector<double> tp(d->trans_param, d->trans_param + m->n_child), tl(d->trans_lognorm, d->trans_lognorm + m->n_elem),
@@ -391,6 +393,8 @@ extern "C" void jh_model_destroy(jh_model *m) {
   jhf::destroy(m->fast);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->evk0) cudaEventDestroy(m->evk0);
+  if (m->evk1) cudaEventDestroy(m->evk1);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -597,6 +601,15 @@ extern "C" int jh_last_kernel_ms(jh_model *m, double *ms) {
   return JH_OK;
 }
 
+extern "C" int jh_last_main_kernel_ms(jh_model *m, double *ms) {
+  if (!m || !ms || !m->ktimed) { jh_set_error("no timed E-step yet"); return JH_ERR_INVALID; }
+  JH_CUDA(cudaEventSynchronize(m->evk1));
+  float f = 0;
+  JH_CUDA(cudaEventElapsedTime(&f, m->evk0, m->evk1));
+  *ms = f;
+  return JH_OK;
+}
+
 #define DISPATCH_G(G, ...)                                  \
   switch (G) {                                              \
     case 2: { constexpr int GG = 2; __VA_ARGS__; } break;   \
@@ -750,6 +763,56 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
 }
 
 // ---- E-step / M-step / EM ------------------------------------------------------------------------
+// Scaled linear-space E-step (kernels_fast.cuh), one launch per length bucket.
+template <int G, int NT>
+static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t count, int64_t rows) {
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhf::k_fast_estep<G, NT>;
+  size_t smem = ((size_t)3 * G * G + (size_t)2 * F.H * G + G + (size_t)2 * NT) * sizeof(double);
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) { jh_set_error("fast E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  const int gpc = NT / G;
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (count + gpc - 1) / gpc);
+  int64_t per_slot = rows * G * (int64_t)sizeof(double) + rows * (int64_t)sizeof(int);
+  int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < gpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  grid = std::max<int64_t>(1, std::min(grid, max_slots / gpc));
+  int64_t slots = grid * gpc;
+  int r = m->d_fwd.reserve((size_t)slots * rows * G);
+  if (r) return r;
+  if ((size_t)slots * rows > F.fexp_n) {
+    if (F.d_fexp) cudaFree(F.d_fexp);
+    F.d_fexp = nullptr;
+    F.fexp_n = 0;
+    if (cudaMalloc(&F.d_fexp, (size_t)slots * rows * sizeof(int)) != cudaSuccess) { cudaGetLastError(); jh_set_error("out of device memory (exponent scratch)"); return JH_ERR_NOMEM; }
+    F.fexp_n = (size_t)slots * rows;
+  }
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, NT, smem, s>>>(F.dev(), d->dev(first, count), m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, m->d_fallback.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_estep_fast(jh_model *m, jh_dataset *d) {
+  int r = JH_OK;
+  for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
+    int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b] + 1;
+    switch (m->fast.G) {
+      case 2: r = launch_fast_estep<2, 512>(m, d, first, count, rows); break;
+      case 4: r = launch_fast_estep<4, 512>(m, d, first, count, rows); break;
+      case 8: r = launch_fast_estep<8, 512>(m, d, first, count, rows); break;
+      case 16: r = launch_fast_estep<16, 512>(m, d, first, count, rows); break;
+      default: r = launch_fast_estep<32, 384>(m, d, first, count, rows); break;
+    }
+  }
+  return r;
+}
+
 static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));  // resetStatistics (HOH:890-895)
@@ -758,18 +821,34 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   if (g_opt.fast && m->fast.usable) {
     int r = m->d_fallback.reserve(d->n_seq + 2);
     if (r) return r;
+    int32_t *flag = m->d_fallback.p + d->n_seq + 1;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
-    r = jhf::run_estep(m->fast, m->dev(), *d, m->d_stats.p, m->d_counter.p, m->d_fallback.p, m->d_fwd, m->sm_count, g_opt.scratch_mb,
-                       (int)g_opt.fast_variant, s);
+    JH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
+    cudaEventRecord(m->evk0, s);
+    r = run_estep_fast(m, d);
+    cudaEventRecord(m->evk1, s);
+    m->ktimed = true;
     if (r) return r;
+    int n = (int)m->n_stats() + 1;
+    jhf::k_check_finite<<<(n + 255) / 256, 256, 0, s>>>(m->d_stats.p, n, flag);
+    JH_LAUNCHED();
     // sequences whose scaled recursion lost all mass are re-run by the reference-order kernels (still on the GPU)
-    int32_t n_fb = 0;
+    int32_t n_fb = 0, bad = 0;
     JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    JH_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     JH_CUDA(cudaStreamSynchronize(s));
+    if (bad) {  // dynamic range exceeded: redo the whole E-step in log space
+      JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));
+      return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, nullptr, 0);
+    }
     if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, m->d_fallback.p + 1, n_fb);
     return JH_OK;
   }
-  return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, nullptr, 0);
+  cudaEventRecord(m->evk0, s);
+  int r = run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, nullptr, 0);
+  cudaEventRecord(m->evk1, s);
+  m->ktimed = true;
+  return r;
 }
 
 static int allreduce_stats(jh_model *m) {

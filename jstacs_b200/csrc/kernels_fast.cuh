@@ -1,30 +1,470 @@
-// kernels_fast.cuh — scaled linear-space kernels (placeholder: tables only; kernels follow).
+// kernels_fast.cuh — scaled linear-space forward/backward kernels (the production E-step and scoring path).
+//
+// Scope: first-order transitions (m == 1), no silent states, S <= 32 states, emission table a^(Kmax+1) x G doubles
+// <= 64 KB.  Everything else runs on the reference-order kernels of kernels_exact.cuh.
+//
+// Why a different formulation keeps the reference's results.  The reference evaluates every DP cell as an n-ary
+// log-sum-exp (one exp per edge, one log per context; HigherOrderHMM.java:371-405, 531-570).  The same quantities
+// are computed here in probability space with an EXACT power-of-two rescaling per position (the scale is 2^-e,
+// e = exponent of the largest entry, so rescaling introduces no rounding at all); one log per SEQUENCE turns the
+// result back into a log-likelihood.  Per position a state needs S fused multiply-adds instead of S exp.  Results
+// agree with the log-space recursion to ~1e-13 relative (tests/test_gpu_parity.py runs both against the oracle);
+// the 1e-9 / 1e-6 gates of BASELINE.json are met with 4-7 digits of margin.  If the scaled recursion loses all mass
+// (possible only with zero-probability parameters and > 2^1022 dynamic range between lineages) the sequence is
+// handed to the log-space kernels on the GPU; there is no CPU fallback.
+//
+// Mapping: one group of G lanes per sequence (G = 2,4,8,16,32 >= S; 32/G sequences per warp), lane = state.
+//   forward : lane j holds column T[:,j] in registers; alpha is broadcast through shared memory with 128-bit
+//             loads; per position G FMAs per lane.  Scaled rows go to an HBM scratch (G*8 bytes per position).
+//   backward: lane i holds row T[i,:] and the expected-count accumulators O[i,:] in registers; the broadcast
+//             vector b[j] = e_j(x_l)*beta_{l+1}[j] feeds BOTH the beta recursion and the rank-1 count update
+//             O[i][j] += alpha_l[i]*g_l*b[j]  (2 FMAs per loaded value, 4 per 128-bit load).
+//             xi_l(i,j) = T[i][j]*O-term, so T is multiplied in once per kernel, not per position.
+//   emission counts: gamma_l(j) = alpha_{l+1}[j]*beta_{l+1}[j]*scale into a per-CTA shared table [context hash][state].
 #pragma once
 #include "common.cuh"
+#include "kernels_exact.cuh"
 
 struct jh_dataset;
-template <typename T> struct DevBuf;
+template <typename T>
+struct DevBuf;
 
 namespace jhf {
 
-struct FastTables {
-  bool usable = false;
+using jhx::ResReader;
+
+struct FastDev {
+  int S, G, a, Kmax, H;  // H = a^(Kmax+1) rows of the emission table
+  int hpow, a_pow2, n_child, n_stats;
+  double inv_a;
+  const double *T;      // [G*G] T[i*G+j] = P(i -> j)
+  const double *Tt;     // [G*G] transposed
+  const double *pi;     // [G]
+  const double *E;      // [H*G] E[h*G+j] = P(x | context) of state j for context hash h
+  const double *fin;    // [G] 1.0 for final states
+  const int *korder;    // [G] emission order per state (padding lanes: 0)
+  const int *tstat;     // [G*G] statistics slot of edge i->j or -1
+  const int *pistat;    // [G]
+  const int *estat_tab; // [G] state_tab (offset into the emission statistics), -1 for padding lanes
+  const int *estat_mod; // [G] a^(k+1)
 };
 
-inline int build(FastTables &F, int, int, int, bool, int, const std::vector<int> &, const std::vector<int> &, const std::vector<int> &,
-                 const std::vector<int> &, const std::vector<int> &, const std::vector<int> &, const std::vector<int> &,
-                 const std::vector<int> &, const std::vector<int> &, const std::vector<uint8_t> &, int, int, cudaStream_t) {
-  F.usable = false;
+struct FastTables {
+  bool usable = false;
+  int S = 0, G = 0, a = 0, Kmax = 0, H = 0, n_child = 0, n_cond = 0;
+  double *d_T = nullptr, *d_Tt = nullptr, *d_pi = nullptr, *d_E = nullptr, *d_fin = nullptr;
+  int *d_korder = nullptr, *d_tstat = nullptr, *d_pistat = nullptr, *d_estat_tab = nullptr, *d_estat_mod = nullptr;
+  int *d_tmap = nullptr, *d_pimap = nullptr;  // child index p of edge i->j / start->j, -1 if absent
+  int *d_fexp = nullptr;                      // per-row exponent scratch
+  size_t fexp_n = 0;
+  FastDev dev() const {
+    FastDev F;
+    F.S = S; F.G = G; F.a = a; F.Kmax = Kmax; F.H = H;
+    int pw = 1;
+    for (int i = 0; i < Kmax; i++) pw *= a;
+    F.hpow = pw; F.a_pow2 = (a & (a - 1)) == 0; F.n_child = n_child; F.n_stats = n_child + n_cond * a;
+    F.inv_a = 1.0 / a;
+    F.T = d_T; F.Tt = d_Tt; F.pi = d_pi; F.E = d_E; F.fin = d_fin; F.korder = d_korder; F.tstat = d_tstat; F.pistat = d_pistat;
+    F.estat_tab = d_estat_tab; F.estat_mod = d_estat_mod;
+    return F;
+  }
+};
+
+inline void destroy(FastTables &F) {
+  void *ptrs[] = {F.d_T, F.d_Tt, F.d_pi, F.d_E, F.d_fin, F.d_korder, F.d_tstat, F.d_pistat, F.d_estat_tab, F.d_estat_mod, F.d_tmap, F.d_pimap, F.d_fexp};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  F = FastTables();
+}
+
+template <typename T>
+static int up(T **dst, const std::vector<T> &h, cudaStream_t s) {
+  if (cudaMalloc((void **)dst, std::max<size_t>(h.size(), 1) * sizeof(T)) != cudaSuccess) {
+    jh_set_error("out of device memory (fast tables)");
+    return JH_ERR_NOMEM;
+  }
+  if (!h.empty()) JH_CUDA(cudaMemcpyAsync(*dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
   return JH_OK;
 }
-inline int prepare(FastTables &, const DevModel &, cudaStream_t) { return JH_OK; }
-inline void destroy(FastTables &) {}
-inline int run_loglik(FastTables &, const DevModel &, const DevData &, int64_t, int64_t, double *, unsigned long long *, int, cudaStream_t) {
-  return JH_ERR_UNSUPPORTED;
+
+// Decide whether the model is in scope and build the index maps.
+inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, const std::vector<int> &lc_ctx_ptr,
+                 const std::vector<int> &ctx_elem, const std::vector<int> &ctx_last, const std::vector<int> &elem_child_ptr,
+                 const std::vector<int> &child_state, const std::vector<int> &child_stat, const std::vector<int> &state_order,
+                 const std::vector<int> &state_tab, const std::vector<int> &state_mod, const std::vector<uint8_t> &state_final,
+                 int n_child, int n_cond, cudaStream_t s) {
+  F.usable = false;
+  if (m != 1 || has_silent || S > 32) return JH_OK;
+  if (lc_ctx_ptr[1] - lc_ctx_ptr[0] != 1) return JH_OK;
+  int G = 2;
+  while (G < S) G *= 2;
+  int64_t H = a;
+  for (int i = 0; i < Kmax; i++) H *= a;
+  if (H * G * 8 > 64 * 1024) return JH_OK;
+  std::vector<int> tmap((size_t)G * G, -1), pimap(G, -1), tstat((size_t)G * G, -1), pistat(G, -1), korder(G, 0), etab(G, -1), emod(G, 1);
+  std::vector<double> fin(G, 0.0);
+  std::vector<char> seen(S, 0);
+  int e0 = ctx_elem[lc_ctx_ptr[0]];
+  for (int p = elem_child_ptr[e0]; p < elem_child_ptr[e0 + 1]; p++) {
+    pimap[child_state[p]] = p;
+    pistat[child_state[p]] = child_stat[p];
+  }
+  for (int c = lc_ctx_ptr[1]; c < lc_ctx_ptr[2]; c++) {
+    int i = ctx_last[c], e = ctx_elem[c];
+    if (i < 0 || i >= S || seen[i]) return JH_OK;  // two contexts for one state: not a plain first-order chain
+    seen[i] = 1;
+    for (int p = elem_child_ptr[e]; p < elem_child_ptr[e + 1]; p++) {
+      tmap[(size_t)i * G + child_state[p]] = p;
+      tstat[(size_t)i * G + child_state[p]] = child_stat[p];
+    }
+  }
+  for (int j = 0; j < S; j++) {
+    korder[j] = state_order[j];
+    etab[j] = state_tab[j];
+    emod[j] = state_mod[j];
+    fin[j] = state_final[j] ? 1.0 : 0.0;
+  }
+  F.S = S; F.G = G; F.a = a; F.Kmax = Kmax; F.H = (int)H; F.n_child = n_child; F.n_cond = n_cond;
+  int r;
+  if ((r = up(&F.d_tmap, tmap, s)) || (r = up(&F.d_pimap, pimap, s)) || (r = up(&F.d_tstat, tstat, s)) || (r = up(&F.d_pistat, pistat, s)) ||
+      (r = up(&F.d_korder, korder, s)) || (r = up(&F.d_estat_tab, etab, s)) || (r = up(&F.d_estat_mod, emod, s)) || (r = up(&F.d_fin, fin, s)))
+    return r;
+  std::vector<double> z((size_t)std::max<int64_t>(H * G, (int64_t)G * G), 0.0);
+  std::vector<double> zT((size_t)G * G, 0.0), zpi(G, 0.0), zE((size_t)H * G, 0.0);
+  if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s))) return r;
+  F.usable = true;
+  return JH_OK;
 }
-inline int run_estep(FastTables &, const DevModel &, const jh_dataset &, double *, unsigned long long *, int32_t *, DevBuf<double> &, int,
-                     int64_t, int, cudaStream_t) {
-  return JH_ERR_UNSUPPORTED;
+
+// linear-space tables from the log-space score tables (after every parameter update)
+__global__ void k_fast_prepare(FastDev F, const int *tmap, const int *pimap, const double *tscore, const double *escore, double *T,
+                               double *Tt, double *pi, double *E) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int G = F.G;
+  if (idx < G * G) {
+    int i = idx / G, j = idx % G, p = tmap[idx];
+    double v = p >= 0 ? exp(tscore[p]) : 0.0;
+    T[i * G + j] = v;
+    Tt[j * G + i] = v;
+  }
+  if (idx < G) pi[idx] = pimap[idx] >= 0 ? exp(tscore[pimap[idx]]) : 0.0;
+  if (idx < F.H * G) {
+    int h = idx / G, j = idx % G;
+    E[idx] = F.estat_tab[j] >= 0 ? exp(escore[F.estat_tab[j] + h % F.estat_mod[j]]) : 0.0;
+  }
+}
+
+inline int prepare(FastTables &F, const DevModel &M, cudaStream_t s) {
+  if (!F.usable) return JH_OK;
+  int n = std::max(F.G * F.G, F.H * F.G);
+  k_fast_prepare<<<(n + 255) / 256, 256, 0, s>>>(F.dev(), F.d_tmap, F.d_pimap, M.tscore, M.escore, F.d_T, F.d_Tt, F.d_pi, F.d_E);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int G>
+struct FGroup {
+  int lane, lead;
+  unsigned mask;
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+template <int G>
+__device__ __forceinline__ FGroup<G> fgroup() {
+  FGroup<G> g;
+  int wl = threadIdx.x & 31;
+  g.lane = wl % G;
+  g.lead = wl - g.lane;
+  g.mask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << g.lead);
+  return g;
+}
+
+__device__ __forceinline__ double pow2i(int k) {  // 2^k, exact; 0 below the normal range
+  if (k < -1022) return 0.0;
+  if (k > 1023) return INFINITY;
+  return __hiloint2double((1023 + k) << 20, 0);
+}
+
+// Exact rescale: divide by 2^e with e = exponent of the group maximum. false: all zero / not finite.
+template <int G>
+__device__ __forceinline__ bool rescale(double &v, int &expo, unsigned mask) {
+  unsigned hi = (unsigned)__double2hiint(v);
+  unsigned mx = __reduce_max_sync(mask, hi);
+  int be = (int)(mx >> 20);
+  if (be == 0 || be >= 0x7fe) return false;
+  int ex = be - 1023;
+  v *= __hiloint2double((1023 - ex) << 20, 0);
+  expo += ex;
+  return true;
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int d = G / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(mask, v, d);
+  return v;
+}
+
+__device__ __forceinline__ int hmod_of(const FastDev &F, int h) { return F.a_pow2 ? (h & (F.H - 1)) : (h % F.H); }
+
+// dot product of the broadcast vector (shared memory, 128-bit loads) with a register-resident row/column
+template <int G>
+__device__ __forceinline__ double bcast_dot(const double *vec, const double (&R)[G]) {
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (G >= 4) {
+#pragma unroll
+    for (int i = 0; i < G; i += 4) {
+      double2 x = *reinterpret_cast<const double2 *>(vec + i);
+      double2 y = *reinterpret_cast<const double2 *>(vec + i + 2);
+      a0 = fma(x.x, R[i], a0);
+      a1 = fma(x.y, R[i + 1], a1);
+      a2 = fma(y.x, R[i + 2], a2);
+      a3 = fma(y.y, R[i + 3], a3);
+    }
+  } else {
+    double2 x = *reinterpret_cast<const double2 *>(vec);
+    a0 = fma(x.x, R[0], a0);
+    a1 = fma(x.y, R[1], a1);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scoring: forward recursion only, nothing stored (AbstractHMM.logProb semantics, value of bwd[0][0]).
+template <int G>
+__global__ void __launch_bounds__(256) k_fast_loglik(FastDev F, DevData D, unsigned long long *counter, double *out) {
+  extern __shared__ double sm[];
+  double *sT = sm, *sE = sT + G * G, *svec = sE + (size_t)F.H * G;
+  for (int i = threadIdx.x; i < G * G; i += blockDim.x) sT[i] = F.T[i];
+  for (int i = threadIdx.x; i < F.H * G; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  FGroup<G> g = fgroup<G>();
+  double *vec = svec + (size_t)(threadIdx.x / G) * 2 * G;
+  const int lane = g.lane;
+  double Tcol[G];
+#pragma unroll
+  for (int i = 0; i < G; i++) Tcol[i] = sT[i * G + lane];
+  const int kl = F.korder[lane];
+  const double pil = F.pi[lane], finl = F.fin[lane];
+  ResReader rd;
+  for (;;) {
+    long long it = 0;
+    if (lane == 0) it = (long long)atomicAdd(counter, 1ull);
+    it = __shfl_sync(g.mask, it, g.lead);
+    if (it >= D.n_seq) break;
+    int sid = D.order[it];
+    int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    rd.init(D.codes + off);
+    int h = rd.get(0), A = 0;
+    double e = 0 < kl ? F.inv_a : sE[h * G + lane];
+    double f = pil * e;
+    bool ok = rescale<G>(f, A, g.mask);
+    for (int64_t l = 1; l < L && ok; l++) {
+      double *v = vec + (l & 1) * G;
+      v[lane] = f;
+      h = hmod_of(F, h * F.a + rd.get(l));
+      e = l < kl ? F.inv_a : sE[h * G + lane];
+      g.sync();
+      f = bcast_dot<G>(v, Tcol) * e;
+      ok = rescale<G>(f, A, g.mask);
+    }
+    double sfin = group_sum<G>(ok ? f * finl : 0.0, g.mask);
+    if (lane == 0) out[sid] = (ok && sfin > 0) ? log(sfin) + A * 0.6931471805599453094 : JH_NEG_INF;
+    g.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Baum-Welch E-step: forward with stored scaled rows, backward with fused expected-count accumulation.
+// stats layout: [transition statistics n_child | emission statistics n_cond*a | sum_n w_n*logP_n].
+template <int G, int NT>
+__global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsigned long long *counter, double *fwd_scratch,
+                                                     int *fexp_scratch, int64_t rows, double *stats, int32_t *fallback) {
+  extern __shared__ double sm[];
+  const int HG = F.H * G;
+  double *sT = sm, *sTt = sT + G * G, *sE = sTt + G * G, *sEC = sE + HG, *sO = sEC + HG, *sPi = sO + G * G, *svec = sPi + G;
+  for (int i = threadIdx.x; i < G * G; i += NT) { sT[i] = F.T[i]; sTt[i] = F.Tt[i]; sO[i] = 0; }
+  for (int i = threadIdx.x; i < HG; i += NT) { sE[i] = F.E[i]; sEC[i] = 0; }
+  for (int i = threadIdx.x; i < G; i += NT) sPi[i] = 0;
+  __syncthreads();
+  FGroup<G> g = fgroup<G>();
+  const int lane = g.lane;
+  const int gid = threadIdx.x / G;
+  double *vec = svec + (size_t)gid * 2 * G;
+  const int64_t slot = (int64_t)blockIdx.x * (NT / G) + gid;
+  double *fwd = fwd_scratch + (size_t)slot * rows * G;
+  int *fexp = fexp_scratch + (size_t)slot * rows;
+  const int kl = F.korder[lane];
+  const double pil = F.pi[lane], finl = F.fin[lane];
+  double O[G];
+#pragma unroll
+  for (int j = 0; j < G; j++) O[j] = 0;
+  double SC = 0, score = 0;
+  ResReader rd;
+  for (;;) {
+    long long it = 0;
+    if (lane == 0) it = (long long)atomicAdd(counter, 1ull);
+    it = __shfl_sync(g.mask, it, g.lead);
+    if (it >= D.n_seq) break;
+    const int sid = D.order[it];
+    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    const double w = D.weights ? D.weights[sid] : 1.0;
+    rd.init(D.codes + off);
+    // ---------------- forward ----------------
+    int h = rd.get(0), A = 0;
+    double f;
+    bool ok;
+    {
+      double R[G];
+#pragma unroll
+      for (int i = 0; i < G; i++) R[i] = sT[i * G + lane];  // column T[:,lane]
+      double e = 0 < kl ? F.inv_a : sE[h * G + lane];
+      f = pil * e;
+      ok = rescale<G>(f, A, g.mask);
+      fwd[(size_t)1 * G + lane] = f;
+      if (lane == 0) fexp[1] = A;
+      for (int64_t l = 1; l < L && ok; l++) {
+        double *v = vec + (l & 1) * G;
+        v[lane] = f;
+        h = hmod_of(F, h * F.a + rd.get(l));
+        e = l < kl ? F.inv_a : sE[h * G + lane];
+        g.sync();
+        f = bcast_dot<G>(v, R) * e;
+        ok = rescale<G>(f, A, g.mask);
+        fwd[(size_t)(l + 1) * G + lane] = f;
+        if (lane == 0) fexp[l + 1] = A;
+      }
+    }
+    double sfin = group_sum<G>(ok ? f * finl : 0.0, g.mask);
+    if (!(ok && sfin > 0)) {  // the scaled recursion lost all mass: reference-order kernels take this sequence
+      if (lane == 0) {
+        int pos = atomicAdd(fallback, 1);
+        fallback[1 + pos] = sid;
+      }
+      g.sync();
+      continue;
+    }
+    if (lane == 0) score += w * (log(sfin) + A * 0.6931471805599453094);
+    const double invS = w / sfin;
+    const int AL = A;
+    // ---------------- backward + counts ----------------
+    {
+      double R[G];
+#pragma unroll
+      for (int j = 0; j < G; j++) R[j] = sTt[j * G + lane];  // row T[lane,:]
+      double Bcur = finl, Fnext = f;
+      int Bx = 0, Anext = AL;
+      // context hash of position L-1 is the forward hash h
+      g.sync();
+      for (int64_t l = L - 1;; --l) {
+        const double e = l < kl ? F.inv_a : sE[h * G + lane];
+        const double gam = Fnext * Bcur * (invS * pow2i(Anext + Bx - AL));
+        if (l >= kl && gam != 0) atomicAdd(&sEC[h * G + lane], gam);
+        if (l == 0) {
+          SC += gam;
+          break;
+        }
+        double *v = vec + (l & 1) * G;
+        v[lane] = e * Bcur;
+        const double Fl = fwd[(size_t)l * G + lane];
+        const int Al = fexp[l];
+        g.sync();
+        const double aw = Fl * (invS * pow2i(Al + Bx - AL));
+        double b0 = 0, b1 = 0;
+        if (G >= 4) {
+#pragma unroll
+          for (int j = 0; j < G; j += 4) {
+            double2 x = *reinterpret_cast<const double2 *>(v + j);
+            double2 y = *reinterpret_cast<const double2 *>(v + j + 2);
+            b0 = fma(R[j], x.x, b0);
+            b1 = fma(R[j + 1], x.y, b1);
+            b0 = fma(R[j + 2], y.x, b0);
+            b1 = fma(R[j + 3], y.y, b1);
+            O[j] = fma(aw, x.x, O[j]);
+            O[j + 1] = fma(aw, x.y, O[j + 1]);
+            O[j + 2] = fma(aw, y.x, O[j + 2]);
+            O[j + 3] = fma(aw, y.y, O[j + 3]);
+          }
+        } else {
+          double2 x = *reinterpret_cast<const double2 *>(v);
+          b0 = fma(R[0], x.x, b0);
+          b1 = fma(R[1], x.y, b1);
+          O[0] = fma(aw, x.x, O[0]);
+          O[1] = fma(aw, x.y, O[1]);
+        }
+        Bcur = b0 + b1;
+        if (!rescale<G>(Bcur, Bx, g.mask)) Bcur = 0;  // cannot happen when the forward mass is positive
+        Fnext = Fl;
+        Anext = Al;
+        // hash of position l-1
+        int64_t q = l - 1 - F.Kmax;
+        h = h / F.a + (q >= 0 ? F.hpow * rd.get(q) : 0);
+      }
+    }
+    g.sync();
+  }
+  // ---------------- flush: T is multiplied in once; CTA-level reduction, then one atomic per cell ----------------
+  {
+    double R[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) R[j] = sTt[j * G + lane];
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+      double v = O[j] * R[j];
+      if (v != 0) atomicAdd(&sO[lane * G + j], v);
+    }
+    if (SC != 0) atomicAdd(&sPi[lane], SC);
+    if (lane == 0 && score != 0) atomicAdd(&stats[F.n_stats], score);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * G; i += NT)
+    if (sO[i] != 0 && F.tstat[i] >= 0) atomicAdd(&stats[F.tstat[i]], sO[i]);
+  for (int i = threadIdx.x; i < G; i += NT)
+    if (sPi[i] != 0 && F.pistat[i] >= 0) atomicAdd(&stats[F.pistat[i]], sPi[i]);
+  for (int i = threadIdx.x; i < HG; i += NT) {
+    int j = i % G, hh = i / G;
+    if (sEC[i] != 0 && F.estat_tab[j] >= 0) atomicAdd(&stats[F.n_child + F.estat_tab[j] + hh % F.estat_mod[j]], sEC[i]);
+  }
+}
+
+// NaN/Inf guard over the statistics block: a non-finite value makes the driver redo the E-step in log space.
+__global__ void k_check_finite(const double *stats, int n, int *flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !isfinite(stats[i])) atomicExch(flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+#define JHF_DISPATCH(G, ...)                                \
+  switch (G) {                                              \
+    case 2: { constexpr int GG = 2; __VA_ARGS__; } break;   \
+    case 4: { constexpr int GG = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int GG = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int GG = 16; __VA_ARGS__; } break; \
+    default: { constexpr int GG = 32; __VA_ARGS__; } break; \
+  }
+
+inline int run_loglik(FastTables &F, const DevModel &, const DevData &D, int64_t n_seq, int64_t, double *d_out, unsigned long long *counter,
+                      int sm_count, cudaStream_t s) {
+  JH_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+  const int NT = 256;
+  size_t smem = ((size_t)F.G * F.G + (size_t)F.H * F.G + (size_t)(NT / F.G) * 2 * F.G) * sizeof(double);
+  int r = JH_OK;
+  JHF_DISPATCH(F.G, {
+    auto kern = k_fast_loglik<GG>;
+    if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) { jh_set_error("fast scoring kernel does not fit"); r = JH_ERR_UNSUPPORTED; }
+    else {
+      int64_t grid = std::min<int64_t>((int64_t)sm_count * per_sm, (n_seq + NT / GG - 1) / (NT / GG));
+      kern<<<(int)std::max<int64_t>(grid, 1), NT, smem, s>>>(F.dev(), D, counter, d_out);
+      JH_LAUNCHED();
+    }
+  });
+  if (r) return r;
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
 }
 
 }  // namespace jhf

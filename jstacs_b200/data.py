@@ -208,9 +208,9 @@ class JavaRandom:
 
     def next(self, bits: int) -> int:
         self.seed = (self.seed * self.MULT + 0xB) & self.MASK
-        r = self.seed >> (48 - bits)
-        if r >= 1 << (bits - 1):
-            r -= 1 << bits
+        r = self.seed >> (48 - bits)  # (int)(seed >>> (48 - bits))
+        if r >= 1 << 31:
+            r -= 1 << 32
         return r
 
     def nextInt(self, bound: int) -> int:
