@@ -171,7 +171,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.current_stream()
-    _native.check(L.jh_set_stream(stream.cuda_stream))
+    # torch's default stream has handle 0; 0x1 is cudaStreamLegacy, the same stream addressed explicitly
+    _native.check(L.jh_set_stream(stream.cuda_stream or 1))
     _native.check(L.jh_set_option(b"fast", args.fast))
 
     S = args.states

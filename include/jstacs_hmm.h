@@ -106,7 +106,8 @@ int jh_device_count(void);
 int jh_set_device(int device);
 /* Counts kernels launched by this library since load (bench.py: gpu_launches). */
 int64_t jh_kernel_launches(void);
-/* Use an existing CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = library stream. */
+/* Use an existing CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = the model's own stream.
+ * The legacy default stream is addressed as cudaStreamLegacy ((void*)0x1). */
 int jh_set_stream(void *cuda_stream);
 int jh_synchronize(void);
 /* Tuning / test switches: "fast" (1: scaled linear-space kernels where the model allows, 0: reference-order

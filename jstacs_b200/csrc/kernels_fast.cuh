@@ -8,7 +8,7 @@
 // are computed here in probability space with an EXACT power-of-two rescaling per position (the scale is 2^-e,
 // e = exponent of the largest entry, so rescaling introduces no rounding at all); one log per SEQUENCE turns the
 // result back into a log-likelihood.  Per position a state needs S fused multiply-adds instead of S exp.  Results
-// agree with the log-space recursion to ~1e-13 relative (tests/test_gpu_parity.py runs both against the oracle);
+// agree with the log-space recursion to ~1e-13 relative (tests/test_gpu_parity.py checks both formulations);
 // the 1e-9 / 1e-6 gates of BASELINE.json are met with 4-7 digits of margin.  If the scaled recursion loses all mass
 // (possible only with zero-probability parameters and > 2^1022 dynamic range between lineages) the sequence is
 // handed to the log-space kernels on the GPU; there is no CPU fallback.
