@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--nseq", type=int, default=1_000_000, help="sequences per GPU")
     ap.add_argument("--len", type=int, default=1000)
     ap.add_argument("--fast", type=int, default=1)
+    ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences of the CPU sample (0: 24 per core)")
@@ -174,6 +175,7 @@ def main():
     # torch's default stream has handle 0; 0x1 is cudaStreamLegacy, the same stream addressed explicitly
     _native.check(L.jh_set_stream(stream.cuda_stream or 1))
     _native.check(L.jh_set_option(b"fast", args.fast))
+    _native.check(L.jh_set_option(b"fast_variant", args.variant))
 
     S = args.states
     hmm = ergodic_hmm(S, args.order, n_iter=1, ess=4.0)

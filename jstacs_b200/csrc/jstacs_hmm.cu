@@ -764,12 +764,13 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
 
 // ---- E-step / M-step / EM ------------------------------------------------------------------------
 // Scaled linear-space E-step (kernels_fast.cuh), one launch per length bucket.
-template <int G, int NT>
+template <int G, int NT, bool POW2>
 static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t count, int64_t rows) {
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhf::k_fast_estep<G, NT>;
-  size_t smem = ((size_t)3 * G * G + (size_t)2 * F.H * G + G + (size_t)2 * NT) * sizeof(double);
+  auto kern = jhf::k_fast_estep<G, NT, POW2>;
+  const int gpc_ = NT / G;
+  size_t smem = ((size_t)3 * G * G + (size_t)F.H * G + G + (size_t)2 * NT) * sizeof(double) + (size_t)gpc_ * (16 * G) * 2 + (size_t)gpc_ * (16 * G + 16);
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -792,7 +793,7 @@ static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t 
     F.fexp_n = (size_t)slots * rows;
   }
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  kern<<<(int)grid, NT, smem, s>>>(F.dev(), d->dev(first, count), m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, m->d_fallback.p);
+  kern<<<(int)grid, NT, smem, s>>>(F.dev(), d->dev(first, count), m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, F.d_ec, m->d_fallback.p);
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
   return JH_OK;
@@ -800,17 +801,26 @@ static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t 
 
 static int run_estep_fast(jh_model *m, jh_dataset *d) {
   int r = JH_OK;
+  JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * m->fast.H * m->fast.G, m->st()));
   for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
     int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b] + 1;
+    const bool p2 = (m->a & (m->a - 1)) == 0;
+#define JH_FE(GG, NTT) (p2 ? launch_fast_estep<GG, NTT, true>(m, d, first, count, rows) : launch_fast_estep<GG, NTT, false>(m, d, first, count, rows))
     switch (m->fast.G) {
-      case 2: r = launch_fast_estep<2, 512>(m, d, first, count, rows); break;
-      case 4: r = launch_fast_estep<4, 512>(m, d, first, count, rows); break;
-      case 8: r = launch_fast_estep<8, 512>(m, d, first, count, rows); break;
-      case 16: r = launch_fast_estep<16, 512>(m, d, first, count, rows); break;
-      default: r = launch_fast_estep<32, 384>(m, d, first, count, rows); break;
+      case 2: r = JH_FE(2, 512); break;
+      case 4: r = JH_FE(4, 512); break;
+      case 8: r = JH_FE(8, 512); break;
+      case 16: r = JH_FE(16, 512); break;
+      default: r = g_opt.fast_variant == 1 ? JH_FE(32, 384) : JH_FE(32, 256); break;
     }
+#undef JH_FE
   }
-  return r;
+  if (r) return r;
+  int n = m->fast.H * m->fast.G;
+  jhf::k_fast_fold_ec<<<(n + 255) / 256, 256, 0, m->st()>>>(m->fast.dev(), m->fast.d_ec, m->d_stats.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
 }
 
 static int estep_device(jh_model *m, jh_dataset *d, int mode) {

@@ -56,6 +56,7 @@ struct FastTables {
   int *d_korder = nullptr, *d_tstat = nullptr, *d_pistat = nullptr, *d_estat_tab = nullptr, *d_estat_mod = nullptr;
   int *d_tmap = nullptr, *d_pimap = nullptr;  // child index p of edge i->j / start->j, -1 if absent
   int *d_fexp = nullptr;                      // per-row exponent scratch
+  double *d_ec = nullptr;                     // [H*G] global emission-count table
   size_t fexp_n = 0;
   FastDev dev() const {
     FastDev F;
@@ -71,7 +72,7 @@ struct FastTables {
 };
 
 inline void destroy(FastTables &F) {
-  void *ptrs[] = {F.d_T, F.d_Tt, F.d_pi, F.d_E, F.d_fin, F.d_korder, F.d_tstat, F.d_pistat, F.d_estat_tab, F.d_estat_mod, F.d_tmap, F.d_pimap, F.d_fexp};
+  void *ptrs[] = {F.d_T, F.d_Tt, F.d_pi, F.d_E, F.d_fin, F.d_korder, F.d_tstat, F.d_pistat, F.d_estat_tab, F.d_estat_mod, F.d_tmap, F.d_pimap, F.d_fexp, F.d_ec};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   F = FastTables();
@@ -131,7 +132,7 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
     return r;
   std::vector<double> z((size_t)std::max<int64_t>(H * G, (int64_t)G * G), 0.0);
   std::vector<double> zT((size_t)G * G, 0.0), zpi(G, 0.0), zE((size_t)H * G, 0.0);
-  if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s))) return r;
+  if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s)) || (r = up(&F.d_ec, zE, s))) return r;
   F.usable = true;
   return JH_OK;
 }
@@ -186,17 +187,17 @@ __device__ __forceinline__ double pow2i(int k) {  // 2^k, exact; 0 below the nor
   return __hiloint2double((1023 + k) << 20, 0);
 }
 
-// Exact rescale: divide by 2^e with e = exponent of the group maximum. false: all zero / not finite.
+// Exact rescale: divide by 2^e with e = exponent of the group maximum (branch free).
+// Returns false when the maximum is zero/denormal or not finite; the value is then left to die as 0 / NaN and the
+// caller's sticky flag (or the final finite check) routes the sequence to the log-space kernels.
 template <int G>
 __device__ __forceinline__ bool rescale(double &v, int &expo, unsigned mask) {
   unsigned hi = (unsigned)__double2hiint(v);
   unsigned mx = __reduce_max_sync(mask, hi);
   int be = (int)(mx >> 20);
-  if (be == 0 || be >= 0x7fe) return false;
-  int ex = be - 1023;
-  v *= __hiloint2double((1023 - ex) << 20, 0);
-  expo += ex;
-  return true;
+  v *= __hiloint2double((2046 - be) << 20, 0);  // 2^-(be-1023); be == 0 keeps zeros zero
+  expo += be - 1023;
+  return (unsigned)(be - 1) < 0x7fdu;
 }
 
 template <int G>
@@ -260,14 +261,14 @@ __global__ void __launch_bounds__(256) k_fast_loglik(FastDev F, DevData D, unsig
     double e = 0 < kl ? F.inv_a : sE[h * G + lane];
     double f = pil * e;
     bool ok = rescale<G>(f, A, g.mask);
-    for (int64_t l = 1; l < L && ok; l++) {
+    for (int64_t l = 1; l < L; l++) {
       double *v = vec + (l & 1) * G;
       v[lane] = f;
       h = hmod_of(F, h * F.a + rd.get(l));
       e = l < kl ? F.inv_a : sE[h * G + lane];
       g.sync();
       f = bcast_dot<G>(v, Tcol) * e;
-      ok = rescale<G>(f, A, g.mask);
+      ok &= rescale<G>(f, A, g.mask);
     }
     double sfin = group_sum<G>(ok ? f * finl : 0.0, g.mask);
     if (lane == 0) out[sid] = (ok && sfin > 0) ? log(sfin) + A * 0.6931471805599453094 : JH_NEG_INF;
@@ -276,76 +277,162 @@ __global__ void __launch_bounds__(256) k_fast_loglik(FastDev F, DevData D, unsig
 }
 
 // ------------------------------------------------------------------------------------------------
+// Residue staging: a group loads G aligned 16-byte chunks (128-bit loads, one per lane) of its sequence into shared
+// memory, turns them into context hashes h(p) = sum_{i<=K} a^i x[p-i] (uint16) once, and the position loops then
+// read one broadcast uint16 per position in either direction — no per-position hash arithmetic.
+template <int G>
+struct HashTile {
+  static constexpr int T = 16 * G;  // positions per tile
+  uint8_t *raw;                     // [16 halo + T]
+  uint16_t *hs;                     // [T]
+  const uint8_t *base;              // 16-byte aligned address at or before the first residue
+  int mis;                          // residue 0 sits at base[mis]
+  int cur;                          // tile currently staged (-1: none)
+  __device__ __forceinline__ void init(uint8_t *r, uint16_t *h, const uint8_t *seq) {
+    raw = r; hs = h;
+    mis = (int)((unsigned long long)seq & 15ull);
+    base = seq - mis;
+    cur = -1;
+  }
+  // stage tile tau: positions [tau*T - mis, (tau+1)*T - mis)
+  template <bool POW2>
+  __device__ __forceinline__ void load(const FastDev &F, int tau, int lane, unsigned mask, int ashift, int hmask, int K) {
+    const int64_t start = (int64_t)tau * T - mis;  // position of raw[16]
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(base + (int64_t)tau * T) + lane);
+    *reinterpret_cast<uint4 *>(raw + 16 + 16 * lane) = v;
+    if (lane == 0) {
+      uint4 hv = make_uint4(0, 0, 0, 0);
+      if (start > 0) hv = __ldg(reinterpret_cast<const uint4 *>(base + (int64_t)tau * T) - 1);
+      *reinterpret_cast<uint4 *>(raw) = hv;
+    }
+    __syncwarp(mask);
+    // rolling hash over this lane's 16 positions, seeded with the K residues before them
+    const int64_t p0 = start + 16 * lane;
+    int h = 0;
+    for (int i = K; i >= 1; i--) {
+      int64_t q = p0 - i;
+      int x = q >= 0 ? raw[16 + 16 * lane - i] : 0;
+      h = POW2 ? ((h << ashift) | x) : (h * F.a + x);
+    }
+    if (POW2) {
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
+      unsigned out[8];
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        int x = (int)((w[u >> 2] >> ((u & 3) * 8)) & 0xffu);
+        if (p0 + u < 0) x = 0;
+        h = ((h << ashift) | x) & hmask;
+        if (u & 1) out[u >> 1] |= (unsigned)h << 16;
+        else out[u >> 1] = (unsigned)h;
+      }
+      uint4 *dst = reinterpret_cast<uint4 *>(hs + 16 * lane);
+      dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+      dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    } else {  // general alphabets: rolled loop, runtime modulo
+      for (int u = 0; u < 16; u++) {
+        int x = p0 + u < 0 ? 0 : raw[16 + 16 * lane + u];
+        h = (h * F.a + x) % F.H;
+        hs[16 * lane + u] = (uint16_t)h;
+      }
+    }
+    __syncwarp(mask);
+    cur = tau;
+  }
+};
+
 // Baum-Welch E-step: forward with stored scaled rows, backward with fused expected-count accumulation.
 // stats layout: [transition statistics n_child | emission statistics n_cond*a | sum_n w_n*logP_n].
-template <int G, int NT>
+// gEC: global [H*G] emission-count table (fire-and-forget fp64 reductions), folded into stats by k_fast_fold_ec.
+template <int G, int NT, bool POW2>
 __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsigned long long *counter, double *fwd_scratch,
-                                                     int *fexp_scratch, int64_t rows, double *stats, int32_t *fallback) {
+                                                     int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback) {
   extern __shared__ double sm[];
+  constexpr int GPC = NT / G;  // groups per CTA
+  constexpr int T = HashTile<G>::T;
   const int HG = F.H * G;
-  double *sT = sm, *sTt = sT + G * G, *sE = sTt + G * G, *sEC = sE + HG, *sO = sEC + HG, *sPi = sO + G * G, *svec = sPi + G;
+  double *sT = sm, *sTt = sT + G * G, *sE = sTt + G * G, *sO = sE + HG, *sPi = sO + G * G, *svec = sPi + G;
+  uint16_t *shs = reinterpret_cast<uint16_t *>(svec + (size_t)GPC * 2 * G);
+  uint8_t *sraw = reinterpret_cast<uint8_t *>(shs + (size_t)GPC * T);
   for (int i = threadIdx.x; i < G * G; i += NT) { sT[i] = F.T[i]; sTt[i] = F.Tt[i]; sO[i] = 0; }
-  for (int i = threadIdx.x; i < HG; i += NT) { sE[i] = F.E[i]; sEC[i] = 0; }
+  for (int i = threadIdx.x; i < HG; i += NT) sE[i] = F.E[i];
   for (int i = threadIdx.x; i < G; i += NT) sPi[i] = 0;
   __syncthreads();
   FGroup<G> g = fgroup<G>();
   const int lane = g.lane;
   const int gid = threadIdx.x / G;
   double *vec = svec + (size_t)gid * 2 * G;
-  const int64_t slot = (int64_t)blockIdx.x * (NT / G) + gid;
-  double *fwd = fwd_scratch + (size_t)slot * rows * G;
-  int *fexp = fexp_scratch + (size_t)slot * rows;
+  HashTile<G> tile;
+  const int64_t slot = (int64_t)blockIdx.x * GPC + gid;
+  double *const fwd = fwd_scratch + (size_t)slot * rows * G + lane;
+  int *const fexp = fexp_scratch + (size_t)slot * rows;
   const int kl = F.korder[lane];
-  const double pil = F.pi[lane], finl = F.fin[lane];
+  const double pil = F.pi[lane], finl = F.fin[lane], inv_a = F.inv_a;
+  const double *const sEl = sE + lane;
+  double *const gECl = gEC + lane;
+  int ashift = 0;
+  while ((1 << ashift) < F.a) ashift++;
+  const int hmask = F.H - 1;
+  const bool lane0 = lane == 0;
   double O[G];
 #pragma unroll
   for (int j = 0; j < G; j++) O[j] = 0;
   double SC = 0, score = 0;
-  ResReader rd;
   for (;;) {
     long long it = 0;
-    if (lane == 0) it = (long long)atomicAdd(counter, 1ull);
+    if (lane0) it = (long long)atomicAdd(counter, 1ull);
     it = __shfl_sync(g.mask, it, g.lead);
     if (it >= D.n_seq) break;
     const int sid = D.order[it];
-    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    const int64_t off = D.offsets[sid];
+    const int L = (int)(D.offsets[sid + 1] - off);
     const double w = D.weights ? D.weights[sid] : 1.0;
-    rd.init(D.codes + off);
+    tile.init(sraw + (size_t)gid * (T + 16), shs + (size_t)gid * T, D.codes + off);
+    const int mis = tile.mis;
     // ---------------- forward ----------------
-    int h = rd.get(0), A = 0;
+    int A = 0;
     double f;
     bool ok;
     {
       double R[G];
 #pragma unroll
       for (int i = 0; i < G; i++) R[i] = sT[i * G + lane];  // column T[:,lane]
-      double e = 0 < kl ? F.inv_a : sE[h * G + lane];
+      tile.template load<POW2>(F, 0, lane, g.mask, ashift, hmask, F.Kmax);
+      int h = tile.hs[mis];
+      double e = 0 < kl ? inv_a : sEl[h * G];
       f = pil * e;
       ok = rescale<G>(f, A, g.mask);
-      fwd[(size_t)1 * G + lane] = f;
-      if (lane == 0) fexp[1] = A;
-      for (int64_t l = 1; l < L && ok; l++) {
-        double *v = vec + (l & 1) * G;
+      double *fp = fwd + G;
+      int *ep = fexp + 1;
+      *fp = f;
+      if (lane0) *ep = A;
+      int par = 0;
+      for (int l = 1; l < L; l++) {
+        const int tp = l + mis;  // index into the tile stream
+        if ((tp & (T - 1)) == 0) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+        double *v = vec + par;
+        par ^= G;
         v[lane] = f;
-        h = hmod_of(F, h * F.a + rd.get(l));
-        e = l < kl ? F.inv_a : sE[h * G + lane];
+        h = tile.hs[tp & (T - 1)];
+        e = l < kl ? inv_a : sEl[h * G];
         g.sync();
         f = bcast_dot<G>(v, R) * e;
-        ok = rescale<G>(f, A, g.mask);
-        fwd[(size_t)(l + 1) * G + lane] = f;
-        if (lane == 0) fexp[l + 1] = A;
+        ok &= rescale<G>(f, A, g.mask);
+        fp += G;
+        ep += 1;
+        *fp = f;
+        if (lane0) *ep = A;
       }
     }
     double sfin = group_sum<G>(ok ? f * finl : 0.0, g.mask);
     if (!(ok && sfin > 0)) {  // the scaled recursion lost all mass: reference-order kernels take this sequence
-      if (lane == 0) {
+      if (lane0) {
         int pos = atomicAdd(fallback, 1);
         fallback[1 + pos] = sid;
       }
       g.sync();
       continue;
     }
-    if (lane == 0) score += w * (log(sfin) + A * 0.6931471805599453094);
+    if (lane0) score += w * (log(sfin) + A * 0.6931471805599453094);
     const double invS = w / sfin;
     const int AL = A;
     // ---------------- backward + counts ----------------
@@ -353,25 +440,40 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
       double R[G];
 #pragma unroll
       for (int j = 0; j < G; j++) R[j] = sTt[j * G + lane];  // row T[lane,:]
-      double Bcur = finl, Fnext = f;
+      // invS = w / P_scaled is folded into the backward vector, so every posterior below is already weighted
+      double Bcur = finl * invS, Fnext = f;
       int Bx = 0, Anext = AL;
-      // context hash of position L-1 is the forward hash h
+      rescale<G>(Bcur, Bx, g.mask);
+      // software pipeline: rows l-1 and l-2 are in flight while row l is consumed
+      const double *fp = fwd + (size_t)(L - 1) * G;
+      const int *ep = fexp + (L - 1);
+      double Fq0 = 0, Fq1 = 0;
+      int Aq0 = 0, Aq1 = 0;
+      if (L >= 2) { Fq0 = *fp; Aq0 = *ep; }
+      if (L >= 3) { Fq1 = *(fp - G); Aq1 = *(ep - 1); }
+      int par = 0;
       g.sync();
-      for (int64_t l = L - 1;; --l) {
-        const double e = l < kl ? F.inv_a : sE[h * G + lane];
-        const double gam = Fnext * Bcur * (invS * pow2i(Anext + Bx - AL));
-        if (l >= kl && gam != 0) atomicAdd(&sEC[h * G + lane], gam);
-        if (l == 0) {
-          SC += gam;
-          break;
-        }
-        double *v = vec + (l & 1) * G;
+      for (int l = L - 1; l >= 1; --l) {
+        const int tp = l + mis;
+        if (tile.cur != tp / T) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+        const int h = tile.hs[tp & (T - 1)];
+        const double e = l < kl ? inv_a : sEl[h * G];
+        const int k1 = max(-1023, min(1024, Anext + Bx - AL));
+        const double gam = Fnext * Bcur * __hiloint2double((1023 + k1) << 20, 0);  // posterior of state `lane` at position l
+        if (l >= kl) atomicAdd(gECl + h * G, gam);
+        double *v = vec + par;
+        par ^= G;
         v[lane] = e * Bcur;
-        const double Fl = fwd[(size_t)l * G + lane];
-        const int Al = fexp[l];
+        const double Fl = Fq0;
+        const int Al = Aq0;
+        Fq0 = Fq1; Aq0 = Aq1;
+        if (l >= 3) { Fq1 = *(fp - 2 * G); Aq1 = *(ep - 2); }
+        fp -= G;
+        ep -= 1;
         g.sync();
-        const double aw = Fl * (invS * pow2i(Al + Bx - AL));
-        double b0 = 0, b1 = 0;
+        const int k2 = max(-1023, min(1024, Al + Bx - AL));
+        const double aw = Fl * __hiloint2double((1023 + k2) << 20, 0);
+        double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
         if (G >= 4) {
 #pragma unroll
           for (int j = 0; j < G; j += 4) {
@@ -379,8 +481,8 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
             double2 y = *reinterpret_cast<const double2 *>(v + j + 2);
             b0 = fma(R[j], x.x, b0);
             b1 = fma(R[j + 1], x.y, b1);
-            b0 = fma(R[j + 2], y.x, b0);
-            b1 = fma(R[j + 3], y.y, b1);
+            b2 = fma(R[j + 2], y.x, b2);
+            b3 = fma(R[j + 3], y.y, b3);
             O[j] = fma(aw, x.x, O[j]);
             O[j + 1] = fma(aw, x.y, O[j + 1]);
             O[j + 2] = fma(aw, y.x, O[j + 2]);
@@ -393,39 +495,47 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
           O[0] = fma(aw, x.x, O[0]);
           O[1] = fma(aw, x.y, O[1]);
         }
-        Bcur = b0 + b1;
-        if (!rescale<G>(Bcur, Bx, g.mask)) Bcur = 0;  // cannot happen when the forward mass is positive
+        Bcur = (b0 + b1) + (b2 + b3);
+        rescale<G>(Bcur, Bx, g.mask);  // cannot fail when the forward mass is positive; NaN would reach the finite check
         Fnext = Fl;
         Anext = Al;
-        // hash of position l-1
-        int64_t q = l - 1 - F.Kmax;
-        h = h / F.a + (q >= 0 ? F.hpow * rd.get(q) : 0);
+      }
+      {  // position 0: posterior of the first state = start-element statistic (+ emission statistic for order 0)
+        const int h = (tile.cur == 0 ? tile.hs[mis] : 0);
+        int hh = h;
+        if (tile.cur != 0) { tile.template load<POW2>(F, 0, lane, g.mask, ashift, hmask, F.Kmax); hh = tile.hs[mis]; }
+        const int k1 = max(-1023, min(1024, Anext + Bx - AL));
+        const double gam = Fnext * Bcur * __hiloint2double((1023 + k1) << 20, 0);
+        if (0 >= kl) atomicAdd(gECl + hh * G, gam);
+        SC += gam;
       }
     }
     g.sync();
   }
   // ---------------- flush: T is multiplied in once; CTA-level reduction, then one atomic per cell ----------------
   {
-    double R[G];
-#pragma unroll
-    for (int j = 0; j < G; j++) R[j] = sTt[j * G + lane];
 #pragma unroll
     for (int j = 0; j < G; j++) {
-      double v = O[j] * R[j];
+      double v = O[j] * sTt[j * G + lane];
       if (v != 0) atomicAdd(&sO[lane * G + j], v);
     }
     if (SC != 0) atomicAdd(&sPi[lane], SC);
-    if (lane == 0 && score != 0) atomicAdd(&stats[F.n_stats], score);
+    if (lane0 && score != 0) atomicAdd(&stats[F.n_stats], score);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < G * G; i += NT)
     if (sO[i] != 0 && F.tstat[i] >= 0) atomicAdd(&stats[F.tstat[i]], sO[i]);
   for (int i = threadIdx.x; i < G; i += NT)
     if (sPi[i] != 0 && F.pistat[i] >= 0) atomicAdd(&stats[F.pistat[i]], sPi[i]);
-  for (int i = threadIdx.x; i < HG; i += NT) {
-    int j = i % G, hh = i / G;
-    if (sEC[i] != 0 && F.estat_tab[j] >= 0) atomicAdd(&stats[F.n_child + F.estat_tab[j] + hh % F.estat_mod[j]], sEC[i]);
-  }
+}
+
+// emission-count table [H][G] -> emission statistics (several context hashes share a cell when a state's order < Kmax)
+__global__ void k_fast_fold_ec(FastDev F, const double *gEC, double *stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F.H * F.G) return;
+  int j = i % F.G, hh = i / F.G;
+  double v = gEC[i];
+  if (v != 0 && F.estat_tab[j] >= 0) atomicAdd(&stats[F.n_child + F.estat_tab[j] + hh % F.estat_mod[j]], v);
 }
 
 // NaN/Inf guard over the statistics block: a non-finite value makes the driver redo the E-step in log space.
