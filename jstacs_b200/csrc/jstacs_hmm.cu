@@ -770,7 +770,7 @@ static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t 
   cudaStream_t s = m->st();
   auto kern = jhf::k_fast_estep<G, NT, POW2>;
   const int gpc_ = NT / G;
-  size_t smem = ((size_t)3 * G * G + (size_t)F.H * G + G + (size_t)2 * NT) * sizeof(double) + (size_t)gpc_ * (16 * G) * 2 + (size_t)gpc_ * (16 * G + 16);
+  size_t smem = ((size_t)3 * G * G + (size_t)F.H * G + G + (size_t)2 * NT) * sizeof(double) + (size_t)gpc_ * (16 * G) * 2 + (size_t)gpc_ * (16 * G + 16) + (size_t)gpc_ * 8 * (G * 8 + 16);
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));

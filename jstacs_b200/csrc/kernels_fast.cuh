@@ -209,27 +209,53 @@ __device__ __forceinline__ double group_sum(double v, unsigned mask) {
 
 __device__ __forceinline__ int hmod_of(const FastDev &F, int h) { return F.a_pow2 ? (h & (F.H - 1)) : (h % F.H); }
 
-// dot product of the broadcast vector (shared memory, 128-bit loads) with a register-resident row/column
+// dot product of the broadcast vector (shared memory, 128-bit loads) with a register-resident row/column;
+// 8 independent accumulators so that the DFMA chain never waits on its own latency
 template <int G>
 __device__ __forceinline__ double bcast_dot(const double *vec, const double (&R)[G]) {
-  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-  if (G >= 4) {
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = 0, a6 = 0, a7 = 0;
+  if (G >= 8) {
 #pragma unroll
-    for (int i = 0; i < G; i += 4) {
+    for (int i = 0; i < G; i += 8) {
       double2 x = *reinterpret_cast<const double2 *>(vec + i);
       double2 y = *reinterpret_cast<const double2 *>(vec + i + 2);
+      double2 z = *reinterpret_cast<const double2 *>(vec + i + 4);
+      double2 u = *reinterpret_cast<const double2 *>(vec + i + 6);
       a0 = fma(x.x, R[i], a0);
       a1 = fma(x.y, R[i + 1], a1);
       a2 = fma(y.x, R[i + 2], a2);
       a3 = fma(y.y, R[i + 3], a3);
+      a4 = fma(z.x, R[i + 4], a4);
+      a5 = fma(z.y, R[i + 5], a5);
+      a6 = fma(u.x, R[i + 6], a6);
+      a7 = fma(u.y, R[i + 7], a7);
     }
+  } else if (G == 4) {
+    double2 x = *reinterpret_cast<const double2 *>(vec);
+    double2 y = *reinterpret_cast<const double2 *>(vec + 2);
+    a0 = x.x * R[0];
+    a1 = x.y * R[1];
+    a2 = y.x * R[2];
+    a3 = y.y * R[3];
   } else {
     double2 x = *reinterpret_cast<const double2 *>(vec);
-    a0 = fma(x.x, R[0], a0);
-    a1 = fma(x.y, R[1], a1);
+    a0 = x.x * R[0];
+    a1 = x.y * R[1];
   }
-  return (a0 + a1) + (a2 + a3);
+  return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // Scoring: forward recursion only, nothing stored (AbstractHMM.logProb semantics, value of bwd[0][0]).
@@ -353,6 +379,7 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
   double *sT = sm, *sTt = sT + G * G, *sE = sTt + G * G, *sO = sE + HG, *sPi = sO + G * G, *svec = sPi + G;
   uint16_t *shs = reinterpret_cast<uint16_t *>(svec + (size_t)GPC * 2 * G);
   uint8_t *sraw = reinterpret_cast<uint8_t *>(shs + (size_t)GPC * T);
+  uint8_t *sring = sraw + (size_t)GPC * (T + 16);  // [GPC][RING][G*8+16]
   for (int i = threadIdx.x; i < G * G; i += NT) { sT[i] = F.T[i]; sTt[i] = F.Tt[i]; sO[i] = 0; }
   for (int i = threadIdx.x; i < HG; i += NT) sE[i] = F.E[i];
   for (int i = threadIdx.x; i < G; i += NT) sPi[i] = 0;
@@ -406,15 +433,26 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
       *fp = f;
       if (lane0) *ep = A;
       int par = 0;
-      for (int l = 1; l < L; l++) {
-        const int tp = l + mis;  // index into the tile stream
+      // emission of the next position is fetched one iteration ahead (hash -> table -> register)
+      double e_next = inv_a;
+      if (L > 1) {
+        const int tp = 1 + mis;
         if ((tp & (T - 1)) == 0) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+        h = tile.hs[tp & (T - 1)];
+        e_next = 1 < kl ? inv_a : sEl[h * G];
+      }
+      for (int l = 1; l < L; l++) {
         double *v = vec + par;
         par ^= G;
         v[lane] = f;
-        h = tile.hs[tp & (T - 1)];
-        e = l < kl ? inv_a : sEl[h * G];
+        e = e_next;
         g.sync();
+        if (l + 1 < L) {
+          const int tp = l + 1 + mis;  // index into the tile stream
+          if ((tp & (T - 1)) == 0) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+          h = tile.hs[tp & (T - 1)];
+          e_next = (l + 1) < kl ? inv_a : sEl[h * G];
+        }
         f = bcast_dot<G>(v, R) * e;
         ok &= rescale<G>(f, A, g.mask);
         fp += G;
@@ -444,33 +482,52 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
       double Bcur = finl * invS, Fnext = f;
       int Bx = 0, Anext = AL;
       rescale<G>(Bcur, Bx, g.mask);
-      // software pipeline: rows l-1 and l-2 are in flight while row l is consumed
-      const double *fp = fwd + (size_t)(L - 1) * G;
-      const int *ep = fexp + (L - 1);
-      double Fq0 = 0, Fq1 = 0;
-      int Aq0 = 0, Aq1 = 0;
-      if (L >= 2) { Fq0 = *fp; Aq0 = *ep; }
-      if (L >= 3) { Fq1 = *(fp - G); Aq1 = *(ep - 1); }
+      // forward rows come back through a shared-memory ring filled by cp.async, DEPTH positions ahead:
+      // no registers are tied up and no instruction waits on a load that was issued less than DEPTH iterations ago
+      constexpr int DEPTH = 6, RING = 8;
+      char *const ring = reinterpret_cast<char *>(sring) + (size_t)gid * RING * (G * 8 + 16);
+      auto slot_of = [&](int r) { return ring + (size_t)(r & (RING - 1)) * (G * 8 + 16); };
+      auto issue = [&](int r) {
+        if (r >= 1) {
+          char *sl = slot_of(r);
+          cp_async8(sl + lane * 8, fwd + (size_t)r * G);
+          if (lane0) cp_async4(sl + G * 8, fexp + r);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int d = 1; d <= DEPTH; d++) issue(L - d);
       int par = 0;
+      // hash / emission of position l are fetched one iteration ahead
+      int h_next;
+      double e_next;
+      {
+        const int tp = L - 1 + mis;
+        if (tile.cur != tp / T) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+        h_next = tile.hs[tp & (T - 1)];
+        e_next = (L - 1) < kl ? inv_a : sEl[h_next * G];
+      }
       g.sync();
       for (int l = L - 1; l >= 1; --l) {
-        const int tp = l + mis;
-        if (tile.cur != tp / T) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
-        const int h = tile.hs[tp & (T - 1)];
-        const double e = l < kl ? inv_a : sEl[h * G];
+        const int h = h_next;
+        const double e = e_next;
         const int k1 = max(-1023, min(1024, Anext + Bx - AL));
         const double gam = Fnext * Bcur * __hiloint2double((1023 + k1) << 20, 0);  // posterior of state `lane` at position l
         if (l >= kl) atomicAdd(gECl + h * G, gam);
         double *v = vec + par;
         par ^= G;
         v[lane] = e * Bcur;
-        const double Fl = Fq0;
-        const int Al = Aq0;
-        Fq0 = Fq1; Aq0 = Aq1;
-        if (l >= 3) { Fq1 = *(fp - 2 * G); Aq1 = *(ep - 2); }
-        fp -= G;
-        ep -= 1;
+        cp_async_wait<DEPTH - 1>();
         g.sync();
+        const char *sl = slot_of(l);
+        const double Fl = *reinterpret_cast<const double *>(sl + lane * 8);
+        const int Al = *reinterpret_cast<const int *>(sl + G * 8);
+        {  // next position: tile, hash, emission
+          const int tp = l - 1 + mis;
+          if (tile.cur != tp / T) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+          h_next = tile.hs[tp & (T - 1)];
+          e_next = (l - 1) < kl ? inv_a : sEl[h_next * G];
+        }
         const int k2 = max(-1023, min(1024, Al + Bx - AL));
         const double aw = Fl * __hiloint2double((1023 + k2) << 20, 0);
         double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
@@ -499,14 +556,13 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
         rescale<G>(Bcur, Bx, g.mask);  // cannot fail when the forward mass is positive; NaN would reach the finite check
         Fnext = Fl;
         Anext = Al;
+        issue(l - DEPTH);
       }
+      cp_async_wait<0>();
       {  // position 0: posterior of the first state = start-element statistic (+ emission statistic for order 0)
-        const int h = (tile.cur == 0 ? tile.hs[mis] : 0);
-        int hh = h;
-        if (tile.cur != 0) { tile.template load<POW2>(F, 0, lane, g.mask, ashift, hmask, F.Kmax); hh = tile.hs[mis]; }
         const int k1 = max(-1023, min(1024, Anext + Bx - AL));
         const double gam = Fnext * Bcur * __hiloint2double((1023 + k1) << 20, 0);
-        if (0 >= kl) atomicAdd(gECl + hh * G, gam);
+        if (0 >= kl) atomicAdd(gECl + h_next * G, gam);
         SC += gam;
       }
     }
