@@ -764,25 +764,27 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
 
 // ---- E-step / M-step / EM ------------------------------------------------------------------------
 // Scaled linear-space E-step (kernels_fast.cuh), one launch per length bucket.
-template <int G, int NT, bool POW2>
+template <int G, int NT, bool POW2, int NS>
 static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t count, int64_t rows) {
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhf::k_fast_estep<G, NT, POW2>;
-  const int gpc_ = NT / G;
-  size_t smem = ((size_t)3 * G * G + (size_t)F.H * G + G + (size_t)2 * NT) * sizeof(double) + (size_t)gpc_ * (16 * G) * 2 + (size_t)gpc_ * (16 * G + 16) + (size_t)gpc_ * 8 * (G * 8 + 16);
+  auto kern = jhf::k_fast_estep<G, NT, POW2, NS>;
+  const int gpc = NT / G;
+  // tables T, Tt, O-reduction [3 G^2], E [H G], pi [G], broadcast vectors [gpc][2][NS][G], hash tiles, raw tiles, cp.async ring
+  size_t smem = ((size_t)3 * G * G + (size_t)F.H * G + G + (size_t)gpc * 2 * NS * G) * sizeof(double) +
+                (size_t)gpc * NS * (16 * G) * 2 + (size_t)gpc * NS * (16 * G + 16) + (size_t)gpc * NS * 8 * (G * 8 + 16);
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) { jh_set_error("fast E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
   if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
-  const int gpc = NT / G;
-  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (count + gpc - 1) / gpc);
+  const int spc = gpc * NS;  // sequences in flight per CTA
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (count + spc - 1) / spc);
   int64_t per_slot = rows * G * (int64_t)sizeof(double) + rows * (int64_t)sizeof(int);
   int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
-  if (max_slots < gpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
-  grid = std::max<int64_t>(1, std::min(grid, max_slots / gpc));
-  int64_t slots = grid * gpc;
+  if (max_slots < spc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  grid = std::max<int64_t>(1, std::min(grid, max_slots / spc));
+  int64_t slots = grid * spc;
   int r = m->d_fwd.reserve((size_t)slots * rows * G);
   if (r) return r;
   if ((size_t)slots * rows > F.fexp_n) {
@@ -805,13 +807,15 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
   for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
     int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b] + 1;
     const bool p2 = (m->a & (m->a - 1)) == 0;
-#define JH_FE(GG, NTT) (p2 ? launch_fast_estep<GG, NTT, true>(m, d, first, count, rows) : launch_fast_estep<GG, NTT, false>(m, d, first, count, rows))
+#define JH_FE(GG, NTT, NSS) (p2 ? launch_fast_estep<GG, NTT, true, NSS>(m, d, first, count, rows) : launch_fast_estep<GG, NTT, false, NSS>(m, d, first, count, rows))
     switch (m->fast.G) {
-      case 2: r = JH_FE(2, 512); break;
-      case 4: r = JH_FE(4, 512); break;
-      case 8: r = JH_FE(8, 512); break;
-      case 16: r = JH_FE(16, 512); break;
-      default: r = g_opt.fast_variant == 1 ? JH_FE(32, 384) : JH_FE(32, 256); break;
+      case 2: r = JH_FE(2, 512, 2); break;
+      case 4: r = JH_FE(4, 512, 2); break;
+      case 8: r = JH_FE(8, 512, 2); break;
+      case 16: r = JH_FE(16, 256, 2); break;
+      default:  // fast_variant: 0 = two sequences per warp in lock step (default), 1 = one sequence per warp, 2 = one sequence, 12 warps
+        r = g_opt.fast_variant == 1 ? JH_FE(32, 256, 1) : g_opt.fast_variant == 2 ? JH_FE(32, 384, 1) : JH_FE(32, 256, 2);
+        break;
     }
 #undef JH_FE
   }

@@ -22,6 +22,8 @@
 //             xi_l(i,j) = T[i][j]*O-term, so T is multiplied in once per kernel, not per position.
 //   emission counts: gamma_l(j) = alpha_{l+1}[j]*beta_{l+1}[j]*scale into a per-CTA shared table [context hash][state].
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels_exact.cuh"
 
@@ -369,17 +371,24 @@ struct HashTile {
 // Baum-Welch E-step: forward with stored scaled rows, backward with fused expected-count accumulation.
 // stats layout: [transition statistics n_child | emission statistics n_cond*a | sum_n w_n*logP_n].
 // gEC: global [H*G] emission-count table (fire-and-forget fp64 reductions), folded into stats by k_fast_fold_ec.
-template <int G, int NT, bool POW2>
+//
+// NS sequences per group advance in lock step (NS = 1 or 2): they share the register-resident T row/column and the
+// count accumulators O, and their independent dependency chains are interleaved instruction by instruction, which is
+// what keeps the FP64 pipe fed with only 8 warps per SM (244 registers per thread).  Sequences arrive sorted by
+// decreasing length, so sequence 0 of a group is the longer one: the head of its backward sweep and the tail of its
+// forward sweep run alone (NA = 1), the common part runs joint (NA = NS).
+template <int G, int NT, bool POW2, int NS>
 __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsigned long long *counter, double *fwd_scratch,
                                                      int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback) {
   extern __shared__ double sm[];
   constexpr int GPC = NT / G;  // groups per CTA
   constexpr int T = HashTile<G>::T;
+  constexpr int DEPTH = 6, RING = 8, SLOTB = G * 8 + 16;
   const int HG = F.H * G;
   double *sT = sm, *sTt = sT + G * G, *sE = sTt + G * G, *sO = sE + HG, *sPi = sO + G * G, *svec = sPi + G;
-  uint16_t *shs = reinterpret_cast<uint16_t *>(svec + (size_t)GPC * 2 * G);
-  uint8_t *sraw = reinterpret_cast<uint8_t *>(shs + (size_t)GPC * T);
-  uint8_t *sring = sraw + (size_t)GPC * (T + 16);  // [GPC][RING][G*8+16]
+  uint16_t *shs = reinterpret_cast<uint16_t *>(svec + (size_t)GPC * 2 * NS * G);
+  uint8_t *sraw = reinterpret_cast<uint8_t *>(shs + (size_t)GPC * NS * T);
+  uint8_t *sring = sraw + (size_t)GPC * NS * (T + 16);  // [GPC][NS][RING][SLOTB]
   for (int i = threadIdx.x; i < G * G; i += NT) { sT[i] = F.T[i]; sTt[i] = F.Tt[i]; sO[i] = 0; }
   for (int i = threadIdx.x; i < HG; i += NT) sE[i] = F.E[i];
   for (int i = threadIdx.x; i < G; i += NT) sPi[i] = 0;
@@ -387,11 +396,8 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
   FGroup<G> g = fgroup<G>();
   const int lane = g.lane;
   const int gid = threadIdx.x / G;
-  double *vec = svec + (size_t)gid * 2 * G;
-  HashTile<G> tile;
-  const int64_t slot = (int64_t)blockIdx.x * GPC + gid;
-  double *const fwd = fwd_scratch + (size_t)slot * rows * G + lane;
-  int *const fexp = fexp_scratch + (size_t)slot * rows;
+  double *const vec = svec + (size_t)gid * 2 * NS * G;  // [parity][NS][G]
+  const int64_t slot0 = ((int64_t)blockIdx.x * GPC + gid) * NS;
   const int kl = F.korder[lane];
   const double pil = F.pi[lane], finl = F.fin[lane], inv_a = F.inv_a;
   const double *const sEl = sE + lane;
@@ -404,166 +410,252 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
 #pragma unroll
   for (int j = 0; j < G; j++) O[j] = 0;
   double SC = 0, score = 0;
+  HashTile<G> tile[NS];
+  double *fwd[NS];
+  int *fexp[NS];
+  char *ring[NS];
+#pragma unroll
+  for (int s = 0; s < NS; s++) {
+    fwd[s] = fwd_scratch + (size_t)(slot0 + s) * rows * G + lane;
+    fexp[s] = fexp_scratch + (size_t)(slot0 + s) * rows;
+    ring[s] = reinterpret_cast<char *>(sring) + (size_t)(gid * NS + s) * RING * SLOTB;
+  }
   for (;;) {
     long long it = 0;
-    if (lane0) it = (long long)atomicAdd(counter, 1ull);
+    if (lane0) it = (long long)atomicAdd(counter, (unsigned long long)NS);
     it = __shfl_sync(g.mask, it, g.lead);
     if (it >= D.n_seq) break;
-    const int sid = D.order[it];
-    const int64_t off = D.offsets[sid];
-    const int L = (int)(D.offsets[sid + 1] - off);
-    const double w = D.weights ? D.weights[sid] : 1.0;
-    tile.init(sraw + (size_t)gid * (T + 16), shs + (size_t)gid * T, D.codes + off);
-    const int mis = tile.mis;
-    // ---------------- forward ----------------
-    int A = 0;
-    double f;
-    bool ok;
+    int L[NS], sid[NS], mis[NS];
+    double w[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      const bool valid = it + s < D.n_seq;
+      sid[s] = valid ? D.order[it + s] : -1;
+      int64_t off = 0;
+      L[s] = 0;
+      w[s] = 0;
+      if (valid) {
+        off = D.offsets[sid[s]];
+        L[s] = (int)(D.offsets[sid[s] + 1] - off);
+        w[s] = D.weights ? D.weights[sid[s]] : 1.0;
+      }
+      tile[s].init(sraw + (size_t)(gid * NS + s) * (T + 16), shs + (size_t)(gid * NS + s) * T, D.codes + off);
+      mis[s] = tile[s].mis;
+    }
+    const int Ljoint = L[NS - 1];  // the shortest one (order is by decreasing length)
+    // ======================= forward =======================
+    int A[NS];
+    double f[NS];
+    bool ok[NS];
     {
       double R[G];
 #pragma unroll
       for (int i = 0; i < G; i++) R[i] = sT[i * G + lane];  // column T[:,lane]
-      tile.template load<POW2>(F, 0, lane, g.mask, ashift, hmask, F.Kmax);
-      int h = tile.hs[mis];
-      double e = 0 < kl ? inv_a : sEl[h * G];
-      f = pil * e;
-      ok = rescale<G>(f, A, g.mask);
-      double *fp = fwd + G;
-      int *ep = fexp + 1;
-      *fp = f;
-      if (lane0) *ep = A;
-      int par = 0;
-      // emission of the next position is fetched one iteration ahead (hash -> table -> register)
-      double e_next = inv_a;
-      if (L > 1) {
-        const int tp = 1 + mis;
-        if ((tp & (T - 1)) == 0) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
-        h = tile.hs[tp & (T - 1)];
-        e_next = 1 < kl ? inv_a : sEl[h * G];
-      }
-      for (int l = 1; l < L; l++) {
-        double *v = vec + par;
-        par ^= G;
-        v[lane] = f;
-        e = e_next;
-        g.sync();
-        if (l + 1 < L) {
-          const int tp = l + 1 + mis;  // index into the tile stream
-          if ((tp & (T - 1)) == 0) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
-          h = tile.hs[tp & (T - 1)];
-          e_next = (l + 1) < kl ? inv_a : sEl[h * G];
+      double e_next[NS];
+      double *fp[NS];
+      int *ep[NS];
+#pragma unroll
+      for (int s = 0; s < NS; s++) {
+        A[s] = 0; f[s] = 0; ok[s] = true; e_next[s] = inv_a;
+        fp[s] = fwd[s] + G;
+        ep[s] = fexp[s] + 1;
+        if (L[s] > 0) {
+          tile[s].template load<POW2>(F, 0, lane, g.mask, ashift, hmask, F.Kmax);
+          int h = tile[s].hs[mis[s]];
+          double e = 0 < kl ? inv_a : sEl[h * G];
+          f[s] = pil * e;
+          ok[s] = rescale<G>(f[s], A[s], g.mask);
+          *fp[s] = f[s];
+          if (lane0) *ep[s] = A[s];
+          if (L[s] > 1) {
+            const int tp = 1 + mis[s];
+            if ((tp & (T - 1)) == 0) tile[s].template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+            h = tile[s].hs[tp & (T - 1)];
+            e_next[s] = 1 < kl ? inv_a : sEl[h * G];
+          }
         }
-        f = bcast_dot<G>(v, R) * e;
-        ok &= rescale<G>(f, A, g.mask);
-        fp += G;
-        ep += 1;
-        *fp = f;
-        if (lane0) *ep = A;
+      }
+      int par = 0;
+      auto fstep = [&](auto na_tag, int t) {  // rows t -> t+1 of the first NA sequences
+        constexpr int NA = decltype(na_tag)::value;
+        double *v = vec + par;
+        par ^= NS * G;
+        double e[NA];
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+          v[s * G + lane] = f[s];
+          e[s] = e_next[s];
+        }
+        g.sync();
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+          if (t + 1 < L[s]) {  // emission of the next position, one iteration ahead (hash -> table -> register)
+            const int tp = t + 1 + mis[s];
+            if ((tp & (T - 1)) == 0) tile[s].template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+            const int h = tile[s].hs[tp & (T - 1)];
+            e_next[s] = (t + 1) < kl ? inv_a : sEl[h * G];
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < NA; s++) f[s] = bcast_dot<G>(v + s * G, R) * e[s];
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+          ok[s] &= rescale<G>(f[s], A[s], g.mask);
+          fp[s] += G;
+          ep[s] += 1;
+          *fp[s] = f[s];
+          if (lane0) *ep[s] = A[s];
+        }
+      };
+      for (int t = 1; t < Ljoint; t++) fstep(std::integral_constant<int, NS>(), t);
+      if (NS > 1)
+        for (int t = Ljoint < 1 ? 1 : Ljoint; t < L[0]; t++) fstep(std::integral_constant<int, 1>(), t);
+    }
+    double invS[NS];
+    int AL[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+      double sfin = group_sum<G>((ok[s] && L[s] > 0) ? f[s] * finl : 0.0, g.mask);
+      AL[s] = A[s];
+      invS[s] = 0;
+      if (L[s] > 0) {
+        if (ok[s] && sfin > 0) {
+          invS[s] = w[s] / sfin;
+          if (lane0) score += w[s] * (log(sfin) + A[s] * 0.6931471805599453094);
+        } else if (lane0) {  // the scaled recursion lost all mass: the reference-order kernels take this sequence
+          int pos = atomicAdd(fallback, 1);
+          fallback[1 + pos] = sid[s];
+        }
       }
     }
-    double sfin = group_sum<G>(ok ? f * finl : 0.0, g.mask);
-    if (!(ok && sfin > 0)) {  // the scaled recursion lost all mass: reference-order kernels take this sequence
-      if (lane0) {
-        int pos = atomicAdd(fallback, 1);
-        fallback[1 + pos] = sid;
-      }
-      g.sync();
-      continue;
-    }
-    if (lane0) score += w * (log(sfin) + A * 0.6931471805599453094);
-    const double invS = w / sfin;
-    const int AL = A;
-    // ---------------- backward + counts ----------------
-    {
+    // ======================= backward + counts =======================
+    // A sequence that fell back (or an empty slot) runs with weight 0: every posterior it produces is exactly 0.
+    if (L[0] > 0) {
       double R[G];
 #pragma unroll
       for (int j = 0; j < G; j++) R[j] = sTt[j * G + lane];  // row T[lane,:]
-      // invS = w / P_scaled is folded into the backward vector, so every posterior below is already weighted
-      double Bcur = finl * invS, Fnext = f;
-      int Bx = 0, Anext = AL;
-      rescale<G>(Bcur, Bx, g.mask);
-      // forward rows come back through a shared-memory ring filled by cp.async, DEPTH positions ahead:
-      // no registers are tied up and no instruction waits on a load that was issued less than DEPTH iterations ago
-      constexpr int DEPTH = 6, RING = 8;
-      char *const ring = reinterpret_cast<char *>(sring) + (size_t)gid * RING * (G * 8 + 16);
-      auto slot_of = [&](int r) { return ring + (size_t)(r & (RING - 1)) * (G * 8 + 16); };
-      auto issue = [&](int r) {
-        if (r >= 1) {
-          char *sl = slot_of(r);
-          cp_async8(sl + lane * 8, fwd + (size_t)r * G);
-          if (lane0) cp_async4(sl + G * 8, fexp + r);
+      double Bcur[NS], Fnext[NS], e_next[NS];
+      int Bx[NS], Anext[NS], h_next[NS];
+      // forward rows come back through a shared-memory ring filled by cp.async DEPTH positions ahead
+      auto issue = [&](int t) {  // rows t - DEPTH of every sequence that has them
+        const int r = t - DEPTH;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+          if (r >= 1 && r <= L[s] - 1) {
+            char *sl = ring[s] + (size_t)(r & (RING - 1)) * SLOTB;
+            cp_async8(sl + lane * 8, fwd[s] + (size_t)r * G);
+            if (lane0) cp_async4(sl + G * 8, fexp[s] + r);
+          }
         }
         cp_async_commit();
       };
 #pragma unroll
-      for (int d = 1; d <= DEPTH; d++) issue(L - d);
-      int par = 0;
-      // hash / emission of position l are fetched one iteration ahead
-      int h_next;
-      double e_next;
-      {
-        const int tp = L - 1 + mis;
-        if (tile.cur != tp / T) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
-        h_next = tile.hs[tp & (T - 1)];
-        e_next = (L - 1) < kl ? inv_a : sEl[h_next * G];
+      for (int s = 0; s < NS; s++) {
+        // invS = w / P_scaled is folded into the backward vector: every posterior below is already weighted
+        Bcur[s] = finl * invS[s];
+        Bx[s] = 0;
+        rescale<G>(Bcur[s], Bx[s], g.mask);
+        Fnext[s] = f[s];
+        Anext[s] = AL[s];
+        h_next[s] = 0;
+        e_next[s] = inv_a;
+        if (L[s] > 0) {
+          const int tp = L[s] - 1 + mis[s];
+          if (tile[s].cur != tp / T) tile[s].template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+          h_next[s] = tile[s].hs[tp & (T - 1)];
+          e_next[s] = (L[s] - 1) < kl ? inv_a : sEl[h_next[s] * G];
+        }
       }
+      for (int d = 0; d < DEPTH; d++) issue(L[0] - 1 + DEPTH - d);
+      int par = 0;
       g.sync();
-      for (int l = L - 1; l >= 1; --l) {
-        const int h = h_next;
-        const double e = e_next;
-        const int k1 = max(-1023, min(1024, Anext + Bx - AL));
-        const double gam = Fnext * Bcur * __hiloint2double((1023 + k1) << 20, 0);  // posterior of state `lane` at position l
-        if (l >= kl) atomicAdd(gECl + h * G, gam);
+      auto bstep = [&](auto na_tag, int t) {  // position t >= 1 of the first NA sequences
+        constexpr int NA = decltype(na_tag)::value;
         double *v = vec + par;
-        par ^= G;
-        v[lane] = e * Bcur;
+        par ^= NS * G;
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+          const int k1 = max(-1023, min(1024, Anext[s] + Bx[s] - AL[s]));
+          const double gam = Fnext[s] * Bcur[s] * __hiloint2double((1023 + k1) << 20, 0);  // posterior of state `lane` at t
+          if (t >= kl) atomicAdd(gECl + h_next[s] * G, gam);
+          v[s * G + lane] = e_next[s] * Bcur[s];
+        }
         cp_async_wait<DEPTH - 1>();
         g.sync();
-        const char *sl = slot_of(l);
-        const double Fl = *reinterpret_cast<const double *>(sl + lane * 8);
-        const int Al = *reinterpret_cast<const int *>(sl + G * 8);
-        {  // next position: tile, hash, emission
-          const int tp = l - 1 + mis;
-          if (tile.cur != tp / T) tile.template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
-          h_next = tile.hs[tp & (T - 1)];
-          e_next = (l - 1) < kl ? inv_a : sEl[h_next * G];
+        double aw[NA], Fl[NA];
+        int Al[NA];
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+          const char *sl = ring[s] + (size_t)(t & (RING - 1)) * SLOTB;
+          Fl[s] = *reinterpret_cast<const double *>(sl + lane * 8);
+          Al[s] = *reinterpret_cast<const int *>(sl + G * 8);
+          {  // next position: tile, hash, emission
+            const int tp = t - 1 + mis[s];
+            if (tile[s].cur != tp / T) tile[s].template load<POW2>(F, tp / T, lane, g.mask, ashift, hmask, F.Kmax);
+            h_next[s] = tile[s].hs[tp & (T - 1)];
+            e_next[s] = (t - 1) < kl ? inv_a : sEl[h_next[s] * G];
+          }
+          const int k2 = max(-1023, min(1024, Al[s] + Bx[s] - AL[s]));
+          aw[s] = Fl[s] * __hiloint2double((1023 + k2) << 20, 0);
         }
-        const int k2 = max(-1023, min(1024, Al + Bx - AL));
-        const double aw = Fl * __hiloint2double((1023 + k2) << 20, 0);
-        double b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        double b[NA][4];
+#pragma unroll
+        for (int s = 0; s < NA; s++) b[s][0] = b[s][1] = b[s][2] = b[s][3] = 0;
         if (G >= 4) {
 #pragma unroll
           for (int j = 0; j < G; j += 4) {
-            double2 x = *reinterpret_cast<const double2 *>(v + j);
-            double2 y = *reinterpret_cast<const double2 *>(v + j + 2);
-            b0 = fma(R[j], x.x, b0);
-            b1 = fma(R[j + 1], x.y, b1);
-            b2 = fma(R[j + 2], y.x, b2);
-            b3 = fma(R[j + 3], y.y, b3);
-            O[j] = fma(aw, x.x, O[j]);
-            O[j + 1] = fma(aw, x.y, O[j + 1]);
-            O[j + 2] = fma(aw, y.x, O[j + 2]);
-            O[j + 3] = fma(aw, y.y, O[j + 3]);
+            double2 x[NA], y[NA];
+#pragma unroll
+            for (int s = 0; s < NA; s++) {
+              x[s] = *reinterpret_cast<const double2 *>(v + s * G + j);
+              y[s] = *reinterpret_cast<const double2 *>(v + s * G + j + 2);
+            }
+#pragma unroll
+            for (int s = 0; s < NA; s++) {
+              b[s][0] = fma(R[j], x[s].x, b[s][0]);
+              b[s][1] = fma(R[j + 1], x[s].y, b[s][1]);
+              b[s][2] = fma(R[j + 2], y[s].x, b[s][2]);
+              b[s][3] = fma(R[j + 3], y[s].y, b[s][3]);
+            }
+#pragma unroll
+            for (int s = 0; s < NA; s++) {
+              O[j] = fma(aw[s], x[s].x, O[j]);
+              O[j + 1] = fma(aw[s], x[s].y, O[j + 1]);
+              O[j + 2] = fma(aw[s], y[s].x, O[j + 2]);
+              O[j + 3] = fma(aw[s], y[s].y, O[j + 3]);
+            }
           }
         } else {
-          double2 x = *reinterpret_cast<const double2 *>(v);
-          b0 = fma(R[0], x.x, b0);
-          b1 = fma(R[1], x.y, b1);
-          O[0] = fma(aw, x.x, O[0]);
-          O[1] = fma(aw, x.y, O[1]);
+#pragma unroll
+          for (int s = 0; s < NA; s++) {
+            double2 x = *reinterpret_cast<const double2 *>(v + s * G);
+            b[s][0] = fma(R[0], x.x, b[s][0]);
+            b[s][1] = fma(R[1], x.y, b[s][1]);
+            O[0] = fma(aw[s], x.x, O[0]);
+            O[1] = fma(aw[s], x.y, O[1]);
+          }
         }
-        Bcur = (b0 + b1) + (b2 + b3);
-        rescale<G>(Bcur, Bx, g.mask);  // cannot fail when the forward mass is positive; NaN would reach the finite check
-        Fnext = Fl;
-        Anext = Al;
-        issue(l - DEPTH);
-      }
+#pragma unroll
+        for (int s = 0; s < NA; s++) {
+          Bcur[s] = (b[s][0] + b[s][1]) + (b[s][2] + b[s][3]);
+          rescale<G>(Bcur[s], Bx[s], g.mask);  // cannot fail when the forward mass is positive; NaN reaches the finite check
+          Fnext[s] = Fl[s];
+          Anext[s] = Al[s];
+        }
+        issue(t);
+      };
+      if (NS > 1)
+        for (int t = L[0] - 1; t >= (Ljoint < 1 ? 1 : Ljoint); --t) bstep(std::integral_constant<int, 1>(), t);
+      for (int t = (NS > 1 ? Ljoint : L[0]) - 1; t >= 1; --t) bstep(std::integral_constant<int, NS>(), t);
       cp_async_wait<0>();
-      {  // position 0: posterior of the first state = start-element statistic (+ emission statistic for order 0)
-        const int k1 = max(-1023, min(1024, Anext + Bx - AL));
-        const double gam = Fnext * Bcur * __hiloint2double((1023 + k1) << 20, 0);
-        if (0 >= kl) atomicAdd(gECl + h_next * G, gam);
-        SC += gam;
+#pragma unroll
+      for (int s = 0; s < NS; s++) {  // position 0: posterior of the first state = start-element statistic
+        if (L[s] > 0) {
+          const int k1 = max(-1023, min(1024, Anext[s] + Bx[s] - AL[s]));
+          const double gam = Fnext[s] * Bcur[s] * __hiloint2double((1023 + k1) << 20, 0);
+          if (0 >= kl) atomicAdd(gECl + h_next[s] * G, gam);
+          SC += gam;
+        }
       }
     }
     g.sync();
