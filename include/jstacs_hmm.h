@@ -209,6 +209,8 @@ int jh_stats_device(jh_model *m, void **dev_ptr, int64_t *n_doubles);
 /* ---- measurement helpers (bench.py) ------------------------------------- */
 /* Sustained FP64 FMA rate of this device in TFLOP/s (2 flops per DFMA), a register-resident DFMA chain. */
 int jh_measure_fp64_peak(double *tflops);
+/* DFMA rate with `chains` independent FMA chains per thread at a given residency (latency/ILP probe, profiles/). */
+int jh_probe_fp64(int chains, int threads, int blocks_per_sm, double *tflops);
 /* Device time in ms of the kernels of the last compute call (CUDA events on the library stream). */
 int jh_last_kernel_ms(jh_model *m, double *ms);
 /* Device time in ms of the E-step kernel launches alone (the dominant kernel) of the last E-step. */

@@ -165,4 +165,21 @@ __global__ void k_fp64_peak(double *out, int iters, double seed) {
   if (s == 12345.678) out[0] = s;
 }
 
+// DFMA latency/throughput probe: C independent chains per thread
+template <int C>
+__global__ void k_fp64_chains(double *out, int iters, double seed) {
+  double a[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) a[c] = seed + c;
+  const double m = 0.9999999, k = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < C; c++) a[c] = fma(a[c], m, k);
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < C; c++) s += a[c];
+  if (s == 12345.678) out[0] = s;
+}
+
 }  // namespace jha
