@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences of the CPU sample (0: 24 per core)")
+    ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences of the CPU sample (0: 400 per core)")
     return ap.parse_args()
 
 
@@ -94,7 +94,7 @@ def cpu_sample(args, threads: int):
     from jstacs_b200.workloads import ergodic_hmm, make_data
     from oracle import binding
 
-    n = args.cpu_seqs or 24 * threads
+    n = args.cpu_seqs or 400 * threads  # ~10-20 s of host work on this workload
     hmm = ergodic_hmm(args.states, args.order, ess=4.0)
     data = make_data(n, args.len)
     om = binding.OracleModel(hmm.ir())

@@ -211,6 +211,8 @@ int jh_stats_device(jh_model *m, void **dev_ptr, int64_t *n_doubles);
 int jh_measure_fp64_peak(double *tflops);
 /* DFMA rate with `chains` independent FMA chains per thread at a given residency (latency/ILP probe, profiles/). */
 int jh_probe_fp64(int chains, int threads, int blocks_per_sm, double *tflops);
+/* FP64 tensor-core (DMMA m8n8k4) rate, same arguments; a hardware-ceiling measurement, not used by the product kernels. */
+int jh_probe_dmma(int chains, int threads, int blocks_per_sm, double *tflops);
 /* Device time in ms of the kernels of the last compute call (CUDA events on the library stream). */
 int jh_last_kernel_ms(jh_model *m, double *ms);
 /* Device time in ms of the E-step kernel launches alone (the dominant kernel) of the last E-step. */

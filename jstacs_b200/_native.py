@@ -122,6 +122,7 @@ def lib():
         "jh_last_kernel_ms": (C.c_int, [vp, _P_F64]),
         "jh_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
         "jh_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _P_F64]),
+        "jh_probe_dmma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P_F64]),
         "jh_last_main_kernel_ms": (C.c_int, [vp, _P_F64]),
     }
     for name, (res, args) in sig.items():

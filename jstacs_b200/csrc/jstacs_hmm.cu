@@ -1056,3 +1056,39 @@ extern "C" int jh_probe_fp64(int chains, int threads, int blocks_per_sm, double 
   *tflops = 2.0 * chains * iters * (double)threads * blocks / (best * 1e-3) / 1e12;
   return JH_OK;
 }
+
+// Probe (profiles/): FP64 tensor-core (DMMA m8n8k4) rate in TFLOP/s — a measurement of the hardware ceiling only.
+extern "C" int jh_probe_dmma(int chains, int threads, int blocks_per_sm, double *tflops) {
+  int r = ensure_device();
+  if (r) return r;
+  cudaDeviceProp prop;
+  JH_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  double *d_out;
+  JH_CUDA(cudaMalloc(&d_out, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 1 << 14, blocks = prop.multiProcessorCount * blocks_per_sm;
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    switch (chains) {
+      case 1: jha::k_dmma_chains<1><<<blocks, threads>>>(d_out, iters, 1.0 + rep); break;
+      case 2: jha::k_dmma_chains<2><<<blocks, threads>>>(d_out, iters, 1.0 + rep); break;
+      case 4: jha::k_dmma_chains<4><<<blocks, threads>>>(d_out, iters, 1.0 + rep); break;
+      case 8: jha::k_dmma_chains<8><<<blocks, threads>>>(d_out, iters, 1.0 + rep); break;
+      default: jha::k_dmma_chains<16><<<blocks, threads>>>(d_out, iters, 1.0 + rep); chains = 16; break;
+    }
+    JH_LAUNCHED();
+    cudaEventRecord(e1);
+    JH_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = 2.0 * 256.0 * chains * iters * (double)(threads / 32) * blocks / (best * 1e-3) / 1e12;
+  return JH_OK;
+}

@@ -182,4 +182,23 @@ __global__ void k_fp64_chains(double *out, int iters, double seed) {
   if (s == 12345.678) out[0] = s;
 }
 
+// FP64 tensor-core probe (measurement only; the product kernels are SIMT): C independent m8n8k4 DMMA accumulator chains
+// per warp.  One DMMA = 8*8*4 FMAs per warp.
+template <int C>
+__global__ void k_dmma_chains(double *out, int iters, double seed) {
+  double c0[C], c1[C];
+#pragma unroll
+  for (int c = 0; c < C; c++) { c0[c] = seed + c; c1[c] = seed - c; }
+  double a = 0.9999999 + 1e-9 * (threadIdx.x & 31), b = 1.0000001;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < C; c++)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0[c]), "+d"(c1[c]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int c = 0; c < C; c++) s += c0[c] + c1[c];
+  if (s == 12345.678) out[0] = s;
+}
+
 }  // namespace jha

@@ -16,3 +16,9 @@ for threads, bps in ((128, 1), (256, 1), (384, 1), (512, 1), (512, 2), (512, 4))
     for chains in (1, 2, 4, 8, 16):
         _native.check(L.jh_probe_fp64(chains, threads, bps, C.byref(v)))
         print(f"{chains:6d} {threads:7d} {bps:9d} {threads * bps // 32:8d} {v.value:8.2f}")
+
+print("DMMA m8n8k4: chains threads blocks/SM warps/SM TFLOP/s")
+for threads, bps in ((128, 1), (256, 1), (512, 1), (512, 2)):
+    for chains in (1, 2, 4, 8):
+        _native.check(L.jh_probe_dmma(chains, threads, bps, C.byref(v)))
+        print(f"{chains:6d} {threads:7d} {bps:9d} {threads * bps // 32:8d} {v.value:8.2f}")
