@@ -292,7 +292,7 @@ def main():
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
-                    "traffic": None, "kernel": "k_fast_estep" if args.fast else "k_exact_fb", "kernel_ms": k_ms,
+                    "traffic": None, "kernel": ("k_mma_estep" if args.variant == 0 and S >= 5 else "k_fast_estep") if args.fast else "k_exact_fb", "kernel_ms": k_ms,
                     "flop_per_residue": flop_per_res, "peak_source": "DFMA-chain microbenchmark measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry)",
                     "nominal_reference_flop_per_residue": nominal_per_res,
                     "nominal_frac": nominal_per_res * residues / (k_ms * 1e-3) / 1e12 / peak if peak else None,

@@ -11,6 +11,7 @@
 #include "kernels_aux.cuh"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_mma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
@@ -169,6 +170,14 @@ struct jh_dataset {
   DevBuf<int32_t> d_order;
   DevBuf<double> d_weights;
   bool has_weights = false;
+  // octets: 8 consecutive sequences of a bucket advance in lock step through one warp (kernels_mma.cuh);
+  // bucket b owns octets [bucket_oct_ptr[b], bucket_oct_ptr[b+1]); hash records are built lazily per (alphabet, Kmax)
+  std::vector<int32_t> oct_seq;
+  std::vector<int64_t> oct_hbase, bucket_oct_ptr;
+  DevBuf<int32_t> d_oct_seq;
+  DevBuf<int64_t> d_oct_hbase;
+  DevBuf<uint16_t> d_hashes;
+  int hash_a = -1, hash_K = -1;
   DevData dev(int64_t first = 0, int64_t count = -1) const {
     DevData D;
     D.codes = d_codes.p; D.offsets = d_offsets.p; D.weights = has_weights ? d_weights.p : nullptr;
@@ -484,6 +493,19 @@ extern "C" int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, i
     d->bucket_len.push_back(L0);
     d->bucket_ptr.push_back(j);
     i = j;
+  }
+  d->bucket_oct_ptr.push_back(0);
+  {
+    int64_t rec = 0;
+    for (size_t b = 0; b + 1 < d->bucket_ptr.size(); b++) {
+      for (int64_t i = d->bucket_ptr[b]; i < d->bucket_ptr[b + 1]; i += 8) {
+        for (int64_t k = i; k < i + 8; k++) d->oct_seq.push_back(k < d->bucket_ptr[b + 1] ? d->order[k] : -1);
+        d->oct_hbase.push_back(rec);
+        rec += offsets[d->order[i] + 1] - offsets[d->order[i]];  // the first sequence of an octet is its longest
+      }
+      d->bucket_oct_ptr.push_back((int64_t)d->oct_hbase.size());
+    }
+    d->oct_hbase.push_back(rec);  // total number of records
   }
   cudaStream_t s = g_have_user_stream ? g_user_stream : (cudaStream_t)0;
   if ((r = d->d_codes.alloc((size_t)d->n_res + 64)) || (r = d->d_offsets.alloc(n_seq + 1)) || (r = d->d_order.alloc(n_seq)) ||
@@ -801,10 +823,75 @@ static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t 
   return JH_OK;
 }
 
+// Context-hash records of the octets (kernels_mma.cuh), built once per data set and (alphabet, emission order).
+static int ensure_octet_hashes(jh_model *m, jh_dataset *d) {
+  if (d->hash_a == m->a && d->hash_K == m->Kmax && d->d_hashes.p) return JH_OK;
+  cudaStream_t s = m->st();
+  int r;
+  const int64_t n_oct = (int64_t)d->oct_hbase.size() - 1, n_rec = d->oct_hbase[n_oct];
+  if (!d->d_oct_seq.p) {
+    if ((r = d->d_oct_seq.upload(d->oct_seq, s)) || (r = d->d_oct_hbase.upload(d->oct_hbase, s))) return r;
+  }
+  if ((r = d->d_hashes.reserve((size_t)n_rec * 8 + 8))) return r;
+  if (n_oct > 0) {
+    jhm::k_hash_octets<<<(int)std::min<int64_t>(n_oct, 148 * 16), 128, 0, s>>>(d->d_codes.p, d->d_offsets.p, d->d_oct_seq.p, d->d_oct_hbase.p, n_oct,
+                                                                           m->a, m->Kmax, d->d_hashes.p);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+  }
+  JH_CUDA(cudaStreamSynchronize(s));  // the host vectors are borrowed by the async uploads
+  d->hash_a = m->a;
+  d->hash_K = m->Kmax;
+  return JH_OK;
+}
+
+// Octet E-step (kernels_mma.cuh): one launch per length bucket, 8 warps per CTA, one CTA per SM, octets fetched dynamically.
+template <int NT>
+static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
+  using C = jhm::MmaCfg<NT>;
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhm::k_mma_estep<NT>;
+  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b] + 1;
+  if (n_oct <= 0) return JH_OK;
+  size_t smem = C::smem_bytes(F.H);
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, smem));
+  if (per_sm < 1) { jh_set_error("octet E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
+  const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+  const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  grid = std::max<int64_t>(1, std::min(grid, max_slots / C::WARPS));
+  const int64_t slots = grid * C::WARPS;
+  int r = m->d_fwd.reserve((size_t)slots * rows * 8 * C::G);
+  if (r) return r;
+  if ((size_t)slots * rows * 8 > F.fexp_n) {
+    if (F.d_fexp) cudaFree(F.d_fexp);
+    F.d_fexp = nullptr;
+    F.fexp_n = 0;
+    if (cudaMalloc(&F.d_fexp, (size_t)slots * rows * 8 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); jh_set_error("out of device memory (exponent scratch)"); return JH_ERR_NOMEM; }
+    F.fexp_n = (size_t)slots * rows * 8;
+  }
+  jhm::OctData D;
+  D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
+  D.weights = d->has_weights ? d->d_weights.p : nullptr; D.n_oct = n_oct;
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, C::NTHREADS, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, F.d_ec, m->d_fallback.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
 static int run_estep_fast(jh_model *m, jh_dataset *d) {
   int r = JH_OK;
   JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * m->fast.H * m->fast.G, m->st()));
-  for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
+  const bool octets = g_opt.fast_variant == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
+  for (size_t b = 0; octets && b + 1 < d->bucket_ptr.size() && !r; b++)
+    r = m->fast.G == 8 ? launch_mma_estep<1>(m, d, b) : m->fast.G == 16 ? launch_mma_estep<2>(m, d, b) : launch_mma_estep<4>(m, d, b);
+  for (size_t b = 0; !octets && b + 1 < d->bucket_ptr.size() && !r; b++) {
     int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b] + 1;
     const bool p2 = (m->a & (m->a - 1)) == 0;
 #define JH_FE(GG, NTT, NSS) (p2 ? launch_fast_estep<GG, NTT, true, NSS>(m, d, first, count, rows) : launch_fast_estep<GG, NTT, false, NSS>(m, d, first, count, rows))
@@ -813,7 +900,7 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
       case 4: r = JH_FE(4, 512, 2); break;
       case 8: r = JH_FE(8, 512, 2); break;
       case 16: r = JH_FE(16, 256, 2); break;
-      default:  // fast_variant: 0 = two sequences per warp in lock step (default), 1 = one sequence per warp, 2 = one sequence, 12 warps
+      default:  // fast_variant: 0 = octets on the FP64 MMA path (above); 3 = two sequences per warp in lock step, 1 = one sequence per warp, 2 = one sequence, 12 warps
         r = g_opt.fast_variant == 1 ? JH_FE(32, 256, 1) : g_opt.fast_variant == 2 ? JH_FE(32, 384, 1) : JH_FE(32, 256, 2);
         break;
     }
@@ -838,6 +925,7 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
     int32_t *flag = m->d_fallback.p + d->n_seq + 1;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
     JH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
+    if (g_opt.fast_variant == 0 && m->fast.G >= 8 && (r = ensure_octet_hashes(m, d))) return r;
     cudaEventRecord(m->evk0, s);
     r = run_estep_fast(m, d);
     cudaEventRecord(m->evk1, s);

@@ -1,0 +1,411 @@
+// kernels_mma.cuh — Baum-Welch E-step with EIGHT sequences per warp in lock step ("octets"), the production E-step
+// for dense first-order models with 5..32 states.
+//
+// Same scaled linear-space formulation as kernels_fast.cuh (exact power-of-two rescaling per position, one log per
+// sequence, results identical to ~1e-13), different mapping.  Per position the three products of an octet
+//     forward   alpha'[n][j]  = sum_i alpha[n][i] T[i][j]              ( 8 x G  by  G x G )
+//     backward  beta' [n][i]  = sum_j b[n][j] T[i][j],  b = e * beta   ( 8 x G  by  G x G )
+//     counts    O[i][j]      += sum_n alpha[n][i] b[n][j]              ( G x 8  by  8 x G )
+// are small fp64 matrix products.  They are issued as warp-wide m8n8k4 FP64 MMA instructions: on B200 the measured
+// DMMA rate equals the DFMA rate (37.0 vs 36.9 TFLOP/s, profiles/probe_fp64.py), so the ceiling is the same FP64
+// pipe, but one DMMA replaces 8 DFMA + 4 shared-memory broadcast loads, which removes the issue-slot and
+// latency limits of the lane-per-state kernel (36 % of the FP64 peak, profiles/r1_estep_simt.md).
+//
+// Register layouts (lane l, r = l>>2 the sequence of the octet, q = l&3):
+//   RL  lane holds X[n = r][state 8t + 2q + b], t < NT, b < 2.  This is the D-fragment layout of the recursion
+//       products AND, with the state permutation sigma(k,q) = 8(k>>1) + 2q + (k&1), their A-fragment layout:
+//       the result of one step feeds the next without any data movement.
+//   TL  lane holds X[n = 4kk + q][state 8t + r], kk < 2: A- and B-fragment layout of the count product, whose
+//       reduction index is the SEQUENCE.  alpha comes from the forward scratch anyway (cp.async ring in shared
+//       memory, read in either layout), b makes one round trip through shared memory per position.
+//
+// Residues are not touched here: the context hashes h(p) = sum_{i<=K} a^i x[p-i] depend only on the data, so they
+// are computed ONCE per data set into octet-interleaved uint16 records (k_hash_octets) and streamed (2 B/residue/pass).
+#pragma once
+#include "kernels_fast.cuh"
+
+namespace jhm {
+
+using jhf::FastDev;
+
+struct OctData {
+  const int32_t *oct_seq;    // [n_oct*8] sequence ids of the octet rows, -1 = empty row; row 0 is the longest
+  const int64_t *oct_hbase;  // [n_oct] first hash record of the octet
+  const uint16_t *hashes;    // records of 8 uint16: [oct_hbase[o] + position][row]
+  const int64_t *offsets;    // [n_seq+1]
+  const double *weights;     // [n_seq] or nullptr
+  int64_t n_oct;
+};
+
+// One thread per hash record (8 sequences at one position).  h(p) uses the K residues before p (fewer at the start).
+__global__ void k_hash_octets(const uint8_t *codes, const int64_t *offsets, const int32_t *oct_seq, const int64_t *oct_hbase,
+                              int64_t n_oct, int a, int K, uint16_t *hashes) {
+  for (int64_t o = blockIdx.x; o < n_oct; o += gridDim.x) {
+    int64_t off[8];
+    int len[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      int sid = oct_seq[o * 8 + r];
+      off[r] = sid >= 0 ? offsets[sid] : 0;
+      len[r] = sid >= 0 ? (int)(offsets[sid + 1] - offsets[sid]) : 0;
+    }
+    uint4 *rec = reinterpret_cast<uint4 *>(hashes + oct_hbase[o] * 8);
+    for (int p = threadIdx.x; p < len[0]; p += blockDim.x) {
+      unsigned hv[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        int h = 0;
+        if (p < len[r]) {
+          int pw = 1;
+          for (int i = 0; i <= K && p - i >= 0; i++) {
+            h += pw * codes[off[r] + p - i];
+            pw *= a;
+          }
+        }
+        hv[r] = (unsigned)h;
+      }
+      rec[p] = make_uint4(hv[0] | (hv[1] << 16), hv[2] | (hv[3] << 16), hv[4] | (hv[5] << 16), hv[6] | (hv[7] << 16));
+    }
+  }
+}
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, const double a, const double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ double pow2_clamped(int k) {  // 2^k for k in [-1023, 1024): 0 below, finite above
+  k = max(-1023, min(1023, k));
+  return __hiloint2double((1023 + k) << 20, 0);
+}
+
+// exact rescale of the NV values a lane holds of its sequence: divide by 2^e, e = exponent of the row maximum
+template <int NV>
+__device__ __forceinline__ bool rescale_row(double (&v)[NV], int &expo) {
+  unsigned hi = (unsigned)__double2hiint(v[0]);
+#pragma unroll
+  for (int i = 1; i < NV; i++) hi = max(hi, (unsigned)__double2hiint(v[i]));
+  hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+  hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 2));
+  const int be = (int)(hi >> 20);
+  const double f = __hiloint2double((2046 - be) << 20, 0);  // 2^-(be-1023); be == 0 keeps zeros zero
+#pragma unroll
+  for (int i = 0; i < NV; i++) v[i] *= f;
+  expo += be - 1023;
+  // "ok": the row maximum is a normal number with 60 binades of head room below it, so that every component within
+  // 2^-60 of the maximum is still normal (nothing that matters at 1e-16 relative has been flushed)
+  return (unsigned)(be - 61) < (0x7feu - 61u);
+}
+
+template <int NT>
+struct MmaCfg {
+  static constexpr int G = 8 * NT, NV = 2 * NT, WARPS = 8, NTHREADS = 256;
+  static constexpr int RSTRIDE = NT >= 2 ? G * 8 + 64 : G * 8;  // bytes between the sequences of a tile (bank spread of RL accesses)
+  static constexpr int RING = 4;
+  static constexpr int SLOTB = 8 * RSTRIDE + 32;                // 8 rows + 8 exponents
+  static constexpr int WARPB = RING * SLOTB + 2 * 8 * RSTRIDE + 64;
+  static size_t smem_bytes(int H) { return ((size_t)H * G + (size_t)G * G + G) * sizeof(double) + (size_t)WARPS * WARPB; }
+};
+
+// stats layout: [transition statistics n_child | emission statistics n_cond*a | sum_n w_n*logP_n]; gEC as in kernels_fast.cuh
+template <int NT>
+__global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch,
+                                                      int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback) {
+  using C = MmaCfg<NT>;
+  constexpr int G = C::G, NV = C::NV, RSTRIDE = C::RSTRIDE, RING = C::RING, SLOTB = C::SLOTB;
+  extern __shared__ double sm[];
+  const int HG = F.H * G;
+  double *sE = sm, *sO = sE + HG, *sPi = sO + G * G;
+  char *swarp = reinterpret_cast<char *>(sPi + G) + (size_t)(threadIdx.x >> 5) * C::WARPB;
+  char *ring = swarp;                        // [RING][SLOTB]
+  char *bbuf = swarp + RING * SLOTB;         // [2][8*RSTRIDE]
+  int *sbx = reinterpret_cast<int *>(bbuf + 2 * 8 * RSTRIDE);  // [2][8]
+  for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
+  for (int i = threadIdx.x; i < G * G + G; i += blockDim.x) sO[i] = 0;
+  __syncthreads();
+  const int l = threadIdx.x & 31, r = l >> 2, q = l & 3;
+  const unsigned FULL = 0xffffffffu;
+  const int64_t slot = (int64_t)blockIdx.x * C::WARPS + (threadIdx.x >> 5);
+  double *const fw = fwd_scratch + (size_t)slot * rows * 8 * G + r * G + 2 * q;  // + t*8*G + 8*tp (+b)
+  int *const fe = fexp_scratch + (size_t)slot * rows * 8;                       // + t*8 + row
+  const double inv_a = F.inv_a;
+  // per-lane constants of the RL layout: state of value v is 8*(v>>1) + 2q + (v&1)
+  double finv[NV], piv[NV];
+  int kmin = 0;  // positions below Kmax need the per-state order check
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    const int s = 8 * (v >> 1) + 2 * q + (v & 1);
+    finv[v] = F.fin[s];
+    piv[v] = F.pi[s];
+  }
+  kmin = F.Kmax;
+  double O[NT][NT][2];
+#pragma unroll
+  for (int i = 0; i < NT; i++)
+#pragma unroll
+    for (int j = 0; j < NT; j++) O[i][j][0] = O[i][j][1] = 0;
+  double SC[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) SC[v] = 0;
+  double score = 0;
+
+  // emission probabilities of position pos (context hash h) for the lane's NV states
+  auto emis = [&](double (&e)[NV], int h, int pos) {
+    const double *row = sE + (size_t)h * G + 2 * q;
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const double2 x = *reinterpret_cast<const double2 *>(row + 8 * t);
+      e[2 * t] = x.x;
+      e[2 * t + 1] = x.y;
+    }
+    if (pos < kmin) {  // HigherOrderDiscreteEmission: condition not available -> uniform (ACDE:447-450)
+#pragma unroll
+      for (int v = 0; v < NV; v++)
+        if (pos < F.korder[8 * (v >> 1) + 2 * q + (v & 1)]) e[v] = inv_a;
+    }
+  };
+
+  for (;;) {
+    long long o = 0;
+    if (l == 0) o = (long long)atomicAdd(counter, 1ull);
+    o = __shfl_sync(FULL, o, 0);
+    if (o >= D.n_oct) break;
+    const int sid = D.oct_seq[o * 8 + r];
+    int Lr = 0;
+    double w = 0;
+    if (sid >= 0) {
+      Lr = (int)(D.offsets[sid + 1] - D.offsets[sid]);
+      w = D.weights ? D.weights[sid] : 1.0;
+    }
+    const int Lmax = __shfl_sync(FULL, Lr, 0);
+    const int Lmin = __reduce_min_sync(FULL, Lr);
+    const uint16_t *const hrow = D.hashes + D.oct_hbase[o] * 8 + r;  // + position*8
+    // ================================ forward ================================
+    double A[NV];
+    int Aexp = 0;
+    bool ok = true;
+    {
+      double Bf[NV][NT];  // B fragments of T: Bf[k][t] = T[sigma(k,q)][8t + r]
+#pragma unroll
+      for (int k = 0; k < NV; k++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) Bf[k][t] = F.T[(8 * (k >> 1) + 2 * q + (k & 1)) * G + 8 * t + r];
+      double e[NV];
+      emis(e, hrow[0], 0);
+#pragma unroll
+      for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv[v] * e[v] : 0.0;
+      ok = rescale_row<NV>(A, Aexp);
+#pragma unroll
+      for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(fw + 8 * t) = make_double2(A[2 * t], A[2 * t + 1]);
+      if (q == 0) fe[r] = Aexp;
+      if (Lmax > 1) emis(e, hrow[8], 1);
+      for (int t = 0; t + 1 < Lmax; t++) {  // row t -> t+1
+        int hn = 0;
+        if (t + 2 < Lmax) hn = hrow[(size_t)(t + 2) * 8];
+        double Dv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) Dv[v] = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) dmma(Dv[2 * tp], Dv[2 * tp + 1], A[k], Bf[k][tp]);
+#pragma unroll
+        for (int v = 0; v < NV; v++) Dv[v] *= e[v];
+        int nexp = Aexp;
+        const bool nok = rescale_row<NV>(Dv, nexp);
+        if (t + 1 < Lmin) {  // every sequence of the octet is still running
+#pragma unroll
+          for (int v = 0; v < NV; v++) A[v] = Dv[v];
+          Aexp = nexp;
+          ok &= nok;
+        } else {  // ragged tail: finished sequences keep their last row in registers and store zeros
+          const bool act = t + 1 < Lr;
+#pragma unroll
+          for (int v = 0; v < NV; v++) {
+            A[v] = act ? Dv[v] : A[v];
+            Dv[v] = act ? Dv[v] : 0.0;
+          }
+          Aexp = act ? nexp : Aexp;
+          ok &= nok || !act;
+        }
+        double *dst = fw + (size_t)(t + 1) * 8 * G;
+#pragma unroll
+        for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(dst + 8 * tp) = make_double2(Dv[2 * tp], Dv[2 * tp + 1]);
+        if (q == 0) fe[(size_t)(t + 1) * 8 + r] = nexp;
+        if (t + 2 < Lmax) emis(e, hn, t + 2);
+      }
+    }
+    // ---- termination: P(x) = sum over final states, one log per sequence ----
+    double sfin = 0;
+#pragma unroll
+    for (int v = 0; v < NV; v++) sfin += A[v] * finv[v];
+    sfin += __shfl_xor_sync(FULL, sfin, 1);
+    sfin += __shfl_xor_sync(FULL, sfin, 2);
+    const int AL = Aexp;
+    double invS = 0;
+    if (Lr > 0) {
+      if (ok && sfin > 0) {
+        invS = w / sfin;
+        if (q == 0) score += w * (log(sfin) + AL * 0.6931471805599453094);
+      } else if (q == 0) {  // the scaled recursion lost (or nearly lost) its mass: the log-space kernels take this sequence
+        int pos = atomicAdd(fallback, 1);
+        fallback[1 + pos] = sid;
+      }
+    }
+    // ================================ backward + counts ================================
+    {
+      double Bb[NV][NT];  // B fragments of T^T: Bb[k][t] = T[8t + r][sigma(k,q)]
+#pragma unroll
+      for (int k = 0; k < NV; k++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) Bb[k][t] = F.T[(8 * t + r) * G + 8 * (k >> 1) + 2 * q + (k & 1)];
+      double beta[NV];
+      int Bx = 0;
+#pragma unroll
+      for (int v = 0; v < NV; v++) beta[v] = finv[v] * invS;  // 1/P(x) and the weight are folded in: posteriors come out weighted
+      rescale_row<NV>(beta, Bx);
+      const double *const fsrc = fwd_scratch + (size_t)slot * rows * 8 * G + r * G + 2 * q;
+      auto issue = [&](int row) {  // forward row `row` (8 sequences x G doubles + 8 exponents) -> ring slot row & 3
+        if (row >= 0) {
+          char *sl = ring + (size_t)(row & (RING - 1)) * SLOTB;
+          const double *src = fsrc + (size_t)row * 8 * G;
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) cp_async16(sl + r * RSTRIDE + (8 * tp + 2 * q) * 8, src + 8 * tp);
+          if (l < 8) jhf::cp_async4(sl + 8 * RSTRIDE + l * 4, fe + (size_t)row * 8 + l);
+        }
+        jhf::cp_async_commit();
+      };
+      __syncwarp();
+      issue(Lmax - 1);
+      issue(Lmax - 2);
+      issue(Lmax - 3);
+      int h = hrow[(size_t)(Lmax - 1) * 8];
+      double e[NV];
+      emis(e, h, Lmax - 1);
+      int par = 0;
+      for (int t = Lmax - 1; t >= 1; --t) {  // consumes position t: beta_t -> beta_{t-1}, counts of the edges (t-1 -> t)
+        const int hn = hrow[(size_t)(t - 1) * 8];
+        jhf::cp_async_wait<1>();
+        __syncwarp();
+        const char *slt = ring + (size_t)(t & (RING - 1)) * SLOTB;
+        const char *slp = ring + (size_t)((t - 1) & (RING - 1)) * SLOTB;
+        const bool ragged = t >= Lmin;
+        const bool act = t < Lr;
+        {  // emission statistic of position t: gamma_t = alpha_t * beta_t * 2^(A_t + Bx - AL)
+          const int At = *reinterpret_cast<const int *>(slt + 8 * RSTRIDE + r * 4);
+          double sc = pow2_clamped(At + Bx - AL);
+          if (ragged && !act) sc = 0.0;
+          double *gdst = gEC + (size_t)h * G + 2 * q;
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) {
+            const double2 a2 = *reinterpret_cast<const double2 *>(slt + r * RSTRIDE + (8 * tp + 2 * q) * 8);
+            const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
+            if (t >= kmin) {
+              atomicAdd(gdst + 8 * tp, g0);
+              atomicAdd(gdst + 8 * tp + 1, g1);
+            } else {
+              if (t >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
+              if (t >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);
+            }
+          }
+        }
+        double b[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) b[v] = (ragged && !act) ? 0.0 : e[v] * beta[v];
+        char *bb = bbuf + (size_t)par * 8 * RSTRIDE;
+#pragma unroll
+        for (int tp = 0; tp < NT; tp++)
+          *reinterpret_cast<double2 *>(bb + r * RSTRIDE + (8 * tp + 2 * q) * 8) = make_double2(b[2 * tp], b[2 * tp + 1]);
+        if (q == 0) sbx[par * 8 + r] = Bx - AL;
+        __syncwarp();
+        // beta_{t-1}[n][i] = sum_j b[n][j] T[i][j]
+        double Dv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) Dv[v] = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) dmma(Dv[2 * tp], Dv[2 * tp + 1], b[k], Bb[k][tp]);
+        // O[i][j] += sum_n alpha_{t-1}[n][i] 2^(A_{t-1}[n] + Bx[n] - AL[n]) b[n][j]   (T[i][j] is multiplied in at the end)
+        {
+          double aT[2][NT], bT[2][NT];
+#pragma unroll
+          for (int kk = 0; kk < 2; kk++) {
+            const int n = 4 * kk + q;
+            const int ea = *reinterpret_cast<const int *>(slp + 8 * RSTRIDE + n * 4);
+            const double f = pow2_clamped(ea + sbx[par * 8 + n]);
+#pragma unroll
+            for (int tp = 0; tp < NT; tp++) {
+              aT[kk][tp] = *reinterpret_cast<const double *>(slp + n * RSTRIDE + (8 * tp + r) * 8) * f;
+              bT[kk][tp] = *reinterpret_cast<const double *>(bb + n * RSTRIDE + (8 * tp + r) * 8);
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+            for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+              for (int tj = 0; tj < NT; tj++) dmma(O[ti][tj][0], O[ti][tj][1], aT[kk][ti], bT[kk][tj]);
+        }
+        int nbx = Bx;
+        rescale_row<NV>(Dv, nbx);  // cannot fail while the forward mass is positive; NaN reaches the finite check
+        if (!ragged || act) {
+#pragma unroll
+          for (int v = 0; v < NV; v++) beta[v] = Dv[v];
+          Bx = nbx;
+        }
+        h = hn;
+        emis(e, h, t - 1);
+        issue(t - 3);
+        par ^= 1;
+      }
+      jhf::cp_async_wait<0>();
+      __syncwarp();
+      {  // position 0: emission statistic and the statistic of the start element
+        const char *sl0 = ring;
+        const int A0 = *reinterpret_cast<const int *>(sl0 + 8 * RSTRIDE + r * 4);
+        const double sc = Lr > 0 ? pow2_clamped(A0 + Bx - AL) : 0.0;
+        double *gdst = gEC + (size_t)h * G + 2 * q;
+#pragma unroll
+        for (int tp = 0; tp < NT; tp++) {
+          const double2 a2 = *reinterpret_cast<const double2 *>(sl0 + r * RSTRIDE + (8 * tp + 2 * q) * 8);
+          const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
+          if (0 >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
+          if (0 >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);
+          SC[2 * tp] += g0;
+          SC[2 * tp + 1] += g1;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---------------- flush: T is multiplied in once; CTA-level reduction, then one atomic per cell ----------------
+#pragma unroll
+  for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+    for (int tj = 0; tj < NT; tj++)
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int i = 8 * ti + r, j = 8 * tj + 2 * q + b;
+        const double v = O[ti][tj][b] * F.T[i * G + j];
+        if (v != 0) atomicAdd(&sO[i * G + j], v);
+      }
+#pragma unroll
+  for (int v = 0; v < NV; v++) {  // start statistic: sum over the sequences of the octet (lanes with equal q), then one atomic
+    double s = SC[v];
+    s += __shfl_xor_sync(FULL, s, 4);
+    s += __shfl_xor_sync(FULL, s, 8);
+    s += __shfl_xor_sync(FULL, s, 16);
+    if (r == 0 && s != 0) atomicAdd(&sPi[8 * (v >> 1) + 2 * q + (v & 1)], s);
+  }
+  if (score != 0) atomicAdd(&stats[F.n_stats], score);
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * G; i += blockDim.x)
+    if (sO[i] != 0 && F.tstat[i] >= 0) atomicAdd(&stats[F.tstat[i]], sO[i]);
+  for (int i = threadIdx.x; i < G; i += blockDim.x)
+    if (sPi[i] != 0 && F.pistat[i] >= 0) atomicAdd(&stats[F.pistat[i]], sPi[i]);
+}
+
+}  // namespace jhm

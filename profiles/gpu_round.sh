@@ -17,7 +17,7 @@ for w in $what; do
       ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv $SMALL > gpurun_out/${tag}_ncu_launches.log 2>&1
       echo "launch list rc=$?"
       $SMALL > gpurun_out/${tag}_plain_small2.log 2>&1 &&
-      ncu --set full --clock-control none --import-source on -k regex:k_fast_estep -c 1 -f -o gpurun_out/${tag}_prof $SMALL > gpurun_out/${tag}_ncu_full.log 2>&1
+      ncu --set full --clock-control none --import-source on -k regex:k_mma_estep -c 1 -f -o gpurun_out/${tag}_prof $SMALL > gpurun_out/${tag}_ncu_full.log 2>&1
       echo "ncu full rc=$?";;
   esac
 done

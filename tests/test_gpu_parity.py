@@ -239,6 +239,56 @@ def test_zero_probability_parameters(nat, oracle_lib, fast):
     np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 3], ids=["octets_dmma", "warp_per_sequence", "two_sequences_per_warp"])
+@pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
+def test_fast_estep_variants_agree_with_oracle(nat, oracle_lib, name, variant):
+    """Every mapping of the scaled E-step (octets on the FP64 MMA path, lane-per-state SIMT) gives the oracle's counts:
+    ragged octets, a last octet with empty rows, weights, sequences shorter than the emission order."""
+    nat.check(nat.lib().jh_set_option(b"fast", 1))
+    nat.check(nat.lib().jh_set_option(b"fast_variant", variant))
+    try:
+        hmm = MODELS[name]()
+        om = oracle_lib.OracleModel(hmm.ir())
+        rng = np.random.default_rng(11)
+        lens = np.concatenate([rng.integers(1, 6, 9), rng.integers(30, 400, 50), [1, 2, 3, 700]])
+        data = dataset_of([random_dna(rng, int(L)) for L in lens])
+        w = rng.random(lens.size) + 0.25
+        eng, nd = hmm._engine(), hmm._data(data)
+        for weights in (None, w):
+            nd.set_weights(weights)
+            ts, es, sc = eng.estep(nd)
+            rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+            np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+            np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+            assert sc == pytest.approx(rsc, rel=LL_RTOL)
+    finally:
+        nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
+
+
+def test_full_size_properties_cfg3_sample(nat):
+    """BASELINE cfg3 model (32 states, order-3 emissions) on 16k x 1 kb sequences: size-independent properties.
+    Transition counts add up to the residues, emission counts to the residues with a full context, the score is the
+    sum of the per-sequence log-likelihoods, and the octet kernel agrees with the lane-per-state kernel."""
+    hmm = ergodic_hmm(32, 3, n_iter=3, ess=4.0)
+    data = make_data(16_000, 1000)
+    eng, nd = hmm._engine(), hmm._data(data)
+    ts, es, sc = eng.estep(nd)
+    assert ts.sum() == pytest.approx(1.6e7, rel=1e-10)
+    assert es.sum() == pytest.approx(1.6e7 - 3 * 1.6e4, rel=1e-10)
+    ll = eng.loglik(nd)
+    assert sc == pytest.approx(ll.sum(), rel=1e-11)
+    nat.check(nat.lib().jh_set_option(b"fast_variant", 3))
+    try:
+        ts2, es2, sc2 = eng.estep(nd)
+    finally:
+        nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
+    np.testing.assert_allclose(ts, ts2, rtol=1e-10)
+    np.testing.assert_allclose(es, es2, rtol=1e-10, atol=1e-12)
+    assert sc == pytest.approx(sc2, rel=1e-13)
+    hmm.train(data)
+    assert (np.diff(hmm.last_objectives[0]) >= -1e-6).all()
+
+
 def test_java_random_workload_and_ragged_buckets(nat, oracle_lib, fast):
     """cfg4-style ragged lengths on the java.util.Random stream; length buckets must not change results or order."""
     lens = ragged_lengths(48, seed=42, lo=20.0, decades=2.0)
