@@ -832,7 +832,8 @@ static int ensure_octet_hashes(jh_model *m, jh_dataset *d) {
   if (!d->d_oct_seq.p) {
     if ((r = d->d_oct_seq.upload(d->oct_seq, s)) || (r = d->d_oct_hbase.upload(d->oct_hbase, s))) return r;
   }
-  if ((r = d->d_hashes.reserve((size_t)n_rec * 8 + 8))) return r;
+  if ((r = d->d_hashes.reserve((size_t)(n_rec + 4) * 8))) return r;  // one zero record in front, three behind (prefetch overrun)
+  JH_CUDA(cudaMemsetAsync(d->d_hashes.p, 0, (size_t)(n_rec + 4) * 8 * sizeof(uint16_t), s));
   if (n_oct > 0) {
     jhm::k_hash_octets<<<(int)std::min<int64_t>(n_oct, 148 * 16), 128, 0, s>>>(d->d_codes.p, d->d_offsets.p, d->d_oct_seq.p, d->d_oct_hbase.p, n_oct,
                                                                            m->a, m->Kmax, d->d_hashes.p);
@@ -887,7 +888,7 @@ static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
 
 static int run_estep_fast(jh_model *m, jh_dataset *d) {
   int r = JH_OK;
-  JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * m->fast.H * m->fast.G, m->st()));
+  JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * jhf::EC_REPLICAS * m->fast.H * m->fast.G, m->st()));
   const bool octets = g_opt.fast_variant == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
   for (size_t b = 0; octets && b + 1 < d->bucket_ptr.size() && !r; b++)
     r = m->fast.G == 8 ? launch_mma_estep<1>(m, d, b) : m->fast.G == 16 ? launch_mma_estep<2>(m, d, b) : launch_mma_estep<4>(m, d, b);

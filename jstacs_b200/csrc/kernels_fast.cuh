@@ -33,6 +33,8 @@ struct DevBuf;
 
 namespace jhf {
 
+constexpr int EC_REPLICAS = 16;  // copies of the global emission-count table (spreads the fp64 reductions over L2 slices)
+
 using jhx::ResReader;
 
 struct FastDev {
@@ -58,7 +60,7 @@ struct FastTables {
   int *d_korder = nullptr, *d_tstat = nullptr, *d_pistat = nullptr, *d_estat_tab = nullptr, *d_estat_mod = nullptr;
   int *d_tmap = nullptr, *d_pimap = nullptr;  // child index p of edge i->j / start->j, -1 if absent
   int *d_fexp = nullptr;                      // per-row exponent scratch
-  double *d_ec = nullptr;                     // [H*G] global emission-count table
+  double *d_ec = nullptr;                     // [EC_REPLICAS][H*G] global emission-count tables
   size_t fexp_n = 0;
   FastDev dev() const {
     FastDev F;
@@ -134,7 +136,9 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
     return r;
   std::vector<double> z((size_t)std::max<int64_t>(H * G, (int64_t)G * G), 0.0);
   std::vector<double> zT((size_t)G * G, 0.0), zpi(G, 0.0), zE((size_t)H * G, 0.0);
-  if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s)) || (r = up(&F.d_ec, zE, s))) return r;
+  if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s))) return r;
+  std::vector<double> zEC((size_t)EC_REPLICAS * H * G, 0.0);
+  if ((r = up(&F.d_ec, zEC, s))) return r;
   F.usable = true;
   return JH_OK;
 }
@@ -682,7 +686,8 @@ __global__ void k_fast_fold_ec(FastDev F, const double *gEC, double *stats) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F.H * F.G) return;
   int j = i % F.G, hh = i / F.G;
-  double v = gEC[i];
+  double v = 0;
+  for (int rep = 0; rep < EC_REPLICAS; rep++) v += gEC[(size_t)rep * F.H * F.G + i];
   if (v != 0 && F.estat_tab[j] >= 0) atomicAdd(&stats[F.n_child + F.estat_tab[j] + hh % F.estat_mod[j]], v);
 }
 

@@ -26,6 +26,8 @@
 
 namespace jhm {
 
+using jhf::EC_REPLICAS;
+
 using jhf::FastDev;
 
 struct OctData {
@@ -49,7 +51,7 @@ __global__ void k_hash_octets(const uint8_t *codes, const int64_t *offsets, cons
       off[r] = sid >= 0 ? offsets[sid] : 0;
       len[r] = sid >= 0 ? (int)(offsets[sid + 1] - offsets[sid]) : 0;
     }
-    uint4 *rec = reinterpret_cast<uint4 *>(hashes + oct_hbase[o] * 8);
+    uint4 *rec = reinterpret_cast<uint4 *>(hashes + (oct_hbase[o] + 1) * 8);  // record 0 of the buffer is a zero pad
     for (int p = threadIdx.x; p < len[0]; p += blockDim.x) {
       unsigned hv[8];
 #pragma unroll
@@ -76,6 +78,15 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
+// predicated forms (no divergent branch in the position loops)
+__device__ __forceinline__ void cp_async16_if(bool p, void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("{\n .reg .pred p;\n setp.ne.s32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(sa), "l"(gmem), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ void cp_async4_if(bool p, void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("{\n .reg .pred p;\n setp.ne.s32 p, %2, 0;\n @p cp.async.ca.shared.global [%0], [%1], 4;\n}\n" ::"r"(sa), "l"(gmem), "r"((int)p) : "memory");
+}
 __device__ __forceinline__ double pow2_clamped(int k) {  // 2^k for k in [-1023, 1024): 0 below, finite above
   k = max(-1023, min(1023, k));
   return __hiloint2double((1023 + k) << 20, 0);
@@ -99,14 +110,38 @@ __device__ __forceinline__ bool rescale_row(double (&v)[NV], int &expo) {
   return (unsigned)(be - 61) < (0x7feu - 61u);
 }
 
+__device__ __forceinline__ double piv_of(const FastDev &F, int s) { return F.pi[s]; }
+
+// emission probabilities of position pos (context hash h) for the NV states of a lane in the RL layout
+template <int NT, bool GEN>
+__device__ __forceinline__ void emis_rl(const FastDev &F, const double *sE, int q, double (&e)[2 * NT], int h, int pos) {
+  const double *row = sE + (size_t)h * (8 * NT) + 2 * q;
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    const double2 x = *reinterpret_cast<const double2 *>(row + 8 * t);
+    e[2 * t] = x.x;
+    e[2 * t + 1] = x.y;
+  }
+  if (GEN && pos < F.Kmax) {  // HigherOrderDiscreteEmission: condition not available -> uniform (ACDE:447-450)
+#pragma unroll
+    for (int v = 0; v < 2 * NT; v++)
+      if (pos < F.korder[8 * (v >> 1) + 2 * q + (v & 1)]) e[v] = F.inv_a;
+  }
+}
+
 template <int NT>
 struct MmaCfg {
   static constexpr int G = 8 * NT, NV = 2 * NT, WARPS = 8, NTHREADS = 256;
-  static constexpr int RSTRIDE = NT >= 2 ? G * 8 + 64 : G * 8;  // bytes between the sequences of a tile (bank spread of RL accesses)
+  static constexpr int ROWB = G * 8;              // bytes of one sequence's row of a tile (no padding: XOR swizzle below)
   static constexpr int RING = 4;
-  static constexpr int SLOTB = 8 * RSTRIDE + 32;                // 8 rows + 8 exponents
-  static constexpr int WARPB = RING * SLOTB + 2 * 8 * RSTRIDE + 64;
+  static constexpr int SLOTB = 8 * ROWB + 32;     // 8 rows + 8 exponents
+  static constexpr int WARPB = RING * SLOTB + 2 * 8 * ROWB + 64;
   static size_t smem_bytes(int H) { return ((size_t)H * G + (size_t)G * G + G) * sizeof(double) + (size_t)WARPS * WARPB; }
+  // Tiles [sequence n][state] live in shared memory in 16-byte chunks; chunk c of row n is stored at c ^ swz(n).
+  // With this both access patterns are bank-conflict free: RL (lane (r,q): 16 bytes at chunk 4t+q of row r) because the
+  // two rows of a quarter warp differ in bit 2 of the chunk, TL (lane (r,q): 8 bytes of state 8t+r of row 4kk+q) because
+  // the four rows of a half warp land in four different 32-byte bank groups.
+  __device__ static __forceinline__ int swz(int n) { return NT >= 2 ? ((n & 2) | ((n & 1) << 2)) : (n & 2); }
 };
 
 // stats layout: [transition statistics n_child | emission statistics n_cond*a | sum_n w_n*logP_n]; gEC as in kernels_fast.cuh
@@ -114,14 +149,14 @@ template <int NT>
 __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch,
                                                       int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback) {
   using C = MmaCfg<NT>;
-  constexpr int G = C::G, NV = C::NV, RSTRIDE = C::RSTRIDE, RING = C::RING, SLOTB = C::SLOTB;
+  constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
   const int HG = F.H * G;
   double *sE = sm, *sO = sE + HG, *sPi = sO + G * G;
   char *swarp = reinterpret_cast<char *>(sPi + G) + (size_t)(threadIdx.x >> 5) * C::WARPB;
-  char *ring = swarp;                        // [RING][SLOTB]
-  char *bbuf = swarp + RING * SLOTB;         // [2][8*RSTRIDE]
-  int *sbx = reinterpret_cast<int *>(bbuf + 2 * 8 * RSTRIDE);  // [2][8]
+  char *const ring = swarp;                        // [RING][SLOTB]
+  char *const bbuf = swarp + RING * SLOTB;         // [2][8*ROWB]
+  int *const sbx = reinterpret_cast<int *>(bbuf + 2 * 8 * ROWB);  // [2][8]
   for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
   for (int i = threadIdx.x; i < G * G + G; i += blockDim.x) sO[i] = 0;
   __syncthreads();
@@ -130,17 +165,21 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
   const int64_t slot = (int64_t)blockIdx.x * C::WARPS + (threadIdx.x >> 5);
   double *const fw = fwd_scratch + (size_t)slot * rows * 8 * G + r * G + 2 * q;  // + t*8*G + 8*tp (+b)
   int *const fe = fexp_scratch + (size_t)slot * rows * 8;                       // + t*8 + row
-  const double inv_a = F.inv_a;
-  // per-lane constants of the RL layout: state of value v is 8*(v>>1) + 2q + (v&1)
-  double finv[NV], piv[NV];
-  int kmin = 0;  // positions below Kmax need the per-state order check
+  const int kmin = F.Kmax;  // positions below Kmax need the per-state order check
+  // emission-count table: EC_REPLICAS copies spread the fp64 reductions over the L2 slices (one 64 KB table kept a few
+  // slices at 80 % atomic-unit load while the average was 28 %, profiles/r1_estep_octets.md); k_fast_fold_ec sums them
+  double *const gECw = gEC + (size_t)(slot % EC_REPLICAS) * HG;
+  // byte offsets inside a swizzled tile: RL chunk of (row r, tile tp), TL element of (row 4kk+q, state 8tp+r)
+  int rl_off[NT], tl_off[2][NT];
 #pragma unroll
-  for (int v = 0; v < NV; v++) {
-    const int s = 8 * (v >> 1) + 2 * q + (v & 1);
-    finv[v] = F.fin[s];
-    piv[v] = F.pi[s];
+  for (int tp = 0; tp < NT; tp++) {
+    rl_off[tp] = r * ROWB + (((4 * tp + q) ^ C::swz(r)) << 4);
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+      const int n = 4 * kk + q, s = 8 * tp + r;
+      tl_off[kk][tp] = n * ROWB + ((((s >> 1) ^ C::swz(n)) << 4) | ((s & 1) << 3));
+    }
   }
-  kmin = F.Kmax;
   double O[NT][NT][2];
 #pragma unroll
   for (int i = 0; i < NT; i++)
@@ -151,21 +190,8 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
   for (int v = 0; v < NV; v++) SC[v] = 0;
   double score = 0;
 
-  // emission probabilities of position pos (context hash h) for the lane's NV states
-  auto emis = [&](double (&e)[NV], int h, int pos) {
-    const double *row = sE + (size_t)h * G + 2 * q;
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-      const double2 x = *reinterpret_cast<const double2 *>(row + 8 * t);
-      e[2 * t] = x.x;
-      e[2 * t + 1] = x.y;
-    }
-    if (pos < kmin) {  // HigherOrderDiscreteEmission: condition not available -> uniform (ACDE:447-450)
-#pragma unroll
-      for (int v = 0; v < NV; v++)
-        if (pos < F.korder[8 * (v >> 1) + 2 * q + (v & 1)]) e[v] = inv_a;
-    }
-  };
+  using GeneralStep = std::true_type;
+  using UniformStep = std::false_type;
 
   for (;;) {
     long long o = 0;
@@ -181,7 +207,9 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
     }
     const int Lmax = __shfl_sync(FULL, Lr, 0);
     const int Lmin = __reduce_min_sync(FULL, Lr);
-    const uint16_t *const hrow = D.hashes + D.oct_hbase[o] * 8 + r;  // + position*8
+    // hash records: one zero record in front of the buffer and one behind it, so the prefetches below may run one or two
+    // positions past either end of the octet
+    const uint16_t *const hrow = D.hashes + (D.oct_hbase[o] + 1) * 8 + r;  // + position*8
     // ================================ forward ================================
     double A[NV];
     int Aexp = 0;
@@ -193,17 +221,18 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 #pragma unroll
         for (int t = 0; t < NT; t++) Bf[k][t] = F.T[(8 * (k >> 1) + 2 * q + (k & 1)) * G + 8 * t + r];
       double e[NV];
-      emis(e, hrow[0], 0);
+      emis_rl<NT, true>(F, sE, q, e, hrow[0], 0);
 #pragma unroll
-      for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv[v] * e[v] : 0.0;
+      for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv_of(F, 8 * (v >> 1) + 2 * q + (v & 1)) * e[v] : 0.0;
       ok = rescale_row<NV>(A, Aexp);
 #pragma unroll
       for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(fw + 8 * t) = make_double2(A[2 * t], A[2 * t + 1]);
       if (q == 0) fe[r] = Aexp;
-      if (Lmax > 1) emis(e, hrow[8], 1);
-      for (int t = 0; t + 1 < Lmax; t++) {  // row t -> t+1
-        int hn = 0;
-        if (t + 2 < Lmax) hn = hrow[(size_t)(t + 2) * 8];
+      emis_rl<NT, true>(F, sE, q, e, hrow[8], 1);
+      int h2 = hrow[16];  // hash of position t+2, loaded one step ahead of its use
+      auto fstep = [&](auto general, int t) {  // row t -> t+1
+        constexpr bool GEN = decltype(general)::value;
+        const int h3 = hrow[(size_t)(t + 3) * 8];
         double Dv[NV];
 #pragma unroll
         for (int v = 0; v < NV; v++) Dv[v] = 0;
@@ -215,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
         for (int v = 0; v < NV; v++) Dv[v] *= e[v];
         int nexp = Aexp;
         const bool nok = rescale_row<NV>(Dv, nexp);
-        if (t + 1 < Lmin) {  // every sequence of the octet is still running
+        if (!GEN) {  // every sequence of the octet is still running
 #pragma unroll
           for (int v = 0; v < NV; v++) A[v] = Dv[v];
           Aexp = nexp;
@@ -234,13 +263,20 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 #pragma unroll
         for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(dst + 8 * tp) = make_double2(Dv[2 * tp], Dv[2 * tp + 1]);
         if (q == 0) fe[(size_t)(t + 1) * 8 + r] = nexp;
-        if (t + 2 < Lmax) emis(e, hn, t + 2);
-      }
+        emis_rl<NT, GEN>(F, sE, q, e, h2, t + 2);
+        h2 = h3;
+      };
+      // uniform steps: t+1 < Lmin (all sequences running) and t+2 >= Kmax (no order check for the emission fetched)
+      int t = 0;
+      const int t_lo = min(max(kmin - 2, 0), Lmax - 1), t_hi = max(min(Lmin - 1, Lmax - 1), t_lo);
+      for (; t < t_lo; t++) fstep(GeneralStep(), t);
+      for (; t < t_hi; t++) fstep(UniformStep(), t);
+      for (; t + 1 < Lmax; t++) fstep(GeneralStep(), t);
     }
     // ---- termination: P(x) = sum over final states, one log per sequence ----
     double sfin = 0;
 #pragma unroll
-    for (int v = 0; v < NV; v++) sfin += A[v] * finv[v];
+    for (int v = 0; v < NV; v++) sfin += A[v] * F.fin[8 * (v >> 1) + 2 * q + (v & 1)];
     sfin += __shfl_xor_sync(FULL, sfin, 1);
     sfin += __shfl_xor_sync(FULL, sfin, 2);
     const int AL = Aexp;
@@ -264,17 +300,15 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       double beta[NV];
       int Bx = 0;
 #pragma unroll
-      for (int v = 0; v < NV; v++) beta[v] = finv[v] * invS;  // 1/P(x) and the weight are folded in: posteriors come out weighted
+      for (int v = 0; v < NV; v++) beta[v] = F.fin[8 * (v >> 1) + 2 * q + (v & 1)] * invS;  // 1/P(x) and the weight are folded in
       rescale_row<NV>(beta, Bx);
-      const double *const fsrc = fwd_scratch + (size_t)slot * rows * 8 * G + r * G + 2 * q;
       auto issue = [&](int row) {  // forward row `row` (8 sequences x G doubles + 8 exponents) -> ring slot row & 3
-        if (row >= 0) {
-          char *sl = ring + (size_t)(row & (RING - 1)) * SLOTB;
-          const double *src = fsrc + (size_t)row * 8 * G;
+        const bool have = row >= 0;
+        char *sl = ring + (size_t)(row & (RING - 1)) * SLOTB;
+        const double *src = fw + (int64_t)row * 8 * G;
 #pragma unroll
-          for (int tp = 0; tp < NT; tp++) cp_async16(sl + r * RSTRIDE + (8 * tp + 2 * q) * 8, src + 8 * tp);
-          if (l < 8) jhf::cp_async4(sl + 8 * RSTRIDE + l * 4, fe + (size_t)row * 8 + l);
-        }
+        for (int tp = 0; tp < NT; tp++) cp_async16_if(have, sl + rl_off[tp], src + 8 * tp);
+        cp_async4_if(have && l < 8, sl + 8 * ROWB + l * 4, fe + (int64_t)row * 8 + l);
         jhf::cp_async_commit();
       };
       __syncwarp();
@@ -282,44 +316,27 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       issue(Lmax - 2);
       issue(Lmax - 3);
       int h = hrow[(size_t)(Lmax - 1) * 8];
+      int h1 = hrow[(size_t)(Lmax - 2) * 8];  // hash of position t-1, loaded one step ahead of its use
       double e[NV];
-      emis(e, h, Lmax - 1);
+      emis_rl<NT, true>(F, sE, q, e, h, Lmax - 1);
       int par = 0;
-      for (int t = Lmax - 1; t >= 1; --t) {  // consumes position t: beta_t -> beta_{t-1}, counts of the edges (t-1 -> t)
-        const int hn = hrow[(size_t)(t - 1) * 8];
-        jhf::cp_async_wait<1>();
-        __syncwarp();
-        const char *slt = ring + (size_t)(t & (RING - 1)) * SLOTB;
-        const char *slp = ring + (size_t)((t - 1) & (RING - 1)) * SLOTB;
-        const bool ragged = t >= Lmin;
-        const bool act = t < Lr;
-        {  // emission statistic of position t: gamma_t = alpha_t * beta_t * 2^(A_t + Bx - AL)
-          const int At = *reinterpret_cast<const int *>(slt + 8 * RSTRIDE + r * 4);
-          double sc = pow2_clamped(At + Bx - AL);
-          if (ragged && !act) sc = 0.0;
-          double *gdst = gEC + (size_t)h * G + 2 * q;
-#pragma unroll
-          for (int tp = 0; tp < NT; tp++) {
-            const double2 a2 = *reinterpret_cast<const double2 *>(slt + r * RSTRIDE + (8 * tp + 2 * q) * 8);
-            const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
-            if (t >= kmin) {
-              atomicAdd(gdst + 8 * tp, g0);
-              atomicAdd(gdst + 8 * tp + 1, g1);
-            } else {
-              if (t >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
-              if (t >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);
-            }
-          }
-        }
+      auto bstep = [&](auto general, int t) {  // consumes position t: beta_t -> beta_{t-1}, counts of the edges (t-1 -> t)
+        constexpr bool GEN = decltype(general)::value;
+        const int h2 = hrow[(size_t)(t - 2) * 8];
+        const bool act = !GEN || t < Lr;
+        // critical path first: b = e * beta feeds the recursion product straight from registers
         double b[NV];
 #pragma unroll
-        for (int v = 0; v < NV; v++) b[v] = (ragged && !act) ? 0.0 : e[v] * beta[v];
-        char *bb = bbuf + (size_t)par * 8 * RSTRIDE;
+        for (int v = 0; v < NV; v++) b[v] = act ? e[v] * beta[v] : 0.0;
+        char *bb = bbuf + (size_t)par * 8 * ROWB;
 #pragma unroll
-        for (int tp = 0; tp < NT; tp++)
-          *reinterpret_cast<double2 *>(bb + r * RSTRIDE + (8 * tp + 2 * q) * 8) = make_double2(b[2 * tp], b[2 * tp + 1]);
+        for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(bb + rl_off[tp]) = make_double2(b[2 * tp], b[2 * tp + 1]);
         if (q == 0) sbx[par * 8 + r] = Bx - AL;
+        jhf::cp_async_wait<1>();  // rows t and t-1 have landed; row t-2 may still be in flight
         __syncwarp();
+        issue(t - 3);  // two steps ahead of its first use; its slot held row t+1, last read before this __syncwarp
+        const char *slt = ring + (size_t)(t & (RING - 1)) * SLOTB;
+        const char *slp = ring + (size_t)((t - 1) & (RING - 1)) * SLOTB;
         // beta_{t-1}[n][i] = sum_j b[n][j] T[i][j]
         double Dv[NV];
 #pragma unroll
@@ -328,18 +345,36 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
         for (int k = 0; k < NV; k++)
 #pragma unroll
           for (int tp = 0; tp < NT; tp++) dmma(Dv[2 * tp], Dv[2 * tp + 1], b[k], Bb[k][tp]);
+        {  // emission statistic of position t: gamma_t = alpha_t * beta_t * 2^(A_t + Bx - AL)
+          const int At = *reinterpret_cast<const int *>(slt + 8 * ROWB + r * 4);
+          double sc = pow2_clamped(At + Bx - AL);
+          if (!act) sc = 0.0;
+          double *gdst = gECw + (size_t)h * G + 2 * q;
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) {
+            const double2 a2 = *reinterpret_cast<const double2 *>(slt + rl_off[tp]);
+            const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
+            if (!GEN || t >= kmin) {
+              atomicAdd(gdst + 8 * tp, g0);
+              atomicAdd(gdst + 8 * tp + 1, g1);
+            } else {
+              if (t >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
+              if (t >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);
+            }
+          }
+        }
         // O[i][j] += sum_n alpha_{t-1}[n][i] 2^(A_{t-1}[n] + Bx[n] - AL[n]) b[n][j]   (T[i][j] is multiplied in at the end)
         {
           double aT[2][NT], bT[2][NT];
 #pragma unroll
           for (int kk = 0; kk < 2; kk++) {
             const int n = 4 * kk + q;
-            const int ea = *reinterpret_cast<const int *>(slp + 8 * RSTRIDE + n * 4);
+            const int ea = *reinterpret_cast<const int *>(slp + 8 * ROWB + n * 4);
             const double f = pow2_clamped(ea + sbx[par * 8 + n]);
 #pragma unroll
             for (int tp = 0; tp < NT; tp++) {
-              aT[kk][tp] = *reinterpret_cast<const double *>(slp + n * RSTRIDE + (8 * tp + r) * 8) * f;
-              bT[kk][tp] = *reinterpret_cast<const double *>(bb + n * RSTRIDE + (8 * tp + r) * 8);
+              aT[kk][tp] = *reinterpret_cast<const double *>(slp + tl_off[kk][tp]) * f;
+              bT[kk][tp] = *reinterpret_cast<const double *>(bb + tl_off[kk][tp]);
             }
           }
 #pragma unroll
@@ -351,26 +386,32 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
         }
         int nbx = Bx;
         rescale_row<NV>(Dv, nbx);  // cannot fail while the forward mass is positive; NaN reaches the finite check
-        if (!ragged || act) {
+        if (act) {
 #pragma unroll
           for (int v = 0; v < NV; v++) beta[v] = Dv[v];
           Bx = nbx;
         }
-        h = hn;
-        emis(e, h, t - 1);
-        issue(t - 3);
+        h = h1;
+        h1 = h2;
+        emis_rl<NT, GEN>(F, sE, q, e, h, t - 1);
         par ^= 1;
-      }
+      };
+      // uniform steps: t < Lmin (all sequences running) and t-1 >= Kmax (no order checks)
+      int t = Lmax - 1;
+      const int t_hi = min(Lmin - 1, Lmax - 1), t_lo = max(kmin + 1, 1);
+      for (; t > t_hi && t >= 1; --t) bstep(GeneralStep(), t);
+      for (; t >= t_lo; --t) bstep(UniformStep(), t);
+      for (; t >= 1; --t) bstep(GeneralStep(), t);
       jhf::cp_async_wait<0>();
       __syncwarp();
       {  // position 0: emission statistic and the statistic of the start element
         const char *sl0 = ring;
-        const int A0 = *reinterpret_cast<const int *>(sl0 + 8 * RSTRIDE + r * 4);
+        const int A0 = *reinterpret_cast<const int *>(sl0 + 8 * ROWB + r * 4);
         const double sc = Lr > 0 ? pow2_clamped(A0 + Bx - AL) : 0.0;
-        double *gdst = gEC + (size_t)h * G + 2 * q;
+        double *gdst = gECw + (size_t)h * G + 2 * q;
 #pragma unroll
         for (int tp = 0; tp < NT; tp++) {
-          const double2 a2 = *reinterpret_cast<const double2 *>(sl0 + r * RSTRIDE + (8 * tp + 2 * q) * 8);
+          const double2 a2 = *reinterpret_cast<const double2 *>(sl0 + rl_off[tp]);
           const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
           if (0 >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
           if (0 >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);

@@ -5,7 +5,7 @@
 tag=$1; shift
 what="$*"; [ -z "$what" ] && what="tests bench ncu"
 mkdir -p gpurun_out
-SMALL="python bench.py --nseq 20000 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+SMALL="python bench.py --nseq ${NSEQ:-37888} --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_gpu.txt 2>&1
 for w in $what; do
   case $w in
