@@ -105,9 +105,10 @@ __device__ __forceinline__ bool rescale_row(double (&v)[NV], int &expo) {
 #pragma unroll
   for (int i = 0; i < NV; i++) v[i] *= f;
   expo += be - 1023;
-  // "ok": the row maximum is a normal number with 60 binades of head room below it, so that every component within
-  // 2^-60 of the maximum is still normal (nothing that matters at 1e-16 relative has been flushed)
-  return (unsigned)(be - 61) < (0x7feu - 61u);
+  // "ok": the row maximum is a normal number with 80 binades of head room below it, so that every component within
+  // 2^-60 of the maximum was still normal at every position since the last rescale (a row maximum grows by at most
+  // a factor 32 = 2^5 per position, RS = 4 positions between rescales): nothing that matters at 1e-16 was flushed
+  return (unsigned)(be - 81) < (0x7feu - 81u);
 }
 
 __device__ __forceinline__ double piv_of(const FastDev &F, int s) { return F.pi[s]; }
@@ -190,8 +191,14 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
   for (int v = 0; v < NV; v++) SC[v] = 0;
   double score = 0;
 
-  using GeneralStep = std::true_type;
-  using UniformStep = std::false_type;
+  // step kinds: general (ragged octet or position below the emission order, rescales), uniform with / without rescale.
+  // Uniform steps rescale every RS-th position only: between two rescales a row maximum grows by at
+  // most a factor G (column sums of T), so RS positions without rescaling stay far inside the 60 + 5*RS binades of head
+  // room that rescale_row's "ok" test demands.
+  using GeneralStep = std::integral_constant<int, 2>;
+  using UniformStep = std::integral_constant<int, 1>;
+  using UniformStepNoRescale = std::integral_constant<int, 0>;
+  constexpr int RS = 4;
 
   for (;;) {
     long long o = 0;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       emis_rl<NT, true>(F, sE, q, e, hrow[8], 1);
       int h2 = hrow[16];  // hash of position t+2, loaded one step ahead of its use
       auto fstep = [&](auto general, int t) {  // row t -> t+1
-        constexpr bool GEN = decltype(general)::value;
+        constexpr bool GEN = decltype(general)::value == 2, RESC = decltype(general)::value != 0;
         const int h3 = hrow[(size_t)(t + 3) * 8];
         double Dv[NV];
 #pragma unroll
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 #pragma unroll
         for (int v = 0; v < NV; v++) Dv[v] *= e[v];
         int nexp = Aexp;
-        const bool nok = rescale_row<NV>(Dv, nexp);
+        const bool nok = RESC ? rescale_row<NV>(Dv, nexp) : true;
         if (!GEN) {  // every sequence of the octet is still running
 #pragma unroll
           for (int v = 0; v < NV; v++) A[v] = Dv[v];
@@ -270,6 +277,11 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       int t = 0;
       const int t_lo = min(max(kmin - 2, 0), Lmax - 1), t_hi = max(min(Lmin - 1, Lmax - 1), t_lo);
       for (; t < t_lo; t++) fstep(GeneralStep(), t);
+      for (; t + RS <= t_hi; t += RS) {
+#pragma unroll
+        for (int u = 0; u < RS - 1; u++) fstep(UniformStepNoRescale(), t + u);
+        fstep(UniformStep(), t + RS - 1);
+      }
       for (; t < t_hi; t++) fstep(UniformStep(), t);
       for (; t + 1 < Lmax; t++) fstep(GeneralStep(), t);
     }
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       emis_rl<NT, true>(F, sE, q, e, h, Lmax - 1);
       int par = 0;
       auto bstep = [&](auto general, int t) {  // consumes position t: beta_t -> beta_{t-1}, counts of the edges (t-1 -> t)
-        constexpr bool GEN = decltype(general)::value;
+        constexpr bool GEN = decltype(general)::value == 2, RESC = decltype(general)::value != 0;
         const int h2 = hrow[(size_t)(t - 2) * 8];
         const bool act = !GEN || t < Lr;
         // critical path first: b = e * beta feeds the recursion product straight from registers
@@ -385,7 +397,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
               for (int tj = 0; tj < NT; tj++) dmma(O[ti][tj][0], O[ti][tj][1], aT[kk][ti], bT[kk][tj]);
         }
         int nbx = Bx;
-        rescale_row<NV>(Dv, nbx);  // cannot fail while the forward mass is positive; NaN reaches the finite check
+        if (RESC) rescale_row<NV>(Dv, nbx);  // cannot fail while the forward mass is positive; NaN reaches the finite check
         if (act) {
 #pragma unroll
           for (int v = 0; v < NV; v++) beta[v] = Dv[v];
@@ -400,6 +412,11 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       int t = Lmax - 1;
       const int t_hi = min(Lmin - 1, Lmax - 1), t_lo = max(kmin + 1, 1);
       for (; t > t_hi && t >= 1; --t) bstep(GeneralStep(), t);
+      for (; t - RS + 1 >= t_lo; t -= RS) {
+#pragma unroll
+        for (int u = 0; u < RS - 1; u++) bstep(UniformStepNoRescale(), t - u);
+        bstep(UniformStep(), t - RS + 1);
+      }
       for (; t >= t_lo; --t) bstep(UniformStep(), t);
       for (; t >= 1; --t) bstep(GeneralStep(), t);
       jhf::cp_async_wait<0>();
