@@ -1,0 +1,54 @@
+"""Device-time throughput of every BASELINE.json config shape (kernel time from the library's CUDA events; the
+host<->device copies of the C-ABI call are excluded).  usage: python profiles/bench_configs.py [scale]
+scale < 1 shrinks the sequence counts (default 0.1).  One JSON line per config."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+import __graft_entry__ as g
+
+g.build()
+from jstacs_b200 import _native
+from jstacs_b200.workloads import banded_hmm, ergodic_hmm, make_data, ragged_lengths
+
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
+only = sys.argv[2:] or None
+
+
+def run(name, hmm, data, what, reps=3):
+    if only and name not in only:
+        return
+    eng, nd = hmm._engine(), hmm._data(data)
+    res, S = data.getNumberOfResidues(), hmm.getNumberOfStates()
+    fn = {"estep": lambda: eng.estep(nd, fetch=False), "loglik": lambda: eng.loglik(nd), "viterbi": lambda: eng.viterbi(nd),
+          "decode": lambda: eng.posterior_decode(nd)}[what]
+    fn()
+    ms = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn()
+        _native.check(_native.lib().jh_synchronize())
+        wall = (time.perf_counter() - t0) * 1e3
+        ms.append((eng.last_main_kernel_ms() if what == "estep" else eng.last_kernel_ms(), wall))
+    k = float(np.median([m[0] for m in ms]))
+    print(json.dumps({"config": name, "op": what, "states": S, "n_seq": data.getNumberOfElements(), "residues": res, "kernel_ms": round(k, 3),
+                      "call_ms": round(float(np.median([m[1] for m in ms])), 3), "residues_states_per_s": res * S / (k * 1e-3),
+                      "residues_per_s": res / (k * 1e-3)}), flush=True)
+    nd.close()
+
+
+n = lambda x: max(64, int(x * scale))
+run("cfg1_bw_s2_k1", ergodic_hmm(2, 1), make_data(10_000, 1000), "estep")
+run("cfg2_viterbi_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "viterbi")
+run("cfg2_bw_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "estep")
+run("cfg3_bw_s32_k3", ergodic_hmm(32, 3, ess=4.0), make_data(n(1_000_000), 1000), "estep")
+run("cfg3_loglik_s32_k3", ergodic_hmm(32, 3, ess=4.0), make_data(n(1_000_000), 1000), "loglik")
+run("cfg3_decode_s32_k3", ergodic_hmm(32, 3, ess=4.0), make_data(n(200_000), 1000), "decode")
+lens = ragged_lengths(n(100_000), seed=42)
+run("cfg4_loglik_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "loglik")
+run("cfg4_bw_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "estep")
+run("cfg5_loglik_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "loglik")
