@@ -291,13 +291,16 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        # dram bytes per launch from the ncu --set full capture of this kernel (profiles/r1_estep_octets.md: 518 B per residue,
+        # forward rows written once and read once; lane-per-state kernel: 488 B per residue), scaled to this launch
+        traffic_per_res = 518.0 if (args.fast and args.variant == 0 and S >= 5) else (488.0 if args.fast else None)
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
-                    "traffic": None, "kernel": ("k_mma_estep" if args.variant == 0 and S >= 5 else "k_fast_estep") if args.fast else "k_exact_fb", "kernel_ms": k_ms,
+                    "traffic": traffic_per_res * residues if traffic_per_res else None, "kernel": ("k_mma_estep" if args.variant == 0 and S >= 5 else "k_fast_estep") if args.fast else "k_exact_fb", "kernel_ms": k_ms,
                     "flop_per_residue": flop_per_res, "peak_source": "DFMA-chain microbenchmark measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry)",
                     "nominal_reference_flop_per_residue": nominal_per_res,
                     "nominal_frac": nominal_per_res * residues / (k_ms * 1e-3) / 1e12 / peak if peak else None,
                     "hbm": {"algorithmic_bytes_per_residue": 2.0, "achieved_gbs": 2.0 * residues / (k_ms * 1e-3) / 1e9,
-                            "implementation_bytes_per_residue": 2.0 + 16.0 * 32 + 8, "peak_gbs": hbm_peak,
+                            "implementation_bytes_per_residue": traffic_per_res, "peak_gbs": hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
