@@ -12,6 +12,7 @@
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
 #include "kernels_mma.cuh"
+#include "kernels_viterbi.cuh"
 
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
@@ -241,7 +242,14 @@ static int prep_scores(jh_model *m) {
   jha::k_prep_scores<<<(n + 255) / 256, 256, 0, m->st()>>>(m->params());
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
-  return jhf::prepare(m->fast, m->dev(), m->st());
+  int r = jhf::prepare(m->fast, m->dev(), m->st());
+  if (r || !m->fast.usable) return r;
+  jhf::FastTables &F = m->fast;
+  int nv = std::max(F.G * F.G, F.H * F.G);
+  jhv::k_viterbi_prepare<<<(nv + 255) / 256, 256, 0, m->st()>>>(F.dev(), F.d_tmap, F.d_pimap, m->d_tscore.p, m->d_escore.p, F.d_vT, F.d_vpi, F.d_vfin, F.d_vE);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
 }
 
 extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
@@ -677,8 +685,59 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
 }
 
 // ---- Viterbi ------------------------------------------------------------------------------------
+static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
+
+// Lane-per-sequence Viterbi (kernels_viterbi.cuh): plain first-order models with sorted child lists; one launch per bucket.
+template <int S>
+static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_scores) {
+  using C = jhv::VitCfg<S>;
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhv::k_viterbi_lanes<S>;
+  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b];
+  if (n_oct <= 0) return JH_OK;
+  const int NT = 128, wpc = NT / 32;
+  size_t smem = ((size_t)S * S + S + (size_t)F.H * S) * sizeof(double);
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) { jh_set_error("Viterbi kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  const int64_t n_quads = (n_oct + 3) / 4;
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_quads + wpc - 1) / wpc);
+  const int64_t per_slot = rows * 32 * C::CB;
+  const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  grid = std::max<int64_t>(1, std::min(grid, max_slots / wpc));
+  int r = m->d_choice.reserve((size_t)grid * wpc * per_slot);
+  if (r) return r;
+  jhv::VitTables V;
+  V.T = F.d_vT; V.pi = F.d_vpi; V.fin = F.d_vfin; V.E = F.d_vE; V.korder = F.d_korder; V.H = F.H; V.Kmax = F.Kmax; V.log_uniform = -log((double)F.a);
+  jhm::OctData D;
+  D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
+  D.weights = nullptr; D.n_oct = n_oct;
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, NT, smem, s>>>(V, D, m->d_counter.p, m->d_choice.p, rows, d_paths, d_scores);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
 // One launch per length bucket so that the per-slot scratch follows the bucket's longest sequence.
 static int run_viterbi(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_scores, double *d_stats) {
+  if (!d_stats && g_opt.fast && m->fast.usable && m->fast.sorted_children) {  // decoding: one sequence per lane
+    int r = ensure_octet_hashes(m, d);
+    for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
+      switch (m->fast.G) {
+        case 2: r = launch_viterbi_lanes<2>(m, d, b, d_paths, d_scores); break;
+        case 4: r = launch_viterbi_lanes<4>(m, d, b, d_paths, d_scores); break;
+        case 8: r = launch_viterbi_lanes<8>(m, d, b, d_paths, d_scores); break;
+        case 16: r = launch_viterbi_lanes<16>(m, d, b, d_paths, d_scores); break;
+        default: r = launch_viterbi_lanes<32>(m, d, b, d_paths, d_scores); break;
+      }
+    }
+    return r;
+  }
   if (m->max_children > 254) { jh_set_error("more than 254 children per context"); return JH_ERR_UNSUPPORTED; }
   int G = group_size(m), r = JH_OK;
   cudaStream_t s = m->st();

@@ -59,6 +59,8 @@ struct FastTables {
   double *d_T = nullptr, *d_Tt = nullptr, *d_pi = nullptr, *d_E = nullptr, *d_fin = nullptr;
   int *d_korder = nullptr, *d_tstat = nullptr, *d_pistat = nullptr, *d_estat_tab = nullptr, *d_estat_mod = nullptr;
   int *d_tmap = nullptr, *d_pimap = nullptr;  // child index p of edge i->j / start->j, -1 if absent
+  bool sorted_children = false;               // every context lists its children in ascending state order (kernels_viterbi.cuh)
+  double *d_vT = nullptr, *d_vpi = nullptr, *d_vfin = nullptr, *d_vE = nullptr;  // log-space dense tables of the lane-per-sequence Viterbi
   int *d_fexp = nullptr;                      // per-row exponent scratch
   double *d_ec = nullptr;                     // [EC_REPLICAS][H*G] global emission-count tables
   size_t fexp_n = 0;
@@ -76,7 +78,7 @@ struct FastTables {
 };
 
 inline void destroy(FastTables &F) {
-  void *ptrs[] = {F.d_T, F.d_Tt, F.d_pi, F.d_E, F.d_fin, F.d_korder, F.d_tstat, F.d_pistat, F.d_estat_tab, F.d_estat_mod, F.d_tmap, F.d_pimap, F.d_fexp, F.d_ec};
+  void *ptrs[] = {F.d_T, F.d_Tt, F.d_pi, F.d_E, F.d_fin, F.d_korder, F.d_tstat, F.d_pistat, F.d_estat_tab, F.d_estat_mod, F.d_tmap, F.d_pimap, F.d_fexp, F.d_ec, F.d_vT, F.d_vpi, F.d_vfin, F.d_vE};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   F = FastTables();
@@ -110,9 +112,11 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
   std::vector<double> fin(G, 0.0);
   std::vector<char> seen(S, 0);
   int e0 = ctx_elem[lc_ctx_ptr[0]];
+  bool sorted = true;
   for (int p = elem_child_ptr[e0]; p < elem_child_ptr[e0 + 1]; p++) {
     pimap[child_state[p]] = p;
     pistat[child_state[p]] = child_stat[p];
+    if (p > elem_child_ptr[e0] && child_state[p] <= child_state[p - 1]) sorted = false;
   }
   for (int c = lc_ctx_ptr[1]; c < lc_ctx_ptr[2]; c++) {
     int i = ctx_last[c], e = ctx_elem[c];
@@ -121,6 +125,7 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
     for (int p = elem_child_ptr[e]; p < elem_child_ptr[e + 1]; p++) {
       tmap[(size_t)i * G + child_state[p]] = p;
       tstat[(size_t)i * G + child_state[p]] = child_stat[p];
+      if (p > elem_child_ptr[e] && child_state[p] <= child_state[p - 1]) sorted = false;
     }
   }
   for (int j = 0; j < S; j++) {
@@ -139,6 +144,8 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
   if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s))) return r;
   std::vector<double> zEC((size_t)EC_REPLICAS * H * G, 0.0);
   if ((r = up(&F.d_ec, zEC, s))) return r;
+  if ((r = up(&F.d_vT, zT, s)) || (r = up(&F.d_vpi, zpi, s)) || (r = up(&F.d_vfin, zpi, s)) || (r = up(&F.d_vE, zE, s))) return r;
+  F.sorted_children = sorted;
   F.usable = true;
   return JH_OK;
 }
