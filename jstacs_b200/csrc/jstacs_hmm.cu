@@ -650,20 +650,62 @@ extern "C" int jh_last_main_kernel_ms(jh_model *m, double *ms) {
   }
 
 // ---- log-likelihood --------------------------------------------------------------------------
-static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out) {
+static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int32_t *d_list = nullptr, int64_t n_list = 0) {
   int G = group_size(m), r = JH_OK;
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
   DISPATCH_G(G, {
     LaunchPlan pl;
-    r = plan_launch(m, jhx::k_exact_loglik<GG>, GG, 0, d->n_seq, 0, &pl);
+    r = plan_launch(m, jhx::k_exact_loglik<GG>, GG, 0, d_list ? n_list : d->n_seq, 0, &pl);
     if (!r) {
-      jhx::k_exact_loglik<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(), m->d_counter.p, d_out);
+      jhx::k_exact_loglik<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(), m->d_counter.p, d_out, d_list, n_list);
       JH_LAUNCHED();
     }
   });
   if (r) return r;
   JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
+
+// Octet scoring (kernels_mma.cuh): ONE launch over all octets (longest first, fetched dynamically: no scratch to size);
+// sequences the scaled recursion could not score are re-run by the log-space kernel.
+template <int NT>
+static int launch_mma_loglik(jh_model *m, jh_dataset *d, double *d_out) {
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhm::k_mma_loglik<NT>;
+  const int64_t n_oct = (int64_t)d->oct_hbase.size() - 1;
+  size_t smem = (size_t)F.H * F.G * sizeof(double);
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+  if (per_sm < 1) { jh_set_error("octet scoring kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + 7) / 8));
+  jhm::OctData D;
+  D.oct_seq = d->d_oct_seq.p; D.oct_hbase = d->d_oct_hbase.p; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
+  D.weights = nullptr; D.n_oct = n_oct;
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, 256, smem, s>>>(F.dev(), D, m->d_counter.p, d_out, m->d_fallback.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_loglik_octets(jh_model *m, jh_dataset *d, double *d_out) {
+  int r = ensure_octet_hashes(m, d);
+  if (r) return r;
+  if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  r = m->fast.G == 8 ? launch_mma_loglik<1>(m, d, d_out) : m->fast.G == 16 ? launch_mma_loglik<2>(m, d, d_out) : launch_mma_loglik<4>(m, d, d_out);
+  if (r) return r;
+  int32_t n_fb = 0;
+  JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  if (n_fb > 0) return run_loglik_exact(m, d, d_out, m->d_fallback.p + 1, n_fb);
   return JH_OK;
 }
 
@@ -675,7 +717,8 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
   DevBuf<double> d_out;
   if ((r = d_out.alloc(d->n_seq))) return r;
   timing_begin(m);
-  if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
+  if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
+  else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
   else r = run_loglik_exact(m, d, d_out.p);
   timing_end(m);
   if (r) return r;
@@ -826,6 +869,63 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   return JH_OK;
 }
 
+// Octet posterior decoding (kernels_mma.cuh), one launch per length bucket.
+template <int NT>
+static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_ll) {
+  using C = jhm::MmaCfg<NT>;
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhm::k_mma_decode<NT>;
+  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b] + 1;
+  if (n_oct <= 0) return JH_OK;
+  size_t smem = (size_t)F.H * C::G * sizeof(double) + (size_t)C::WARPS * C::RING * C::SLOTB;
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, smem));
+  if (per_sm < 1) { jh_set_error("octet decoding kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
+  const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+  const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  grid = std::max<int64_t>(1, std::min(grid, max_slots / C::WARPS));
+  const int64_t slots = grid * C::WARPS;
+  int r = m->d_fwd.reserve((size_t)slots * rows * 8 * C::G);
+  if (r) return r;
+  if ((size_t)slots * rows * 8 > F.fexp_n) {
+    if (F.d_fexp) cudaFree(F.d_fexp);
+    F.d_fexp = nullptr;
+    F.fexp_n = 0;
+    if (cudaMalloc(&F.d_fexp, (size_t)slots * rows * 8 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); jh_set_error("out of device memory (exponent scratch)"); return JH_ERR_NOMEM; }
+    F.fexp_n = (size_t)slots * rows * 8;
+  }
+  jhm::OctData D;
+  D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
+  D.weights = nullptr; D.n_oct = n_oct;
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, C::NTHREADS, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, d_paths, d_ll, m->d_fallback.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) {
+  int r = ensure_octet_hashes(m, d);
+  if (r) return r;
+  if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++)
+    r = m->fast.G == 8 ? launch_mma_decode<1>(m, d, b, d_paths, d_ll) : m->fast.G == 16 ? launch_mma_decode<2>(m, d, b, d_paths, d_ll)
+                                                                                        : launch_mma_decode<4>(m, d, b, d_paths, d_ll);
+  if (r) return r;
+  int32_t n_fb = 0;
+  JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_DECODE, d_paths, d_ll, nullptr, m->d_fallback.p + 1, n_fb);
+  return JH_OK;
+}
+
 extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik) {
   int r = check_pair(m, d);
   if (r) return r;
@@ -834,7 +934,8 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
   DevBuf<double> d_ll;
   if ((r = d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
   timing_begin(m);
-  r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
+  if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
+  else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
   timing_end(m);
   if (r) return r;
   if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, m->st()));

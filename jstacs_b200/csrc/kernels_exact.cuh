@@ -174,16 +174,18 @@ __device__ __forceinline__ void init_last_layer(const DevModel &M, const Group<G
 // ------------------------------------------------------------------------------------------------
 // AbstractHMM.logProb (AbstractHMM.java:1049-1070): backward sweep, result bwd[0][0]; nothing is stored.
 template <int G>
-__global__ void __launch_bounds__(256) k_exact_loglik(DevModel M, DevData D, unsigned long long *counter, double *out) {
+__global__ void __launch_bounds__(256) k_exact_loglik(DevModel M, DevData D, unsigned long long *counter, double *out,
+                                                      const int32_t *seq_list, int64_t n_list) {
   extern __shared__ double smem[];
   Group<G> g = make_group<G>(M, smem);
   ResReader rd;
+  const int64_t n_work = seq_list ? n_list : D.n_seq;
   for (;;) {
     long long it = 0;
     if (g.lane == 0) it = (long long)atomicAdd(counter, 1ull);
     it = g.bcast(it);
-    if (it >= D.n_seq) break;
-    int sid = D.order[it];
+    if (it >= n_work) break;
+    int sid = seq_list ? seq_list[it] : D.order[it];
     int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
     rd.init(D.codes + off);
     double *nxt = g.v0, *cur = g.v1;

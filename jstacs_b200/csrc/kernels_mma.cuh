@@ -130,6 +130,92 @@ __device__ __forceinline__ void emis_rl(const FastDev &F, const double *sE, int 
   }
 }
 
+// step kinds: general (ragged octet or position below the emission order, rescales), uniform with / without rescale.
+// Uniform steps rescale every RS-th position only: between two rescales a row maximum grows by at
+// most a factor G (column sums of T), so RS positions without rescaling stay far inside the 60 + 5*RS binades of head
+// room that rescale_row's "ok" test demands.
+using GeneralStep = std::integral_constant<int, 2>;
+using UniformStep = std::integral_constant<int, 1>;
+using UniformStepNoRescale = std::integral_constant<int, 0>;
+constexpr int RS = 4;
+
+// Scaled forward recursion of one octet (lane (r,q) of the warp).  On return A holds the last row of the lane's sequence
+// (scaled by 2^-Aexp), ok says that no rescale came near the denormal range.  STORE: rows and exponents go to the scratch.
+template <int NT, bool STORE>
+__device__ __forceinline__ void octet_forward(const FastDev &F, const double *sE, const int r, const int q, const uint16_t *hrow, const int Lr,
+                                              const int Lmax, const int Lmin, double *fw, int *fe, double (&A)[2 * NT], int &Aexp, bool &ok) {
+  constexpr int G = 8 * NT, NV = 2 * NT;
+  const int kmin = F.Kmax;
+  {
+      double Bf[NV][NT];  // B fragments of T: Bf[k][t] = T[sigma(k,q)][8t + r]
+#pragma unroll
+      for (int k = 0; k < NV; k++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) Bf[k][t] = F.T[(8 * (k >> 1) + 2 * q + (k & 1)) * G + 8 * t + r];
+      double e[NV];
+      emis_rl<NT, true>(F, sE, q, e, hrow[0], 0);
+#pragma unroll
+      for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv_of(F, 8 * (v >> 1) + 2 * q + (v & 1)) * e[v] : 0.0;
+      ok = rescale_row<NV>(A, Aexp);
+      if (STORE) {
+#pragma unroll
+        for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(fw + 8 * t) = make_double2(A[2 * t], A[2 * t + 1]);
+        if (q == 0) fe[r] = Aexp;
+      }
+      emis_rl<NT, true>(F, sE, q, e, hrow[8], 1);
+      int h2 = hrow[16];  // hash of position t+2, loaded one step ahead of its use
+      auto fstep = [&](auto general, int t) {  // row t -> t+1
+        constexpr bool GEN = decltype(general)::value == 2, RESC = decltype(general)::value != 0;
+        const int h3 = hrow[(size_t)(t + 3) * 8];
+        double Dv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) Dv[v] = 0;
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) dmma(Dv[2 * tp], Dv[2 * tp + 1], A[k], Bf[k][tp]);
+#pragma unroll
+        for (int v = 0; v < NV; v++) Dv[v] *= e[v];
+        int nexp = Aexp;
+        const bool nok = RESC ? rescale_row<NV>(Dv, nexp) : true;
+        if (!GEN) {  // every sequence of the octet is still running
+#pragma unroll
+          for (int v = 0; v < NV; v++) A[v] = Dv[v];
+          Aexp = nexp;
+          ok &= nok;
+        } else {  // ragged tail: finished sequences keep their last row in registers and store zeros
+          const bool act = t + 1 < Lr;
+#pragma unroll
+          for (int v = 0; v < NV; v++) {
+            A[v] = act ? Dv[v] : A[v];
+            Dv[v] = act ? Dv[v] : 0.0;
+          }
+          Aexp = act ? nexp : Aexp;
+          ok &= nok || !act;
+        }
+        if (STORE) {
+          double *dst = fw + (size_t)(t + 1) * 8 * G;
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(dst + 8 * tp) = make_double2(Dv[2 * tp], Dv[2 * tp + 1]);
+          if (q == 0) fe[(size_t)(t + 1) * 8 + r] = nexp;
+        }
+        emis_rl<NT, GEN>(F, sE, q, e, h2, t + 2);
+        h2 = h3;
+      };
+      // uniform steps: t+1 < Lmin (all sequences running) and t+2 >= Kmax (no order check for the emission fetched)
+      int t = 0;
+      const int t_lo = min(max(kmin - 2, 0), Lmax - 1), t_hi = max(min(Lmin - 1, Lmax - 1), t_lo);
+      for (; t < t_lo; t++) fstep(GeneralStep(), t);
+      for (; t + RS <= t_hi; t += RS) {
+#pragma unroll
+        for (int u = 0; u < RS - 1; u++) fstep(UniformStepNoRescale(), t + u);
+        fstep(UniformStep(), t + RS - 1);
+      }
+      for (; t < t_hi; t++) fstep(UniformStep(), t);
+      for (; t + 1 < Lmax; t++) fstep(GeneralStep(), t);
+  }
+}
+
 template <int NT>
 struct MmaCfg {
   static constexpr int G = 8 * NT, NV = 2 * NT, WARPS = 8, NTHREADS = 256;
@@ -191,14 +277,6 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
   for (int v = 0; v < NV; v++) SC[v] = 0;
   double score = 0;
 
-  // step kinds: general (ragged octet or position below the emission order, rescales), uniform with / without rescale.
-  // Uniform steps rescale every RS-th position only: between two rescales a row maximum grows by at
-  // most a factor G (column sums of T), so RS positions without rescaling stay far inside the 60 + 5*RS binades of head
-  // room that rescale_row's "ok" test demands.
-  using GeneralStep = std::integral_constant<int, 2>;
-  using UniformStep = std::integral_constant<int, 1>;
-  using UniformStepNoRescale = std::integral_constant<int, 0>;
-  constexpr int RS = 4;
 
   for (;;) {
     long long o = 0;
@@ -221,70 +299,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
     double A[NV];
     int Aexp = 0;
     bool ok = true;
-    {
-      double Bf[NV][NT];  // B fragments of T: Bf[k][t] = T[sigma(k,q)][8t + r]
-#pragma unroll
-      for (int k = 0; k < NV; k++)
-#pragma unroll
-        for (int t = 0; t < NT; t++) Bf[k][t] = F.T[(8 * (k >> 1) + 2 * q + (k & 1)) * G + 8 * t + r];
-      double e[NV];
-      emis_rl<NT, true>(F, sE, q, e, hrow[0], 0);
-#pragma unroll
-      for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv_of(F, 8 * (v >> 1) + 2 * q + (v & 1)) * e[v] : 0.0;
-      ok = rescale_row<NV>(A, Aexp);
-#pragma unroll
-      for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(fw + 8 * t) = make_double2(A[2 * t], A[2 * t + 1]);
-      if (q == 0) fe[r] = Aexp;
-      emis_rl<NT, true>(F, sE, q, e, hrow[8], 1);
-      int h2 = hrow[16];  // hash of position t+2, loaded one step ahead of its use
-      auto fstep = [&](auto general, int t) {  // row t -> t+1
-        constexpr bool GEN = decltype(general)::value == 2, RESC = decltype(general)::value != 0;
-        const int h3 = hrow[(size_t)(t + 3) * 8];
-        double Dv[NV];
-#pragma unroll
-        for (int v = 0; v < NV; v++) Dv[v] = 0;
-#pragma unroll
-        for (int k = 0; k < NV; k++)
-#pragma unroll
-          for (int tp = 0; tp < NT; tp++) dmma(Dv[2 * tp], Dv[2 * tp + 1], A[k], Bf[k][tp]);
-#pragma unroll
-        for (int v = 0; v < NV; v++) Dv[v] *= e[v];
-        int nexp = Aexp;
-        const bool nok = RESC ? rescale_row<NV>(Dv, nexp) : true;
-        if (!GEN) {  // every sequence of the octet is still running
-#pragma unroll
-          for (int v = 0; v < NV; v++) A[v] = Dv[v];
-          Aexp = nexp;
-          ok &= nok;
-        } else {  // ragged tail: finished sequences keep their last row in registers and store zeros
-          const bool act = t + 1 < Lr;
-#pragma unroll
-          for (int v = 0; v < NV; v++) {
-            A[v] = act ? Dv[v] : A[v];
-            Dv[v] = act ? Dv[v] : 0.0;
-          }
-          Aexp = act ? nexp : Aexp;
-          ok &= nok || !act;
-        }
-        double *dst = fw + (size_t)(t + 1) * 8 * G;
-#pragma unroll
-        for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(dst + 8 * tp) = make_double2(Dv[2 * tp], Dv[2 * tp + 1]);
-        if (q == 0) fe[(size_t)(t + 1) * 8 + r] = nexp;
-        emis_rl<NT, GEN>(F, sE, q, e, h2, t + 2);
-        h2 = h3;
-      };
-      // uniform steps: t+1 < Lmin (all sequences running) and t+2 >= Kmax (no order check for the emission fetched)
-      int t = 0;
-      const int t_lo = min(max(kmin - 2, 0), Lmax - 1), t_hi = max(min(Lmin - 1, Lmax - 1), t_lo);
-      for (; t < t_lo; t++) fstep(GeneralStep(), t);
-      for (; t + RS <= t_hi; t += RS) {
-#pragma unroll
-        for (int u = 0; u < RS - 1; u++) fstep(UniformStepNoRescale(), t + u);
-        fstep(UniformStep(), t + RS - 1);
-      }
-      for (; t < t_hi; t++) fstep(UniformStep(), t);
-      for (; t + 1 < Lmax; t++) fstep(GeneralStep(), t);
-    }
+    octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw, fe, A, Aexp, ok);
     // ---- termination: P(x) = sum over final states, one log per sequence ----
     double sfin = 0;
 #pragma unroll
@@ -464,6 +479,202 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
     if (sO[i] != 0 && F.tstat[i] >= 0) atomicAdd(&stats[F.tstat[i]], sO[i]);
   for (int i = threadIdx.x; i < G; i += blockDim.x)
     if (sPi[i] != 0 && F.pistat[i] >= 0) atomicAdd(&stats[F.pistat[i]], sPi[i]);
+}
+
+// Scoring (AbstractHMM.logProb, AbstractHMM.java:1049-1070: the value of bwd[0][0]) with the octet forward recursion;
+// nothing is stored.  A sequence whose scaled recursion came near the denormal range is listed in `fallback`
+// ([0] = count, then ids) and scored by the log-space kernel afterwards.
+template <int NT>
+__global__ void __launch_bounds__(256) k_mma_loglik(FastDev F, OctData D, unsigned long long *counter, double *out, int32_t *fallback) {
+  constexpr int G = 8 * NT, NV = 2 * NT;
+  extern __shared__ double sm[];
+  const int HG = F.H * G;
+  double *sE = sm;
+  for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  const int l = threadIdx.x & 31, r = l >> 2, q = l & 3;
+  const unsigned FULL = 0xffffffffu;
+  for (;;) {
+    long long o = 0;
+    if (l == 0) o = (long long)atomicAdd(counter, 1ull);
+    o = __shfl_sync(FULL, o, 0);
+    if (o >= D.n_oct) break;
+    const int sid = D.oct_seq[o * 8 + r];
+    int Lr = 0;
+    if (sid >= 0) Lr = (int)(D.offsets[sid + 1] - D.offsets[sid]);
+    const int Lmax = __shfl_sync(FULL, Lr, 0);
+    const int Lmin = __reduce_min_sync(FULL, Lr);
+    const uint16_t *const hrow = D.hashes + (D.oct_hbase[o] + 1) * 8 + r;
+    double A[NV];
+    int Aexp = 0;
+    bool ok = true;
+    octet_forward<NT, false>(F, sE, r, q, hrow, Lr, Lmax, Lmin, nullptr, nullptr, A, Aexp, ok);
+    double sfin = 0;
+#pragma unroll
+    for (int v = 0; v < NV; v++) sfin += A[v] * F.fin[8 * (v >> 1) + 2 * q + (v & 1)];
+    sfin += __shfl_xor_sync(FULL, sfin, 1);
+    sfin += __shfl_xor_sync(FULL, sfin, 2);
+    if (q == 0 && Lr > 0) {
+      if (ok && sfin > 0) out[sid] = log(sfin) + Aexp * 0.6931471805599453094;
+      else {
+        out[sid] = JH_NEG_INF;
+        int pos = atomicAdd(fallback, 1);
+        fallback[1 + pos] = sid;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Posterior decoding (HigherOrderHMM.fillLogStatePosteriorMatrix :294-329 + AbstractHMM.decodeStatePosterior
+// AbstractHMM.java:1125-1139): per position the state with the largest posterior, lowest index on ties.  The posterior
+// of state j at position t is alpha_t[j] * beta_t[j] up to a positive factor that is constant over the states of a
+// position (the scales and 1/P(x)), so the decision needs neither exponents nor a logarithm.  Same octet mapping as the
+// E-step: forward rows through the HBM scratch and a cp.async ring, backward recursion on the FP64 MMA path, no count
+// product.  paths: int32 per residue (CSR by the data set offsets), loglik optional.
+template <int NT>
+__global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch, int *fexp_scratch,
+                                                       int64_t rows, int32_t *paths, double *loglik, int32_t *fallback) {
+  using C = MmaCfg<NT>;
+  constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
+  extern __shared__ double sm[];
+  const int HG = F.H * G;
+  double *sE = sm;
+  char *const ring = reinterpret_cast<char *>(sE + HG) + (size_t)(threadIdx.x >> 5) * (RING * SLOTB);
+  for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  const int l = threadIdx.x & 31, r = l >> 2, q = l & 3;
+  const unsigned FULL = 0xffffffffu;
+  const int64_t slot = (int64_t)blockIdx.x * C::WARPS + (threadIdx.x >> 5);
+  double *const fw = fwd_scratch + (size_t)slot * rows * 8 * G + r * G + 2 * q;
+  int *const fe = fexp_scratch + (size_t)slot * rows * 8;
+  int rl_off[NT];
+#pragma unroll
+  for (int tp = 0; tp < NT; tp++) rl_off[tp] = r * ROWB + (((4 * tp + q) ^ C::swz(r)) << 4);
+  // state with the largest product among the lane's NV values, then over the four lanes of the sequence
+  auto best_state = [&](const double (&a)[NV], const double (&b)[NV]) {
+    double best = a[0] * b[0];
+    int arg = 2 * q;
+#pragma unroll
+    for (int v = 1; v < NV; v++) {
+      const double g = a[v] * b[v];
+      const int st = 8 * (v >> 1) + 2 * q + (v & 1);
+      if (g > best) { best = g; arg = st; }  // ascending state order inside the lane: strict '>' keeps the lowest index
+    }
+#pragma unroll
+    for (int d = 1; d <= 2; d <<= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, d);
+      const int oa = __shfl_xor_sync(FULL, arg, d);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    return arg;
+  };
+  for (;;) {
+    long long o = 0;
+    if (l == 0) o = (long long)atomicAdd(counter, 1ull);
+    o = __shfl_sync(FULL, o, 0);
+    if (o >= D.n_oct) break;
+    const int sid = D.oct_seq[o * 8 + r];
+    int Lr = 0;
+    int64_t off = 0;
+    if (sid >= 0) {
+      off = D.offsets[sid];
+      Lr = (int)(D.offsets[sid + 1] - off);
+    }
+    const int Lmax = __shfl_sync(FULL, Lr, 0);
+    const int Lmin = __reduce_min_sync(FULL, Lr);
+    const uint16_t *const hrow = D.hashes + (D.oct_hbase[o] + 1) * 8 + r;
+    double A[NV];
+    int Aexp = 0;
+    bool ok = true;
+    octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw, fe, A, Aexp, ok);
+    double sfin = 0;
+#pragma unroll
+    for (int v = 0; v < NV; v++) sfin += A[v] * F.fin[8 * (v >> 1) + 2 * q + (v & 1)];
+    sfin += __shfl_xor_sync(FULL, sfin, 1);
+    sfin += __shfl_xor_sync(FULL, sfin, 2);
+    const bool good = Lr > 0 && ok && sfin > 0;
+    if (q == 0 && Lr > 0) {
+      if (loglik) loglik[sid] = good ? log(sfin) + Aexp * 0.6931471805599453094 : JH_NEG_INF;
+      if (!good) {  // decoded by the log-space kernel afterwards
+        int pos = atomicAdd(fallback, 1);
+        fallback[1 + pos] = sid;
+      }
+    }
+    // ---- backward: beta only, decision per position ----
+    double Bb[NV][NT];
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+#pragma unroll
+      for (int t = 0; t < NT; t++) Bb[k][t] = F.T[(8 * t + r) * G + 8 * (k >> 1) + 2 * q + (k & 1)];
+    double beta[NV];
+    int Bx = 0;
+#pragma unroll
+    for (int v = 0; v < NV; v++) beta[v] = F.fin[8 * (v >> 1) + 2 * q + (v & 1)];
+    auto issue = [&](int row) {
+      const bool have = row >= 0;
+      char *sl = ring + (size_t)(row & (RING - 1)) * SLOTB;
+      const double *src = fw + (int64_t)row * 8 * G;
+#pragma unroll
+      for (int tp = 0; tp < NT; tp++) cp_async16_if(have, sl + rl_off[tp], src + 8 * tp);
+      jhf::cp_async_commit();
+    };
+    __syncwarp();
+    issue(Lmax - 1);
+    issue(Lmax - 2);
+    issue(Lmax - 3);
+    int h = hrow[(size_t)(Lmax - 1) * 8];
+    int h1 = hrow[(size_t)(Lmax - 2) * 8];
+    double e[NV];
+    emis_rl<NT, true>(F, sE, q, e, h, Lmax - 1);
+    int32_t *const prow = paths + off;
+    for (int t = Lmax - 1; t >= 0; --t) {
+      const int h2 = t >= 2 ? hrow[(size_t)(t - 2) * 8] : 0;
+      const bool act = t < Lr;
+      double b[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) b[v] = e[v] * beta[v];
+      jhf::cp_async_wait<2>();  // row t has landed
+      __syncwarp();
+      const char *slt = ring + (size_t)(t & (RING - 1)) * SLOTB;
+      double Dv[NV];
+#pragma unroll
+      for (int v = 0; v < NV; v++) Dv[v] = 0;
+      if (t > 0) {
+#pragma unroll
+        for (int k = 0; k < NV; k++)
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) dmma(Dv[2 * tp], Dv[2 * tp + 1], b[k], Bb[k][tp]);
+      }
+      double Fa[NV];
+#pragma unroll
+      for (int tp = 0; tp < NT; tp++) {
+        const double2 a2 = *reinterpret_cast<const double2 *>(slt + rl_off[tp]);
+        Fa[2 * tp] = a2.x;
+        Fa[2 * tp + 1] = a2.y;
+      }
+      const int arg = best_state(Fa, beta);
+      if (q == 0 && act && good) prow[t] = arg;
+      __syncwarp();
+      issue(t - 3);
+      if (t > 0) {
+        int nbx = Bx;
+        rescale_row<NV>(Dv, nbx);
+        if (t >= Lmin) {
+#pragma unroll
+          for (int v = 0; v < NV; v++) beta[v] = act ? Dv[v] : beta[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; v++) beta[v] = Dv[v];
+        }
+        h = h1;
+        h1 = h2;
+        emis_rl<NT, true>(F, sE, q, e, h, t - 1);
+      }
+    }
+    jhf::cp_async_wait<0>();
+    __syncwarp();
+  }
 }
 
 }  // namespace jhm

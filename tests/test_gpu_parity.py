@@ -265,6 +265,28 @@ def test_fast_estep_variants_agree_with_oracle(nat, oracle_lib, name, variant):
         nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
 
 
+@pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
+def test_posterior_decoding_octets_ragged(nat, oracle_lib, fast, name):
+    """decodeStatePosterior(getStatePosteriorMatrixFor(seq)) fused on the device for a ragged data set (octets with
+    unequal rows, a last octet with empty rows, sequences shorter than the emission order)."""
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(21)
+    lens = np.concatenate([rng.integers(1, 5, 6), rng.integers(20, 300, 37), [1, 2, 450]])
+    data = dataset_of([random_dna(rng, int(L)) for L in lens])
+    dec = hmm.decodePosteriorPathsFor(data)
+    ll_ref = om.loglik(data.codes, data.offsets)
+    for i in range(data.getNumberOfElements()):
+        ref = om.posterior(data.getElementAt(i).codes)
+        ref_path = om.decode_posterior(ref)
+        path, ll = dec[i]
+        assert ll == pytest.approx(ll_ref[i], rel=LL_RTOL)
+        srt = np.sort(ref, axis=0)
+        clear = srt[-1] - srt[-2] > 1e-9
+        assert path.shape == ref_path.shape and np.array_equal(path[clear], ref_path[clear])
+        assert clear.mean() > 0.95
+
+
 def test_full_size_properties_cfg3_sample(nat):
     """BASELINE cfg3 model (32 states, order-3 emissions) on 16k x 1 kb sequences: size-independent properties.
     Transition counts add up to the residues, emission counts to the residues with a full context, the score is the
