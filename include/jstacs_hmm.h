@@ -151,10 +151,24 @@ int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_residues, in
  * (AbstractHMM.java:1049-1070): backward recursion, result bwd[0][0]. out[n_seq]. */
 int jh_loglik(jh_model *m, jh_dataset *d, double *out);
 
+/* AbstractHMM.getLogProbFor(seq, start, end) (AbstractHMM.java:985-998) for MANY sub-sequences at once, e.g. the sliding
+ * windows of projects/xanthogenomes/NHMMer.java:225-244: window i scores positions start[i]..end[i] (inclusive) of
+ * sequence seq_index[i]; layer 0 is the window start, but higher-order emissions see the residues before it, exactly as
+ * HigherOrderDiscreteEmission.getConditionIndex does with absolute positions (:138-146). Works for every model the
+ * library accepts (silent states, transition order > 1). out[n_win]. */
+int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start,
+                      const int64_t *end, double *out);
+
 /* AbstractHMM.getViterbiPathsFor(DataSet) (AbstractHMM.java:894-900) ==
  * HigherOrderHMM.viterbi (:617-708) per sequence.  paths: int32, CSR by the dataset offsets
  * (models without silent states emit exactly one state per residue); scores[n_seq]. */
 int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores);
+/* The same for ANY model, in particular with silent states (profile HMMs: HMMFactory.createProfileHMM,
+ * parseProfileHMMFromHMMer), whose paths contain the silent states and therefore have variable length
+ * (HigherOrderHMM.java:617-708 including the trailing silent states :667-705): sequence n writes at most
+ * path_ptr[n+1]-path_ptr[n] states at paths[path_ptr[n]] (rest -1); path_len[n] = states of the path, -1 if no
+ * child could be chosen (the reference fails there). A safe capacity is L*(1+n_silent)+n_silent. */
+int jh_viterbi_paths(jh_model *m, jh_dataset *d, int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores);
 
 /* AbstractHMM.getLogStatePosteriorMatrixFor(start,end,seq) (AbstractHMM.java:776-797):
  * out[S][L] row-major for sequence seq_index. */

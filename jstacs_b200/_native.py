@@ -109,6 +109,8 @@ def lib():
         "jh_dataset_set_weights": (C.c_int, [vp, _P_F64]),
         "jh_loglik": (C.c_int, [vp, vp, _P_F64]),
         "jh_viterbi": (C.c_int, [vp, vp, _P_I32, _P_F64]),
+        "jh_viterbi_paths": (C.c_int, [vp, vp, _P_I32, _P_I64, _P_I64, _P_F64]),
+        "jh_loglik_windows": (C.c_int, [vp, vp, C.c_int64, _P_I64, _P_I64, _P_I64, _P_F64]),
         "jh_posterior": (C.c_int, [vp, vp, C.c_int64, _P_F64]),
         "jh_posterior_decode": (C.c_int, [vp, vp, _P_I32, _P_F64]),
         "jh_estep": (C.c_int, [vp, vp, C.c_int, _P_F64, _P_F64, _P_F64]),
@@ -224,6 +226,26 @@ class NativeModel:
         scores = np.zeros(max(data.n_seq, 1))
         check(lib().jh_viterbi(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(scores)))
         return paths[:data.n_res], scores[:data.n_seq]
+
+    def viterbi_paths(self, data: NativeData, capacity: np.ndarray):
+        """General form (silent states): CSR capacity per sequence -> (list of paths, scores, path_len)."""
+        ptr = np.zeros(data.n_seq + 1, dtype=np.int64)
+        np.cumsum(np.asarray(capacity, dtype=np.int64), out=ptr[1:])
+        paths = np.full(max(int(ptr[-1]), 1), -1, dtype=np.int32)
+        plen = np.zeros(max(data.n_seq, 1), dtype=np.int64)
+        scores = np.zeros(max(data.n_seq, 1))
+        check(lib().jh_viterbi_paths(self.h, data.h, paths.ctypes.data_as(_P_I32), ptr.ctypes.data_as(_P_I64), plen.ctypes.data_as(_P_I64),
+                                     _f64(scores)))
+        return [paths[ptr[i]:ptr[i] + max(plen[i], 0)] for i in range(data.n_seq)], scores[:data.n_seq], plen[:data.n_seq]
+
+    def loglik_windows(self, data: NativeData, seq_index, start, end) -> np.ndarray:
+        si, st, en = (np.ascontiguousarray(a, dtype=np.int64) for a in (seq_index, start, end))
+        if not (si.size == st.size == en.size):
+            raise ValueError("seq_index, start and end need the same length")
+        out = np.zeros(max(si.size, 1))
+        check(lib().jh_loglik_windows(self.h, data.h, si.size, si.ctypes.data_as(_P_I64), st.ctypes.data_as(_P_I64), en.ctypes.data_as(_P_I64),
+                                      _f64(out)))
+        return out[:si.size]
 
     def posterior(self, data: NativeData, index: int, n_states: int, length: int) -> np.ndarray:
         out = np.zeros(max(n_states * length, 1))

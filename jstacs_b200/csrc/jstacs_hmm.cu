@@ -11,6 +11,7 @@
 #include "kernels_aux.cuh"
 #include "kernels_exact.cuh"
 #include "kernels_fast.cuh"
+#include "kernels_general.cuh"
 #include "kernels_mma.cuh"
 #include "kernels_viterbi.cuh"
 
@@ -114,10 +115,13 @@ struct jh_model {
   std::vector<int> state_emis, emis_order, emis_cond_ptr;
   std::vector<uint8_t> state_silent, state_final;
   std::vector<int> child_elem, child_next, child_stat, in_ptr, in_src, in_p, state_order, state_tab, state_mod, row_flag;
+  std::vector<int> sin_ptr, sin_src, sin_p;  // silent in-edges inside a layer (kernels_general.cuh)
   // device
   DevBuf<int> d_lc_ctx_ptr, d_ctx_elem, d_ctx_last, d_elem_child_ptr, d_child_state, d_child_next, d_child_stat, d_in_ptr,
       d_in_src, d_in_p, d_state_order, d_state_tab, d_state_mod, d_child_elem, d_trans_index, d_row_flag;
-  DevBuf<unsigned char> d_is_final;
+  DevBuf<unsigned char> d_is_final, d_silent;
+  DevBuf<int> d_sin_ptr, d_sin_src, d_sin_p;
+  DevBuf<double> d_rows;       // rolling DP rows of the thread-per-sequence kernels
   DevBuf<double> d_trans_param, d_trans_lognorm, d_trans_hyper, d_emis_param, d_emis_lognorm, d_emis_hyper, d_tscore, d_escore;
   DevBuf<double> d_stats;      // [n_child | n_cond*a | score | pad]
   DevBuf<double> d_objective;  // per-iteration objective
@@ -148,6 +152,11 @@ struct jh_model {
     M.in_ptr = d_in_ptr.p; M.in_src = d_in_src.p; M.in_p = d_in_p.p; M.state_order = d_state_order.p; M.state_tab = d_state_tab.p;
     M.state_mod = d_state_mod.p; M.escore = d_escore.p; M.is_final = d_is_final.p;
     return M;
+  }
+  jhg::GenModel gen() const {
+    jhg::GenModel X;
+    X.silent = d_silent.p; X.sin_ptr = d_sin_ptr.p; X.sin_src = d_sin_src.p; X.sin_p = d_sin_p.p;
+    return X;
   }
   jha::DevParams params() const {
     jha::DevParams P;
@@ -349,6 +358,35 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
     }
     for (int t = nct; t <= m->Cmax; t++) ip[t] = q;
   }
+  // silent in-edges per layer class (sources in the same layer; order = source context, then child)
+  m->sin_ptr.assign((size_t)(m->m + 1) * (m->Cmax + 1), 0);
+  m->sin_src.assign((size_t)(m->m + 1) * std::max(m->n_child, 1), 0);
+  m->sin_p.assign((size_t)(m->m + 1) * std::max(m->n_child, 1), 0);
+  for (int lc = 0; lc <= m->m; lc++) {
+    int nc = m->lc_ctx_ptr[lc + 1] - m->lc_ctx_ptr[lc];
+    std::vector<std::vector<std::pair<int, int>>> in(nc);
+    for (int c = 0; c < nc; c++) {
+      int e = m->ctx_elem[m->lc_ctx_ptr[lc] + c];
+      for (int p = m->elem_child_ptr[e]; p < m->elem_child_ptr[e + 1]; p++) {
+        if (!m->state_silent[m->child_state[p]]) continue;
+        int t = m->child_next[(size_t)lc * m->n_child + p];
+        if (t < 0 || t >= nc) return fail(JH_ERR_INVALID, "a silent child leads to a context that does not exist in its layer");
+        if (t <= c) return fail(JH_ERR_INVALID, "silent states are not in topological order");
+        in[t].push_back({c, p});
+      }
+    }
+    int *ip = m->sin_ptr.data() + (size_t)lc * (m->Cmax + 1);
+    int q = 0;
+    for (int t = 0; t < nc; t++) {
+      ip[t] = q;
+      for (auto &sp : in[t]) {
+        m->sin_src[(size_t)lc * m->n_child + q] = sp.first;
+        m->sin_p[(size_t)lc * m->n_child + q] = sp.second;
+        q++;
+      }
+    }
+    for (int t = nc; t <= m->Cmax; t++) ip[t] = q;
+  }
   m->state_order.resize(m->S); m->state_tab.resize(m->S); m->state_mod.resize(m->S);
   m->row_flag.assign(std::max(m->n_cond, 1), 1);
   for (int e = 0; e < m->n_emis; e++)
@@ -384,7 +422,7 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   UP(d_child_state, m->child_state) UP(d_child_next, m->child_next) UP(d_child_stat, m->child_stat) UP(d_in_ptr, m->in_ptr)
   UP(d_in_src, m->in_src) UP(d_in_p, m->in_p) UP(d_state_order, m->state_order) UP(d_state_tab, m->state_tab)
   UP(d_state_mod, m->state_mod) UP(d_child_elem, m->child_elem) UP(d_trans_index, m->trans_index) UP(d_row_flag, m->row_flag)
-  UP(d_is_final, fin) UP(d_trans_param, tp) UP(d_trans_lognorm, tl) UP(d_trans_hyper, th) UP(d_emis_param, ep)
+  UP(d_is_final, fin) UP(d_silent, m->state_silent) UP(d_sin_ptr, m->sin_ptr) UP(d_sin_src, m->sin_src) UP(d_sin_p, m->sin_p) UP(d_trans_param, tp) UP(d_trans_lognorm, tl) UP(d_trans_hyper, th) UP(d_emis_param, ep)
   UP(d_emis_lognorm, el) UP(d_emis_hyper, eh)
 #undef UP
   if ((r = m->d_tscore.alloc(m->n_child)) || (r = m->d_escore.alloc((size_t)m->n_cond * m->a)) ||
@@ -576,7 +614,6 @@ extern "C" int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_r
 static int check_pair(jh_model *m, jh_dataset *d) {
   if (!m || !d) { jh_set_error("null handle"); return JH_ERR_INVALID; }
   if (d->alphabet != m->a) { jh_set_error("The AlphabetContainer of the data set and the model do not match."); return JH_ERR_ALPHABET; }
-  if (m->has_silent) { jh_set_error("silent states are not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   if (m->m < 1) { jh_set_error("transition order 0 is not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   return JH_OK;
 }
@@ -667,6 +704,72 @@ static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int
   return JH_OK;
 }
 
+// ---- thread-per-sequence kernels for the general context graph (kernels_general.cuh) ----------------------------
+// threads of the grid: bounded by the work and by the DP scratch each thread needs
+static int plan_general(jh_model *m, int64_t work, size_t bytes_per_thread, int *grid, int64_t *nthreads) {
+  const int NT = 128;
+  int64_t n = std::min<int64_t>((int64_t)m->sm_count * 1024, (work + NT - 1) / NT * NT);
+  int64_t cap = g_opt.scratch_mb * 1024 * 1024 / (int64_t)std::max<size_t>(bytes_per_thread, 1);
+  cap = cap / 32 * 32;
+  if (cap < 32) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  n = std::max<int64_t>(32, std::min(n, cap));
+  *grid = (int)((n + NT - 1) / NT);
+  *nthreads = (int64_t)*grid * NT;
+  if (*nthreads > cap) {  // a partial last block is not possible: shrink to whole blocks or run one small block
+    *grid = (int)std::max<int64_t>(1, cap / NT);
+    *nthreads = (int64_t)*grid * NT;
+    if (*nthreads > cap) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  }
+  return JH_OK;
+}
+
+static int run_general_loglik(jh_model *m, jh_dataset *d, const jhg::WorkList &W, double *d_out) {
+  int grid;
+  int64_t nthreads;
+  int r = plan_general(m, W.n, (size_t)2 * m->Cmax * sizeof(double), &grid, &nthreads);
+  if (r) return r;
+  if ((r = m->d_rows.reserve((size_t)2 * m->Cmax * nthreads))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  jhg::k_general_loglik<<<grid, 128, 0, s>>>(m->dev(), m->gen(), d->dev(), W, m->d_counter.p, m->d_rows.p, d_out);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_general_viterbi(jh_model *m, jh_dataset *d, int32_t *d_paths, const int64_t *d_path_ptr, int64_t *d_path_len, double *d_scores,
+                               double *d_stats) {
+  if (m->max_children > 254) { jh_set_error("more than 254 children per context"); return JH_ERR_UNSUPPORTED; }
+  int grid;
+  int64_t nthreads;
+  const int64_t layers = d->max_len + 1;
+  int r = plan_general(m, d->n_seq, (size_t)2 * m->Cmax * sizeof(double) + (size_t)layers * m->Cmax, &grid, &nthreads);
+  if (r) return r;
+  if ((r = m->d_rows.reserve((size_t)2 * m->Cmax * nthreads)) || (r = m->d_choice.reserve((size_t)layers * m->Cmax * nthreads))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  jhg::k_general_viterbi<<<grid, 128, 0, s>>>(m->dev(), m->gen(), d->dev(), m->d_counter.p, m->d_rows.p, m->d_choice.p, layers, d_paths, d_path_ptr,
+                                             d_path_len, d_scores, d_stats);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_general_estep(jh_model *m, jh_dataset *d) {
+  int grid;
+  int64_t nthreads;
+  const int64_t layers = d->max_len + 1;
+  int r = plan_general(m, d->n_seq, (size_t)(2 + layers) * m->Cmax * sizeof(double), &grid, &nthreads);
+  if (r) return r;
+  if ((r = m->d_rows.reserve((size_t)2 * m->Cmax * nthreads)) || (r = m->d_fwd.reserve((size_t)layers * m->Cmax * nthreads))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  jhg::k_general_estep<<<grid, 128, 0, s>>>(m->dev(), m->gen(), d->dev(), m->d_counter.p, m->d_rows.p, m->d_fwd.p, layers, m->d_stats.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
 static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
 
 // Octet scoring (kernels_mma.cuh): ONE launch over all octets (longest first, fetched dynamically: no scratch to size);
@@ -717,13 +820,50 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
   DevBuf<double> d_out;
   if ((r = d_out.alloc(d->n_seq))) return r;
   timing_begin(m);
-  if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
+  if (m->has_silent) {
+    jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
+    r = run_general_loglik(m, d, W, d_out.p);
+  } else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
   else r = run_loglik_exact(m, d, d_out.p);
   timing_end(m);
   if (r) return r;
   JH_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
   JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+extern "C" int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start, const int64_t *end,
+                                 double *out) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (n_win == 0) return JH_OK;
+  if (n_win < 0 || !seq_index || !start || !end || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  std::vector<int32_t> sid(n_win);
+  for (int64_t i = 0; i < n_win; i++) {
+    if (seq_index[i] < 0 || seq_index[i] >= d->n_seq) { jh_set_error("window %lld: sequence index out of range", (long long)i); return JH_ERR_INVALID; }
+    const int64_t L = d->offsets[seq_index[i] + 1] - d->offsets[seq_index[i]];
+    if (start[i] < 0 || end[i] >= L || end[i] < start[i]) {  // the reference raises on these too (AbstractHMM.java:985-998)
+      jh_set_error("window %lld: [%lld,%lld] is not inside a sequence of length %lld", (long long)i, (long long)start[i], (long long)end[i], (long long)L);
+      return JH_ERR_INVALID;
+    }
+    sid[i] = (int32_t)seq_index[i];
+  }
+  DevBuf<int32_t> d_sid;
+  DevBuf<int64_t> d_se;
+  DevBuf<double> d_out;
+  if ((r = d_sid.alloc(n_win)) || (r = d_se.alloc(2 * n_win)) || (r = d_out.alloc(n_win))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemcpyAsync(d_sid.p, sid.data(), sizeof(int32_t) * n_win, cudaMemcpyHostToDevice, s));
+  JH_CUDA(cudaMemcpyAsync(d_se.p, start, sizeof(int64_t) * n_win, cudaMemcpyHostToDevice, s));
+  JH_CUDA(cudaMemcpyAsync(d_se.p + n_win, end, sizeof(int64_t) * n_win, cudaMemcpyHostToDevice, s));
+  jhg::WorkList W{d_sid.p, d_se.p, d_se.p + n_win, n_win};
+  timing_begin(m);
+  r = run_general_loglik(m, d, W, d_out.p);
+  timing_end(m);
+  if (r) return r;
+  JH_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * n_win, cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
   return JH_OK;
 }
 
@@ -803,9 +943,33 @@ static int run_viterbi(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_s
   return JH_OK;
 }
 
+extern "C" int jh_viterbi_paths(jh_model *m, jh_dataset *d, int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (d->n_seq == 0) return JH_OK;
+  if (paths && !path_ptr) { jh_set_error("paths without path_ptr"); return JH_ERR_INVALID; }
+  DevBuf<int32_t> d_paths;
+  DevBuf<int64_t> d_ptr, d_len;
+  DevBuf<double> d_scores;
+  cudaStream_t s = m->st();
+  const int64_t total = paths ? path_ptr[d->n_seq] : 0;
+  if ((r = d_paths.alloc(total)) || (r = d_ptr.alloc(d->n_seq + 1)) || (r = d_len.alloc(d->n_seq)) || (r = d_scores.alloc(d->n_seq))) return r;
+  if (paths) JH_CUDA(cudaMemcpyAsync(d_ptr.p, path_ptr, sizeof(int64_t) * (d->n_seq + 1), cudaMemcpyHostToDevice, s));
+  timing_begin(m);
+  r = run_general_viterbi(m, d, paths ? d_paths.p : nullptr, d_ptr.p, d_len.p, d_scores.p, nullptr);
+  timing_end(m);
+  if (r) return r;
+  if (paths && total) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+  if (path_len) JH_CUDA(cudaMemcpyAsync(path_len, d_len.p, sizeof(int64_t) * d->n_seq, cudaMemcpyDeviceToHost, s));
+  if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+
 extern "C" int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores) {
   int r = check_pair(m, d);
   if (r) return r;
+  if (m->has_silent) { jh_set_error("models with silent states emit paths of variable length: use jh_viterbi_paths"); return JH_ERR_UNSUPPORTED; }
   if (d->n_seq == 0) return JH_OK;
   DevBuf<int32_t> d_paths;
   DevBuf<double> d_scores;
@@ -851,6 +1015,7 @@ static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, 
 extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out) {
   int r = check_pair(m, d);
   if (r) return r;
+  if (m->has_silent) { jh_set_error("state posteriors of models with silent states are not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   if (seq_index < 0 || seq_index >= d->n_seq || !out) { jh_set_error("sequence index out of range"); return JH_ERR_INVALID; }
   int64_t L = d->offsets[seq_index + 1] - d->offsets[seq_index];
   DevBuf<double> d_post;
@@ -929,6 +1094,7 @@ static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
 extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik) {
   int r = check_pair(m, d);
   if (r) return r;
+  if (m->has_silent) { jh_set_error("state posteriors of models with silent states are not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   if (d->n_seq == 0) return JH_OK;
   DevBuf<int32_t> d_paths;
   DevBuf<double> d_ll;
@@ -1079,6 +1245,13 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));  // resetStatistics (HOH:890-895)
   if (d->n_seq == 0) return JH_OK;
+  if (m->has_silent) {  // general context graph: one sequence per thread, reference order
+    cudaEventRecord(m->evk0, s);
+    int r = mode == JH_MODE_VITERBI ? run_general_viterbi(m, d, nullptr, nullptr, nullptr, nullptr, m->d_stats.p) : run_general_estep(m, d);
+    cudaEventRecord(m->evk1, s);
+    m->ktimed = true;
+    return r;
+  }
   if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, nullptr, nullptr, m->d_stats.p);
   if (g_opt.fast && m->fast.usable) {
     int r = m->d_fallback.reserve(d->n_seq + 2);

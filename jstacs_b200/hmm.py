@@ -773,19 +773,31 @@ class HigherOrderHMM:
             raise WrongAlphabetException("The AlphabetContainer of the sequence and the model do not match.")
         if endpos is None:
             endpos = sequence.getLength() - 1
-        if startpos != 0 and any(e.order > 0 for e in self.emission):
-            raise NotImplementedError("window scoring with higher-order emissions needs absolute-position contexts "
-                                      "(HigherOrderDiscreteEmission.java:138-146); not on the native path yet")
-        if endpos < startpos or endpos >= sequence.getLength():
+        if startpos < 0 or endpos < startpos or endpos >= sequence.getLength():
             raise WrongLengthException("invalid start/end position")
-        ds = DataSet("", Sequence(self.alphabets, sequence.codes[startpos:endpos + 1]), con=self.alphabets)
-        return float(self.getLogScoreFor(ds)[0])
+        ds = DataSet("", sequence, con=self.alphabets)
+        return float(self.getLogProbForWindows(ds, [0], [startpos], [endpos])[0])
+
+    def getLogProbForWindows(self, data: DataSet, seq_index, start, end):
+        """getLogProbFor(data.getElementAt(seq_index[i]), start[i], end[i]) for many windows in one call (the sliding
+        window scan of projects/xanthogenomes/NHMMer.java:225-244); higher-order emissions see the residues before the
+        window start, like HigherOrderDiscreteEmission.getConditionIndex (:138-146)."""
+        eng = self._engine()
+        self._push_params()
+        return eng.loglik_windows(self._data(data), seq_index, start, end)
 
     # ---- decoding ------------------------------------------------------------------------------
     def getViterbiPathsFor(self, data: DataSet):
         """AbstractHMM.getViterbiPathsFor (:894-900) -> list of (IntList path, Double score)."""
         eng = self._engine()
         self._push_params()
+        n_silent = sum(1 for i in self.emissionIdx if self.emission[i].order < 0)
+        if n_silent:  # paths contain the silent states: variable length (HigherOrderHMM.java:617-708)
+            lens = np.diff(data.offsets)
+            paths, scores, plen = eng.viterbi_paths(self._data(data), lens * (1 + n_silent) + n_silent)
+            if (plen < 0).any():
+                raise ValueError("Impossible path")
+            return [(p, float(sc)) for p, sc in zip(paths, scores)]
         paths, scores = eng.viterbi(self._data(data))
         off = data.offsets
         return [(paths[off[i]:off[i + 1]], float(scores[i])) for i in range(data.getNumberOfElements())]

@@ -7,7 +7,7 @@ Every test runs the reference-order kernels (fast=0) and, where the model allows
 import numpy as np
 import pytest
 
-from helpers import dataset_of, ergodic_hmm, order2_hmm, random_dna, sparse_hmm
+from helpers import dataset_of, ergodic_hmm, order2_hmm, random_dna, silent_hmm, sparse_hmm
 from jstacs_b200 import (DNA, BaumWelchParameterSet, DataSet, DiscreteEmission, HigherOrderHMM, IterationCondition,
                          Sequence, SmallDifferenceOfFunctionEvaluationsCondition, TransitionElement, ViterbiParameterSet,
                          WrongAlphabetException)
@@ -285,6 +285,72 @@ def test_posterior_decoding_octets_ragged(nat, oracle_lib, fast, name):
         clear = srt[-1] - srt[-2] > 1e-9
         assert path.shape == ref_path.shape and np.array_equal(path[clear], ref_path[clear])
         assert clear.mean() > 0.95
+
+
+# ---- general context graph: silent states (profile-like HMM), one sequence per thread --------------------------
+def test_silent_states_loglik_viterbi_counts_training(nat, oracle_lib):
+    """silent states + trailing silent states on the GPU, reference order (kernels_general.cuh)."""
+    hmm = silent_hmm()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(8, 45, lo=1, hi=40)
+    # scoring
+    np.testing.assert_allclose(hmm.getLogScoreFor(data), om.loglik(data.codes, data.offsets), rtol=1e-12)
+    # Viterbi: paths contain the silent states, bit-exact scores
+    rp, rs, rl = om.viterbi(data.codes, data.offsets)
+    res = hmm.getViterbiPathsFor(data)
+    for (p, sc), p_ref, s_ref in zip(res, rp, rs):
+        assert np.array_equal(p, p_ref) and sc == s_ref
+    assert any(len(p) > L for (p, _), L in zip(res, np.diff(data.offsets)))  # silent states really are on the paths
+    # E-step, both modes
+    eng, nd = hmm._engine(), hmm._data(data)
+    w = np.random.default_rng(1).random(data.getNumberOfElements()) + 0.5
+    for weights in (None, w):
+        nd.set_weights(weights)
+        ts, es, sc = eng.estep(nd)
+        rts, res_, rsc = om.estep(data.codes, data.offsets, weights)
+        np.testing.assert_allclose(ts, rts, rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(es, res_, rtol=1e-10, atol=1e-12)
+        assert sc == pytest.approx(rsc, rel=1e-12)
+        ts, es, sc = eng.estep(nd, mode=nat.MODE_VITERBI)
+        rts, res_, rsc = om.estep(data.codes, data.offsets, weights, mode=0)
+        np.testing.assert_allclose(ts, rts, rtol=1e-13)
+        np.testing.assert_allclose(es, res_, rtol=1e-13)
+        assert sc == pytest.approx(rsc, rel=1e-13)
+    nd.set_weights(None)
+    # EM
+    hmm.trainingParameter = BaumWelchParameterSet(1, IterationCondition(5), 1)
+    hmm.train(data)
+    robj = om.train(data.codes, data.offsets, max_iter=5)
+    np.testing.assert_allclose(hmm.last_objectives[0], robj, rtol=LL_RTOL)
+    for g, r in zip(hmm._engine().get_params(), om.get_params()):
+        fin = np.isfinite(r)
+        assert np.array_equal(np.isfinite(g), fin)
+        np.testing.assert_allclose(g[fin], r[fin], rtol=0, atol=PARAM_TOL)
+
+
+@pytest.mark.parametrize("name", ["erg_s3_k0_map", "erg_s5_k2", "order2_s3", "sparse", "silent"])
+def test_window_scoring_sees_the_residues_before_the_window(nat, oracle_lib, name):
+    """getLogProbFor(seq, start, end) for many windows in one call: layer 0 is the window start, the emission contexts
+    use absolute positions (HigherOrderDiscreteEmission.java:138-146)."""
+    hmm = silent_hmm() if name == "silent" else MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(9, 7, lo=30, hi=80)
+    rng = np.random.default_rng(4)
+    si, st, en = [], [], []
+    for i in range(data.getNumberOfElements()):
+        L = data.getElementAt(i).getLength()
+        for _ in range(12):
+            a = int(rng.integers(0, L))
+            b = int(rng.integers(a, L))
+            si.append(i); st.append(a); en.append(b)
+        si.append(i); st.append(0); en.append(L - 1)
+    got = hmm.getLogProbForWindows(data, si, st, en)
+    ref = np.array([om.loglik_window(data.getElementAt(i).codes, a, b) for i, a, b in zip(si, st, en)])
+    np.testing.assert_allclose(got, ref, rtol=1e-12)
+    seq = data.getElementAt(2)
+    assert hmm.getLogProbFor(seq, 5, 20) == pytest.approx(om.loglik_window(seq.codes, 5, 20), rel=1e-12)
+    with pytest.raises(nat.NativeError):
+        hmm.getLogProbForWindows(data, [0], [5], [10_000])
 
 
 def test_full_size_properties_cfg3_sample(nat):
