@@ -56,8 +56,9 @@ public final class JstacsHmmNative {
 	public static final MethodHandle jh_dataset_destroy = h( "jh_dataset_destroy", FunctionDescriptor.ofVoid( P ) );
 	public static final MethodHandle jh_dataset_set_weights = h( "jh_dataset_set_weights", FunctionDescriptor.of( I, P, P ) );
 	public static final MethodHandle jh_loglik = h( "jh_loglik", FunctionDescriptor.of( I, P, P, P ) );
-	public static final MethodHandle jh_loglik_windows = h( "jh_loglik_windows", FunctionDescriptor.of( I, P, P, J, P, P, P, J, P ) );
+	public static final MethodHandle jh_loglik_windows = h( "jh_loglik_windows", FunctionDescriptor.of( I, P, P, J, P, P, P, P ) );
 	public static final MethodHandle jh_viterbi = h( "jh_viterbi", FunctionDescriptor.of( I, P, P, P, P ) );
+	public static final MethodHandle jh_viterbi_paths = h( "jh_viterbi_paths", FunctionDescriptor.of( I, P, P, P, P, P, P ) );
 	public static final MethodHandle jh_posterior = h( "jh_posterior", FunctionDescriptor.of( I, P, P, J, P ) );
 	public static final MethodHandle jh_posterior_decode = h( "jh_posterior_decode", FunctionDescriptor.of( I, P, P, P, P ) );
 	public static final MethodHandle jh_estep = h( "jh_estep", FunctionDescriptor.of( I, P, P, I, P, P, P ) );

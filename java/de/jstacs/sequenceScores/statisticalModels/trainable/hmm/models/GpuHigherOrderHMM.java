@@ -308,30 +308,69 @@ public class GpuHigherOrderHMM extends DifferentiableHigherOrderHMM {
 		}
 	}
 
-	/** AbstractHMM.getViterbiPathsFor(DataSet) (AbstractHMM.java:894-900): bit-identical paths and scores. */
+	/**
+	 * AbstractHMM.getViterbiPathsFor(DataSet) (AbstractHMM.java:894-900): bit-identical paths and scores.  Uses the
+	 * general entry point <code>jh_viterbi_paths</code>, so models with silent states (paths of variable length,
+	 * HigherOrderHMM.java:667-705) work as well.
+	 */
 	@Override
 	@SuppressWarnings( "unchecked" )
 	public Pair<IntList, Double>[] getViterbiPathsFor( DataSet data ) throws Exception {
-		int n = data.getNumberOfElements();
+		int n = data.getNumberOfElements(), nSilent = 0;
+		for( int i = 0; i < states.length; i++ ) {
+			nSilent += states[i].isSilent() ? 1 : 0;
+		}
 		Pair<IntList, Double>[] res = new Pair[n];
 		try( Arena arena = Arena.ofConfined() ) {
 			MemorySegment ds = createDataSet( arena, data, null ), model = createModel( arena );
 			try {
+				MemorySegment ptr = arena.allocate( ValueLayout.JAVA_LONG, n + 1L );
 				long total = 0;
 				for( int i = 0; i < n; i++ ) {
-					total += data.getElementAt( i ).getLength();
+					ptr.setAtIndex( ValueLayout.JAVA_LONG, i, total );
+					total += (long) data.getElementAt( i ).getLength() * ( 1 + nSilent ) + nSilent;
 				}
-				MemorySegment paths = arena.allocate( ValueLayout.JAVA_INT, Math.max( total, 1 ) ), scores = arena.allocate( ValueLayout.JAVA_DOUBLE, Math.max( n, 1 ) );
-				JstacsHmmNative.check( (int) JstacsHmmNative.jh_viterbi.invokeExact( model, ds, paths, scores ) );
-				long p = 0;
+				ptr.setAtIndex( ValueLayout.JAVA_LONG, n, total );
+				MemorySegment paths = arena.allocate( ValueLayout.JAVA_INT, Math.max( total, 1 ) ), scores = arena.allocate( ValueLayout.JAVA_DOUBLE, Math.max( n, 1 ) ),
+						len = arena.allocate( ValueLayout.JAVA_LONG, Math.max( n, 1 ) );
+				JstacsHmmNative.check( (int) JstacsHmmNative.jh_viterbi_paths.invokeExact( model, ds, paths, ptr, len, scores ) );
 				for( int i = 0; i < n; i++ ) {
-					int L = data.getElementAt( i ).getLength();
-					IntList path = new IntList( L );
-					for( int l = 0; l < L; l++, p++ ) {
-						path.add( paths.getAtIndex( ValueLayout.JAVA_INT, p ) );
+					long p = ptr.getAtIndex( ValueLayout.JAVA_LONG, i ), L = len.getAtIndex( ValueLayout.JAVA_LONG, i );
+					if( L < 0 ) {
+						throw new IllegalArgumentException( "Impossible path" );
+					}
+					IntList path = new IntList( (int) L );
+					for( long l = 0; l < L; l++ ) {
+						path.add( paths.getAtIndex( ValueLayout.JAVA_INT, p + l ) );
 					}
 					res[i] = new Pair<IntList, Double>( path, scores.getAtIndex( ValueLayout.JAVA_DOUBLE, i ) );
 				}
+			} finally {
+				JstacsHmmNative.jh_model_destroy.invokeExact( model );
+				JstacsHmmNative.jh_dataset_destroy.invokeExact( ds );
+			}
+		} catch( Exception e ) {
+			throw e;
+		} catch( Throwable t ) {
+			throw new RuntimeException( t );
+		}
+		return res;
+	}
+
+	/**
+	 * <code>getLogProbFor(data.getElementAt(seqIndex[i]), start[i], end[i])</code> (AbstractHMM.java:985-998) for many
+	 * windows in one call — the sliding-window scan of projects/xanthogenomes/NHMMer.java:225-244.
+	 */
+	public double[] getLogProbForWindows( DataSet data, long[] seqIndex, long[] start, long[] end ) throws Exception {
+		double[] res = new double[seqIndex.length];
+		try( Arena arena = Arena.ofConfined() ) {
+			MemorySegment ds = createDataSet( arena, data, null ), model = createModel( arena );
+			try {
+				MemorySegment out = arena.allocate( ValueLayout.JAVA_DOUBLE, Math.max( res.length, 1 ) );
+				JstacsHmmNative.check( (int) JstacsHmmNative.jh_loglik_windows.invokeExact( model, ds, (long) res.length,
+						arena.allocateFrom( ValueLayout.JAVA_LONG, seqIndex ), arena.allocateFrom( ValueLayout.JAVA_LONG, start ),
+						arena.allocateFrom( ValueLayout.JAVA_LONG, end ), out ) );
+				MemorySegment.copy( out, ValueLayout.JAVA_DOUBLE, 0, res, 0, res.length );
 			} finally {
 				JstacsHmmNative.jh_model_destroy.invokeExact( model );
 				JstacsHmmNative.jh_dataset_destroy.invokeExact( ds );
