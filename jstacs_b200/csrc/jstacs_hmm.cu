@@ -13,6 +13,7 @@
 #include "kernels_fast.cuh"
 #include "kernels_general.cuh"
 #include "kernels_mma.cuh"
+#include "kernels_sparse.cuh"
 #include "kernels_viterbi.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -27,6 +28,7 @@ struct Options {
   int64_t scratch_mb = 24576;  // upper bound of DP scratch memory
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
+  int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
 };
 static Options g_opt;
 
@@ -130,6 +132,8 @@ struct jh_model {
   DevBuf<unsigned long long> d_counter;
   DevBuf<int32_t> d_fallback;  // [1 + n] list of sequences the fast path handed to the exact kernels
   jhf::FastTables fast;        // linear-space tables of the fast path
+  jhs::SparseTables sparse;    // edge lists of the sparse path (33..256 states)
+  DevBuf<double> d_ck_alpha, d_ck_beta;  // checkpoint vectors of chromosome-scale decoding
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timed = false, ktimed = false;
@@ -188,6 +192,10 @@ struct jh_dataset {
   DevBuf<int64_t> d_oct_hbase;
   DevBuf<uint16_t> d_hashes;
   int hash_a = -1, hash_K = -1;
+  // chunk list of the sparse decoding path (kernels_sparse.cuh), built per chunk length
+  int64_t chunk_len = 0, n_chunks = 0;
+  DevBuf<int64_t> d_chunk_ptr;
+  DevBuf<int32_t> d_chunk_seq, d_chunk_idx;
   DevData dev(int64_t first = 0, int64_t count = -1) const {
     DevData D;
     D.codes = d_codes.p; D.offsets = d_offsets.p; D.weights = has_weights ? d_weights.p : nullptr;
@@ -228,6 +236,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "scratch_mb") g_opt.scratch_mb = value;
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = value;
   else if (n == "fast_variant") g_opt.fast_variant = value;
+  else if (n == "chunk") g_opt.chunk = std::max<int64_t>(16, value);
   else {
     jh_set_error("unknown option '%s'", n.c_str());
     return JH_ERR_INVALID;
@@ -251,6 +260,14 @@ static int prep_scores(jh_model *m) {
   jha::k_prep_scores<<<(n + 255) / 256, 256, 0, m->st()>>>(m->params());
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
+  if (m->sparse.usable) {
+    jhs::SparseTables &P = m->sparse;
+    int np = std::max(P.IND * P.SP, P.H * P.SP);
+    jhs::k_sparse_prepare<<<(np + 255) / 256, 256, 0, m->st()>>>(P.dev(), P.IND, P.d_in_p, P.d_out_p, P.d_pimap, P.d_etab, P.d_emod, m->d_tscore.p,
+                                                               m->d_escore.p, P.d_in_T, P.d_out_T, P.d_pi, P.d_E);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+  }
   int r = jhf::prepare(m->fast, m->dev(), m->st());
   if (r || !m->fast.usable) return r;
   jhf::FastTables &F = m->fast;
@@ -435,6 +452,11 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
     delete m;
     return r;
   }
+  if ((r = jhs::build(m->sparse, m->S, m->a, m->m, m->has_silent, m->Kmax, m->lc_ctx_ptr, m->ctx_elem, m->ctx_last, m->elem_child_ptr, m->child_state,
+                      m->state_order, m->state_tab, m->state_mod, m->state_final, s)) != 0) {
+    delete m;
+    return r;
+  }
   if ((r = prep_scores(m)) != 0) { delete m; return r; }
   if (cudaStreamSynchronize(s) != cudaSuccess) return fail(JH_ERR_CUDA, "model upload failed");
   *out = m;
@@ -446,6 +468,7 @@ extern "C" void jh_model_destroy(jh_model *m) {
   cudaSetDevice(g_device);
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   jhf::destroy(m->fast);
+  jhs::destroy(m->sparse);
   if (m->ev0) cudaEventDestroy(m->ev0);
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->evk0) cudaEventDestroy(m->evk0);
@@ -687,7 +710,7 @@ extern "C" int jh_last_main_kernel_ms(jh_model *m, double *ms) {
   }
 
 // ---- log-likelihood --------------------------------------------------------------------------
-static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int32_t *d_list = nullptr, int64_t n_list = 0) {
+static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int32_t *d_list, int64_t n_list) {
   int G = group_size(m), r = JH_OK;
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
@@ -770,6 +793,112 @@ static int run_general_estep(jh_model *m, jh_dataset *d) {
   return JH_OK;
 }
 
+// ---- sparse path (kernels_sparse.cuh): 33..256 states, chromosome-scale sequences ----------------------------------
+#define DISPATCH_SPARSE(P, ...)                                                             \
+  switch ((P).SPL * 100 + (P).IND) {                                                        \
+    case 204: { constexpr int SPL_ = 2, IND_ = 4; __VA_ARGS__; } break;                     \
+    case 208: { constexpr int SPL_ = 2, IND_ = 8; __VA_ARGS__; } break;                     \
+    case 216: { constexpr int SPL_ = 2, IND_ = 16; __VA_ARGS__; } break;                    \
+    case 404: { constexpr int SPL_ = 4, IND_ = 4; __VA_ARGS__; } break;                     \
+    case 408: { constexpr int SPL_ = 4, IND_ = 8; __VA_ARGS__; } break;                     \
+    default: { constexpr int SPL_ = 8, IND_ = 4; __VA_ARGS__; } break;                      \
+  }
+
+static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK) {
+  if (d->chunk_len == CK && d->d_chunk_ptr.p) return JH_OK;
+  std::vector<int64_t> ptr(d->n_seq + 1, 0);
+  for (int64_t i = 0; i < d->n_seq; i++) ptr[i + 1] = ptr[i] + (d->offsets[i + 1] - d->offsets[i] + CK - 1) / CK;
+  const int64_t n = ptr[d->n_seq];
+  if (n > 0x7fffffff) { jh_set_error("too many chunks"); return JH_ERR_UNSUPPORTED; }
+  std::vector<int32_t> cs(std::max<int64_t>(n, 1)), ci(std::max<int64_t>(n, 1));
+  int64_t g = 0;
+  for (int64_t k = 0; k < d->n_seq; k++) {  // longest sequences first
+    const int32_t sid = d->order[k];
+    for (int64_t c = 0; c < ptr[sid + 1] - ptr[sid]; c++, g++) { cs[g] = sid; ci[g] = (int32_t)c; }
+  }
+  cudaStream_t s = m->st();
+  int r;
+  if ((r = d->d_chunk_ptr.upload(ptr, s)) || (r = d->d_chunk_seq.upload(cs, s)) || (r = d->d_chunk_idx.upload(ci, s))) return r;
+  JH_CUDA(cudaStreamSynchronize(s));
+  d->chunk_len = CK;
+  d->n_chunks = n;
+  return JH_OK;
+}
+
+// phase 1: n_dir = 1 scoring only, n_dir = 2 forward and backward warps with checkpoints
+static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll) {
+  jhs::SparseTables &P = m->sparse;
+  cudaStream_t s = m->st();
+  int r = m->d_fallback.reserve(d->n_seq + 2);
+  if (r) return r;
+  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  const int64_t items = d->n_seq * n_dir;
+  const int NT = items <= 2 * (int64_t)m->sm_count ? 32 : 128;  // few long sequences: one warp per SM
+  const size_t smem = ((size_t)P.H * P.SP + (size_t)(NT / 32) * 2 * P.SP) * sizeof(double);
+  DISPATCH_SPARSE(P, {
+    auto kern = jhs::k_sparse_pass1<SPL_, IND_>;
+    if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) { jh_set_error("sparse kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
+    int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, (items + NT / 32 - 1) / (NT / 32)));
+    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), n_dir, d->chunk_len > 0 ? d->chunk_len : 1, n_dir == 2 ? d->d_chunk_ptr.p : nullptr,
+                                     n_dir == 2 ? m->d_ck_alpha.p : nullptr, n_dir == 2 ? m->d_ck_beta.p : nullptr, m->d_counter.p, d_ll, m->d_fallback.p);
+    JH_LAUNCHED();
+  });
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int32_t *d_list, int64_t n_list);
+
+static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
+  int r = run_sparse_pass1(m, d, 1, d_out);
+  if (r) return r;
+  int32_t n_fb = 0;
+  JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  if (n_fb > 0) return run_loglik_exact(m, d, d_out, m->d_fallback.p + 1, n_fb);
+  return JH_OK;
+}
+
+static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, double *d_loglik, double *d_post, const int32_t *d_list, int64_t n_list);
+
+// posterior decoding in two exact phases: checkpoints every `chunk` positions, then all chunks in parallel
+static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) {
+  jhs::SparseTables &P = m->sparse;
+  cudaStream_t s = m->st();
+  const int64_t CK = g_opt.chunk;
+  int r = ensure_chunks(m, d, CK);
+  if (r) return r;
+  if ((r = m->d_ck_alpha.reserve((size_t)(d->n_chunks + 1) * P.SP)) || (r = m->d_ck_beta.reserve((size_t)(d->n_chunks + 1) * P.SP))) return r;
+  if ((r = run_sparse_pass1(m, d, 2, d_ll))) return r;
+  const int NT = 128, wpc = NT / 32;
+  const size_t smem = ((size_t)P.H * P.SP + (size_t)wpc * 2 * P.SP) * sizeof(double);
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  DISPATCH_SPARSE(P, {
+    auto kern = jhs::k_sparse_decode_chunks<SPL_, IND_>;
+    if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) { jh_set_error("sparse decoding kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
+    int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);
+    const int64_t per_slot = CK * P.SP * (int64_t)sizeof(double);
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, g_opt.scratch_mb * 1024 * 1024 / per_slot / wpc));
+    if ((r = m->d_fwd.reserve((size_t)grid * wpc * CK * P.SP))) return r;
+    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_ck_alpha.p,
+                                     m->d_ck_beta.p, m->d_counter.p, m->d_fwd.p, d_paths);
+    JH_LAUNCHED();
+  });
+  JH_CUDA(cudaGetLastError());
+  int32_t n_fb = 0;
+  JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_DECODE, d_paths, d_ll, nullptr, m->d_fallback.p + 1, n_fb);
+  return JH_OK;
+}
+
 static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
 
 // Octet scoring (kernels_mma.cuh): ONE launch over all octets (longest first, fetched dynamically: no scratch to size);
@@ -823,9 +952,10 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
   if (m->has_silent) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_loglik(m, d, W, d_out.p);
-  } else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
+  } else if (g_opt.fast && m->sparse.usable) r = run_loglik_sparse(m, d, d_out.p);
+  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
-  else r = run_loglik_exact(m, d, d_out.p);
+  else r = run_loglik_exact(m, d, d_out.p, nullptr, 0);
   timing_end(m);
   if (r) return r;
   JH_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
@@ -1100,7 +1230,8 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
   DevBuf<double> d_ll;
   if ((r = d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
   timing_begin(m);
-  if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
+  if (g_opt.fast && m->sparse.usable) r = run_decode_sparse(m, d, d_paths.p, d_ll.p);
+  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
   else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
   timing_end(m);
   if (r) return r;

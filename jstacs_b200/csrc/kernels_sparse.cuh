@@ -1,0 +1,444 @@
+// kernels_sparse.cuh — scaled linear-space kernels for SPARSE first-order models with 33..256 states and for
+// chromosome-scale sequences (BASELINE cfg5: 128 states, 4 children per state, 24 sequences of 10-250 Mb, forward-backward +
+// posterior decoding).  Same exact power-of-two rescaling as kernels_fast.cuh; the transition structure is kept as
+// padded in-/out-edge lists (ELL, at most IND edges per state) held in registers.
+//
+// Mapping: one WARP per sequence or chunk, SPL = S_pad/32 consecutive states per lane, the DP vector double-buffered in
+// shared memory (gathered by edge list, written back with 128-bit stores), the context hash rolled warp-uniformly
+// straight from the residues.
+//
+// A chromosome cannot be decoded the way the reference does it (two full (L+1) x C matrices: 256 GB for 250 Mb x 128
+// states).  The forward/backward recursions are inherently sequential in the position, so the decoding is
+// split in two exact phases:
+//   1. k_sparse_pass1: per sequence one warp runs the forward recursion and a second warp the backward recursion over the
+//      WHOLE sequence, concurrently, storing only a checkpoint vector every CK positions (1 KB per 4096 residues) — and the
+//      log-likelihood.  This phase is latency bound (one dependent step per position).
+//   2. k_sparse_decode_chunks: every chunk of CK positions is independent given its two checkpoints: a warp recomputes the
+//      forward rows of the chunk into a scratch, runs the backward recursion through the chunk and writes the state with
+//      the largest posterior per position (alpha_t[j] * beta_t[j], lowest index on ties, AbstractHMM.java:1125-1139).
+//      Thousands of chunks run in parallel, whatever the number of sequences.
+// Scoring alone is phase 1 without the backward warp and without checkpoints.
+#pragma once
+#include "kernels_exact.cuh"
+
+namespace jhs {
+
+using jhx::ResReader;
+
+struct SparseDev {
+  int S, SP, a, Kmax, H, hpow, a_pow2;
+  double inv_a;
+  const int *in_src;     // [IND][SP] source state of in-edge k of state j (padding: j itself, weight 0)
+  const double *in_T;    // [IND][SP] P(src -> j)
+  const int *out_dst;    // [IND][SP] target state of out-edge k of state i
+  const double *out_T;   // [IND][SP] P(i -> dst)
+  const double *pi;      // [SP]
+  const double *fin;     // [SP] 1.0 for final states
+  const double *E;       // [H][SP] emission probability by context hash
+  const int *korder;     // [SP]
+};
+
+struct SparseTables {
+  bool usable = false;
+  int S = 0, SP = 0, SPL = 0, IND = 0, a = 0, Kmax = 0, H = 0;
+  int *d_in_src = nullptr, *d_out_dst = nullptr, *d_in_p = nullptr, *d_out_p = nullptr, *d_pimap = nullptr, *d_korder = nullptr,
+      *d_etab = nullptr, *d_emod = nullptr;
+  double *d_in_T = nullptr, *d_out_T = nullptr, *d_pi = nullptr, *d_fin = nullptr, *d_E = nullptr;
+  SparseDev dev() const {
+    SparseDev F;
+    F.S = S; F.SP = SP; F.a = a; F.Kmax = Kmax; F.H = H;
+    int pw = 1;
+    for (int i = 0; i < Kmax; i++) pw *= a;
+    F.hpow = pw; F.a_pow2 = (a & (a - 1)) == 0; F.inv_a = 1.0 / a;
+    F.in_src = d_in_src; F.in_T = d_in_T; F.out_dst = d_out_dst; F.out_T = d_out_T; F.pi = d_pi; F.fin = d_fin; F.E = d_E; F.korder = d_korder;
+    return F;
+  }
+};
+
+inline void destroy(SparseTables &F) {
+  void *ptrs[] = {F.d_in_src, F.d_out_dst, F.d_in_p, F.d_out_p, F.d_pimap, F.d_korder, F.d_etab, F.d_emod, F.d_in_T, F.d_out_T, F.d_pi, F.d_fin, F.d_E};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  F = SparseTables();
+}
+
+template <typename T>
+static int up(T **dst, const std::vector<T> &h, cudaStream_t s) {
+  if (cudaMalloc((void **)dst, std::max<size_t>(h.size(), 1) * sizeof(T)) != cudaSuccess) {
+    jh_set_error("out of device memory (sparse tables)");
+    return JH_ERR_NOMEM;
+  }
+  if (!h.empty()) JH_CUDA(cudaMemcpyAsync(*dst, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  return JH_OK;
+}
+
+// Scope test + edge lists: plain first-order chain, no silent states, 33..256 states, at most 16 edges in and out per state.
+inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax, const std::vector<int> &lc_ctx_ptr, const std::vector<int> &ctx_elem,
+                 const std::vector<int> &ctx_last, const std::vector<int> &elem_child_ptr, const std::vector<int> &child_state,
+                 const std::vector<int> &state_order, const std::vector<int> &state_tab, const std::vector<int> &state_mod,
+                 const std::vector<uint8_t> &state_final, cudaStream_t s) {
+  F.usable = false;
+  if (m != 1 || has_silent || S <= 32 || S > 256) return JH_OK;
+  if (lc_ctx_ptr[1] - lc_ctx_ptr[0] != 1) return JH_OK;
+  const int SPL = S <= 64 ? 2 : S <= 128 ? 4 : 8, SP = 32 * SPL;
+  int64_t H = a;
+  for (int i = 0; i < Kmax; i++) H *= a;
+  if (H * SP * 8 > 96 * 1024) return JH_OK;
+  std::vector<std::vector<std::pair<int, int>>> in(S), out(S);  // (other state, child index)
+  std::vector<char> seen(S, 0);
+  for (int c = lc_ctx_ptr[1]; c < lc_ctx_ptr[2]; c++) {
+    int i = ctx_last[c], e = ctx_elem[c];
+    if (i < 0 || i >= S || seen[i]) return JH_OK;
+    seen[i] = 1;
+    for (int p = elem_child_ptr[e]; p < elem_child_ptr[e + 1]; p++) {
+      out[i].push_back({child_state[p], p});
+      in[child_state[p]].push_back({i, p});
+    }
+  }
+  size_t deg = 1;
+  for (int j = 0; j < S; j++) deg = std::max(deg, std::max(in[j].size(), out[j].size()));
+  if (deg > 16) return JH_OK;
+  const int IND = deg <= 4 ? 4 : deg <= 8 ? 8 : 16;
+  if (SPL * IND > 32) return JH_OK;  // both edge lists of a lane have to fit into registers
+  std::vector<int> in_src((size_t)IND * SP), out_dst((size_t)IND * SP), in_p((size_t)IND * SP, -1), out_p((size_t)IND * SP, -1), pimap(SP, -1),
+      korder(SP, 0), etab(SP, -1), emod(SP, 1);
+  std::vector<double> fin(SP, 0.0);
+  for (int k = 0; k < IND; k++)
+    for (int j = 0; j < SP; j++) {
+      in_src[(size_t)k * SP + j] = j;
+      out_dst[(size_t)k * SP + j] = j;
+      if (j < S && k < (int)in[j].size()) { in_src[(size_t)k * SP + j] = in[j][k].first; in_p[(size_t)k * SP + j] = in[j][k].second; }
+      if (j < S && k < (int)out[j].size()) { out_dst[(size_t)k * SP + j] = out[j][k].first; out_p[(size_t)k * SP + j] = out[j][k].second; }
+    }
+  int e0 = ctx_elem[lc_ctx_ptr[0]];
+  for (int p = elem_child_ptr[e0]; p < elem_child_ptr[e0 + 1]; p++) pimap[child_state[p]] = p;
+  for (int j = 0; j < S; j++) {
+    korder[j] = state_order[j];
+    etab[j] = state_tab[j];
+    emod[j] = state_mod[j];
+    fin[j] = state_final[j] ? 1.0 : 0.0;
+  }
+  F.S = S; F.SP = SP; F.SPL = SPL; F.IND = IND; F.a = a; F.Kmax = Kmax; F.H = (int)H;
+  int r;
+  std::vector<double> zE((size_t)H * SP, 0.0), zT((size_t)IND * SP, 0.0), zp(SP, 0.0);
+  if ((r = up(&F.d_in_src, in_src, s)) || (r = up(&F.d_out_dst, out_dst, s)) || (r = up(&F.d_in_p, in_p, s)) || (r = up(&F.d_out_p, out_p, s)) ||
+      (r = up(&F.d_pimap, pimap, s)) || (r = up(&F.d_korder, korder, s)) || (r = up(&F.d_etab, etab, s)) || (r = up(&F.d_emod, emod, s)) ||
+      (r = up(&F.d_fin, fin, s)) || (r = up(&F.d_in_T, zT, s)) || (r = up(&F.d_out_T, zT, s)) || (r = up(&F.d_pi, zp, s)) || (r = up(&F.d_E, zE, s)))
+    return r;
+  F.usable = true;
+  return JH_OK;
+}
+
+// probabilities from the log-space score tables (after every parameter update)
+__global__ void k_sparse_prepare(SparseDev F, int IND, const int *in_p, const int *out_p, const int *pimap, const int *etab, const int *emod,
+                                 const double *tscore, const double *escore, double *in_T, double *out_T, double *pi, double *E) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < IND * F.SP) {
+    in_T[idx] = in_p[idx] >= 0 ? exp(tscore[in_p[idx]]) : 0.0;
+    out_T[idx] = out_p[idx] >= 0 ? exp(tscore[out_p[idx]]) : 0.0;
+  }
+  if (idx < F.SP) pi[idx] = pimap[idx] >= 0 ? exp(tscore[pimap[idx]]) : 0.0;
+  if (idx < F.H * F.SP) {
+    int h = idx / F.SP, j = idx % F.SP;
+    E[idx] = etab[j] >= 0 ? exp(escore[etab[j] + h % emod[j]]) : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int hmod_of(const SparseDev &F, int h) { return F.a_pow2 ? (h & (F.H - 1)) : (h % F.H); }
+__device__ __forceinline__ int hash_at(const SparseDev &F, ResReader &rd, int64_t pos) {
+  int h = 0, pw = 1;
+  for (int i = 0; i <= F.Kmax; i++) {
+    int64_t q = pos - i;
+    if (q < 0) break;
+    h += pw * rd.get(q);
+    pw *= F.a;
+  }
+  return h;
+}
+__device__ __forceinline__ int hash_back(const SparseDev &F, ResReader &rd, int h, int64_t pos) {  // pos -> pos-1
+  int64_t q = pos - 1 - F.Kmax;
+  return h / F.a + (q >= 0 ? F.hpow * rd.get(q) : 0);
+}
+
+// exact rescale of the warp's vector: divide by 2^e, e = exponent of the maximum; false when the maximum has left the
+// safe range (80 binades above the denormals, see kernels_mma.cuh)
+template <int SPL>
+__device__ __forceinline__ bool rescale_warp(double (&v)[SPL], long long &expo) {
+  unsigned hi = (unsigned)__double2hiint(v[0]);
+#pragma unroll
+  for (int i = 1; i < SPL; i++) hi = max(hi, (unsigned)__double2hiint(v[i]));
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  const int be = (int)(hi >> 20);
+  const double f = __hiloint2double((2046 - be) << 20, 0);
+#pragma unroll
+  for (int i = 0; i < SPL; i++) v[i] *= f;
+  expo += be - 1023;
+  return (unsigned)(be - 81) < (0x7feu - 81u);
+}
+
+template <int SPL>
+__device__ __forceinline__ void store_vec(double *dst, const double (&v)[SPL]) {  // dst: the lane's SPL consecutive slots
+  if (SPL == 1) dst[0] = v[0];
+  else {
+#pragma unroll
+    for (int u = 0; u < SPL; u += 2) *reinterpret_cast<double2 *>(dst + u) = make_double2(v[u], v[u + 1]);
+  }
+}
+template <int SPL>
+__device__ __forceinline__ void load_vec(const double *src, double (&v)[SPL]) {
+  if (SPL == 1) v[0] = src[0];
+  else {
+#pragma unroll
+    for (int u = 0; u < SPL; u += 2) {
+      const double2 x = *reinterpret_cast<const double2 *>(src + u);
+      v[u] = x.x;
+      v[u + 1] = x.y;
+    }
+  }
+}
+
+// emission probabilities of the lane's states at position pos (context hash h)
+template <int SPL>
+__device__ __forceinline__ void emis(const SparseDev &F, const double *sE, int lane, double (&e)[SPL], int h, int64_t pos) {
+  load_vec<SPL>(sE + (size_t)h * F.SP + SPL * lane, e);
+  if (pos < F.Kmax) {
+#pragma unroll
+    for (int u = 0; u < SPL; u++)
+      if (pos < F.korder[SPL * lane + u]) e[u] = F.inv_a;
+  }
+}
+
+template <int SPL, int IND>
+struct Edges {  // the lane's edge lists in registers: byte offsets into the shared vector and probabilities
+  int off[IND][SPL];
+  double w[IND][SPL];
+  __device__ __forceinline__ void load(const int *idx, const double *T, int SP, int lane) {
+#pragma unroll
+    for (int k = 0; k < IND; k++)
+#pragma unroll
+      for (int u = 0; u < SPL; u++) {
+        off[k][u] = idx[(size_t)k * SP + SPL * lane + u] * 8;
+        w[k][u] = T[(size_t)k * SP + SPL * lane + u];
+      }
+  }
+  // out[u] = sum_k vec[idx[k][u]] * w[k][u]
+  __device__ __forceinline__ void gather(const double *vec, double (&out)[SPL]) const {
+    const char *base = reinterpret_cast<const char *>(vec);
+#pragma unroll
+    for (int u = 0; u < SPL; u++) {
+      double a0 = 0, a1 = 0;
+#pragma unroll
+      for (int k = 0; k < IND; k += 2) {
+        a0 = fma(*reinterpret_cast<const double *>(base + off[k][u]), w[k][u], a0);
+        a1 = fma(*reinterpret_cast<const double *>(base + off[k + 1][u]), w[k + 1][u], a1);
+      }
+      out[u] = a0 + a1;
+    }
+  }
+};
+
+constexpr int RS_SPARSE = 4;  // positions between two rescales
+
+// Phase 1 / scoring.  Work item w: sequence w>>1 ... direction w&1 when both directions run (n_dir == 2), else forward only.
+// ck_alpha / ck_beta: [chunk_ptr[seq] + c][SP]; loglik[seq]; fallback: sequences the scaled recursion could not finish.
+template <int SPL, int IND>
+__global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, int n_dir, int64_t CK, const int64_t *chunk_ptr, double *ck_alpha,
+                                                      double *ck_beta, unsigned long long *counter, double *loglik, int32_t *fallback) {
+  extern __shared__ double sm[];
+  const int SP = F.SP;
+  double *sE = sm;
+  double *vec = sE + (size_t)F.H * SP + (size_t)(threadIdx.x >> 5) * 2 * SP;  // two buffers per warp
+  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  ResReader rd;
+  for (;;) {
+    long long it = 0;
+    if (lane == 0) it = (long long)atomicAdd(counter, 1ull);
+    it = __shfl_sync(FULL, it, 0);
+    if (it >= D.n_seq * n_dir) break;
+    const int sid = D.order[it / n_dir];
+    const bool backward = n_dir == 2 && (it & 1);
+    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    rd.init(D.codes + off);
+    const int64_t cbase = chunk_ptr ? chunk_ptr[sid] : 0;
+    if (!backward) {
+      Edges<SPL, IND> G;
+      G.load(F.in_src, F.in_T, SP, lane);
+      double f[SPL], e[SPL];
+      long long A = 0;
+      bool ok = true;
+      int h = hash_at(F, rd, 0);
+      emis<SPL>(F, sE, lane, e, hmod_of(F, h), 0);
+#pragma unroll
+      for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+      ok = rescale_warp<SPL>(f, A);
+      int par = 0;
+      for (int64_t t = 1; t < L; t++) {
+        double *v = vec + par * SP;
+        par ^= 1;
+        store_vec<SPL>(v + SPL * lane, f);
+        if (ck_alpha && t % CK == 0) store_vec<SPL>(ck_alpha + (size_t)(cbase + t / CK) * SP + SPL * lane, f);  // vector before chunk t/CK
+        h = hmod_of(F, h * F.a + rd.get(t));
+        emis<SPL>(F, sE, lane, e, h, t);
+        __syncwarp();
+        G.gather(v, f);
+#pragma unroll
+        for (int u = 0; u < SPL; u++) f[u] *= e[u];
+        if ((t & (RS_SPARSE - 1)) == 0) ok &= rescale_warp<SPL>(f, A);
+      }
+      ok &= rescale_warp<SPL>(f, A);
+      double sfin = 0;
+#pragma unroll
+      for (int u = 0; u < SPL; u++) sfin += f[u] * F.fin[SPL * lane + u];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) sfin += __shfl_xor_sync(FULL, sfin, d);
+      if (lane == 0) {
+        if (ok && sfin > 0) loglik[sid] = log(sfin) + (double)A * 0.6931471805599453094;
+        else {
+          loglik[sid] = JH_NEG_INF;
+          int pos = atomicAdd(fallback, 1);
+          fallback[1 + pos] = sid;
+        }
+      }
+    } else {
+      Edges<SPL, IND> G;
+      G.load(F.out_dst, F.out_T, SP, lane);
+      double b[SPL], e[SPL];
+      long long Bx = 0;
+#pragma unroll
+      for (int u = 0; u < SPL; u++) b[u] = F.fin[SPL * lane + u];
+      int h = hash_at(F, rd, L - 1);
+      int par = 0;
+      for (int64_t t = L - 1; t >= 1; --t) {  // beta_t -> beta_{t-1}
+        if ((t + 1) % CK == 0 && t + 1 < L) store_vec<SPL>(ck_beta + (size_t)(cbase + t / CK) * SP + SPL * lane, b);  // beta at the last position of chunk t/CK
+        emis<SPL>(F, sE, lane, e, hmod_of(F, h), t);
+        double *v = vec + par * SP;
+        par ^= 1;
+        double x[SPL];
+#pragma unroll
+        for (int u = 0; u < SPL; u++) x[u] = e[u] * b[u];
+        store_vec<SPL>(v + SPL * lane, x);
+        h = hash_back(F, rd, h, t);
+        __syncwarp();
+        G.gather(v, b);
+        if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(b, Bx);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Phase 2: posterior decoding of one chunk per warp.  chunk_seq / chunk_idx: the chunk list; rows: [warp slot][CK][SP].
+template <int SPL, int IND>
+__global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int64_t CK, int64_t n_chunks, const int32_t *chunk_seq,
+                                                              const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
+                                                              const double *ck_beta, unsigned long long *counter, double *rows, int32_t *paths) {
+  extern __shared__ double sm[];
+  const int SP = F.SP;
+  double *sE = sm;
+  double *vec = sE + (size_t)F.H * SP + (size_t)(threadIdx.x >> 5) * 2 * SP;
+  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double *const R = rows + (size_t)slot * CK * SP + SPL * lane;
+  ResReader rd;
+  Edges<SPL, IND> Gin, Gout;
+  Gin.load(F.in_src, F.in_T, SP, lane);
+  Gout.load(F.out_dst, F.out_T, SP, lane);
+  for (;;) {
+    long long g = 0;
+    if (lane == 0) g = (long long)atomicAdd(counter, 1ull);
+    g = __shfl_sync(FULL, g, 0);
+    if (g >= n_chunks) break;
+    const int sid = chunk_seq[g], c = chunk_idx[g];
+    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    const int64_t t0 = (int64_t)c * CK, t1 = min(L, t0 + CK) - 1;
+    const int64_t cb = chunk_ptr[sid] + c;
+    rd.init(D.codes + off);
+    // ---- forward rows of the chunk ----
+    double f[SPL], e[SPL];
+    long long dummy = 0;
+    int h = hmod_of(F, hash_at(F, rd, t0));
+    emis<SPL>(F, sE, lane, e, h, t0);
+    int par = 0;
+    if (c == 0) {
+#pragma unroll
+      for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+    } else {
+      double *v = vec + par * SP;
+      par ^= 1;
+      double a0[SPL];
+      load_vec<SPL>(ck_alpha + (size_t)cb * SP + SPL * lane, a0);
+      store_vec<SPL>(v + SPL * lane, a0);
+      __syncwarp();
+      Gin.gather(v, f);
+#pragma unroll
+      for (int u = 0; u < SPL; u++) f[u] *= e[u];
+    }
+    rescale_warp<SPL>(f, dummy);
+    store_vec<SPL>(R, f);
+    for (int64_t t = t0 + 1; t <= t1; t++) {
+      double *v = vec + par * SP;
+      par ^= 1;
+      store_vec<SPL>(v + SPL * lane, f);
+      h = hmod_of(F, h * F.a + rd.get(t));
+      emis<SPL>(F, sE, lane, e, h, t);
+      __syncwarp();
+      Gin.gather(v, f);
+#pragma unroll
+      for (int u = 0; u < SPL; u++) f[u] *= e[u];
+      if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(f, dummy);
+      store_vec<SPL>(R + (size_t)(t - t0) * SP, f);
+    }
+    // ---- backward through the chunk, decision per position ----
+    double b[SPL];
+    if (t1 == L - 1) {
+#pragma unroll
+      for (int u = 0; u < SPL; u++) b[u] = F.fin[SPL * lane + u];
+    } else {
+      load_vec<SPL>(ck_beta + (size_t)cb * SP + SPL * lane, b);
+    }
+    int hb = hash_at(F, rd, t1);
+    int32_t *const prow = paths + off;
+    for (int64_t t = t1; t >= t0; --t) {
+      double a[SPL];
+      load_vec<SPL>(R + (size_t)(t - t0) * SP, a);
+      // posterior decision: largest alpha_t[j] * beta_t[j], lowest state index on ties
+      double best = a[0] * b[0];
+      int arg = SPL * lane;
+#pragma unroll
+      for (int u = 1; u < SPL; u++) {
+        const double gm = a[u] * b[u];
+        if (gm > best) { best = gm; arg = SPL * lane + u; }
+      }
+#pragma unroll
+      for (int d = 1; d <= 16; d <<= 1) {
+        const double ob = __shfl_xor_sync(FULL, best, d);
+        const int oa = __shfl_xor_sync(FULL, arg, d);
+        if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+      }
+      if (lane == 0) prow[t] = arg;
+      if (t > t0) {
+        emis<SPL>(F, sE, lane, e, hmod_of(F, hb), t);
+        double *v = vec + par * SP;
+        par ^= 1;
+        double x[SPL];
+#pragma unroll
+        for (int u = 0; u < SPL; u++) x[u] = e[u] * b[u];
+        store_vec<SPL>(v + SPL * lane, x);
+        hb = hash_back(F, rd, hb, t);
+        __syncwarp();
+        Gout.gather(v, b);
+        if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(b, dummy);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace jhs

@@ -353,6 +353,35 @@ def test_window_scoring_sees_the_residues_before_the_window(nat, oracle_lib, nam
         hmm.getLogProbForWindows(data, [0], [5], [10_000])
 
 
+# ---- sparse path: 33..256 states, checkpointed chunk-parallel decoding (BASELINE cfg5 shape) ------------------------
+@pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0)])
+@pytest.mark.parametrize("chunk", [16, 64, 2048])
+def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk):
+    hmm = banded_hmm(states, degree, order)
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(states + chunk)
+    lens = np.concatenate([rng.integers(1, 6, 4), rng.integers(40, 400, 9), [chunk, chunk + 1, 2 * chunk - 1, 1]])
+    data = dataset_of([random_dna(rng, int(L)) for L in lens])
+    nat.check(nat.lib().jh_set_option(b"chunk", chunk))
+    try:
+        ll_ref = om.loglik(data.codes, data.offsets)
+        np.testing.assert_allclose(hmm.getLogScoreFor(data), ll_ref, rtol=LL_RTOL)
+        dec = hmm.decodePosteriorPathsFor(data)
+        n_clear = n_all = 0
+        for i in range(data.getNumberOfElements()):
+            ref = om.posterior(data.getElementAt(i).codes)
+            ref_path = om.decode_posterior(ref)
+            path, ll = dec[i]
+            assert ll == pytest.approx(ll_ref[i], rel=LL_RTOL)
+            srt = np.sort(ref, axis=0)
+            clear = srt[-1] - srt[-2] > 1e-9
+            assert path.shape == ref_path.shape and np.array_equal(path[clear], ref_path[clear])
+            n_clear += clear.sum(); n_all += clear.size
+        assert n_clear > 0.9 * n_all
+    finally:
+        nat.check(nat.lib().jh_set_option(b"chunk", 2048))
+
+
 def test_full_size_properties_cfg3_sample(nat):
     """BASELINE cfg3 model (32 states, order-3 emissions) on 16k x 1 kb sequences: size-independent properties.
     Transition counts add up to the residues, emission counts to the residues with a full context, the score is the
