@@ -236,7 +236,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "scratch_mb") g_opt.scratch_mb = value;
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = value;
   else if (n == "fast_variant") g_opt.fast_variant = value;
-  else if (n == "chunk") g_opt.chunk = std::max<int64_t>(16, value);
+  else if (n == "chunk") g_opt.chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
   else {
     jh_set_error("unknown option '%s'", n.c_str());
     return JH_ERR_INVALID;
@@ -843,7 +843,7 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll)
     JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) { jh_set_error("sparse kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
     int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, (items + NT / 32 - 1) / (NT / 32)));
-    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), n_dir, d->chunk_len > 0 ? d->chunk_len : 1, n_dir == 2 ? d->d_chunk_ptr.p : nullptr,
+    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), n_dir, (int)(d->chunk_len > 0 ? d->chunk_len : 1), n_dir == 2 ? d->d_chunk_ptr.p : nullptr,
                                      n_dir == 2 ? m->d_ck_alpha.p : nullptr, n_dir == 2 ? m->d_ck_beta.p : nullptr, m->d_counter.p, d_ll, m->d_fallback.p);
     JH_LAUNCHED();
   });
@@ -887,7 +887,7 @@ static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
     const int64_t per_slot = CK * P.SP * (int64_t)sizeof(double);
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, g_opt.scratch_mb * 1024 * 1024 / per_slot / wpc));
     if ((r = m->d_fwd.reserve((size_t)grid * wpc * CK * P.SP))) return r;
-    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_ck_alpha.p,
+    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), (int)CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_ck_alpha.p,
                                      m->d_ck_beta.p, m->d_counter.p, m->d_fwd.p, d_paths);
     JH_LAUNCHED();
   });

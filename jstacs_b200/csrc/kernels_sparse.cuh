@@ -26,7 +26,7 @@ namespace jhs {
 using jhx::ResReader;
 
 struct SparseDev {
-  int S, SP, a, Kmax, H, hpow, a_pow2;
+  int S, SP, a, Kmax, H, hpow, a_pow2, ashift;  // ashift = log2(a) when a is a power of two
   double inv_a;
   const int *in_src;     // [IND][SP] source state of in-edge k of state j (padding: j itself, weight 0)
   const double *in_T;    // [IND][SP] P(src -> j)
@@ -50,6 +50,8 @@ struct SparseTables {
     int pw = 1;
     for (int i = 0; i < Kmax; i++) pw *= a;
     F.hpow = pw; F.a_pow2 = (a & (a - 1)) == 0; F.inv_a = 1.0 / a;
+    F.ashift = 0;
+    while ((1 << F.ashift) < a) F.ashift++;
     F.in_src = d_in_src; F.in_T = d_in_T; F.out_dst = d_out_dst; F.out_T = d_out_T; F.pi = d_pi; F.fin = d_fin; F.E = d_E; F.korder = d_korder;
     return F;
   }
@@ -158,8 +160,16 @@ __device__ __forceinline__ int hash_at(const SparseDev &F, ResReader &rd, int64_
 }
 __device__ __forceinline__ int hash_back(const SparseDev &F, ResReader &rd, int h, int64_t pos) {  // pos -> pos-1
   int64_t q = pos - 1 - F.Kmax;
-  return h / F.a + (q >= 0 ? F.hpow * rd.get(q) : 0);
+  return (F.a_pow2 ? (h >> F.ashift) : (h / F.a)) + (q >= 0 ? F.hpow * rd.get(q) : 0);
 }
+__device__ __forceinline__ int hash_fwd(const SparseDev &F, ResReader &rd, int h, int64_t pos) {  // pos-1 -> pos
+  return F.a_pow2 ? (((h << F.ashift) | rd.get(pos)) & (F.H - 1)) : ((h * F.a + rd.get(pos)) % F.H);
+}
+// The DP vector lives in shared memory "lane fastest": state j of lane j / SPL sits at slot (j % SPL) * 32 + j / SPL, so
+// the lanes' accesses to their u-th state (and to a neighbour state at a fixed distance, the common banded case) are
+// consecutive doubles: no bank conflicts.
+template <int SPL>
+__device__ __forceinline__ int slot_of(int j) { return (j % SPL) * 32 + j / SPL; }
 
 // exact rescale of the warp's vector: divide by 2^e, e = exponent of the maximum; false when the maximum has left the
 // safe range (80 binades above the denormals, see kernels_mma.cuh)
@@ -198,6 +208,12 @@ __device__ __forceinline__ void load_vec(const double *src, double (&v)[SPL]) {
   }
 }
 
+template <int SPL>
+__device__ __forceinline__ void put_shared(double *vec, int lane, const double (&v)[SPL]) {
+#pragma unroll
+  for (int u = 0; u < SPL; u++) vec[u * 32 + lane] = v[u];
+}
+
 // emission probabilities of the lane's states at position pos (context hash h)
 template <int SPL>
 __device__ __forceinline__ void emis(const SparseDev &F, const double *sE, int lane, double (&e)[SPL], int h, int64_t pos) {
@@ -218,7 +234,7 @@ struct Edges {  // the lane's edge lists in registers: byte offsets into the sha
     for (int k = 0; k < IND; k++)
 #pragma unroll
       for (int u = 0; u < SPL; u++) {
-        off[k][u] = idx[(size_t)k * SP + SPL * lane + u] * 8;
+        off[k][u] = slot_of<SPL>(idx[(size_t)k * SP + SPL * lane + u]) * 8;
         w[k][u] = T[(size_t)k * SP + SPL * lane + u];
       }
   }
@@ -238,12 +254,87 @@ struct Edges {  // the lane's edge lists in registers: byte offsets into the sha
   }
 };
 
-constexpr int RS_SPARSE = 4;  // positions between two rescales
+constexpr int RS_SPARSE = 8;  // positions between two rescales
+
+// ---- residue streams ----------------------------------------------------------------------------------------------
+// The position loops are latency bound (one dependent step per position and warp), so the residues are pulled through
+// registers 16 at a time (one 128-bit load per block, the next block prefetched) and extracted with compile-time shifts;
+// all index arithmetic inside a sequence is 32 bit (Jstacs sequence lengths are ints).
+struct SeqBlocks {
+  const uint4 *base;  // 16-byte aligned address at or before residue 0
+  int mis;            // residue t sits at byte t + mis
+  __device__ __forceinline__ void init(const uint8_t *seq) {
+    mis = (int)((unsigned long long)seq & 15ull);
+    base = reinterpret_cast<const uint4 *>(seq - mis);
+  }
+  __device__ __forceinline__ uint4 load(int blk) const { return blk >= 0 ? __ldg(base + blk) : make_uint4(0, 0, 0, 0); }
+};
+
+// step(t, x[t]) for t = ta .. tb ascending.  Whole 16-byte blocks run word by word (the four words rotate through one
+// register, the four bytes of a word are unrolled), so the loop body stays small enough for the instruction cache — a
+// warp that is alone on its SM cannot hide instruction fetches; the ragged head and tail go position by position.
+template <typename Step>
+__device__ __forceinline__ void for_residues_up(const SeqBlocks &B, int ta, int tb, Step step) {
+  if (tb < ta) return;
+  const uint8_t *bytes = reinterpret_cast<const uint8_t *>(B.base) + B.mis;  // residue t = bytes[t]
+  int t = ta;
+  const int head_end = min(tb + 1, ((ta + B.mis + 15) & ~15) - B.mis);  // first block boundary at or after ta
+  for (; t < head_end; t++) step(t, (int)__ldg(bytes + t));
+  int blk = (t + B.mis) >> 4;
+  uint4 cur = B.load(blk);
+  for (; t + 15 <= tb; t += 16, blk++) {
+    const uint4 nxt = B.load(blk + 1);  // the code buffer is padded: one block past the end is readable
+    unsigned w0 = cur.x, w1 = cur.y, w2 = cur.z, w3 = cur.w;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      step(t + 4 * k, (int)(w0 & 0xffu));
+      step(t + 4 * k + 1, (int)((w0 >> 8) & 0xffu));
+      step(t + 4 * k + 2, (int)((w0 >> 16) & 0xffu));
+      step(t + 4 * k + 3, (int)(w0 >> 24));
+      w0 = w1; w1 = w2; w2 = w3;
+    }
+    cur = nxt;
+  }
+  for (; t <= tb; t++) step(t, (int)__ldg(bytes + t));
+}
+// step(p, x[p]) for p = pb .. pa descending; positions below 0 deliver 0
+template <typename Step>
+__device__ __forceinline__ void for_residues_down(const SeqBlocks &B, int pb, int pa, Step step) {
+  if (pb < pa) return;
+  const uint8_t *bytes = reinterpret_cast<const uint8_t *>(B.base) + B.mis;
+  int p = pb;
+  const int head_end = max(pa - 1, max(-1, ((pb + B.mis + 1) & ~15) - B.mis - 1));  // last position of the block below, >= -1
+  for (; p > head_end; p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+  if (p >= 15) {
+    int blk = (p + B.mis) >> 4;
+    uint4 cur = B.load(blk);
+    for (; p - 15 >= pa && p - 15 >= 0; p -= 16, blk--) {
+      const uint4 nxt = B.load(blk - 1);
+      unsigned w0 = cur.w, w1 = cur.z, w2 = cur.y, w3 = cur.x;
+#pragma unroll 1
+      for (int k = 0; k < 4; k++) {
+        step(p - 4 * k, (int)(w0 >> 24));
+        step(p - 4 * k - 1, (int)((w0 >> 16) & 0xffu));
+        step(p - 4 * k - 2, (int)((w0 >> 8) & 0xffu));
+        step(p - 4 * k - 3, (int)(w0 & 0xffu));
+        w0 = w1; w1 = w2; w2 = w3;
+      }
+      cur = nxt;
+    }
+  }
+  for (; p >= pa; p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+}
+__device__ __forceinline__ int roll_up(const SparseDev &F, int h, int x) {  // h(t-1), x[t] -> h(t)
+  return F.a_pow2 ? (((h << F.ashift) | x) & (F.H - 1)) : ((h * F.a + x) % F.H);
+}
+__device__ __forceinline__ int roll_down(const SparseDev &F, int h, int x) {  // h(t), x[t-1-K] (0 before the start) -> h(t-1)
+  return (F.a_pow2 ? (h >> F.ashift) : (h / F.a)) + F.hpow * x;
+}
 
 // Phase 1 / scoring.  Work item w: sequence w>>1 ... direction w&1 when both directions run (n_dir == 2), else forward only.
 // ck_alpha / ck_beta: [chunk_ptr[seq] + c][SP]; loglik[seq]; fallback: sequences the scaled recursion could not finish.
 template <int SPL, int IND>
-__global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, int n_dir, int64_t CK, const int64_t *chunk_ptr, double *ck_alpha,
+__global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, int n_dir, int CK, const int64_t *chunk_ptr, double *ck_alpha,
                                                       double *ck_beta, unsigned long long *counter, double *loglik, int32_t *fallback) {
   extern __shared__ double sm[];
   const int SP = F.SP;
@@ -254,6 +345,7 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
   ResReader rd;
+  SeqBlocks blocks;
   for (;;) {
     long long it = 0;
     if (lane == 0) it = (long long)atomicAdd(counter, 1ull);
@@ -261,34 +353,46 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
     if (it >= D.n_seq * n_dir) break;
     const int sid = D.order[it / n_dir];
     const bool backward = n_dir == 2 && (it & 1);
-    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    const int64_t off = D.offsets[sid];
+    const int L = (int)(D.offsets[sid + 1] - off);
     rd.init(D.codes + off);
+    blocks.init(D.codes + off);
     const int64_t cbase = chunk_ptr ? chunk_ptr[sid] : 0;
     if (!backward) {
       Edges<SPL, IND> G;
       G.load(F.in_src, F.in_T, SP, lane);
-      double f[SPL], e[SPL];
+      double f[SPL];
       long long A = 0;
       bool ok = true;
       int h = hash_at(F, rd, 0);
-      emis<SPL>(F, sE, lane, e, hmod_of(F, h), 0);
+      {
+        double e[SPL];
+        emis<SPL>(F, sE, lane, e, hmod_of(F, h), 0);
 #pragma unroll
-      for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+        for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+      }
       ok = rescale_warp<SPL>(f, A);
-      int par = 0;
-      for (int64_t t = 1; t < L; t++) {
-        double *v = vec + par * SP;
-        par ^= 1;
-        store_vec<SPL>(v + SPL * lane, f);
-        if (ck_alpha && t % CK == 0) store_vec<SPL>(ck_alpha + (size_t)(cbase + t / CK) * SP + SPL * lane, f);  // vector before chunk t/CK
-        h = hmod_of(F, h * F.a + rd.get(t));
-        emis<SPL>(F, sE, lane, e, h, t);
+      int par = 0, ck_left = CK;  // steps until the next checkpoint (the vector BEFORE chunk c = alpha_{c*CK-1}, stored in step t = c*CK)
+      double *ck_dst = ck_alpha ? ck_alpha + (size_t)(cbase + 1) * SP + SPL * lane : nullptr;
+      auto step = [&](int t, int x) {  // alpha_{t-1} -> alpha_t
+        h = roll_up(F, h, x);
+        double e[SPL];
+        emis<SPL>(F, sE, lane, e, h, t);  // issued first: its latency hides behind the exchange of the vector
+        double *v = vec + par;
+        par ^= SP;
+        put_shared<SPL>(v, lane, f);
+        if (ck_dst && --ck_left == 0) {
+          store_vec<SPL>(ck_dst, f);
+          ck_dst += SP;
+          ck_left = CK;
+        }
         __syncwarp();
         G.gather(v, f);
 #pragma unroll
         for (int u = 0; u < SPL; u++) f[u] *= e[u];
         if ((t & (RS_SPARSE - 1)) == 0) ok &= rescale_warp<SPL>(f, A);
-      }
+      };
+      for_residues_up(blocks, 1, L - 1, step);
       ok &= rescale_warp<SPL>(f, A);
       double sfin = 0;
 #pragma unroll
@@ -312,20 +416,33 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
       for (int u = 0; u < SPL; u++) b[u] = F.fin[SPL * lane + u];
       int h = hash_at(F, rd, L - 1);
       int par = 0;
-      for (int64_t t = L - 1; t >= 1; --t) {  // beta_t -> beta_{t-1}
-        if ((t + 1) % CK == 0 && t + 1 < L) store_vec<SPL>(ck_beta + (size_t)(cbase + t / CK) * SP + SPL * lane, b);  // beta at the last position of chunk t/CK
-        emis<SPL>(F, sE, lane, e, hmod_of(F, h), t);
-        double *v = vec + par * SP;
-        par ^= 1;
-        double x[SPL];
+      emis<SPL>(F, sE, lane, e, hmod_of(F, h), L - 1);
+      // checkpoints: beta at the last position of chunk c, t = (c+1)*CK - 1 < L - 1
+      const int n_full = (L - 1) / CK;            // chunks that end before position L-1
+      int ck_left = n_full > 0 ? (L - 1) - (n_full * CK - 1) : 0x7fffffff;  // steps until t reaches n_full*CK-1
+      double *ck_dst = ck_beta + (size_t)(cbase + n_full - 1) * SP + SPL * lane;
+      const int K1 = F.Kmax + 1;
+      auto step = [&](int p, int x) {  // t = p + K + 1: beta_t -> beta_{t-1}; x = x[t-1-K] completes the hash of t-1
+        const int t = p + K1;
+        if (ck_left == 0) {
+          store_vec<SPL>(ck_dst, b);
+          ck_dst -= SP;
+          ck_left = CK;
+        }
+        --ck_left;
+        double *v = vec + par;
+        par ^= SP;
+        double xb[SPL];
 #pragma unroll
-        for (int u = 0; u < SPL; u++) x[u] = e[u] * b[u];
-        store_vec<SPL>(v + SPL * lane, x);
-        h = hash_back(F, rd, h, t);
+        for (int u = 0; u < SPL; u++) xb[u] = e[u] * b[u];
+        put_shared<SPL>(v, lane, xb);
+        h = roll_down(F, h, x);
+        emis<SPL>(F, sE, lane, e, h, t - 1);  // for the next step, in flight during the exchange
         __syncwarp();
         G.gather(v, b);
         if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(b, Bx);
-      }
+      };
+      for_residues_down(blocks, L - 2 - F.Kmax, -F.Kmax, step);  // t = L-1 .. 1
     }
     __syncwarp();
   }
@@ -333,7 +450,7 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
 
 // Phase 2: posterior decoding of one chunk per warp.  chunk_seq / chunk_idx: the chunk list; rows: [warp slot][CK][SP].
 template <int SPL, int IND>
-__global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int64_t CK, int64_t n_chunks, const int32_t *chunk_seq,
+__global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int CK, int64_t n_chunks, const int32_t *chunk_seq,
                                                               const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
                                                               const double *ck_beta, unsigned long long *counter, double *rows, int32_t *paths) {
   extern __shared__ double sm[];
@@ -347,56 +464,67 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
   const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   double *const R = rows + (size_t)slot * CK * SP + SPL * lane;
   ResReader rd;
+  SeqBlocks blocks;
   Edges<SPL, IND> Gin, Gout;
   Gin.load(F.in_src, F.in_T, SP, lane);
   Gout.load(F.out_dst, F.out_T, SP, lane);
+  const int K1 = F.Kmax + 1;
   for (;;) {
     long long g = 0;
     if (lane == 0) g = (long long)atomicAdd(counter, 1ull);
     g = __shfl_sync(FULL, g, 0);
     if (g >= n_chunks) break;
     const int sid = chunk_seq[g], c = chunk_idx[g];
-    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
-    const int64_t t0 = (int64_t)c * CK, t1 = min(L, t0 + CK) - 1;
+    const int64_t off = D.offsets[sid];
+    const int L = (int)(D.offsets[sid + 1] - off);
+    const int t0 = c * CK, t1 = min(L, t0 + CK) - 1;
     const int64_t cb = chunk_ptr[sid] + c;
     rd.init(D.codes + off);
+    blocks.init(D.codes + off);
     // ---- forward rows of the chunk ----
-    double f[SPL], e[SPL];
+    double f[SPL];
     long long dummy = 0;
     int h = hmod_of(F, hash_at(F, rd, t0));
-    emis<SPL>(F, sE, lane, e, h, t0);
     int par = 0;
-    if (c == 0) {
+    {
+      double e[SPL];
+      emis<SPL>(F, sE, lane, e, h, t0);
+      if (c == 0) {
 #pragma unroll
-      for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
-    } else {
-      double *v = vec + par * SP;
-      par ^= 1;
-      double a0[SPL];
-      load_vec<SPL>(ck_alpha + (size_t)cb * SP + SPL * lane, a0);
-      store_vec<SPL>(v + SPL * lane, a0);
-      __syncwarp();
-      Gin.gather(v, f);
+        for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+      } else {
+        double *v = vec + par;
+        par ^= SP;
+        double a0[SPL];
+        load_vec<SPL>(ck_alpha + (size_t)cb * SP + SPL * lane, a0);
+        put_shared<SPL>(v, lane, a0);
+        __syncwarp();
+        Gin.gather(v, f);
 #pragma unroll
-      for (int u = 0; u < SPL; u++) f[u] *= e[u];
+        for (int u = 0; u < SPL; u++) f[u] *= e[u];
+      }
     }
     rescale_warp<SPL>(f, dummy);
     store_vec<SPL>(R, f);
-    for (int64_t t = t0 + 1; t <= t1; t++) {
-      double *v = vec + par * SP;
-      par ^= 1;
-      store_vec<SPL>(v + SPL * lane, f);
-      h = hmod_of(F, h * F.a + rd.get(t));
+    double *rdst = R;
+    auto fstep = [&](int t, int x) {
+      h = roll_up(F, h, x);
+      double e[SPL];
       emis<SPL>(F, sE, lane, e, h, t);
+      double *v = vec + par;
+      par ^= SP;
+      put_shared<SPL>(v, lane, f);
       __syncwarp();
       Gin.gather(v, f);
 #pragma unroll
       for (int u = 0; u < SPL; u++) f[u] *= e[u];
       if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(f, dummy);
-      store_vec<SPL>(R + (size_t)(t - t0) * SP, f);
-    }
+      rdst += SP;
+      store_vec<SPL>(rdst, f);
+    };
+    for_residues_up(blocks, t0 + 1, t1, fstep);
     // ---- backward through the chunk, decision per position ----
-    double b[SPL];
+    double b[SPL], e[SPL], a[SPL];
     if (t1 == L - 1) {
 #pragma unroll
       for (int u = 0; u < SPL; u++) b[u] = F.fin[SPL * lane + u];
@@ -405,10 +533,9 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
     }
     int hb = hash_at(F, rd, t1);
     int32_t *const prow = paths + off;
-    for (int64_t t = t1; t >= t0; --t) {
-      double a[SPL];
-      load_vec<SPL>(R + (size_t)(t - t0) * SP, a);
-      // posterior decision: largest alpha_t[j] * beta_t[j], lowest state index on ties
+    emis<SPL>(F, sE, lane, e, hmod_of(F, hb), t1);
+    load_vec<SPL>(rdst, a);
+    auto decide = [&](int t) {  // largest alpha_t[j] * beta_t[j], lowest state index on ties
       double best = a[0] * b[0];
       int arg = SPL * lane;
 #pragma unroll
@@ -423,20 +550,26 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
         if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
       }
       if (lane == 0) prow[t] = arg;
-      if (t > t0) {
-        emis<SPL>(F, sE, lane, e, hmod_of(F, hb), t);
-        double *v = vec + par * SP;
-        par ^= 1;
-        double x[SPL];
+    };
+    auto bstep = [&](int p, int x) {  // t = p + K + 1 > t0: decision of position t, then beta_t -> beta_{t-1}
+      const int t = p + K1;
+      double *v = vec + par;
+      par ^= SP;
+      double xb[SPL];
 #pragma unroll
-        for (int u = 0; u < SPL; u++) x[u] = e[u] * b[u];
-        store_vec<SPL>(v + SPL * lane, x);
-        hb = hash_back(F, rd, hb, t);
-        __syncwarp();
-        Gout.gather(v, b);
-        if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(b, dummy);
-      }
-    }
+      for (int u = 0; u < SPL; u++) xb[u] = e[u] * b[u];
+      put_shared<SPL>(v, lane, xb);
+      hb = roll_down(F, hb, x);
+      emis<SPL>(F, sE, lane, e, hb, t - 1);
+      decide(t);  // its shuffles overlap the exchange
+      rdst -= SP;
+      load_vec<SPL>(rdst, a);
+      __syncwarp();
+      Gout.gather(v, b);
+      if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(b, dummy);
+    };
+    for_residues_down(blocks, t1 - K1, t0 + 1 - K1, bstep);  // t = t1 .. t0+1
+    decide(t0);
     __syncwarp();
   }
 }
