@@ -13,6 +13,7 @@
 #include "kernels_fast.cuh"
 #include "kernels_general.cuh"
 #include "kernels_mma.cuh"
+#include "kernels_lanes.cuh"
 #include "kernels_sparse.cuh"
 #include "kernels_viterbi.cuh"
 
@@ -926,6 +927,70 @@ static int launch_mma_loglik(jh_model *m, jh_dataset *d, double *d_out) {
   return JH_OK;
 }
 
+// Lane-per-sequence kernels for 2..4 states (kernels_lanes.cuh).  mode 1: E-step of bucket b; mode 0: scoring of all octets.
+template <int S, int MODE>
+static int launch_lanes(jh_model *m, jh_dataset *d, size_t b, double *d_out) {
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhl::k_lanes<S, MODE>;
+  const int64_t oct0 = MODE == 1 ? d->bucket_oct_ptr[b] : 0;
+  const int64_t n_oct = MODE == 1 ? d->bucket_oct_ptr[b + 1] - oct0 : (int64_t)d->oct_hbase.size() - 1;
+  const int64_t rows = MODE == 1 ? d->bucket_len[b] + 1 : 0;
+  if (n_oct <= 0) return JH_OK;
+  const int NT = 128, wpc = NT / 32, HS = F.H * S;
+  const int ec_smem = MODE == 1 && (size_t)HS * 32 * wpc * sizeof(double) <= 96 * 1024;
+  size_t smem = ((size_t)HS + (ec_smem ? (size_t)HS * 32 * wpc : 0)) * sizeof(double);
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) { jh_set_error("lane-per-sequence kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  const int64_t n_quads = (n_oct + 3) / 4;
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_quads + wpc - 1) / wpc);
+  if (MODE == 1) {
+    const int64_t per_slot = rows * 32 * (S * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+    const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
+    if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+    grid = std::min(grid, max_slots / wpc);
+  }
+  grid = std::max<int64_t>(1, grid);
+  const int64_t slots = grid * wpc;
+  if (MODE == 1) {
+    int r = m->d_fwd.reserve((size_t)slots * rows * 32 * S);
+    if (r) return r;
+    if ((size_t)slots * rows * 32 > F.fexp_n) {
+      if (F.d_fexp) cudaFree(F.d_fexp);
+      F.d_fexp = nullptr;
+      F.fexp_n = 0;
+      if (cudaMalloc(&F.d_fexp, (size_t)slots * rows * 32 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); jh_set_error("out of device memory (exponent scratch)"); return JH_ERR_NOMEM; }
+      F.fexp_n = (size_t)slots * rows * 32;
+    }
+  }
+  jhm::OctData D;
+  D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
+  D.weights = (MODE == 1 && d->has_weights) ? d->d_weights.p : nullptr; D.n_oct = n_oct;
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, NT, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, F.d_ec, m->d_fallback.p, d_out, ec_smem);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+static int run_loglik_lanes(jh_model *m, jh_dataset *d, double *d_out) {
+  int r = ensure_octet_hashes(m, d);
+  if (r) return r;
+  if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  r = m->fast.G == 2 ? launch_lanes<2, 0>(m, d, 0, d_out) : launch_lanes<4, 0>(m, d, 0, d_out);
+  if (r) return r;
+  int32_t n_fb = 0;
+  JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  if (n_fb > 0) return run_loglik_exact(m, d, d_out, m->d_fallback.p + 1, n_fb);
+  return JH_OK;
+}
+
 static int run_loglik_octets(jh_model *m, jh_dataset *d, double *d_out) {
   int r = ensure_octet_hashes(m, d);
   if (r) return r;
@@ -954,6 +1019,7 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
     r = run_general_loglik(m, d, W, d_out.p);
   } else if (g_opt.fast && m->sparse.usable) r = run_loglik_sparse(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
+  else if (g_opt.fast && m->fast.usable && m->fast.G <= 4 && g_opt.fast_variant == 0) r = run_loglik_lanes(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
   else r = run_loglik_exact(m, d, d_out.p, nullptr, 0);
   timing_end(m);
@@ -1347,9 +1413,11 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
   int r = JH_OK;
   JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * jhf::EC_REPLICAS * m->fast.H * m->fast.G, m->st()));
   const bool octets = g_opt.fast_variant == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
+  const bool lanes = g_opt.fast_variant == 0 && m->fast.G <= 4;  // one sequence per lane
+  for (size_t b = 0; lanes && b + 1 < d->bucket_ptr.size() && !r; b++) r = m->fast.G == 2 ? launch_lanes<2, 1>(m, d, b, nullptr) : launch_lanes<4, 1>(m, d, b, nullptr);
   for (size_t b = 0; octets && b + 1 < d->bucket_ptr.size() && !r; b++)
     r = m->fast.G == 8 ? launch_mma_estep<1>(m, d, b) : m->fast.G == 16 ? launch_mma_estep<2>(m, d, b) : launch_mma_estep<4>(m, d, b);
-  for (size_t b = 0; !octets && b + 1 < d->bucket_ptr.size() && !r; b++) {
+  for (size_t b = 0; !octets && !lanes && b + 1 < d->bucket_ptr.size() && !r; b++) {
     int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b] + 1;
     const bool p2 = (m->a & (m->a - 1)) == 0;
 #define JH_FE(GG, NTT, NSS) (p2 ? launch_fast_estep<GG, NTT, true, NSS>(m, d, first, count, rows) : launch_fast_estep<GG, NTT, false, NSS>(m, d, first, count, rows))
@@ -1390,7 +1458,7 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
     int32_t *flag = m->d_fallback.p + d->n_seq + 1;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
     JH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
-    if (g_opt.fast_variant == 0 && m->fast.G >= 8 && (r = ensure_octet_hashes(m, d))) return r;
+    if (g_opt.fast_variant == 0 && (r = ensure_octet_hashes(m, d))) return r;
     cudaEventRecord(m->evk0, s);
     r = run_estep_fast(m, d);
     cudaEventRecord(m->evk1, s);

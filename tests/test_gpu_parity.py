@@ -240,7 +240,7 @@ def test_zero_probability_parameters(nat, oracle_lib, fast):
 
 
 @pytest.mark.parametrize("variant", [0, 1, 3], ids=["octets_dmma", "warp_per_sequence", "two_sequences_per_warp"])
-@pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
+@pytest.mark.parametrize("name", ["erg_s2_k1", "erg_s3_k0_map", "sparse", "erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
 def test_fast_estep_variants_agree_with_oracle(nat, oracle_lib, name, variant):
     """Every mapping of the scaled E-step (octets on the FP64 MMA path, lane-per-state SIMT) gives the oracle's counts:
     ragged octets, a last octet with empty rows, weights, sequences shorter than the emission order."""
@@ -261,6 +261,8 @@ def test_fast_estep_variants_agree_with_oracle(nat, oracle_lib, name, variant):
             np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
             np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
             assert sc == pytest.approx(rsc, rel=LL_RTOL)
+        nd.set_weights(None)
+        np.testing.assert_allclose(eng.loglik(nd), om.loglik(data.codes, data.offsets), rtol=LL_RTOL)
     finally:
         nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
 
