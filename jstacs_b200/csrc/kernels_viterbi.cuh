@@ -171,27 +171,36 @@ __global__ void __launch_bounds__(128) k_viterbi_lanes(VitTables V, OctData D, u
       int32_t *p = paths + off;
       bool ok = ctx != 255u;
       p[0] = ok ? (int32_t)ctx : -1;
-      for (int l = 1; l < Lr; l++) {
-        const uint8_t *src = ch_base + (size_t)l * 32 * CB;
-        unsigned cw[NW];
-        if (NW == 1) cw[0] = *reinterpret_cast<const unsigned *>(src);
-        else if (NW == 2) {
-          const uint2 v = *reinterpret_cast<const uint2 *>(src);
-          cw[0] = v.x; cw[1] = v.y;
-        } else {
+      constexpr int TU = NW <= 2 ? 8 : (NW <= 4 ? 4 : 2);  // positions whose choice words are fetched together
+      for (int l0 = 1; l0 < Lr; l0 += TU) {
+        unsigned cw[TU][NW];
 #pragma unroll
-          for (int w = 0; w < NW; w += 4) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(src + 4 * w);
-            cw[w] = v.x; cw[w + 1] = v.y; cw[w + 2] = v.z; cw[w + 3] = v.w;
+        for (int k = 0; k < TU; k++) {  // independent loads first, the dependent walk afterwards
+          const uint8_t *src = ch_base + (size_t)min(l0 + k, Lr - 1) * 32 * CB;
+          if (NW == 1) cw[k][0] = *reinterpret_cast<const unsigned *>(src);
+          else if (NW == 2) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(src);
+            cw[k][0] = v.x; cw[k][1] = v.y;
+          } else {
+#pragma unroll
+            for (int w = 0; w < NW; w += 4) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(src + 4 * w);
+              cw[k][w] = v.x; cw[k][w + 1] = v.y; cw[k][w + 2] = v.z; cw[k][w + 3] = v.w;
+            }
           }
         }
-        unsigned word = cw[0];
 #pragma unroll
-        for (int w = 1; w < NW; w++) word = (ctx >> 2) == (unsigned)w ? cw[w] : word;
-        const unsigned nxt = (word >> ((ctx & 3u) * 8u)) & 0xffu;
-        ok = ok && nxt != 255u;
-        ctx = ok ? nxt : 0u;
-        p[l] = ok ? (int32_t)ctx : -1;
+        for (int k = 0; k < TU; k++) {
+          if (l0 + k < Lr) {
+            unsigned word = cw[k][0];
+#pragma unroll
+            for (int w = 1; w < NW; w++) word = (ctx >> 2) == (unsigned)w ? cw[k][w] : word;
+            const unsigned nxt = (word >> ((ctx & 3u) * 8u)) & 0xffu;
+            ok = ok && nxt != 255u;
+            ctx = ok ? nxt : 0u;
+            p[l0 + k] = ok ? (int32_t)ctx : -1;
+          }
+        }
       }
     }
     __syncwarp();
