@@ -794,6 +794,23 @@ static int run_general_estep(jh_model *m, jh_dataset *d) {
   return JH_OK;
 }
 
+// posterior matrix of one sequence (d_post) or posterior decoding of a work list with the thread-per-sequence kernel
+static int run_general_posterior(jh_model *m, jh_dataset *d, const jhg::WorkList &W, int64_t max_len, double *d_post, int32_t *d_paths, double *d_ll) {
+  int grid;
+  int64_t nthreads;
+  const int64_t layers = max_len + 1;
+  int r = plan_general(m, W.n, ((size_t)2 * layers * m->Cmax + m->S) * sizeof(double), &grid, &nthreads);
+  if (r) return r;
+  if ((r = m->d_fwd.reserve((size_t)layers * m->Cmax * nthreads)) || (r = m->d_rows.reserve((size_t)(layers * m->Cmax + m->S) * nthreads))) return r;
+  cudaStream_t s = m->st();
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  jhg::k_general_posterior<<<grid, 128, 0, s>>>(m->dev(), m->gen(), d->dev(), W, m->d_counter.p, m->d_fwd.p, m->d_rows.p,
+                                               m->d_rows.p + (size_t)layers * m->Cmax * nthreads, d_post, d_paths, d_ll);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
 // ---- sparse path (kernels_sparse.cuh): 33..256 states, chromosome-scale sequences ----------------------------------
 #define DISPATCH_SPARSE(P, ...)                                                             \
   switch ((P).SPL * 100 + (P).IND) {                                                        \
@@ -1211,7 +1228,6 @@ static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, 
 extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out) {
   int r = check_pair(m, d);
   if (r) return r;
-  if (m->has_silent) { jh_set_error("state posteriors of models with silent states are not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   if (seq_index < 0 || seq_index >= d->n_seq || !out) { jh_set_error("sequence index out of range"); return JH_ERR_INVALID; }
   int64_t L = d->offsets[seq_index + 1] - d->offsets[seq_index];
   DevBuf<double> d_post;
@@ -1219,6 +1235,13 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   if ((r = d_post.alloc((size_t)m->S * L)) || (r = d_list.alloc(1))) return r;
   int32_t sid = (int32_t)seq_index;
   JH_CUDA(cudaMemcpyAsync(d_list.p, &sid, sizeof(int32_t), cudaMemcpyHostToDevice, m->st()));
+  if (m->has_silent) {  // general context graph: silent states score -inf (silentZero, HigherOrderHMM.java:316)
+    jhg::WorkList W{d_list.p, nullptr, nullptr, 1};
+    if ((r = run_general_posterior(m, d, W, L, d_post.p, nullptr, nullptr))) return r;
+    JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
+    JH_CUDA(cudaStreamSynchronize(m->st()));
+    return JH_OK;
+  }
   // scratch sized for this sequence only
   int64_t saved = d->max_len;
   d->max_len = L;
@@ -1290,12 +1313,15 @@ static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
 extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik) {
   int r = check_pair(m, d);
   if (r) return r;
-  if (m->has_silent) { jh_set_error("state posteriors of models with silent states are not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   if (d->n_seq == 0) return JH_OK;
   DevBuf<int32_t> d_paths;
   DevBuf<double> d_ll;
   if ((r = d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
   timing_begin(m);
+  if (m->has_silent) {
+    jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
+    r = run_general_posterior(m, d, W, d->max_len, nullptr, d_paths.p, d_ll.p);
+  } else
   if (g_opt.fast && m->sparse.usable) r = run_decode_sparse(m, d, d_paths.p, d_ll.p);
   else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
   else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);

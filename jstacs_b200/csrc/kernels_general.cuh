@@ -248,6 +248,54 @@ __global__ void __launch_bounds__(128) k_general_viterbi(DevModel M, GenModel X,
   if (stats && score_sum != 0) atomicAdd(&stats[M.n_child + M.n_cond * M.a], score_sum);
 }
 
+// HOH:359-434 fillFwdMatrix in pull form: fwd[l][c] for l = 0..L.  Summand order of the reference's push form: emitting
+// in-edges from the previous layer by (source context, child), then silent in-edges of the same layer.
+__device__ __forceinline__ void general_forward(const DevModel &M, const GenModel &X, ResReader &rd, int64_t L, const Rows &Fw) {
+  int h = 0;  // context hash of position l-1 (emission of the children that entered layer l)
+  for (int64_t l = 0; l <= L; l++) {
+    const int lc = lc_of(M, l);
+    const int nc = M.lc_ctx_ptr[lc + 1] - M.lc_ctx_ptr[lc];
+    const int lcs = lc_of(M, l - 1);  // class of the source layer
+    const int *ip = M.in_ptr + (size_t)lcs * (M.Cmax + 1), *isrc = M.in_src + (size_t)lcs * M.n_child, *ipp = M.in_p + (size_t)lcs * M.n_child;
+    const int *sp = X.sin_ptr + (size_t)lc * (M.Cmax + 1), *ssrc = X.sin_src + (size_t)lc * M.n_child, *spp = X.sin_p + (size_t)lc * M.n_child;
+    if (l > 0) h = l == 1 ? jhx::hash_at(M, rd, 0) : jhx::hash_fwd(M, rd, h, l - 2);
+    for (int c = 0; c < nc; c++) {
+      double offm = JH_NEG_INF;
+      int n = 0;
+      if (l == 0 && c == 0) { offm = 0.0; n = 1; }  // the seed summand 0 (HOH:364-366)
+      if (l > 0)
+        for (int q = ip[c]; q < ip[c + 1]; q++) {
+          const int p = ipp[q];
+          const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], l - 1, h)), M.tscore[p]);
+          if (v > offm) offm = v;
+          n++;
+        }
+      for (int q = sp[c]; q < sp[c + 1]; q++) {
+        const double v = dadd(dadd(Fw.at(l, ssrc[q]), 0.0), M.tscore[spp[q]]);
+        if (v > offm) offm = v;
+        n++;
+      }
+      double r = JH_NEG_INF;
+      if (n > 0 && !isinf(offm)) {
+        double sum = 0;
+        if (l == 0 && c == 0) sum = dadd(sum, exp(dsub(0.0, offm)));
+        if (l > 0)
+          for (int q = ip[c]; q < ip[c + 1]; q++) {
+            const int p = ipp[q];
+            const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], l - 1, h)), M.tscore[p]);
+            sum = dadd(sum, exp(dsub(v, offm)));
+          }
+        for (int q = sp[c]; q < sp[c + 1]; q++) {
+          const double v = dadd(dadd(Fw.at(l, ssrc[q]), 0.0), M.tscore[spp[q]]);
+          sum = dadd(sum, exp(dsub(v, offm)));
+        }
+        r = dadd(offm, log(sum));
+      }
+      Fw.at(l, c) = r;
+    }
+  }
+}
+
 // Baum-Welch E-step for the general graph (HOH:471-571 with add == true): full forward matrix in pull form
 // (summand order of the reference's push form: emitting in-edges from the previous layer by (source context, child),
 // then silent in-edges of the same layer by (source context, child)), then the backward sweep with
@@ -267,50 +315,8 @@ __global__ void __launch_bounds__(128) k_general_estep(DevModel M, GenModel X, D
     const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
     const double w = D.weights ? D.weights[sid] : 1.0;
     rd.init(D.codes + off);
-    // ---------------- forward ----------------
-    int h = 0;  // context hash of position l-1 (emission of the children that entered layer l)
-    for (int64_t l = 0; l <= L; l++) {
-      const int lc = lc_of(M, l);
-      const int nc = M.lc_ctx_ptr[lc + 1] - M.lc_ctx_ptr[lc];
-      const int lcs = lc_of(M, l - 1);  // class of the source layer
-      const int *ip = M.in_ptr + (size_t)lcs * (M.Cmax + 1), *isrc = M.in_src + (size_t)lcs * M.n_child, *ipp = M.in_p + (size_t)lcs * M.n_child;
-      const int *sp = X.sin_ptr + (size_t)lc * (M.Cmax + 1), *ssrc = X.sin_src + (size_t)lc * M.n_child, *spp = X.sin_p + (size_t)lc * M.n_child;
-      if (l > 0) h = l == 1 ? jhx::hash_at(M, rd, 0) : jhx::hash_fwd(M, rd, h, l - 2);
-      for (int c = 0; c < nc; c++) {
-        double offm = JH_NEG_INF;
-        int n = 0;
-        if (l == 0 && c == 0) { offm = 0.0; n = 1; }  // the seed summand 0 (HOH:364-366)
-        if (l > 0)
-          for (int q = ip[c]; q < ip[c + 1]; q++) {
-            const int p = ipp[q];
-            const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], l - 1, h)), M.tscore[p]);
-            if (v > offm) offm = v;
-            n++;
-          }
-        for (int q = sp[c]; q < sp[c + 1]; q++) {
-          const double v = dadd(dadd(Fw.at(l, ssrc[q]), 0.0), M.tscore[spp[q]]);
-          if (v > offm) offm = v;
-          n++;
-        }
-        double r = JH_NEG_INF;
-        if (n > 0 && !isinf(offm)) {
-          double sum = 0;
-          if (l == 0 && c == 0) sum = dadd(sum, exp(dsub(0.0, offm)));
-          if (l > 0)
-            for (int q = ip[c]; q < ip[c + 1]; q++) {
-              const int p = ipp[q];
-              const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], l - 1, h)), M.tscore[p]);
-              sum = dadd(sum, exp(dsub(v, offm)));
-            }
-          for (int q = sp[c]; q < sp[c + 1]; q++) {
-            const double v = dadd(dadd(Fw.at(l, ssrc[q]), 0.0), M.tscore[spp[q]]);
-            sum = dadd(sum, exp(dsub(v, offm)));
-          }
-          r = dadd(offm, log(sum));
-        }
-        Fw.at(l, c) = r;
-      }
-    }
+    general_forward(M, X, rd, L, Fw);
+    int h = 0;
     // res = computeLogScoreFromForward(L) (HOH:1046-1058)
     double res = JH_NEG_INF;
     {
@@ -363,6 +369,53 @@ __global__ void __launch_bounds__(128) k_general_estep(DevModel M, GenModel X, D
     score_sum = dadd(score_sum, dmul(w, B.at(0, 0)));
   }
   if (score_sum != 0) atomicAdd(&stats[n_stats], score_sum);
+}
+
+// HOH:294-329 fillLogStatePosteriorMatrix(silentZero = true) + AHMM:790-797 for the general graph: full forward and
+// backward matrices per thread; post[s][l] = pairwise getLogSum over the contexts of layer l+1 that end in the emitting
+// state s of (fwd + bwd), minus bwd[0][0].  post_out != nullptr: the S x L matrix of work item 0's sequence (row-major);
+// paths != nullptr: AbstractHMM.decodeStatePosterior (AHMM:1125-1139) per position, lowest index on ties.
+// col: [S][thread] scratch column.
+__global__ void __launch_bounds__(128) k_general_posterior(DevModel M, GenModel X, DevData D, WorkList W, unsigned long long *counter, double *fwd,
+                                                           double *bwd, double *col, double *post_out, int32_t *paths, double *loglik) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+  Rows Fw{fwd + tid, nthreads, M.Cmax}, B{bwd + tid, nthreads, M.Cmax};
+  double *const cl = col + tid;  // + s*nthreads
+  ResReader rd;
+  for (;;) {
+    const long long it = (long long)atomicAdd(counter, 1ull);
+    if (it >= W.n) break;
+    const int sid = W.seq ? W.seq[it] : D.order[it];
+    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    rd.init(D.codes + off);
+    general_forward(M, X, rd, L, Fw);
+    bwd_last_layer<false>(M, X, L, B, L, nullptr, 0);
+    int h = L > 0 ? jhx::hash_at(M, rd, L - 1) : 0;
+    for (int64_t l = L - 1; l >= 0; --l) {
+      bwd_layer<false>(M, X, l, B, l, l + 1, l, h, nullptr, 0);
+      if (l > 0) h = jhx::hash_back(M, rd, h, l);
+    }
+    const double lp = B.at(0, 0);
+    if (loglik) loglik[sid] = lp;
+    for (int64_t l = 1; l <= L; l++) {
+      for (int st = 0; st < M.S; st++) cl[(size_t)st * nthreads] = JH_NEG_INF;
+      const int lc = lc_of(M, l);
+      const int nc = M.lc_ctx_ptr[lc + 1] - M.lc_ctx_ptr[lc];
+      for (int c = 0; c < nc; c++) {
+        const int st = M.ctx_last[M.lc_ctx_ptr[lc] + c];
+        if (st >= 0 && !X.silent[st]) cl[(size_t)st * nthreads] = lse2(cl[(size_t)st * nthreads], dadd(Fw.at(l, c), B.at(l, c)));
+      }
+      int best = 0;
+      double bv = dsub(cl[0], lp);
+      if (post_out) post_out[l - 1] = bv;
+      for (int st = 1; st < M.S; st++) {
+        const double v = dsub(cl[(size_t)st * nthreads], lp);
+        if (post_out) post_out[(size_t)st * L + (l - 1)] = v;
+        if (bv < v) { bv = v; best = st; }
+      }
+      if (paths) paths[off + l - 1] = best;
+    }
+  }
 }
 
 }  // namespace jhg

@@ -319,6 +319,20 @@ def test_silent_states_loglik_viterbi_counts_training(nat, oracle_lib):
         np.testing.assert_allclose(es, res_, rtol=1e-13)
         assert sc == pytest.approx(rsc, rel=1e-13)
     nd.set_weights(None)
+    # state posteriors (silent states score -inf: silentZero, HigherOrderHMM.java:316) and posterior decoding
+    mats = hmm.getLogStatePosteriorMatrixFor(data)
+    dec = hmm.decodePosteriorPathsFor(data)
+    ll_ref = om.loglik(data.codes, data.offsets)
+    for i in range(data.getNumberOfElements()):
+        ref = om.posterior(data.getElementAt(i).codes)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(mats[i]), fin)
+        np.testing.assert_allclose(mats[i][fin], ref[fin], rtol=0, atol=1e-10)
+        path, ll = dec[i]
+        assert ll == pytest.approx(ll_ref[i], rel=1e-12)
+        srt = np.sort(ref, axis=0)
+        clear = srt[-1] - srt[-2] > 1e-9
+        assert np.array_equal(path[clear], om.decode_posterior(ref)[clear])
     # EM
     hmm.trainingParameter = BaumWelchParameterSet(1, IterationCondition(5), 1)
     hmm.train(data)
