@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences of the CPU sample (0: 400 per core)")
+    ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="library tuning option (jh_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -176,6 +177,9 @@ def main():
     _native.check(L.jh_set_stream(stream.cuda_stream or 1))
     _native.check(L.jh_set_option(b"fast", args.fast))
     _native.check(L.jh_set_option(b"fast_variant", args.variant))
+    for kv in args.set:
+        name, value = kv.split("=")
+        _native.check(L.jh_set_option(name.encode(), int(value)))
 
     S = args.states
     hmm = ergodic_hmm(S, args.order, n_iter=1, ess=4.0)
