@@ -812,8 +812,21 @@ static int run_general_posterior(jh_model *m, jh_dataset *d, const jhg::WorkList
 }
 
 // ---- sparse path (kernels_sparse.cuh): 33..256 states, chromosome-scale sequences ----------------------------------
+// One warp per sequence/chunk.  Models with more than 32 states always take it; smaller ones when the data set is a few long
+// sequences (the octet kernels need 8 sequences per warp to fill the GPU and (L+1) x 8 x G doubles of scratch per warp).
+static bool prefer_sparse(const jh_model *m, const jh_dataset *d) {
+  if (!g_opt.fast || !m->sparse.usable) return false;
+  if (m->S > 32 || g_opt.fast_variant == 4) return true;
+  if (g_opt.fast_variant != 0) return false;
+  return d->n_seq <= 1024 && d->max_len >= 16384;
+}
+
 #define DISPATCH_SPARSE(P, ...)                                                             \
   switch ((P).SPL * 100 + (P).IND) {                                                        \
+    case 104: { constexpr int SPL_ = 1, IND_ = 4; __VA_ARGS__; } break;                     \
+    case 108: { constexpr int SPL_ = 1, IND_ = 8; __VA_ARGS__; } break;                     \
+    case 116: { constexpr int SPL_ = 1, IND_ = 16; __VA_ARGS__; } break;                    \
+    case 132: { constexpr int SPL_ = 1, IND_ = 32; __VA_ARGS__; } break;                    \
     case 204: { constexpr int SPL_ = 2, IND_ = 4; __VA_ARGS__; } break;                     \
     case 208: { constexpr int SPL_ = 2, IND_ = 8; __VA_ARGS__; } break;                     \
     case 216: { constexpr int SPL_ = 2, IND_ = 16; __VA_ARGS__; } break;                    \
@@ -1034,7 +1047,7 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
   if (m->has_silent) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_loglik(m, d, W, d_out.p);
-  } else if (g_opt.fast && m->sparse.usable) r = run_loglik_sparse(m, d, d_out.p);
+  } else if (prefer_sparse(m, d)) r = run_loglik_sparse(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable && m->fast.G <= 4 && g_opt.fast_variant == 0) r = run_loglik_lanes(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
@@ -1322,7 +1335,7 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_posterior(m, d, W, d->max_len, nullptr, d_paths.p, d_ll.p);
   } else
-  if (g_opt.fast && m->sparse.usable) r = run_decode_sparse(m, d, d_paths.p, d_ll.p);
+  if (prefer_sparse(m, d)) r = run_decode_sparse(m, d, d_paths.p, d_ll.p);
   else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
   else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
   timing_end(m);

@@ -74,15 +74,16 @@ static int up(T **dst, const std::vector<T> &h, cudaStream_t s) {
   return JH_OK;
 }
 
-// Scope test + edge lists: plain first-order chain, no silent states, 33..256 states, at most 16 edges in and out per state.
+// Scope test + edge lists: plain first-order chain, no silent states, up to 256 states, SPL * IND <= 32 (S/32 states per lane times
+// the padded in-/out-degree): dense models up to 32 states, <= 16 edges per state up to 64 states, <= 8 up to 128, <= 4 up to 256.
 inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax, const std::vector<int> &lc_ctx_ptr, const std::vector<int> &ctx_elem,
                  const std::vector<int> &ctx_last, const std::vector<int> &elem_child_ptr, const std::vector<int> &child_state,
                  const std::vector<int> &state_order, const std::vector<int> &state_tab, const std::vector<int> &state_mod,
                  const std::vector<uint8_t> &state_final, cudaStream_t s) {
   F.usable = false;
-  if (m != 1 || has_silent || S <= 32 || S > 256) return JH_OK;
+  if (m != 1 || has_silent || S > 256) return JH_OK;
   if (lc_ctx_ptr[1] - lc_ctx_ptr[0] != 1) return JH_OK;
-  const int SPL = S <= 64 ? 2 : S <= 128 ? 4 : 8, SP = 32 * SPL;
+  const int SPL = S <= 32 ? 1 : S <= 64 ? 2 : S <= 128 ? 4 : 8, SP = 32 * SPL;
   int64_t H = a;
   for (int i = 0; i < Kmax; i++) H *= a;
   if (H * SP * 8 > 96 * 1024) return JH_OK;
@@ -99,8 +100,8 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
   }
   size_t deg = 1;
   for (int j = 0; j < S; j++) deg = std::max(deg, std::max(in[j].size(), out[j].size()));
-  if (deg > 16) return JH_OK;
-  const int IND = deg <= 4 ? 4 : deg <= 8 ? 8 : 16;
+  if (deg > 32) return JH_OK;
+  const int IND = deg <= 4 ? 4 : deg <= 8 ? 8 : deg <= 16 ? 16 : 32;
   if (SPL * IND > 32) return JH_OK;  // both edge lists of a lane have to fit into registers
   std::vector<int> in_src((size_t)IND * SP), out_dst((size_t)IND * SP), in_p((size_t)IND * SP, -1), out_p((size_t)IND * SP, -1), pimap(SP, -1),
       korder(SP, 0), etab(SP, -1), emod(SP, 1);
@@ -192,7 +193,7 @@ __device__ __forceinline__ void store_vec(double *dst, const double (&v)[SPL]) {
   if (SPL == 1) dst[0] = v[0];
   else {
 #pragma unroll
-    for (int u = 0; u < SPL; u += 2) *reinterpret_cast<double2 *>(dst + u) = make_double2(v[u], v[u + 1]);
+    for (int u = 0; u + 1 < SPL; u += 2) *reinterpret_cast<double2 *>(dst + u) = make_double2(v[u], v[u + 1]);
   }
 }
 template <int SPL>
@@ -200,7 +201,7 @@ __device__ __forceinline__ void load_vec(const double *src, double (&v)[SPL]) {
   if (SPL == 1) v[0] = src[0];
   else {
 #pragma unroll
-    for (int u = 0; u < SPL; u += 2) {
+    for (int u = 0; u + 1 < SPL; u += 2) {
       const double2 x = *reinterpret_cast<const double2 *>(src + u);
       v[u] = x.x;
       v[u + 1] = x.y;

@@ -398,6 +398,33 @@ def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, deg
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
 
 
+@pytest.mark.parametrize("name", ["erg_s2_k1", "sparse", "erg_s5_k2", "erg_s16_k1", "erg_s32_k3"])
+def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name):
+    """The checkpointed warp-per-sequence path (taken for a few long sequences) also covers models with <= 32 states:
+    forced here with fast_variant 4 and a tiny chunk length."""
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(5)
+    lens = np.concatenate([rng.integers(1, 6, 3), rng.integers(50, 500, 8), [32, 33, 63]])
+    data = dataset_of([random_dna(rng, int(L)) for L in lens])
+    nat.check(nat.lib().jh_set_option(b"fast_variant", 4))
+    nat.check(nat.lib().jh_set_option(b"chunk", 32))
+    try:
+        ll_ref = om.loglik(data.codes, data.offsets)
+        np.testing.assert_allclose(hmm.getLogScoreFor(data), ll_ref, rtol=LL_RTOL)
+        dec = hmm.decodePosteriorPathsFor(data)
+        for i in range(data.getNumberOfElements()):
+            ref = om.posterior(data.getElementAt(i).codes)
+            path, ll = dec[i]
+            assert ll == pytest.approx(ll_ref[i], rel=LL_RTOL)
+            srt = np.sort(ref, axis=0)
+            clear = srt[-1] - srt[-2] > 1e-9
+            assert np.array_equal(path[clear], om.decode_posterior(ref)[clear])
+    finally:
+        nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
+        nat.check(nat.lib().jh_set_option(b"chunk", 2048))
+
+
 def test_full_size_properties_cfg3_sample(nat):
     """BASELINE cfg3 model (32 states, order-3 emissions) on 16k x 1 kb sequences: size-independent properties.
     Transition counts add up to the residues, emission counts to the residues with a full context, the score is the
