@@ -135,6 +135,9 @@ struct jh_model {
   jhf::FastTables fast;        // linear-space tables of the fast path
   jhs::SparseTables sparse;    // edge lists of the sparse path (33..256 states)
   DevBuf<double> d_ck_alpha, d_ck_beta;  // checkpoint vectors of chromosome-scale decoding
+  DevBuf<long long> d_ck_exp, d_seq_AL;  // E-step: exponents of the checkpoints [2][n_chunks+1], of P(x) [n_seq]
+  DevBuf<double> d_seq_sfin;             // E-step: mantissa of P(x) [n_seq]
+  DevBuf<int> d_rexp;                    // E-step: exponents of the recomputed forward rows [slot][chunk]
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timed = false, ktimed = false;
@@ -194,9 +197,9 @@ struct jh_dataset {
   DevBuf<uint16_t> d_hashes;
   int hash_a = -1, hash_K = -1;
   // chunk list of the sparse decoding path (kernels_sparse.cuh), built per chunk length
-  int64_t chunk_len = 0, n_chunks = 0;
+  int64_t chunk_len = 0, n_chunks = 0, n_long = 0;
   DevBuf<int64_t> d_chunk_ptr;
-  DevBuf<int32_t> d_chunk_seq, d_chunk_idx;
+  DevBuf<int32_t> d_chunk_seq, d_chunk_idx, d_long;  // d_long: sequences of more than one chunk, longest first
   DevData dev(int64_t first = 0, int64_t count = -1) const {
     DevData D;
     D.codes = d_codes.p; D.offsets = d_offsets.p; D.weights = has_weights ? d_weights.p : nullptr;
@@ -454,7 +457,7 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
     return r;
   }
   if ((r = jhs::build(m->sparse, m->S, m->a, m->m, m->has_silent, m->Kmax, m->lc_ctx_ptr, m->ctx_elem, m->ctx_last, m->elem_child_ptr, m->child_state,
-                      m->state_order, m->state_tab, m->state_mod, m->state_final, s)) != 0) {
+                      m->child_stat, m->state_order, m->state_tab, m->state_mod, m->state_final, s)) != 0) {
     delete m;
     return r;
   }
@@ -841,30 +844,35 @@ static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK) {
   for (int64_t i = 0; i < d->n_seq; i++) ptr[i + 1] = ptr[i] + (d->offsets[i + 1] - d->offsets[i] + CK - 1) / CK;
   const int64_t n = ptr[d->n_seq];
   if (n > 0x7fffffff) { jh_set_error("too many chunks"); return JH_ERR_UNSUPPORTED; }
-  std::vector<int32_t> cs(std::max<int64_t>(n, 1)), ci(std::max<int64_t>(n, 1));
+  std::vector<int32_t> cs(std::max<int64_t>(n, 1)), ci(std::max<int64_t>(n, 1)), lg;
   int64_t g = 0;
   for (int64_t k = 0; k < d->n_seq; k++) {  // longest sequences first
     const int32_t sid = d->order[k];
+    if (ptr[sid + 1] - ptr[sid] > 1) lg.push_back(sid);
     for (int64_t c = 0; c < ptr[sid + 1] - ptr[sid]; c++, g++) { cs[g] = sid; ci[g] = (int32_t)c; }
   }
   cudaStream_t s = m->st();
   int r;
-  if ((r = d->d_chunk_ptr.upload(ptr, s)) || (r = d->d_chunk_seq.upload(cs, s)) || (r = d->d_chunk_idx.upload(ci, s))) return r;
+  if ((r = d->d_chunk_ptr.upload(ptr, s)) || (r = d->d_chunk_seq.upload(cs, s)) || (r = d->d_chunk_idx.upload(ci, s)) || (r = d->d_long.upload(lg, s))) return r;
   JH_CUDA(cudaStreamSynchronize(s));
   d->chunk_len = CK;
   d->n_chunks = n;
+  d->n_long = (int64_t)lg.size();
   return JH_OK;
 }
 
 // phase 1: n_dir = 1 scoring only, n_dir = 2 forward and backward warps with checkpoints
-static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll) {
+static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra *extra = nullptr) {
   jhs::SparseTables &P = m->sparse;
   cudaStream_t s = m->st();
   int r = m->d_fallback.reserve(d->n_seq + 2);
   if (r) return r;
+  jhs::Pass1Extra X{};
+  if (extra) X = *extra;
   JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  const int64_t items = d->n_seq * n_dir;
+  const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
+  if (items == 0) return JH_OK;
   const int NT = items <= 2 * (int64_t)m->sm_count ? 32 : 128;  // few long sequences: one warp per SM
   const size_t smem = ((size_t)P.H * P.SP + (size_t)(NT / 32) * 2 * P.SP) * sizeof(double);
   DISPATCH_SPARSE(P, {
@@ -875,7 +883,7 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll)
     if (per_sm < 1) { jh_set_error("sparse kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
     int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, (items + NT / 32 - 1) / (NT / 32)));
     kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), n_dir, (int)(d->chunk_len > 0 ? d->chunk_len : 1), n_dir == 2 ? d->d_chunk_ptr.p : nullptr,
-                                     n_dir == 2 ? m->d_ck_alpha.p : nullptr, n_dir == 2 ? m->d_ck_beta.p : nullptr, m->d_counter.p, d_ll, m->d_fallback.p);
+                                     n_dir == 2 ? m->d_ck_alpha.p : nullptr, n_dir == 2 ? m->d_ck_beta.p : nullptr, m->d_counter.p, d_ll, m->d_fallback.p, X);
     JH_LAUNCHED();
   });
   JH_CUDA(cudaGetLastError());
@@ -927,6 +935,57 @@ static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
   JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   JH_CUDA(cudaStreamSynchronize(s));
   if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_DECODE, d_paths, d_ll, nullptr, m->d_fallback.p + 1, n_fb);
+  return JH_OK;
+}
+
+// Baum-Welch E-step in two exact phases (kernels_sparse.cuh): sequences longer than a chunk get their checkpoints, P(x) and
+// the objective from k_sparse_pass1; then every chunk (and every sequence that is a single chunk) is an independent work item
+// of k_sparse_estep_chunks.  Scratch per resident warp: chunk x SP doubles, whatever the sequence length.
+static int run_estep_sparse(jh_model *m, jh_dataset *d) {
+  jhs::SparseTables &P = m->sparse;
+  cudaStream_t s = m->st();
+  const int64_t CK = g_opt.chunk;
+  int r = ensure_chunks(m, d, CK);
+  if (r) return r;
+  if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
+  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  const int64_t n_stats = m->n_stats();
+  if (d->n_long > 0) {
+    if ((r = m->d_ck_alpha.reserve((size_t)(d->n_chunks + 1) * P.SP)) || (r = m->d_ck_beta.reserve((size_t)(d->n_chunks + 1) * P.SP)) ||
+        (r = m->d_ck_exp.reserve((size_t)2 * (d->n_chunks + 1))) || (r = m->d_seq_sfin.reserve(d->n_seq)) || (r = m->d_seq_AL.reserve(d->n_seq)))
+      return r;
+    jhs::Pass1Extra X{};
+    X.ck_alpha_exp = m->d_ck_exp.p; X.ck_beta_exp = m->d_ck_exp.p + d->n_chunks + 1; X.seq_sfin = m->d_seq_sfin.p; X.seq_AL = m->d_seq_AL.p;
+    X.list = d->d_long.p; X.n_list = d->n_long; X.score = m->d_stats.p + n_stats;
+    if ((r = run_sparse_pass1(m, d, 2, nullptr, &X))) return r;
+  }
+  const int NT = 128, wpc = NT / 32;
+  const size_t smem = ((size_t)P.H * P.SP + (size_t)wpc * 2 * P.SP) * sizeof(double);
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  JH_CUDA(cudaMemsetAsync(P.d_ec, 0, sizeof(double) * jhs::EC_REPLICAS_SPARSE * P.H * P.SP, s));
+  jhs::EstepTables ET{P.d_out_stat, P.d_pistat, (int)n_stats};
+  DISPATCH_SPARSE(P, {
+    auto kern = jhs::k_sparse_estep_chunks<SPL_, IND_>;
+    if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) { jh_set_error("sparse E-step kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
+    if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+    int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);
+    const int64_t rows = std::min<int64_t>(CK, d->max_len);
+    const int64_t per_slot = rows * (P.SP * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, g_opt.scratch_mb * 1024 * 1024 / per_slot / wpc));
+    if ((r = m->d_fwd.reserve((size_t)grid * wpc * rows * P.SP)) || (r = m->d_rexp.reserve((size_t)grid * wpc * rows))) return r;
+    kern<<<(int)grid, NT, smem, s>>>(P.dev(), ET, d->dev(), (int)CK, (int)rows, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p,
+                                     m->d_ck_alpha.p, m->d_ck_beta.p, m->d_ck_exp.p, m->d_ck_exp.p + d->n_chunks + 1, m->d_seq_sfin.p, m->d_seq_AL.p,
+                                     m->d_counter.p, m->d_fwd.p, m->d_rexp.p, m->d_stats.p, P.d_ec, m->d_fallback.p);
+    JH_LAUNCHED();
+  });
+  JH_CUDA(cudaGetLastError());
+  const int n = P.H * P.SP;
+  jhs::k_sparse_fold_ec<<<(n + 255) / 256, 256, 0, s>>>(P.dev(), P.d_etab, P.d_emod, m->n_child, P.d_ec, m->d_stats.p);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
   return JH_OK;
 }
 
@@ -1491,15 +1550,16 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
     return r;
   }
   if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, nullptr, nullptr, m->d_stats.p);
-  if (g_opt.fast && m->fast.usable) {
+  const bool sparse = prefer_sparse(m, d);
+  if (sparse || (g_opt.fast && m->fast.usable)) {
     int r = m->d_fallback.reserve(d->n_seq + 2);
     if (r) return r;
     int32_t *flag = m->d_fallback.p + d->n_seq + 1;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
     JH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
-    if (g_opt.fast_variant == 0 && (r = ensure_octet_hashes(m, d))) return r;
+    if (!sparse && g_opt.fast_variant == 0 && (r = ensure_octet_hashes(m, d))) return r;
     cudaEventRecord(m->evk0, s);
-    r = run_estep_fast(m, d);
+    r = sparse ? run_estep_sparse(m, d) : run_estep_fast(m, d);
     cudaEventRecord(m->evk1, s);
     m->ktimed = true;
     if (r) return r;

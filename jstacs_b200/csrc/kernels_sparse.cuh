@@ -25,6 +25,8 @@ namespace jhs {
 
 using jhx::ResReader;
 
+constexpr int EC_REPLICAS_SPARSE = 8;  // replicas of the emission-count table of the E-step (spread over the L2 slices)
+
 struct SparseDev {
   int S, SP, a, Kmax, H, hpow, a_pow2, ashift;  // ashift = log2(a) when a is a power of two
   double inv_a;
@@ -42,8 +44,8 @@ struct SparseTables {
   bool usable = false;
   int S = 0, SP = 0, SPL = 0, IND = 0, a = 0, Kmax = 0, H = 0;
   int *d_in_src = nullptr, *d_out_dst = nullptr, *d_in_p = nullptr, *d_out_p = nullptr, *d_pimap = nullptr, *d_korder = nullptr,
-      *d_etab = nullptr, *d_emod = nullptr;
-  double *d_in_T = nullptr, *d_out_T = nullptr, *d_pi = nullptr, *d_fin = nullptr, *d_E = nullptr;
+      *d_etab = nullptr, *d_emod = nullptr, *d_out_stat = nullptr, *d_pistat = nullptr;
+  double *d_in_T = nullptr, *d_out_T = nullptr, *d_pi = nullptr, *d_fin = nullptr, *d_E = nullptr, *d_ec = nullptr;
   SparseDev dev() const {
     SparseDev F;
     F.S = S; F.SP = SP; F.a = a; F.Kmax = Kmax; F.H = H;
@@ -58,7 +60,8 @@ struct SparseTables {
 };
 
 inline void destroy(SparseTables &F) {
-  void *ptrs[] = {F.d_in_src, F.d_out_dst, F.d_in_p, F.d_out_p, F.d_pimap, F.d_korder, F.d_etab, F.d_emod, F.d_in_T, F.d_out_T, F.d_pi, F.d_fin, F.d_E};
+  void *ptrs[] = {F.d_in_src, F.d_out_dst, F.d_in_p, F.d_out_p, F.d_pimap, F.d_korder, F.d_etab, F.d_emod, F.d_out_stat, F.d_pistat,
+                  F.d_in_T,   F.d_out_T,   F.d_pi,   F.d_fin,   F.d_E,     F.d_ec};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   F = SparseTables();
@@ -78,7 +81,7 @@ static int up(T **dst, const std::vector<T> &h, cudaStream_t s) {
 // the padded in-/out-degree): dense models up to 32 states, <= 16 edges per state up to 64 states, <= 8 up to 128, <= 4 up to 256.
 inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax, const std::vector<int> &lc_ctx_ptr, const std::vector<int> &ctx_elem,
                  const std::vector<int> &ctx_last, const std::vector<int> &elem_child_ptr, const std::vector<int> &child_state,
-                 const std::vector<int> &state_order, const std::vector<int> &state_tab, const std::vector<int> &state_mod,
+                 const std::vector<int> &child_stat, const std::vector<int> &state_order, const std::vector<int> &state_tab, const std::vector<int> &state_mod,
                  const std::vector<uint8_t> &state_final, cudaStream_t s) {
   F.usable = false;
   if (m != 1 || has_silent || S > 256) return JH_OK;
@@ -104,17 +107,24 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
   const int IND = deg <= 4 ? 4 : deg <= 8 ? 8 : deg <= 16 ? 16 : 32;
   if (SPL * IND > 32) return JH_OK;  // both edge lists of a lane have to fit into registers
   std::vector<int> in_src((size_t)IND * SP), out_dst((size_t)IND * SP), in_p((size_t)IND * SP, -1), out_p((size_t)IND * SP, -1), pimap(SP, -1),
-      korder(SP, 0), etab(SP, -1), emod(SP, 1);
+      korder(SP, 0), etab(SP, -1), emod(SP, 1), out_stat((size_t)IND * SP, -1), pistat(SP, -1);
   std::vector<double> fin(SP, 0.0);
   for (int k = 0; k < IND; k++)
     for (int j = 0; j < SP; j++) {
       in_src[(size_t)k * SP + j] = j;
       out_dst[(size_t)k * SP + j] = j;
       if (j < S && k < (int)in[j].size()) { in_src[(size_t)k * SP + j] = in[j][k].first; in_p[(size_t)k * SP + j] = in[j][k].second; }
-      if (j < S && k < (int)out[j].size()) { out_dst[(size_t)k * SP + j] = out[j][k].first; out_p[(size_t)k * SP + j] = out[j][k].second; }
+      if (j < S && k < (int)out[j].size()) {
+        out_dst[(size_t)k * SP + j] = out[j][k].first;
+        out_p[(size_t)k * SP + j] = out[j][k].second;
+        out_stat[(size_t)k * SP + j] = child_stat[out[j][k].second];
+      }
     }
   int e0 = ctx_elem[lc_ctx_ptr[0]];
-  for (int p = elem_child_ptr[e0]; p < elem_child_ptr[e0 + 1]; p++) pimap[child_state[p]] = p;
+  for (int p = elem_child_ptr[e0]; p < elem_child_ptr[e0 + 1]; p++) {
+    pimap[child_state[p]] = p;
+    pistat[child_state[p]] = child_stat[p];
+  }
   for (int j = 0; j < S; j++) {
     korder[j] = state_order[j];
     etab[j] = state_tab[j];
@@ -123,10 +133,11 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
   }
   F.S = S; F.SP = SP; F.SPL = SPL; F.IND = IND; F.a = a; F.Kmax = Kmax; F.H = (int)H;
   int r;
-  std::vector<double> zE((size_t)H * SP, 0.0), zT((size_t)IND * SP, 0.0), zp(SP, 0.0);
+  std::vector<double> zE((size_t)H * SP, 0.0), zT((size_t)IND * SP, 0.0), zp(SP, 0.0), zEC((size_t)EC_REPLICAS_SPARSE * H * SP, 0.0);
   if ((r = up(&F.d_in_src, in_src, s)) || (r = up(&F.d_out_dst, out_dst, s)) || (r = up(&F.d_in_p, in_p, s)) || (r = up(&F.d_out_p, out_p, s)) ||
       (r = up(&F.d_pimap, pimap, s)) || (r = up(&F.d_korder, korder, s)) || (r = up(&F.d_etab, etab, s)) || (r = up(&F.d_emod, emod, s)) ||
-      (r = up(&F.d_fin, fin, s)) || (r = up(&F.d_in_T, zT, s)) || (r = up(&F.d_out_T, zT, s)) || (r = up(&F.d_pi, zp, s)) || (r = up(&F.d_E, zE, s)))
+      (r = up(&F.d_fin, fin, s)) || (r = up(&F.d_in_T, zT, s)) || (r = up(&F.d_out_T, zT, s)) || (r = up(&F.d_pi, zp, s)) || (r = up(&F.d_E, zE, s)) ||
+      (r = up(&F.d_out_stat, out_stat, s)) || (r = up(&F.d_pistat, pistat, s)) || (r = up(&F.d_ec, zEC, s)))
     return r;
   F.usable = true;
   return JH_OK;
@@ -174,6 +185,11 @@ __device__ __forceinline__ int slot_of(int j) { return (j % SPL) * 32 + j / SPL;
 
 // exact rescale of the warp's vector: divide by 2^e, e = exponent of the maximum; false when the maximum has left the
 // safe range (80 binades above the denormals, see kernels_mma.cuh)
+__device__ __forceinline__ double jhs_pow2(int k) {  // 2^k, 0 below the normal range, largest power above it
+  k = max(-1023, min(1023, k));
+  return __hiloint2double((1023 + k) << 20, 0);
+}
+
 template <int SPL>
 __device__ __forceinline__ bool rescale_warp(double (&v)[SPL], long long &expo) {
   unsigned hi = (unsigned)__double2hiint(v[0]);
@@ -249,6 +265,23 @@ struct Edges {  // the lane's edge lists in registers: byte offsets into the sha
       for (int k = 0; k < IND; k += 2) {
         a0 = fma(*reinterpret_cast<const double *>(base + off[k][u]), w[k][u], a0);
         a1 = fma(*reinterpret_cast<const double *>(base + off[k + 1][u]), w[k + 1][u], a1);
+      }
+      out[u] = a0 + a1;
+    }
+  }
+  // the same gather, and O[k][u] += a[u] * vec[idx[k][u]] with the values it has loaded anyway (expected edge counts)
+  __device__ __forceinline__ void gather_count(const double *vec, double (&out)[SPL], const double (&a)[SPL], double (&O)[IND][SPL]) const {
+    const char *base = reinterpret_cast<const char *>(vec);
+#pragma unroll
+    for (int u = 0; u < SPL; u++) {
+      double a0 = 0, a1 = 0;
+#pragma unroll
+      for (int k = 0; k < IND; k += 2) {
+        const double x0 = *reinterpret_cast<const double *>(base + off[k][u]), x1 = *reinterpret_cast<const double *>(base + off[k + 1][u]);
+        a0 = fma(x0, w[k][u], a0);
+        a1 = fma(x1, w[k + 1][u], a1);
+        O[k][u] = fma(a[u], x0, O[k][u]);
+        O[k + 1][u] = fma(a[u], x1, O[k + 1][u]);
       }
       out[u] = a0 + a1;
     }
@@ -334,9 +367,19 @@ __device__ __forceinline__ int roll_down(const SparseDev &F, int h, int x) {  //
 
 // Phase 1 / scoring.  Work item w: sequence w>>1 ... direction w&1 when both directions run (n_dir == 2), else forward only.
 // ck_alpha / ck_beta: [chunk_ptr[seq] + c][SP]; loglik[seq]; fallback: sequences the scaled recursion could not finish.
+struct Pass1Extra {        // E-step mode (all pointers null otherwise)
+  long long *ck_alpha_exp;   // [n_chunks+1] exponent of each alpha checkpoint
+  long long *ck_beta_exp;    // [n_chunks+1] exponent of each beta checkpoint
+  double *seq_sfin;          // [n_seq] P(x) = seq_sfin * 2^seq_AL, 0 for sequences the scaled recursion could not finish
+  long long *seq_AL;         // [n_seq]
+  const int32_t *list;       // sequences to process (nullptr: all, in D.order)
+  int64_t n_list;
+  double *score;             // += sum_n w_n log P(x_n) over the processed sequences
+};
+
 template <int SPL, int IND>
 __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, int n_dir, int CK, const int64_t *chunk_ptr, double *ck_alpha,
-                                                      double *ck_beta, unsigned long long *counter, double *loglik, int32_t *fallback) {
+                                                      double *ck_beta, unsigned long long *counter, double *loglik, int32_t *fallback, Pass1Extra X) {
   extern __shared__ double sm[];
   const int SP = F.SP;
   double *sE = sm;
@@ -351,8 +394,8 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
     long long it = 0;
     if (lane == 0) it = (long long)atomicAdd(counter, 1ull);
     it = __shfl_sync(FULL, it, 0);
-    if (it >= D.n_seq * n_dir) break;
-    const int sid = D.order[it / n_dir];
+    if (it >= (X.list ? X.n_list : D.n_seq) * n_dir) break;
+    const int sid = X.list ? X.list[it / n_dir] : D.order[it / n_dir];
     const bool backward = n_dir == 2 && (it & 1);
     const int64_t off = D.offsets[sid];
     const int L = (int)(D.offsets[sid + 1] - off);
@@ -375,6 +418,7 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
       ok = rescale_warp<SPL>(f, A);
       int par = 0, ck_left = CK;  // steps until the next checkpoint (the vector BEFORE chunk c = alpha_{c*CK-1}, stored in step t = c*CK)
       double *ck_dst = ck_alpha ? ck_alpha + (size_t)(cbase + 1) * SP + SPL * lane : nullptr;
+      long long *cke_dst = X.ck_alpha_exp ? X.ck_alpha_exp + cbase + 1 : nullptr;
       auto step = [&](int t, int x) {  // alpha_{t-1} -> alpha_t
         h = roll_up(F, h, x);
         double e[SPL];
@@ -386,6 +430,10 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
           store_vec<SPL>(ck_dst, f);
           ck_dst += SP;
           ck_left = CK;
+          if (cke_dst) {
+            if (lane == 0) *cke_dst = A;
+            cke_dst++;
+          }
         }
         __syncwarp();
         G.gather(v, f);
@@ -401,9 +449,15 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
 #pragma unroll
       for (int d = 16; d >= 1; d >>= 1) sfin += __shfl_xor_sync(FULL, sfin, d);
       if (lane == 0) {
-        if (ok && sfin > 0) loglik[sid] = log(sfin) + (double)A * 0.6931471805599453094;
-        else {
-          loglik[sid] = JH_NEG_INF;
+        const bool good = ok && sfin > 0;
+        const double lp = good ? log(sfin) + (double)A * 0.6931471805599453094 : JH_NEG_INF;
+        if (loglik) loglik[sid] = lp;
+        if (X.seq_sfin) {
+          X.seq_sfin[sid] = good ? sfin : 0.0;
+          X.seq_AL[sid] = A;
+          if (good) atomicAdd(X.score, (D.weights ? D.weights[sid] : 1.0) * lp);
+        }
+        if (!good) {
           int pos = atomicAdd(fallback, 1);
           fallback[1 + pos] = sid;
         }
@@ -422,6 +476,7 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
       const int n_full = (L - 1) / CK;            // chunks that end before position L-1
       int ck_left = n_full > 0 ? (L - 1) - (n_full * CK - 1) : 0x7fffffff;  // steps until t reaches n_full*CK-1
       double *ck_dst = ck_beta + (size_t)(cbase + n_full - 1) * SP + SPL * lane;
+      long long *cke_dst = X.ck_beta_exp ? X.ck_beta_exp + cbase + n_full - 1 : nullptr;
       const int K1 = F.Kmax + 1;
       auto step = [&](int p, int x) {  // t = p + K + 1: beta_t -> beta_{t-1}; x = x[t-1-K] completes the hash of t-1
         const int t = p + K1;
@@ -429,6 +484,10 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
           store_vec<SPL>(ck_dst, b);
           ck_dst -= SP;
           ck_left = CK;
+          if (cke_dst) {
+            if (lane == 0) *cke_dst = Bx;
+            cke_dst--;
+          }
         }
         --ck_left;
         double *v = vec + par;
@@ -573,6 +632,235 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
     decide(t0);
     __syncwarp();
   }
+}
+
+// Baum-Welch E-step, one chunk per warp (the count analogue of k_sparse_decode_chunks).  A sequence of one chunk is done
+// entirely here (forward from the start element, P(x), backward with counts); longer sequences come with the checkpoints,
+// their exponents and P(x) = sfin * 2^AL from k_sparse_pass1.  Per position t of the chunk:
+//   gamma_t[j]    = alpha_t[j] beta_t[j] 2^(A_t + B_t - AL) w / sfin           -> emission statistic [hash of t][j], start statistic
+//   xi_t(i -> j)  = alpha_{t-1}[i] T[i][j] vb_t[j] 2^(A_{t-1} + B_t - AL) w / sfin,  vb_t = e_t * beta_t
+// accumulated per out-edge in registers (T is multiplied in at the end), with the values the beta recursion gathers anyway.
+// rows: [slot][ROWS][SP] doubles, rexp: [slot][ROWS] exponents relative to the chunk's base exponent (ROWS = min(CK, longest sequence)).
+// gEC: [EC_REPLICAS_SPARSE][H][SP] emission-count tables; stats: [transition | emission | score].
+
+struct EstepTables {
+  const int *out_stat;     // [IND][SP] statistics slot of out-edge k of state i, -1 for padding
+  const int *pistat;       // [SP]
+  int n_stats;             // index of the score entry
+};
+
+template <int SPL, int IND>
+__global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepTables ET, DevData D, int CK, int ROWS, int64_t n_chunks, const int32_t *chunk_seq,
+                                                             const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
+                                                             const double *ck_beta, const long long *ck_alpha_exp, const long long *ck_beta_exp,
+                                                             const double *seq_sfin, const long long *seq_AL, unsigned long long *counter,
+                                                             double *rows, int *rexp, double *stats, double *gEC, int32_t *fallback) {
+  extern __shared__ double sm[];
+  const int SP = F.SP;
+  double *sE = sm;
+  double *vec = sE + (size_t)F.H * SP + (size_t)(threadIdx.x >> 5) * 2 * SP;
+  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned FULL = 0xffffffffu;
+  const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double *const R = rows + (size_t)slot * ROWS * SP + SPL * lane;
+  int *const RX = rexp + (size_t)slot * ROWS;
+  double *const gECw = gEC + (size_t)(slot % EC_REPLICAS_SPARSE) * F.H * SP + SPL * lane;
+  ResReader rd;
+  SeqBlocks blocks;
+  double O[IND][SPL], SC[SPL];
+#pragma unroll
+  for (int u = 0; u < SPL; u++) {
+    SC[u] = 0;
+#pragma unroll
+    for (int k = 0; k < IND; k++) O[k][u] = 0;
+  }
+  double score = 0;
+  const int K1 = F.Kmax + 1;
+  for (;;) {
+    long long g = 0;
+    if (lane == 0) g = (long long)atomicAdd(counter, 1ull);
+    g = __shfl_sync(FULL, g, 0);
+    if (g >= n_chunks) break;
+    const int sid = chunk_seq[g], c = chunk_idx[g];
+    const int64_t off = D.offsets[sid];
+    const int L = (int)(D.offsets[sid + 1] - off);
+    const int t0 = c * CK, t1 = min(L, t0 + CK) - 1;
+    const int64_t cb = chunk_ptr[sid] + c;
+    const bool single = L <= CK;
+    const double w = D.weights ? D.weights[sid] : 1.0;
+    double sfin = single ? 0.0 : seq_sfin[sid];
+    long long AL = single ? 0 : seq_AL[sid];
+    if (!single && !(sfin > 0)) continue;  // pass 1 could not finish this sequence: the log-space kernels take it
+    rd.init(D.codes + off);
+    blocks.init(D.codes + off);
+    // ---- forward rows of the chunk (exponents relative to A0) ----
+    double f[SPL];
+    long long A = (c == 0) ? 0 : ck_alpha_exp[cb];
+    const long long A0 = A;
+    bool ok = true;
+    int h = hmod_of(F, hash_at(F, rd, t0));
+    int par = 0;
+    double a0[SPL];  // alpha_{t0-1} (the checkpoint), needed again for the first transition of the chunk
+#pragma unroll
+    for (int u = 0; u < SPL; u++) a0[u] = 0;
+    {
+      Edges<SPL, IND> Gin;
+      Gin.load(F.in_src, F.in_T, SP, lane);
+      {
+        double e[SPL];
+        emis<SPL>(F, sE, lane, e, h, t0);
+        if (c == 0) {
+#pragma unroll
+          for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+        } else {
+          double *v = vec + par;
+          par ^= SP;
+          load_vec<SPL>(ck_alpha + (size_t)cb * SP + SPL * lane, a0);
+          put_shared<SPL>(v, lane, a0);
+          __syncwarp();
+          Gin.gather(v, f);
+#pragma unroll
+          for (int u = 0; u < SPL; u++) f[u] *= e[u];
+        }
+      }
+      ok &= rescale_warp<SPL>(f, A);
+      store_vec<SPL>(R, f);
+      if (lane == 0) RX[0] = (int)(A - A0);
+      double *rdst = R;
+      int *xdst = RX;
+      auto fstep = [&](int t, int x) {
+        h = roll_up(F, h, x);
+        double e[SPL];
+        emis<SPL>(F, sE, lane, e, h, t);
+        double *v = vec + par;
+        par ^= SP;
+        put_shared<SPL>(v, lane, f);
+        __syncwarp();
+        Gin.gather(v, f);
+#pragma unroll
+        for (int u = 0; u < SPL; u++) f[u] *= e[u];
+        if ((t & (RS_SPARSE - 1)) == 0) ok &= rescale_warp<SPL>(f, A);
+        rdst += SP;
+        store_vec<SPL>(rdst, f);
+        xdst++;
+        if (lane == 0) *xdst = (int)(A - A0);
+      };
+      for_residues_up(blocks, t0 + 1, t1, fstep);
+    }
+    if (single) {  // the whole sequence is this chunk: P(x) from the last row
+      double s_ = 0;
+#pragma unroll
+      for (int u = 0; u < SPL; u++) s_ += f[u] * F.fin[SPL * lane + u];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) s_ += __shfl_xor_sync(FULL, s_, d);
+      sfin = s_;
+      AL = A;
+      if (!(ok && sfin > 0)) {
+        if (lane == 0) {
+          int pos = atomicAdd(fallback, 1);
+          fallback[1 + pos] = sid;
+        }
+        continue;
+      }
+      if (lane == 0) score += w * (log(sfin) + (double)AL * 0.6931471805599453094);
+    }
+    const double winv = w / sfin;
+    __syncwarp();
+    // ---- backward through the chunk with counts ----
+    Edges<SPL, IND> Gout;
+    Gout.load(F.out_dst, F.out_T, SP, lane);
+    double b[SPL], e[SPL], a[SPL];
+    long long Bx = 0;
+    if (t1 == L - 1) {
+#pragma unroll
+      for (int u = 0; u < SPL; u++) b[u] = F.fin[SPL * lane + u];
+    } else {
+      load_vec<SPL>(ck_beta + (size_t)cb * SP + SPL * lane, b);
+      Bx = ck_beta_exp[cb];
+    }
+    int hb = hash_at(F, rd, t1);
+    emis<SPL>(F, sE, lane, e, hmod_of(F, hb), t1);
+    const double *rsrc = R + (size_t)(t1 - t0) * SP;
+    const int *xsrc = RX + (t1 - t0);
+    load_vec<SPL>(rsrc, a);
+    long long At = A0 + *xsrc;
+    // one position: emission statistic of t, then (with the previous row ap / exponent Ap) the edge statistic and beta_{t-1}
+    auto consume = [&](int t, const double (&ap)[SPL], long long Ap, bool recurse, int x) {
+      const long long kg = At + Bx - AL, kx = Ap + Bx - AL;
+      const double sg = jhs_pow2((int)max(-1100ll, min(1100ll, kg))) * winv, sx = jhs_pow2((int)max(-1100ll, min(1100ll, kx))) * winv;
+      const int hm = hmod_of(F, hb);
+#pragma unroll
+      for (int u = 0; u < SPL; u++) {
+        const double gm = a[u] * b[u] * sg;  // posterior of the lane's state u at position t
+        if (t >= F.Kmax || t >= F.korder[SPL * lane + u]) atomicAdd(gECw + (size_t)hm * SP + u, gm);
+        if (t == 0) SC[u] += gm;
+      }
+      if (t == 0) return;
+      double *v = vec + par;
+      par ^= SP;
+      double xb[SPL], as[SPL];
+#pragma unroll
+      for (int u = 0; u < SPL; u++) {
+        xb[u] = e[u] * b[u];
+        as[u] = ap[u] * sx;
+      }
+      put_shared<SPL>(v, lane, xb);
+      if (recurse) {
+        hb = roll_down(F, hb, x);
+        emis<SPL>(F, sE, lane, e, hb, t - 1);
+      }
+      __syncwarp();
+      Gout.gather_count(v, b, as, O);
+      if ((t & (RS_SPARSE - 1)) == 0) rescale_warp<SPL>(b, Bx);
+    };
+    auto bstep = [&](int p, int x) {  // t = p + K + 1 > t0
+      const int t = p + K1;
+      double ap[SPL];
+      rsrc -= SP;
+      xsrc--;
+      load_vec<SPL>(rsrc, ap);
+      const long long Ap = A0 + *xsrc;
+      consume(t, ap, Ap, true, x);
+#pragma unroll
+      for (int u = 0; u < SPL; u++) a[u] = ap[u];
+      At = Ap;
+    };
+    for_residues_down(blocks, t1 - K1, t0 + 1 - K1, bstep);  // t = t1 .. t0+1
+    consume(t0, a0, A0, false, 0);                           // t = t0: the transition out of the previous chunk (or the start)
+    __syncwarp();
+  }
+  // ---- flush ----
+  {
+    Edges<SPL, IND> Gout;
+    Gout.load(F.out_dst, F.out_T, SP, lane);
+#pragma unroll
+    for (int k = 0; k < IND; k++)
+#pragma unroll
+      for (int u = 0; u < SPL; u++) {
+        const int st = ET.out_stat[(size_t)k * SP + SPL * lane + u];
+        const double v = O[k][u] * Gout.w[k][u];
+        if (st >= 0 && v != 0) atomicAdd(&stats[st], v);
+      }
+#pragma unroll
+    for (int u = 0; u < SPL; u++) {
+      const int st = ET.pistat[SPL * lane + u];
+      if (st >= 0 && SC[u] != 0) atomicAdd(&stats[st], SC[u]);
+    }
+    if (score != 0) atomicAdd(&stats[ET.n_stats], score);
+  }
+}
+
+// emission-count tables [replica][H][SP] -> emission statistics
+__global__ void k_sparse_fold_ec(SparseDev F, const int *etab, const int *emod, int n_child, const double *gEC, double *stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= F.H * F.SP) return;
+  const int hh = i / F.SP, c = i % F.SP;              // c = slot inside the row: lane-major [lane][u] as written by the lanes
+  double v = 0;
+  for (int rep = 0; rep < EC_REPLICAS_SPARSE; rep++) v += gEC[(size_t)rep * F.H * F.SP + i];
+  const int j = c;                                    // rows are written at SPL*lane + u == state index
+  if (v != 0 && etab[j] >= 0) atomicAdd(&stats[n_child + etab[j] + hh % emod[j]], v);
 }
 
 }  // namespace jhs

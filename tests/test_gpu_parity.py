@@ -394,6 +394,17 @@ def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, deg
             assert path.shape == ref_path.shape and np.array_equal(path[clear], ref_path[clear])
             n_clear += clear.sum(); n_all += clear.size
         assert n_clear > 0.9 * n_all
+        # Baum-Welch E-step of the same path: checkpoints + chunk-parallel counts (k_sparse_pass1 + k_sparse_estep_chunks)
+        w = rng.uniform(0.5, 2.0, data.getNumberOfElements())
+        eng, nd = hmm._engine(), hmm._data(data)
+        for weights in (None, w):
+            nd.set_weights(weights)
+            ts, es, sc = eng.estep(nd)
+            rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+            np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+            np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+            assert sc == pytest.approx(rsc, rel=LL_RTOL)
+        nd.set_weights(None)
     finally:
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
 
@@ -420,6 +431,15 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name):
             srt = np.sort(ref, axis=0)
             clear = srt[-1] - srt[-2] > 1e-9
             assert np.array_equal(path[clear], om.decode_posterior(ref)[clear])
+        ts, es, sc = hmm._engine().estep(hmm._data(data))
+        rts, res, rsc = om.estep(data.codes, data.offsets)
+        np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+        np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+        assert sc == pytest.approx(rsc, rel=LL_RTOL)
+        hmm.trainingParameter = BaumWelchParameterSet(1, IterationCondition(3), 1)
+        hmm.train(data)
+        robj = om.train(data.codes, data.offsets, max_iter=3)
+        np.testing.assert_allclose(hmm.last_objectives[0], robj, rtol=LL_RTOL)
     finally:
         nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
