@@ -111,7 +111,9 @@ int64_t jh_kernel_launches(void);
 int jh_set_stream(void *cuda_stream);
 int jh_synchronize(void);
 /* Tuning / test switches: "fast" (1: scaled linear-space kernels where the model allows, 0: reference-order
- * log-space kernels only), "scratch_mb" (DP scratch budget), "blocks_per_sm", "fast_variant". */
+ * log-space kernels only), "scratch_mb" (DP scratch budget), "blocks_per_sm", "fast_variant", "chunk" (positions per
+ * checkpoint of the long-sequence path), "trim_pool" (return unused device-pool memory to the driver, keeping `value`
+ * bytes: device buffers are pooled so that per-call data sets do not pay cudaMalloc/cudaFree). */
 int jh_set_option(const char *name, int64_t value);
 
 /* ---- model ------------------------------------------------------------- */

@@ -40,20 +40,50 @@ void jh_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+// Device buffers come from the device's stream-ordered memory pool with an unlimited release threshold: a data set that
+// is created and destroyed per call (the e2e path: pack -> upload -> train -> free) reuses the pool's memory instead of
+// paying cudaFree's unmap (measured: up to 360 ms for the 3 GB of a 1M x 1 kb data set).  Allocation and release are
+// synchronous like cudaMalloc / cudaFree (nothing in flight can touch a buffer that is handed out again).
+static cudaStream_t g_alloc_stream[64] = {};
+static cudaStream_t alloc_stream() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g_alloc_stream[dev]) {
+    cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  return g_alloc_stream[dev];
+}
+static cudaError_t pool_alloc(void **p, size_t bytes) {
+  cudaStream_t s = alloc_stream();
+  cudaError_t e = cudaMallocAsync(p, bytes, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  return e;
+}
+static void pool_free(void *p) {
+  cudaDeviceSynchronize();
+  cudaFreeAsync(p, alloc_stream());
+}
+
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p);
     p = nullptr;
     n = 0;
   }
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) {
+    if (pool_alloc((void **)&p, count * sizeof(T)) != cudaSuccess) {
       cudaGetLastError();
       p = nullptr;
       jh_set_error("out of device memory allocating %zu bytes", count * sizeof(T));
@@ -240,7 +270,12 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "scratch_mb") g_opt.scratch_mb = value;
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = value;
   else if (n == "fast_variant") g_opt.fast_variant = value;
-  else if (n == "chunk") g_opt.chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
+  else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
+    cudaMemPool_t pool;
+    JH_CUDA(cudaDeviceSynchronize());
+    JH_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+    JH_CUDA(cudaMemPoolTrimTo(pool, (size_t)std::max<int64_t>(0, value)));
+  } else if (n == "chunk") g_opt.chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
   else {
     jh_set_error("unknown option '%s'", n.c_str());
     return JH_ERR_INVALID;

@@ -139,11 +139,14 @@ using UniformStep = std::integral_constant<int, 1>;
 using UniformStepNoRescale = std::integral_constant<int, 0>;
 constexpr int RS = 4;
 
-// Scaled forward recursion of one octet (lane (r,q) of the warp).  On return A holds the last row of the lane's sequence
-// (scaled by 2^-Aexp), ok says that no rescale came near the denormal range.  STORE: rows and exponents go to the scratch.
+// Scaled forward recursion of one octet (lane (r,q) of the warp) over the rows t_from+1 .. t_to.  t_from < 0: the
+// recursion starts with the start element (row 0); otherwise A / Aexp hold row t_from on entry.  On return A holds row
+// min(t_to, Lr-1) of the lane's sequence (scaled by 2^-Aexp); ok is cleared when a rescale came near the denormal range.
+// STORE: rows and exponents go to the scratch, row t at fw + t*8*G and fe + t*8 (the caller shifts the base pointers).
 template <int NT, bool STORE>
 __device__ __forceinline__ void octet_forward(const FastDev &F, const double *sE, const int r, const int q, const uint16_t *hrow, const int Lr,
-                                              const int Lmax, const int Lmin, double *fw, int *fe, double (&A)[2 * NT], int &Aexp, bool &ok) {
+                                              const int Lmax, const int Lmin, double *fw, int *fe, double (&A)[2 * NT], int &Aexp, bool &ok,
+                                              const int t_from = -1, const int t_to = 0x7fffffff) {
   constexpr int G = 8 * NT, NV = 2 * NT;
   const int kmin = F.Kmax;
   {
@@ -153,17 +156,20 @@ __device__ __forceinline__ void octet_forward(const FastDev &F, const double *sE
 #pragma unroll
         for (int t = 0; t < NT; t++) Bf[k][t] = F.T[(8 * (k >> 1) + 2 * q + (k & 1)) * G + 8 * t + r];
       double e[NV];
-      emis_rl<NT, true>(F, sE, q, e, hrow[0], 0);
+      const int ts = max(t_from, 0), te = min(t_to, Lmax - 1);  // steps ts .. te-1 (row t -> t+1)
+      if (t_from < 0) {
+        emis_rl<NT, true>(F, sE, q, e, hrow[0], 0);
 #pragma unroll
-      for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv_of(F, 8 * (v >> 1) + 2 * q + (v & 1)) * e[v] : 0.0;
-      ok = rescale_row<NV>(A, Aexp);
-      if (STORE) {
+        for (int v = 0; v < NV; v++) A[v] = Lr > 0 ? piv_of(F, 8 * (v >> 1) + 2 * q + (v & 1)) * e[v] : 0.0;
+        ok = rescale_row<NV>(A, Aexp);
+        if (STORE) {
 #pragma unroll
-        for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(fw + 8 * t) = make_double2(A[2 * t], A[2 * t + 1]);
-        if (q == 0) fe[r] = Aexp;
+          for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(fw + 8 * t) = make_double2(A[2 * t], A[2 * t + 1]);
+          if (q == 0) fe[r] = Aexp;
+        }
       }
-      emis_rl<NT, true>(F, sE, q, e, hrow[8], 1);
-      int h2 = hrow[16];  // hash of position t+2, loaded one step ahead of its use
+      emis_rl<NT, true>(F, sE, q, e, hrow[(size_t)(ts + 1) * 8], ts + 1);
+      int h2 = hrow[(size_t)(ts + 2) * 8];  // hash of position t+2, loaded one step ahead of its use
       auto fstep = [&](auto general, int t) {  // row t -> t+1
         constexpr bool GEN = decltype(general)::value == 2, RESC = decltype(general)::value != 0;
         const int h3 = hrow[(size_t)(t + 3) * 8];
@@ -203,8 +209,8 @@ __device__ __forceinline__ void octet_forward(const FastDev &F, const double *sE
         h2 = h3;
       };
       // uniform steps: t+1 < Lmin (all sequences running) and t+2 >= Kmax (no order check for the emission fetched)
-      int t = 0;
-      const int t_lo = min(max(kmin - 2, 0), Lmax - 1), t_hi = max(min(Lmin - 1, Lmax - 1), t_lo);
+      int t = ts;
+      const int t_lo = min(max(kmin - 2, ts), te), t_hi = max(min(Lmin - 1, te), t_lo);
       for (; t < t_lo; t++) fstep(GeneralStep(), t);
       for (; t + RS <= t_hi; t += RS) {
 #pragma unroll
@@ -212,7 +218,7 @@ __device__ __forceinline__ void octet_forward(const FastDev &F, const double *sE
         fstep(UniformStep(), t + RS - 1);
       }
       for (; t < t_hi; t++) fstep(UniformStep(), t);
-      for (; t + 1 < Lmax; t++) fstep(GeneralStep(), t);
+      for (; t < te; t++) fstep(GeneralStep(), t);
   }
 }
 
