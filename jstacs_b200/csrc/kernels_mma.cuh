@@ -238,9 +238,24 @@ struct MmaCfg {
 };
 
 // stats layout: [transition statistics n_child | emission statistics n_cond*a | sum_n w_n*logP_n]; gEC as in kernels_fast.cuh
-template <int NT>
+//
+// CHUNKED (long sequences: the (L+1) x 8 x G forward rows of an octet would not leave enough scratch for a full grid): the
+// forward recursion first runs over the whole octet storing only a checkpoint row every CK positions (and P(x)); then the
+// chunks are taken from the last to the first: forward rows of the chunk recomputed from its checkpoint into a scratch of
+// CK+1 rows, backward recursion and counts through the chunk, beta carried in registers across the chunk boundary.  One
+// extra forward pass (+25 % work), scratch independent of the sequence length.  `rows` = rows per slot (CK+1 when chunked),
+// ck_scratch: [slot][ck_rows][8][G] checkpoint rows, ck_exp: [slot][ck_rows][8].
+struct OctChunks {
+  int CK;             // positions per chunk
+  int64_t ck_rows;    // checkpoints per slot
+  double *ck_scratch;
+  int *ck_exp;
+};
+
+template <int NT, bool CHUNKED>
 __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch,
-                                                      int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback) {
+                                                      int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback,
+                                                      OctChunks X) {
   using C = MmaCfg<NT>;
   constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
@@ -305,7 +320,21 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
     double A[NV];
     int Aexp = 0;
     bool ok = true;
-    octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw, fe, A, Aexp, ok);
+    const int CK = CHUNKED ? X.CK : 0x40000000;
+    const int n_ck = CHUNKED ? (Lmax + CK - 1) / CK : 1;
+    double *const ckw = CHUNKED ? X.ck_scratch + (size_t)slot * X.ck_rows * 8 * G + r * G + 2 * q : nullptr;  // + c*8*G + 8*tp
+    int *const cke = CHUNKED ? X.ck_exp + (size_t)slot * X.ck_rows * 8 : nullptr;                            // + c*8 + row
+    if (!CHUNKED) octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw, fe, A, Aexp, ok);
+    else {
+      for (int c = 0; c < n_ck; c++) {  // checkpoint c = row c*CK - 1, the row in front of chunk c
+        octet_forward<NT, false>(F, sE, r, q, hrow, Lr, Lmax, Lmin, nullptr, nullptr, A, Aexp, ok, c * CK - 1, (c + 1) * CK - 1);
+        if (c + 1 < n_ck) {
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(ckw + (size_t)(c + 1) * 8 * G + 8 * tp) = make_double2(A[2 * tp], A[2 * tp + 1]);
+          if (q == 0) cke[(c + 1) * 8 + r] = Aexp;
+        }
+      }
+    }
     // ---- termination: P(x) = sum over final states, one log per sequence ----
     double sfin = 0;
 #pragma unroll
@@ -335,19 +364,23 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 #pragma unroll
       for (int v = 0; v < NV; v++) beta[v] = F.fin[8 * (v >> 1) + 2 * q + (v & 1)] * invS;  // 1/P(x) and the weight are folded in
       rescale_row<NV>(beta, Bx);
+      int row_lo = 0;  // rows below row_lo are not in the scratch (chunked: the scratch holds rows row_lo .. of the current chunk)
       auto issue = [&](int row) {  // forward row `row` (8 sequences x G doubles + 8 exponents) -> ring slot row & 3
-        const bool have = row >= 0;
+        const bool have = row >= (CHUNKED ? row_lo : 0);
         char *sl = ring + (size_t)(row & (RING - 1)) * SLOTB;
-        const double *src = fw + (int64_t)row * 8 * G;
+        const int64_t rel = CHUNKED ? row - row_lo : row;
+        const double *src = fw + rel * 8 * G;
 #pragma unroll
         for (int tp = 0; tp < NT; tp++) cp_async16_if(have, sl + rl_off[tp], src + 8 * tp);
-        cp_async4_if(have && l < 8, sl + 8 * ROWB + l * 4, fe + (int64_t)row * 8 + l);
+        cp_async4_if(have && l < 8, sl + 8 * ROWB + l * 4, fe + rel * 8 + l);
         jhf::cp_async_commit();
       };
       __syncwarp();
-      issue(Lmax - 1);
-      issue(Lmax - 2);
-      issue(Lmax - 3);
+      if (!CHUNKED) {
+        issue(Lmax - 1);
+        issue(Lmax - 2);
+        issue(Lmax - 3);
+      }
       int h = hrow[(size_t)(Lmax - 1) * 8];
       int h1 = hrow[(size_t)(Lmax - 2) * 8];  // hash of position t-1, loaded one step ahead of its use
       double e[NV];
@@ -429,19 +462,42 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
         emis_rl<NT, GEN>(F, sE, q, e, h, t - 1);
         par ^= 1;
       };
-      // uniform steps: t < Lmin (all sequences running) and t-1 >= Kmax (no order checks)
-      int t = Lmax - 1;
-      const int t_hi = min(Lmin - 1, Lmax - 1), t_lo = max(kmin + 1, 1);
-      for (; t > t_hi && t >= 1; --t) bstep(GeneralStep(), t);
-      for (; t - RS + 1 >= t_lo; t -= RS) {
+      for (int c = n_ck - 1; c >= 0; --c) {
+        const int t0 = CHUNKED ? c * CK : 0, t1 = CHUNKED ? min(t0 + CK, Lmax) - 1 : Lmax - 1;
+        if (CHUNKED) {  // forward rows t0-1 .. t1 of the chunk -> scratch rows 0 .. (c == 0: rows 0 .. t1)
+          row_lo = max(t0 - 1, 0);
+          if (c > 0) {
 #pragma unroll
-        for (int u = 0; u < RS - 1; u++) bstep(UniformStepNoRescale(), t - u);
-        bstep(UniformStep(), t - RS + 1);
+            for (int tp = 0; tp < NT; tp++) {
+              const double2 a2 = *reinterpret_cast<const double2 *>(ckw + (size_t)c * 8 * G + 8 * tp);
+              A[2 * tp] = a2.x;
+              A[2 * tp + 1] = a2.y;
+              *reinterpret_cast<double2 *>(fw + 8 * tp) = a2;
+            }
+            Aexp = cke[c * 8 + r];
+            if (q == 0) fe[r] = Aexp;
+          } else Aexp = 0;
+          bool ok2 = true;
+          octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw - (int64_t)row_lo * 8 * G, fe - (int64_t)row_lo * 8, A, Aexp, ok2, t0 - 1, t1);
+          __syncwarp();
+          issue(t1);
+          issue(t1 - 1);
+          issue(t1 - 2);
+        }
+        // uniform steps: t < Lmin (all sequences running) and t-1 >= Kmax (no order checks)
+        int t = t1;
+        const int tl = max(t0, 1), t_hi = min(Lmin - 1, t1), t_lo = max(kmin + 1, tl);
+        for (; t > t_hi && t >= tl; --t) bstep(GeneralStep(), t);
+        for (; t - RS + 1 >= t_lo; t -= RS) {
+#pragma unroll
+          for (int u = 0; u < RS - 1; u++) bstep(UniformStepNoRescale(), t - u);
+          bstep(UniformStep(), t - RS + 1);
+        }
+        for (; t >= t_lo; --t) bstep(UniformStep(), t);
+        for (; t >= tl; --t) bstep(GeneralStep(), t);
+        jhf::cp_async_wait<0>();
+        __syncwarp();
       }
-      for (; t >= t_lo; --t) bstep(UniformStep(), t);
-      for (; t >= 1; --t) bstep(GeneralStep(), t);
-      jhf::cp_async_wait<0>();
-      __syncwarp();
       {  // position 0: emission statistic and the statistic of the start element
         const char *sl0 = ring;
         const int A0 = *reinterpret_cast<const int *>(sl0 + 8 * ROWB + r * 4);

@@ -267,6 +267,34 @@ def test_fast_estep_variants_agree_with_oracle(nat, oracle_lib, name, variant):
         nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
 
 
+@pytest.mark.parametrize("chunk", [8, 13, 64])
+@pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
+def test_chunked_octet_estep_matches_oracle(nat, oracle_lib, name, chunk):
+    """Octet E-step with checkpointed forward rows (long sequences): chunk boundaries inside the ragged tail of an
+    octet, chunks shorter than the emission order + rescale cadence, sequences ending exactly at a boundary."""
+    nat.check(nat.lib().jh_set_option(b"oct_chunk", chunk))
+    nat.check(nat.lib().jh_set_option(b"oct_chunk_force", 1))
+    try:
+        hmm = MODELS[name]()
+        om = oracle_lib.OracleModel(hmm.ir())
+        rng = np.random.default_rng(chunk)
+        lens = np.concatenate([rng.integers(2 * chunk + 1, 6 * chunk, 21), [4 * chunk, 4 * chunk + 1, 4 * chunk - 1, 3 * chunk, 700, 650, 1, 5]])
+        data = dataset_of([random_dna(rng, int(L)) for L in lens])
+        w = rng.random(lens.size) + 0.25
+        eng, nd = hmm._engine(), hmm._data(data)
+        for weights in (None, w):
+            nd.set_weights(weights)
+            ts, es, sc = eng.estep(nd)
+            rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+            np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+            np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+            assert sc == pytest.approx(rsc, rel=LL_RTOL)
+        nd.set_weights(None)
+    finally:
+        nat.check(nat.lib().jh_set_option(b"oct_chunk", 1024))
+        nat.check(nat.lib().jh_set_option(b"oct_chunk_force", 0))
+
+
 @pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
 def test_posterior_decoding_octets_ragged(nat, oracle_lib, fast, name):
     """decodeStatePosterior(getStatePosteriorMatrixFor(seq)) fused on the device for a ragged data set (octets with
