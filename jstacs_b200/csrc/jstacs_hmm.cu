@@ -1364,44 +1364,59 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   return JH_OK;
 }
 
-// Octet posterior decoding (kernels_mma.cuh), one launch per length bucket.
-template <int NT>
-static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_ll) {
+// Octet posterior decoding (kernels_mma.cuh), one launch per length bucket; long buckets chunked like the E-step.
+template <int NT, bool CHUNKED>
+static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem, int32_t *d_paths, double *d_ll) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhm::k_mma_decode<NT>;
-  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b] + 1;
-  if (n_oct <= 0) return JH_OK;
-  size_t smem = (size_t)F.H * C::G * sizeof(double) + (size_t)C::WARPS * C::RING * C::SLOTB;
+  auto kern = jhm::k_mma_decode<NT, CHUNKED>;
+  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
+  const int64_t CK = g_opt.oct_chunk;
+  const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NTHREADS, smem));
-  if (per_sm < 1) { jh_set_error("octet decoding kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
-  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
-  const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+  const int64_t per_slot = (rows + ck_rows) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
   const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
   if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
   grid = std::max<int64_t>(1, std::min(grid, max_slots / C::WARPS));
   const int64_t slots = grid * C::WARPS;
-  int r = m->d_fwd.reserve((size_t)slots * rows * 8 * C::G);
+  int r = m->d_fwd.reserve((size_t)slots * (rows + ck_rows) * 8 * C::G);
   if (r) return r;
-  if ((size_t)slots * rows * 8 > F.fexp_n) {
+  if ((size_t)slots * (rows + ck_rows) * 8 > F.fexp_n) {
     if (F.d_fexp) cudaFree(F.d_fexp);
     F.d_fexp = nullptr;
     F.fexp_n = 0;
-    if (cudaMalloc(&F.d_fexp, (size_t)slots * rows * 8 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); jh_set_error("out of device memory (exponent scratch)"); return JH_ERR_NOMEM; }
-    F.fexp_n = (size_t)slots * rows * 8;
+    if (cudaMalloc(&F.d_fexp, (size_t)slots * (rows + ck_rows) * 8 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); jh_set_error("out of device memory (exponent scratch)"); return JH_ERR_NOMEM; }
+    F.fexp_n = (size_t)slots * (rows + ck_rows) * 8;
   }
   jhm::OctData D;
   D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
   D.weights = nullptr; D.n_oct = n_oct;
+  jhm::OctChunks X{(int)CK, ck_rows, m->d_fwd.p + (size_t)slots * rows * 8 * C::G, F.d_fexp + (size_t)slots * rows * 8};
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  kern<<<(int)grid, C::NTHREADS, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, d_paths, d_ll, m->d_fallback.p);
+  kern<<<(int)grid, C::NTHREADS, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, d_paths, d_ll, m->d_fallback.p, X);
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
   return JH_OK;
+}
+
+template <int NT>
+static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_ll) {
+  using C = jhm::MmaCfg<NT>;
+  jhf::FastTables &F = m->fast;
+  const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b], rows = d->bucket_len[b] + 1;
+  if (n_oct <= 0) return JH_OK;
+  const size_t smem = (size_t)F.H * C::G * sizeof(double) + (size_t)C::WARPS * C::RING * C::SLOTB;
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_decode<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_decode<NT, false>, C::NTHREADS, smem));
+  if (per_sm < 1) { jh_set_error("octet decoding kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
+  const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+  const bool chunked = g_opt.oct_chunk > 0 && rows > 2 * g_opt.oct_chunk &&
+                       (g_opt.oct_chunk_force || grid * C::WARPS * per_slot > g_opt.scratch_mb * 1024 * 1024);
+  return chunked ? launch_mma_decode_impl<NT, true>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false>(m, d, b, grid, smem, d_paths, d_ll);
 }
 
 static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) {

@@ -594,9 +594,10 @@ __global__ void __launch_bounds__(256) k_mma_loglik(FastDev F, OctData D, unsign
 // position (the scales and 1/P(x)), so the decision needs neither exponents nor a logarithm.  Same octet mapping as the
 // E-step: forward rows through the HBM scratch and a cp.async ring, backward recursion on the FP64 MMA path, no count
 // product.  paths: int32 per residue (CSR by the data set offsets), loglik optional.
-template <int NT>
+// CHUNKED: as in k_mma_estep (checkpoint rows every CK positions, rows of one chunk per resident warp).
+template <int NT, bool CHUNKED>
 __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch, int *fexp_scratch,
-                                                       int64_t rows, int32_t *paths, double *loglik, int32_t *fallback) {
+                                                       int64_t rows, int32_t *paths, double *loglik, int32_t *fallback, OctChunks X) {
   using C = MmaCfg<NT>;
   constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
@@ -649,7 +650,21 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
     double A[NV];
     int Aexp = 0;
     bool ok = true;
-    octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw, fe, A, Aexp, ok);
+    const int CK = CHUNKED ? X.CK : 0x40000000;
+    const int n_ck = CHUNKED ? (Lmax + CK - 1) / CK : 1;
+    double *const ckw = CHUNKED ? X.ck_scratch + (size_t)slot * X.ck_rows * 8 * G + r * G + 2 * q : nullptr;
+    int *const cke = CHUNKED ? X.ck_exp + (size_t)slot * X.ck_rows * 8 : nullptr;
+    if (!CHUNKED) octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw, fe, A, Aexp, ok);
+    else {
+      for (int c = 0; c < n_ck; c++) {
+        octet_forward<NT, false>(F, sE, r, q, hrow, Lr, Lmax, Lmin, nullptr, nullptr, A, Aexp, ok, c * CK - 1, (c + 1) * CK - 1);
+        if (c + 1 < n_ck) {
+#pragma unroll
+          for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(ckw + (size_t)(c + 1) * 8 * G + 8 * tp) = make_double2(A[2 * tp], A[2 * tp + 1]);
+          if (q == 0) cke[(c + 1) * 8 + r] = Aexp;
+        }
+      }
+    }
     double sfin = 0;
 #pragma unroll
     for (int v = 0; v < NV; v++) sfin += A[v] * F.fin[8 * (v >> 1) + 2 * q + (v & 1)];
@@ -673,24 +688,47 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
     int Bx = 0;
 #pragma unroll
     for (int v = 0; v < NV; v++) beta[v] = F.fin[8 * (v >> 1) + 2 * q + (v & 1)];
+    int row_lo = 0;
     auto issue = [&](int row) {
-      const bool have = row >= 0;
+      const bool have = row >= (CHUNKED ? row_lo : 0);
       char *sl = ring + (size_t)(row & (RING - 1)) * SLOTB;
-      const double *src = fw + (int64_t)row * 8 * G;
+      const double *src = fw + (int64_t)(CHUNKED ? row - row_lo : row) * 8 * G;
 #pragma unroll
       for (int tp = 0; tp < NT; tp++) cp_async16_if(have, sl + rl_off[tp], src + 8 * tp);
       jhf::cp_async_commit();
     };
     __syncwarp();
-    issue(Lmax - 1);
-    issue(Lmax - 2);
-    issue(Lmax - 3);
+    if (!CHUNKED) {
+      issue(Lmax - 1);
+      issue(Lmax - 2);
+      issue(Lmax - 3);
+    }
     int h = hrow[(size_t)(Lmax - 1) * 8];
     int h1 = hrow[(size_t)(Lmax - 2) * 8];
     double e[NV];
     emis_rl<NT, true>(F, sE, q, e, h, Lmax - 1);
     int32_t *const prow = paths + off;
-    for (int t = Lmax - 1; t >= 0; --t) {
+    for (int c = n_ck - 1; c >= 0; --c) {
+    const int t0 = CHUNKED ? c * CK : 0, t1 = CHUNKED ? min(t0 + CK, Lmax) - 1 : Lmax - 1;
+    if (CHUNKED) {  // forward rows t0 .. t1 of the chunk -> scratch (row t0 first)
+      row_lo = t0;
+      if (c > 0) {
+#pragma unroll
+        for (int tp = 0; tp < NT; tp++) {
+          const double2 a2 = *reinterpret_cast<const double2 *>(ckw + (size_t)c * 8 * G + 8 * tp);
+          A[2 * tp] = a2.x;
+          A[2 * tp + 1] = a2.y;
+        }
+        Aexp = cke[c * 8 + r];
+      } else Aexp = 0;
+      bool ok2 = true;
+      octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw - (int64_t)row_lo * 8 * G, fe - (int64_t)row_lo * 8, A, Aexp, ok2, t0 - 1, t1);
+      __syncwarp();
+      issue(t1);
+      issue(t1 - 1);
+      issue(t1 - 2);
+    }
+    for (int t = t1; t >= t0; --t) {
       const int h2 = t >= 2 ? hrow[(size_t)(t - 2) * 8] : 0;
       const bool act = t < Lr;
       double b[NV];
@@ -736,6 +774,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
     }
     jhf::cp_async_wait<0>();
     __syncwarp();
+    }
   }
 }
 

@@ -56,3 +56,4 @@ run("long_decode_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), 
 run("cfg5_decode_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "decode")
 run("cfg5_bw_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "estep")
 run("long_bw_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), "estep")
+run("cfg4_decode_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode")

@@ -290,6 +290,17 @@ def test_chunked_octet_estep_matches_oracle(nat, oracle_lib, name, chunk):
             np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
             assert sc == pytest.approx(rsc, rel=LL_RTOL)
         nd.set_weights(None)
+        # posterior decoding through the same chunking (k_mma_decode<NT, true>)
+        dec = hmm.decodePosteriorPathsFor(data)
+        ll_ref = om.loglik(data.codes, data.offsets)
+        for i in range(data.getNumberOfElements()):
+            ref = om.posterior(data.getElementAt(i).codes)
+            ref_path = om.decode_posterior(ref)
+            path, ll = dec[i]
+            assert ll == pytest.approx(ll_ref[i], rel=LL_RTOL)
+            srt = np.sort(ref, axis=0)
+            clear = srt[-1] - srt[-2] > 1e-9
+            assert path.shape == ref_path.shape and np.array_equal(path[clear], ref_path[clear])
     finally:
         nat.check(nat.lib().jh_set_option(b"oct_chunk", 1024))
         nat.check(nat.lib().jh_set_option(b"oct_chunk_force", 0))
