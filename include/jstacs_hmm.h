@@ -165,6 +165,9 @@ int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *
  * HigherOrderHMM.viterbi (:617-708) per sequence.  paths: int32, CSR by the dataset offsets
  * (models without silent states emit exactly one state per residue); scores[n_seq]. */
 int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores);
+/* The same with ONE BYTE per residue (models with at most 255 states; 255 = "no state"): a quarter of the device->host
+ * traffic, which dominates the call (cfg2: 1e9 residues = 4 GB of int32).  The shim widens to IntList on the host. */
+int jh_viterbi_u8(jh_model *m, jh_dataset *d, uint8_t *paths, double *scores);
 /* The same for ANY model, in particular with silent states (profile HMMs: HMMFactory.createProfileHMM,
  * parseProfileHMMFromHMMer), whose paths contain the silent states and therefore have variable length
  * (HigherOrderHMM.java:617-708 including the trailing silent states :667-705): sequence n writes at most
@@ -178,6 +181,8 @@ int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out);
 /* AbstractHMM.decodeStatePosterior (:1125-1139) fused with the posterior: paths CSR like
  * jh_viterbi, loglik[n_seq] (may be NULL). */
 int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik);
+/* One byte per residue, as jh_viterbi_u8. */
+int jh_posterior_decode_u8(jh_model *m, jh_dataset *d, uint8_t *paths, double *loglik);
 
 /* One E-step == Compute.oneIteration (HigherOrderHMM.java:1250-1261): resets the statistics,
  * runs baumWelch (mode 1, :723-726) or viterbi(null,...) (mode 0, :617-708) over every sequence,

@@ -109,6 +109,8 @@ def lib():
         "jh_dataset_set_weights": (C.c_int, [vp, _P_F64]),
         "jh_loglik": (C.c_int, [vp, vp, _P_F64]),
         "jh_viterbi": (C.c_int, [vp, vp, _P_I32, _P_F64]),
+        "jh_viterbi_u8": (C.c_int, [vp, vp, _P_U8, _P_F64]),
+        "jh_posterior_decode_u8": (C.c_int, [vp, vp, _P_U8, _P_F64]),
         "jh_viterbi_paths": (C.c_int, [vp, vp, _P_I32, _P_I64, _P_I64, _P_F64]),
         "jh_loglik_windows": (C.c_int, [vp, vp, C.c_int64, _P_I64, _P_I64, _P_I64, _P_F64]),
         "jh_posterior": (C.c_int, [vp, vp, C.c_int64, _P_F64]),
@@ -221,10 +223,15 @@ class NativeModel:
         check(lib().jh_loglik(self.h, data.h, _f64(out)))
         return out[:data.n_seq]
 
-    def viterbi(self, data: NativeData):
-        paths = np.zeros(max(data.n_res, 1), dtype=np.int32)
+    def viterbi(self, data: NativeData, narrow: bool = False):
+        """narrow: one byte per residue (uint8 paths, 255 = no state) instead of int32."""
         scores = np.zeros(max(data.n_seq, 1))
-        check(lib().jh_viterbi(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(scores)))
+        if narrow:
+            paths = np.empty(max(data.n_res, 1), dtype=np.uint8)
+            check(lib().jh_viterbi_u8(self.h, data.h, paths.ctypes.data_as(_P_U8), _f64(scores)))
+        else:
+            paths = np.zeros(max(data.n_res, 1), dtype=np.int32)
+            check(lib().jh_viterbi(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(scores)))
         return paths[:data.n_res], scores[:data.n_seq]
 
     def viterbi_paths(self, data: NativeData, capacity: np.ndarray):
@@ -252,10 +259,14 @@ class NativeModel:
         check(lib().jh_posterior(self.h, data.h, int(index), _f64(out)))
         return out[:n_states * length].reshape(n_states, length)
 
-    def posterior_decode(self, data: NativeData):
-        paths = np.zeros(max(data.n_res, 1), dtype=np.int32)
+    def posterior_decode(self, data: NativeData, narrow: bool = False):
         ll = np.zeros(max(data.n_seq, 1))
-        check(lib().jh_posterior_decode(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(ll)))
+        if narrow:
+            paths = np.empty(max(data.n_res, 1), dtype=np.uint8)
+            check(lib().jh_posterior_decode_u8(self.h, data.h, paths.ctypes.data_as(_P_U8), _f64(ll)))
+        else:
+            paths = np.zeros(max(data.n_res, 1), dtype=np.int32)
+            check(lib().jh_posterior_decode(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(ll)))
         return paths[:data.n_res], ll[:data.n_seq]
 
     def estep(self, data: NativeData, mode: int = MODE_BAUM_WELCH, fetch: bool = True):

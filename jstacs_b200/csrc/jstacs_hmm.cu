@@ -1290,7 +1290,25 @@ extern "C" int jh_viterbi_paths(jh_model *m, jh_dataset *d, int32_t *paths, cons
   return JH_OK;
 }
 
-extern "C" int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores) {
+// paths as int32 (paths) or one byte per residue (paths8, 255 = no state), whichever is not null
+static int copy_paths_out(jh_model *m, jh_dataset *d, const int32_t *d_paths, int32_t *paths, uint8_t *paths8) {
+  cudaStream_t s = m->st();
+  if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, s));
+  if (paths8) {
+    if (m->S > 255) { jh_set_error("byte paths need at most 255 states"); return JH_ERR_UNSUPPORTED; }
+    DevBuf<uint8_t> d8;
+    int r = d8.alloc((size_t)d->n_res + 16);
+    if (r) return r;
+    jha::k_narrow_paths<<<(int)std::min<int64_t>(148 * 8, (d->n_res + 4095) / 4096), 256, 0, s>>>(d_paths, d->n_res, d8.p);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+    JH_CUDA(cudaMemcpyAsync(paths8, d8.p, (size_t)d->n_res, cudaMemcpyDeviceToHost, s));
+    JH_CUDA(cudaStreamSynchronize(s));
+  }
+  return JH_OK;
+}
+
+static int viterbi_impl(jh_model *m, jh_dataset *d, int32_t *paths, uint8_t *paths8, double *scores) {
   int r = check_pair(m, d);
   if (r) return r;
   if (m->has_silent) { jh_set_error("models with silent states emit paths of variable length: use jh_viterbi_paths"); return JH_ERR_UNSUPPORTED; }
@@ -1302,11 +1320,14 @@ extern "C" int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *sc
   r = run_viterbi(m, d, d_paths.p, d_scores.p, nullptr);
   timing_end(m);
   if (r) return r;
-  if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, m->st()));
+  if ((r = copy_paths_out(m, d, d_paths.p, paths, paths8))) return r;
   if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
   JH_CUDA(cudaStreamSynchronize(m->st()));
   return JH_OK;
 }
+
+extern "C" int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores) { return viterbi_impl(m, d, paths, nullptr, scores); }
+extern "C" int jh_viterbi_u8(jh_model *m, jh_dataset *d, uint8_t *paths, double *scores) { return viterbi_impl(m, d, nullptr, paths, scores); }
 
 // ---- forward-backward family (exact) ----------------------------------------------------------
 static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, double *d_loglik, double *d_post,
@@ -1436,7 +1457,7 @@ static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
   return JH_OK;
 }
 
-extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik) {
+static int posterior_decode_impl(jh_model *m, jh_dataset *d, int32_t *paths, uint8_t *paths8, double *loglik) {
   int r = check_pair(m, d);
   if (r) return r;
   if (d->n_seq == 0) return JH_OK;
@@ -1453,11 +1474,14 @@ extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, d
   else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
   timing_end(m);
   if (r) return r;
-  if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, m->st()));
+  if ((r = copy_paths_out(m, d, d_paths.p, paths, paths8))) return r;
   if (loglik) JH_CUDA(cudaMemcpyAsync(loglik, d_ll.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
   JH_CUDA(cudaStreamSynchronize(m->st()));
   return JH_OK;
 }
+
+extern "C" int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik) { return posterior_decode_impl(m, d, paths, nullptr, loglik); }
+extern "C" int jh_posterior_decode_u8(jh_model *m, jh_dataset *d, uint8_t *paths, double *loglik) { return posterior_decode_impl(m, d, nullptr, paths, loglik); }
 
 // ---- E-step / M-step / EM ------------------------------------------------------------------------
 // Scaled linear-space E-step (kernels_fast.cuh), one launch per length bucket.

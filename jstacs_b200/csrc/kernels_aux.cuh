@@ -133,6 +133,25 @@ __global__ void k_log_prior(DevParams P, const double *add, double *out) {
   out[0] = add ? __dadd_rn(res, add[0]) : res;
 }
 
+// int32 state paths -> one byte per residue (255 = no state: the int32 path holds -1), 16 residues per thread
+__global__ void k_narrow_paths(const int32_t *paths, int64_t n, uint8_t *out) {
+  int64_t i = (int64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+  for (; i < n; i += stride) {
+    if (i + 16 <= n) {
+      unsigned w[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int4 v = *reinterpret_cast<const int4 *>(paths + i + 4 * k);
+        w[k] = (unsigned)(v.x & 0xff) | ((unsigned)(v.y & 0xff) << 8) | ((unsigned)(v.z & 0xff) << 16) | ((unsigned)(v.w & 0xff) << 24);
+      }
+      *reinterpret_cast<uint4 *>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (int64_t k = i; k < n; k++) out[k] = (uint8_t)(paths[k] & 0xff);
+    }
+  }
+}
+
 // largest residue code of the packed data (alphabet check of AbstractHMM.java:991-993 done once per data set)
 __global__ void k_max_code(const uint8_t *codes, int64_t n, unsigned int *out) {
   unsigned int mx = 0;

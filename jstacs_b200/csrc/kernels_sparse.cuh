@@ -786,6 +786,16 @@ __global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepT
     const int *xsrc = RX + (t1 - t0);
     load_vec<SPL>(rsrc, a);
     long long At = A0 + *xsrc;
+    // the rows below come back from L2 / HBM: rows t-1 and t-2 are kept in flight in registers (pre0, pre1), row t-3 is
+    // requested at the start of step t
+    double pre0[SPL], pre1[SPL];
+    int pe0 = 0, pe1 = 0;
+#pragma unroll
+    for (int u = 0; u < SPL; u++) pre0[u] = pre1[u] = 0;
+    if (t1 - 1 >= t0) { load_vec<SPL>(rsrc - SP, pre0); pe0 = xsrc[-1]; }
+    if (t1 - 2 >= t0) { load_vec<SPL>(rsrc - 2 * SP, pre1); pe1 = xsrc[-2]; }
+    rsrc -= 2 * SP;  // row of pre1
+    xsrc -= 2;
     // one position: emission statistic of t, then (with the previous row ap / exponent Ap) the edge statistic and beta_{t-1}
     auto consume = [&](int t, const double (&ap)[SPL], long long Ap, bool recurse, int x) {
       const long long kg = At + Bx - AL, kx = Ap + Bx - AL;
@@ -818,10 +828,19 @@ __global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepT
     auto bstep = [&](int p, int x) {  // t = p + K + 1 > t0
       const int t = p + K1;
       double ap[SPL];
+#pragma unroll
+      for (int u = 0; u < SPL; u++) {
+        ap[u] = pre0[u];
+        pre0[u] = pre1[u];
+      }
+      const long long Ap = A0 + pe0;
+      pe0 = pe1;
       rsrc -= SP;
       xsrc--;
-      load_vec<SPL>(rsrc, ap);
-      const long long Ap = A0 + *xsrc;
+      if (t - 3 >= t0) {
+        load_vec<SPL>(rsrc, pre1);
+        pe1 = *xsrc;
+      }
       consume(t, ap, Ap, true, x);
 #pragma unroll
       for (int u = 0; u < SPL; u++) a[u] = ap[u];

@@ -787,8 +787,9 @@ class HigherOrderHMM:
         return eng.loglik_windows(self._data(data), seq_index, start, end)
 
     # ---- decoding ------------------------------------------------------------------------------
-    def getViterbiPathsFor(self, data: DataSet):
-        """AbstractHMM.getViterbiPathsFor (:894-900) -> list of (IntList path, Double score)."""
+    def getViterbiPathsFor(self, data: DataSet, narrow: bool = False):
+        """AbstractHMM.getViterbiPathsFor (:894-900) -> list of (IntList path, Double score).
+        narrow: uint8 paths (255 = no state) through jh_viterbi_u8: a quarter of the device->host traffic."""
         eng = self._engine()
         self._push_params()
         n_silent = sum(1 for i in self.emissionIdx if self.emission[i].order < 0)
@@ -798,7 +799,7 @@ class HigherOrderHMM:
             if (plen < 0).any():
                 raise ValueError("Impossible path")
             return [(p, float(sc)) for p, sc in zip(paths, scores)]
-        paths, scores = eng.viterbi(self._data(data))
+        paths, scores = eng.viterbi(self._data(data), narrow=narrow and self.getNumberOfStates() <= 255)
         off = data.offsets
         return [(paths[off[i]:off[i + 1]], float(scores[i])) for i in range(data.getNumberOfElements())]
 
@@ -837,11 +838,11 @@ class HigherOrderHMM:
         """AbstractHMM.decodeStatePosterior (:1125-1139): np.argmax returns the first maximum == strict '<'."""
         return [np.argmax(p, axis=0).astype(np.int32) for p in statePosterior]
 
-    def decodePosteriorPathsFor(self, data: DataSet):
+    def decodePosteriorPathsFor(self, data: DataSet, narrow: bool = False):
         """Fused getLogStatePosteriorMatrixFor + decodeStatePosterior over a DataSet (no S x L matrix leaves the GPU)."""
         eng = self._engine()
         self._push_params()
-        paths, ll = eng.posterior_decode(self._data(data))
+        paths, ll = eng.posterior_decode(self._data(data), narrow=narrow and self.getNumberOfStates() <= 255)
         off = data.offsets
         return [(paths[off[i]:off[i + 1]], float(ll[i])) for i in range(data.getNumberOfElements())]
 

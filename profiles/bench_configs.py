@@ -17,6 +17,9 @@ from jstacs_b200.workloads import banded_hmm, ergodic_hmm, make_data, ragged_len
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
 only = sys.argv[2:] or None
+for kv in filter(None, os.environ.get("JH_OPTS", "").split(",")):  # library options, e.g. JH_OPTS=oct_chunk=256,oct_chunk_force=1
+    k, v = kv.split("=")
+    _native.check(_native.lib().jh_set_option(k.encode(), int(v)))
 
 
 def run(name, hmm, data, what, reps=3):
@@ -25,7 +28,8 @@ def run(name, hmm, data, what, reps=3):
     eng, nd = hmm._engine(), hmm._data(data)
     res, S = data.getNumberOfResidues(), hmm.getNumberOfStates()
     fn = {"estep": lambda: eng.estep(nd, fetch=False), "loglik": lambda: eng.loglik(nd), "viterbi": lambda: eng.viterbi(nd),
-          "decode": lambda: eng.posterior_decode(nd)}[what]
+          "decode": lambda: eng.posterior_decode(nd), "viterbi_u8": lambda: eng.viterbi(nd, narrow=True),
+          "decode_u8": lambda: eng.posterior_decode(nd, narrow=True)}[what]
     fn()
     ms = []
     for _ in range(reps):
@@ -57,3 +61,5 @@ run("cfg5_decode_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_00
 run("cfg5_bw_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "estep")
 run("long_bw_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), "estep")
 run("cfg4_decode_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode")
+run("cfg2_viterbi_u8_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "viterbi_u8")
+run("cfg4_decode_u8_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode_u8")

@@ -78,6 +78,11 @@ def test_viterbi_paths_bit_exact(nat, oracle_lib, name):
     for (p, s), p_ref, s_ref in zip(res, rp, rs):
         assert np.array_equal(p, p_ref)
         assert s == s_ref  # bit-exact score: only adds and compares
+    # one byte per residue (jh_viterbi_u8 / jh_posterior_decode_u8): same paths, a quarter of the device->host traffic
+    for (p8, s8), (p, s) in zip(hmm.getViterbiPathsFor(data, narrow=True), res):
+        assert p8.dtype == np.uint8 and np.array_equal(p8, p) and s8 == s
+    for (p8, l8), (p, l) in zip(hmm.decodePosteriorPathsFor(data, narrow=True), hmm.decodePosteriorPathsFor(data)):
+        assert p8.dtype == np.uint8 and np.array_equal(p8, p) and l8 == l
 
 
 def test_viterbi_tie_rule_first_child_in_user_order(nat, oracle_lib):
