@@ -30,6 +30,7 @@ struct Options {
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
+  int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
   int64_t oct_chunk = 1024;    // positions per checkpoint of the chunked octet E-step (0: never chunk)
   int64_t oct_chunk_force = 0; // tests: chunk every bucket longer than 2 * oct_chunk
 };
@@ -273,6 +274,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "blocks_per_sm") g_opt.blocks_per_sm = value;
   else if (n == "fast_variant") g_opt.fast_variant = value;
   else if (n == "oct_chunk") g_opt.oct_chunk = value <= 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
+  else if (n == "pass1_cta") g_opt.pass1_cta = value;
   else if (n == "oct_chunk_force") g_opt.oct_chunk_force = value;
   else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
     cudaMemPool_t pool;
@@ -912,6 +914,27 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
   const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
   if (items == 0) return JH_OK;
+  if (g_opt.pass1_cta && P.SP >= 64 && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
+    const size_t smem_c = ((size_t)P.H * P.SP + 2 * (size_t)P.SP + 16) * sizeof(double);
+#define JH_P1C(IND_)                                                                                                                     \
+  {                                                                                                                                      \
+    auto kern = jhs::k_sparse_pass1_cta<IND_>;                                                                                           \
+    if (smem_c > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));               \
+    kern<<<(int)items, P.SP, smem_c, s>>>(P.dev(), d->dev(), n_dir, (int)(d->chunk_len > 0 ? d->chunk_len : 1),                           \
+                                          n_dir == 2 ? d->d_chunk_ptr.p : nullptr, n_dir == 2 ? m->d_ck_alpha.p : nullptr,               \
+                                          n_dir == 2 ? m->d_ck_beta.p : nullptr, d_ll, m->d_fallback.p, X);                              \
+    JH_LAUNCHED();                                                                                                                       \
+  }
+    switch (P.IND) {
+      case 4: JH_P1C(4) break;
+      case 8: JH_P1C(8) break;
+      case 16: JH_P1C(16) break;
+      default: JH_P1C(32) break;
+    }
+#undef JH_P1C
+    JH_CUDA(cudaGetLastError());
+    return JH_OK;
+  }
   const int NT = items <= 2 * (int64_t)m->sm_count ? 32 : 128;  // few long sequences: one warp per SM
   const size_t smem = ((size_t)P.H * P.SP + (size_t)(NT / 32) * 2 * P.SP) * sizeof(double);
   DISPATCH_SPARSE(P, {

@@ -508,6 +508,286 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
   }
 }
 
+// Phase 1 for FEW long sequences (fewer work items than SMs): the recursion is one dependent step per position, so what
+// counts is the latency of a step, not throughput.  One CTA of SP/32 warps per (sequence, direction), ONE STATE PER THREAD.
+// Critical path of a step: shared-memory store of the vector -> CTA barrier -> IND loads -> multiply/FMA -> add; the
+// emission probability of the step is folded into the edge weights before the barrier (off the path: the context hash is
+// known one step ahead).  The power-of-two rescale is lazy: the maximum of the vector of a flagged step travels with the
+// next exchange and the factor is applied to the vector after it (any power of two is exact; the growth per step is
+// bounded), so a rescale costs no barrier of its own.  Aligned 16-residue blocks run as straight-line code (no branches:
+// with four warps on the SM every taken branch is an exposed instruction fetch); blocks that contain a checkpoint, the
+// ragged ends and alphabets that are not a power of two go step by step.
+template <int IND>
+__global__ void __launch_bounds__(256) k_sparse_pass1_cta(SparseDev F, DevData D, int n_dir, int CK, const int64_t *chunk_ptr, double *ck_alpha,
+                                                          double *ck_beta, double *loglik, int32_t *fallback, Pass1Extra X) {
+  extern __shared__ double sm[];
+  const int SP = F.SP, j = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;  // blockDim.x == SP
+  double *sE = sm;
+  double *vbuf = sE + (size_t)F.H * SP;                              // [2][SP]
+  unsigned *mbuf = reinterpret_cast<unsigned *>(vbuf + 2 * SP);     // [2][8] row maxima (high words) of the lazy rescale
+  double *red = reinterpret_cast<double *>(mbuf + 16);              // [8]
+  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  __syncthreads();
+  const unsigned FULL = 0xffffffffu;
+  const int kord = F.korder[j], ash = F.ashift, Hm = F.H - 1, hpow = F.hpow, SPB = SP * 8;
+  const char *const sEb = reinterpret_cast<const char *>(sE);
+  ResReader rd;
+  SeqBlocks blocks;
+  // exact rescale by the exponent of the CTA-wide maximum (two barriers; used at the ends of a sequence only)
+  auto cta_rescale = [&](double &v, long long &expo) {
+    unsigned hi = __reduce_max_sync(FULL, (unsigned)__double2hiint(v));
+    __syncthreads();
+    if (lane == 0) mbuf[warp] = hi;
+    __syncthreads();
+    hi = mbuf[0];
+    for (int w = 1; w < NW; w++) hi = max(hi, mbuf[w]);
+    const int be = (int)(hi >> 20);
+    v *= __hiloint2double((2046 - be) << 20, 0);
+    expo += be - 1023;
+    return (unsigned)(be - 81) < (0x7feu - 81u);
+  };
+  const long long items = (X.list ? X.n_list : D.n_seq) * n_dir;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int sid = X.list ? X.list[it / n_dir] : D.order[it / n_dir];
+    const bool backward = n_dir == 2 && (it & 1);
+    const int64_t off = D.offsets[sid];
+    const int L = (int)(D.offsets[sid + 1] - off);
+    rd.init(D.codes + off);
+    blocks.init(D.codes + off);
+    const int mis = blocks.mis;
+    const uint8_t *const bytes = reinterpret_cast<const uint8_t *>(blocks.base) + mis;  // residue t = bytes[t]
+    const int64_t cbase = chunk_ptr ? chunk_ptr[sid] : 0;
+    int eo[IND];
+    double ew[IND];
+    {
+      const int *idx = backward ? F.out_dst : F.in_src;
+      const double *T = backward ? F.out_T : F.in_T;
+#pragma unroll
+      for (int k = 0; k < IND; k++) {
+        eo[k] = idx[(size_t)k * SP + j] * 8;
+        ew[k] = T[(size_t)k * SP + j];
+      }
+    }
+    auto gather = [&](const double *v, const double (&w)[IND]) {
+      const char *base = reinterpret_cast<const char *>(v);
+      double a0 = *reinterpret_cast<const double *>(base + eo[0]) * w[0], a1 = *reinterpret_cast<const double *>(base + eo[1]) * w[1];
+#pragma unroll
+      for (int k = 2; k < IND; k += 2) {
+        a0 = fma(*reinterpret_cast<const double *>(base + eo[k]), w[k], a0);
+        a1 = fma(*reinterpret_cast<const double *>(base + eo[k + 1]), w[k + 1], a1);
+      }
+      return a0 + a1;
+    };
+    // factor of a published maximum; false when it has left the safe range
+    auto lazy_scale = [&](const unsigned *mb, double &v, long long &expo) {
+      unsigned hi = mb[0];
+      for (int w = 1; w < NW; w++) hi = max(hi, mb[w]);
+      const int be = (int)(hi >> 20);
+      v *= __hiloint2double((2046 - be) << 20, 0);
+      expo += be - 1023;
+      return (unsigned)(be - 81) < (0x7feu - 81u);
+    };
+    auto publish = [&](unsigned *mb, double v) {
+      const unsigned hi = __reduce_max_sync(FULL, (unsigned)__double2hiint(v));
+      if (lane == 0) mb[warp] = hi;
+    };
+    bool pend = false;  // the maximum of the current vector is to be published with the next exchange
+    if (!backward) {
+      double f;
+      long long A = 0;
+      int h = hash_at(F, rd, 0);
+      {
+        double e = sE[(size_t)hmod_of(F, h) * SP + j];
+        if (0 < kord) e = F.inv_a;
+        f = F.pi[j] * e;
+      }
+      bool ok = cta_rescale(f, A);
+      int ck_left = CK;
+      double *ck_dst = ck_alpha ? ck_alpha + (size_t)(cbase + 1) * SP + j : nullptr;
+      long long *cke_dst = X.ck_alpha_exp ? X.ck_alpha_exp + cbase + 1 : nullptr;
+      // exchange buffers and rescale cadence follow the residue ADDRESS (t + mis), so that aligned blocks start in a known state
+      auto step = [&](int t, int x) {  // alpha_{t-1} -> alpha_t
+        h = roll_up(F, h, x);
+        double e = *reinterpret_cast<const double *>(sEb + (size_t)h * SPB + j * 8);
+        if (t < kord) e = F.inv_a;
+        double we[IND];
+#pragma unroll
+        for (int k = 0; k < IND; k++) we[k] = ew[k] * e;
+        const int pr = (t + mis) & 1;
+        double *v = vbuf + pr * SP;
+        unsigned *mb = mbuf + pr * 8;
+        v[j] = f;
+        if (pend) publish(mb, f);
+        if (ck_dst && --ck_left == 0) {
+          *ck_dst = f;
+          ck_dst += SP;
+          ck_left = CK;
+          if (cke_dst) {
+            if (j == 0) *cke_dst = A;
+            cke_dst++;
+          }
+        }
+        __syncthreads();
+        f = gather(v, we);
+        if (pend) ok &= lazy_scale(mb, f, A);
+        pend = ((t + mis) & 7) == 6;
+      };
+      auto fast16 = [&](const uint4 blk) {  // 16 steps of an aligned block: positions >= Kmax, no checkpoint inside, pend false on entry and exit
+        const unsigned wds[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int x = (int)((wds[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+          h = ((h << ash) | x) & Hm;
+          const double e = *reinterpret_cast<const double *>(sEb + (size_t)h * SPB + j * 8);
+          double we[IND];
+#pragma unroll
+          for (int i = 0; i < IND; i++) we[i] = ew[i] * e;
+          double *v = vbuf + (k & 1) * SP;
+          v[j] = f;
+          if (k == 7 || k == 15) publish(mbuf + (k & 1) * 8, f);
+          __syncthreads();
+          f = gather(v, we);
+          if (k == 7 || k == 15) ok &= lazy_scale(mbuf + (k & 1) * 8, f, A);
+        }
+      };
+      int t = 1;
+      if (F.a_pow2) {
+#pragma unroll 1
+        for (; t <= L - 1 && ((((t + mis) & 15) != 0) || t <= F.Kmax); t++) step(t, (int)__ldg(bytes + t));
+        int blk = (t + mis) >> 4;
+        uint4 cur = t + 15 <= L - 1 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (; t + 15 <= L - 1; t += 16, blk++) {
+          const uint4 nxt = blocks.load(blk + 1);  // the code buffer is padded: one block past the end is readable
+          if (ck_dst && ck_left <= 16) {
+#pragma unroll 1
+            for (int k = 0; k < 16; k++) step(t + k, (int)__ldg(bytes + t + k));
+          } else {
+            fast16(cur);
+            ck_left -= 16;
+          }
+          cur = nxt;
+        }
+      }
+#pragma unroll 1
+      for (; t <= L - 1; t++) step(t, (int)__ldg(bytes + t));
+      ok &= cta_rescale(f, A);
+      double sfin = f * F.fin[j];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) sfin += __shfl_xor_sync(FULL, sfin, d);
+      __syncthreads();
+      if (lane == 0) red[warp] = sfin;
+      __syncthreads();
+      if (j == 0) {
+        sfin = 0;
+        for (int w = 0; w < NW; w++) sfin += red[w];
+        const bool good = ok && sfin > 0;
+        const double lp = good ? log(sfin) + (double)A * 0.6931471805599453094 : JH_NEG_INF;
+        if (loglik) loglik[sid] = lp;
+        if (X.seq_sfin) {
+          X.seq_sfin[sid] = good ? sfin : 0.0;
+          X.seq_AL[sid] = A;
+          if (good) atomicAdd(X.score, (D.weights ? D.weights[sid] : 1.0) * lp);
+        }
+        if (!good) {
+          int pos = atomicAdd(fallback, 1);
+          fallback[1 + pos] = sid;
+        }
+      }
+    } else {
+      // beta_{t-1}[i] = sum_k T[i][dst_k] e_t[dst_k] beta_t[dst_k]: the emission probabilities of the NEIGHBOUR states are
+      // folded into the edge weights one step ahead (wq), the exchanged vector is beta itself
+      double b = F.fin[j];
+      long long Bx = 0;
+      int h = hmod_of(F, hash_at(F, rd, L - 1));
+      double wq[IND];
+      auto weights_for = [&](int hh, int pos, double (&w)[IND]) {  // w[k] = T[j][dst_k] * e_pos[dst_k]
+#pragma unroll
+        for (int k = 0; k < IND; k++) {
+          double e = *reinterpret_cast<const double *>(sEb + (size_t)hh * SPB + eo[k]);
+          if (pos < F.Kmax && pos < F.korder[eo[k] >> 3]) e = F.inv_a;
+          w[k] = ew[k] * e;
+        }
+      };
+      weights_for(h, L - 1, wq);
+      const int n_full = (L - 1) / CK;
+      int ck_left = n_full > 0 ? (L - 1) - (n_full * CK - 1) : 0x7fffffff;
+      double *ck_dst = ck_beta + (size_t)(cbase + n_full - 1) * SP + j;
+      long long *cke_dst = X.ck_beta_exp ? X.ck_beta_exp + cbase + n_full - 1 : nullptr;
+      const int K1 = F.Kmax + 1;
+      auto step = [&](int p, int x) {  // t = p + K + 1: beta_t -> beta_{t-1}; x = x[t-1-K] completes the hash of t-1
+        const int t = p + K1;
+        if (ck_left == 0) {
+          *ck_dst = b;
+          ck_dst -= SP;
+          ck_left = CK;
+          if (cke_dst) {
+            if (j == 0) *cke_dst = Bx;
+            cke_dst--;
+          }
+        }
+        --ck_left;
+        const int pr = (p + mis) & 1;
+        double *v = vbuf + pr * SP;
+        unsigned *mb = mbuf + pr * 8;
+        v[j] = b;
+        if (pend) publish(mb, b);
+        h = roll_down(F, h, x);
+        double wn[IND];
+        weights_for(h, t - 1, wn);
+        __syncthreads();
+        b = gather(v, wq);
+        if (pend) lazy_scale(mb, b, Bx);
+        pend = ((p + mis) & 7) == 1;
+#pragma unroll
+        for (int k = 0; k < IND; k++) wq[k] = wn[k];
+      };
+      auto fast16 = [&](const uint4 blk) {  // 16 steps down an aligned block: p >= 0, no checkpoint inside
+        const unsigned wds[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (int k = 15; k >= 0; k--) {
+          const int x = (int)((wds[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+          double *v = vbuf + (k & 1) * SP;
+          v[j] = b;
+          if (k == 8 || k == 0) publish(mbuf + (k & 1) * 8, b);
+          h = (h >> ash) + hpow * x;
+          double wn[IND];
+#pragma unroll
+          for (int i = 0; i < IND; i++) wn[i] = ew[i] * *reinterpret_cast<const double *>(sEb + (size_t)h * SPB + eo[i]);
+          __syncthreads();
+          b = gather(v, wq);
+          if (k == 8 || k == 0) lazy_scale(mbuf + (k & 1) * 8, b, Bx);
+#pragma unroll
+          for (int i = 0; i < IND; i++) wq[i] = wn[i];
+        }
+      };
+      int p = L - 2 - F.Kmax;
+      const int pa = -F.Kmax;
+      if (F.a_pow2) {
+#pragma unroll 1
+        for (; p >= pa && (((p + mis) & 15) != 15 || p < 15); p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+        int blk = (p + mis) >> 4;
+        uint4 cur = p >= 15 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (; p >= 15; p -= 16, blk--) {  // (p + mis) & 15 == 15: the block is bytes[p-15 .. p]
+          const uint4 nxt = blocks.load(blk - 1);
+          if (ck_left <= 16) {
+#pragma unroll 1
+            for (int k = 0; k < 16; k++) step(p - k, (int)__ldg(bytes + p - k));
+          } else {
+            fast16(cur);
+            ck_left -= 16;
+          }
+          cur = nxt;
+        }
+      }
+#pragma unroll 1
+      for (; p >= pa; p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+    }
+    __syncthreads();
+  }
+}
+
 // Phase 2: posterior decoding of one chunk per warp.  chunk_seq / chunk_idx: the chunk list; rows: [warp slot][CK][SP].
 template <int SPL, int IND>
 __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int CK, int64_t n_chunks, const int32_t *chunk_seq,

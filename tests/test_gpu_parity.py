@@ -416,7 +416,11 @@ def test_window_scoring_sees_the_residues_before_the_window(nat, oracle_lib, nam
 # ---- sparse path: 33..256 states, checkpointed chunk-parallel decoding (BASELINE cfg5 shape) ------------------------
 @pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0)])
 @pytest.mark.parametrize("chunk", [16, 64, 2048])
-def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk):
+@pytest.mark.parametrize("cta", [0, 1], ids=["warp_per_sequence", "cta_per_sequence"])
+def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk, cta):
+    """cta: the checkpoint pass as one warp per (sequence, direction) (many sequences) or one CTA with a state per thread
+    and the lazy rescale (few long sequences: latency mode)."""
+    nat.check(nat.lib().jh_set_option(b"pass1_cta", cta))
     hmm = banded_hmm(states, degree, order)
     om = oracle_lib.OracleModel(hmm.ir())
     rng = np.random.default_rng(states + chunk)
@@ -451,6 +455,7 @@ def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, deg
         nd.set_weights(None)
     finally:
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
+        nat.check(nat.lib().jh_set_option(b"pass1_cta", 1))
 
 
 @pytest.mark.parametrize("name", ["erg_s2_k1", "sparse", "erg_s5_k2", "erg_s16_k1", "erg_s32_k3"])
