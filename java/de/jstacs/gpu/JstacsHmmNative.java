@@ -58,9 +58,11 @@ public final class JstacsHmmNative {
 	public static final MethodHandle jh_loglik = h( "jh_loglik", FunctionDescriptor.of( I, P, P, P ) );
 	public static final MethodHandle jh_loglik_windows = h( "jh_loglik_windows", FunctionDescriptor.of( I, P, P, J, P, P, P, P ) );
 	public static final MethodHandle jh_viterbi = h( "jh_viterbi", FunctionDescriptor.of( I, P, P, P, P ) );
+	public static final MethodHandle jh_viterbi_u8 = h( "jh_viterbi_u8", FunctionDescriptor.of( I, P, P, P, P ) );
 	public static final MethodHandle jh_viterbi_paths = h( "jh_viterbi_paths", FunctionDescriptor.of( I, P, P, P, P, P, P ) );
 	public static final MethodHandle jh_posterior = h( "jh_posterior", FunctionDescriptor.of( I, P, P, J, P ) );
 	public static final MethodHandle jh_posterior_decode = h( "jh_posterior_decode", FunctionDescriptor.of( I, P, P, P, P ) );
+	public static final MethodHandle jh_posterior_decode_u8 = h( "jh_posterior_decode_u8", FunctionDescriptor.of( I, P, P, P, P ) );
 	public static final MethodHandle jh_estep = h( "jh_estep", FunctionDescriptor.of( I, P, P, I, P, P, P ) );
 	public static final MethodHandle jh_mstep = h( "jh_mstep", FunctionDescriptor.of( I, P ) );
 	public static final MethodHandle jh_baum_welch = h( "jh_baum_welch", FunctionDescriptor.of( I, P, P, P, P, I, P ) );

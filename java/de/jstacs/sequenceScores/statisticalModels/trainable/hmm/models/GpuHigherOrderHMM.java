@@ -397,14 +397,29 @@ public class GpuHigherOrderHMM extends DifferentiableHigherOrderHMM {
 				for( int i = 0; i < n; i++ ) {
 					total += data.getElementAt( i ).getLength();
 				}
-				MemorySegment paths = arena.allocate( ValueLayout.JAVA_INT, Math.max( total, 1 ) );
-				JstacsHmmNative.check( (int) JstacsHmmNative.jh_posterior_decode.invokeExact( model, ds, paths, MemorySegment.NULL ) );
-				long p = 0;
-				for( int i = 0; i < n; i++ ) {
-					int L = data.getElementAt( i ).getLength();
-					res[i] = new int[L];
-					MemorySegment.copy( paths, ValueLayout.JAVA_INT, 4 * p, res[i], 0, L );
-					p += L;
+				if( states.length <= 255 ) {
+					// one byte per residue over PCIe (a quarter of the int32 traffic), widened here
+					MemorySegment paths = arena.allocate( ValueLayout.JAVA_BYTE, Math.max( total, 1 ) );
+					JstacsHmmNative.check( (int) JstacsHmmNative.jh_posterior_decode_u8.invokeExact( model, ds, paths, MemorySegment.NULL ) );
+					long p = 0;
+					for( int i = 0; i < n; i++ ) {
+						int L = data.getElementAt( i ).getLength();
+						res[i] = new int[L];
+						for( int l = 0; l < L; l++ ) {
+							res[i][l] = paths.get( ValueLayout.JAVA_BYTE, p + l ) & 0xFF;
+						}
+						p += L;
+					}
+				} else {
+					MemorySegment paths = arena.allocate( ValueLayout.JAVA_INT, Math.max( total, 1 ) );
+					JstacsHmmNative.check( (int) JstacsHmmNative.jh_posterior_decode.invokeExact( model, ds, paths, MemorySegment.NULL ) );
+					long p = 0;
+					for( int i = 0; i < n; i++ ) {
+						int L = data.getElementAt( i ).getLength();
+						res[i] = new int[L];
+						MemorySegment.copy( paths, ValueLayout.JAVA_INT, 4 * p, res[i], 0, L );
+						p += L;
+					}
 				}
 			} finally {
 				JstacsHmmNative.jh_model_destroy.invokeExact( model );

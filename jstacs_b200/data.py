@@ -237,6 +237,19 @@ def java_random_dna(n_seq: int, length, first_seed: int = 0x5EED0000, start_inde
     mask = np.uint64(JavaRandom.MASK)
     add = np.uint64(0xB)
     max_len = int(lens.max()) if n_seq else 0
+    if n_seq and n_seq * 64 < max_len:  # few long sequences: vectorise ALONG each sequence with the LCG jump-ahead
+        B = 1 << 20                     # state_{p+k} = state_p * A^k + c * (1 + A + ... + A^(k-1))   (mod 2^48, computed mod 2^64)
+        apow = np.multiply.accumulate(np.concatenate([[np.uint64(1)], np.full(B, mult, dtype=np.uint64)]))  # A^0 .. A^B
+        cacc = np.concatenate([[np.uint64(0)], np.add.accumulate(apow[:-1]) * add])                          # c * sum_{i<k} A^i
+        for n in range(n_seq):
+            state = ((np.uint64(n + start_index) + np.uint64(first_seed)) ^ mult) & mask
+            L = int(lens[n])
+            for p0 in range(0, L, B):
+                k = min(B, L - p0)
+                st = (state * apow[1:k + 1] + cacc[1:k + 1]) & mask  # states after 1 .. k steps
+                codes[offsets[n] + p0:offsets[n] + p0 + k] = (st >> np.uint64(46)).astype(np.uint8)
+                state = st[-1]
+        return DataSet.from_packed(codes, offsets, DNA, f"javaRandom({n_seq})")
     # process sequences in blocks, stepping all LCGs of a block in lock step
     block = 1 << 16
     for b0 in range(0, n_seq, block):

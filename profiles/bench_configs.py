@@ -23,14 +23,17 @@ for kv in filter(None, os.environ.get("JH_OPTS", "").split(",")):  # library opt
 
 
 def run(name, hmm, data, what, reps=3):
-    if only and name not in only:
+    if (only and name not in only) or (name.startswith("full_") and not (only and name in only)):
         return
+    if callable(data):
+        data = data()
     eng, nd = hmm._engine(), hmm._data(data)
     res, S = data.getNumberOfResidues(), hmm.getNumberOfStates()
     fn = {"estep": lambda: eng.estep(nd, fetch=False), "loglik": lambda: eng.loglik(nd), "viterbi": lambda: eng.viterbi(nd),
           "decode": lambda: eng.posterior_decode(nd), "viterbi_u8": lambda: eng.viterbi(nd, narrow=True),
           "decode_u8": lambda: eng.posterior_decode(nd, narrow=True)}[what]
-    fn()
+    if not name.startswith("full_"):
+        fn()  # warm-up
     ms = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -43,6 +46,7 @@ def run(name, hmm, data, what, reps=3):
                       "call_ms": round(float(np.median([m[1] for m in ms])), 3), "residues_states_per_s": res * S / (k * 1e-3),
                       "residues_per_s": res / (k * 1e-3)}), flush=True)
     nd.close()
+    data._native = None
 
 
 n = lambda x: max(64, int(x * scale))
@@ -63,3 +67,17 @@ run("long_bw_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), "est
 run("cfg4_decode_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode")
 run("cfg2_viterbi_u8_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "viterbi_u8")
 run("cfg4_decode_u8_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode_u8")
+# BASELINE configs[4] at FULL size (GRCh38 chromosome lengths in Mb, 3.085e9 residues); only when named explicitly
+GRCH38_MB = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
+_full5 = []
+
+
+def full5():
+    if not _full5:
+        _full5.append(make_data(24, [mb * 1_000_000 for mb in GRCH38_MB]))
+    return _full5[0]
+
+
+run("full_cfg5_loglik", banded_hmm(128, 4, 0), full5, "loglik", reps=1)
+run("full_cfg5_decode_u8", banded_hmm(128, 4, 0), full5, "decode_u8", reps=1)
+run("full_cfg5_bw", banded_hmm(128, 4, 0), full5, "estep", reps=1)
