@@ -682,9 +682,11 @@ extern "C" int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_r
 static int check_pair(jh_model *m, jh_dataset *d) {
   if (!m || !d) { jh_set_error("null handle"); return JH_ERR_INVALID; }
   if (d->alphabet != m->a) { jh_set_error("The AlphabetContainer of the data set and the model do not match."); return JH_ERR_ALPHABET; }
-  if (m->m < 1) { jh_set_error("transition order 0 is not on the native path yet"); return JH_ERR_UNSUPPORTED; }
   return JH_OK;
 }
+// Models that run on the general context-graph kernels (kernels_general.cuh, one sequence per thread): silent states, and
+// transition order 0 (a single context for every layer: every context is final, HigherOrderHMM.java:498, 1046-1058).
+static bool general_model(const jh_model *m) { return m->has_silent || m->m == 0; }
 
 static int group_size(const jh_model *m) {
   int g = 2;
@@ -914,7 +916,7 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
   const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
   if (items == 0) return JH_OK;
-  if (g_opt.pass1_cta && P.SP >= 64 && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
+  if (g_opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
     const size_t smem_c = ((size_t)P.H * P.SP + 2 * (size_t)P.SP + 16) * sizeof(double);
 #define JH_P1C(IND_)                                                                                                                     \
   {                                                                                                                                      \
@@ -1165,7 +1167,7 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
   DevBuf<double> d_out;
   if ((r = d_out.alloc(d->n_seq))) return r;
   timing_begin(m);
-  if (m->has_silent) {
+  if (general_model(m)) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_loglik(m, d, W, d_out.p);
   } else if (prefer_sparse(m, d)) r = run_loglik_sparse(m, d, d_out.p);
@@ -1340,7 +1342,12 @@ static int viterbi_impl(jh_model *m, jh_dataset *d, int32_t *paths, uint8_t *pat
   DevBuf<double> d_scores;
   if ((r = d_paths.alloc(d->n_res)) || (r = d_scores.alloc(d->n_seq))) return r;
   timing_begin(m);
-  r = run_viterbi(m, d, d_paths.p, d_scores.p, nullptr);
+  if (general_model(m)) {  // order 0: one state per residue, the data set offsets are the path pointers
+    DevBuf<int64_t> d_len;
+    if ((r = d_len.alloc(d->n_seq))) return r;
+    r = run_general_viterbi(m, d, d_paths.p, d->d_offsets.p, d_len.p, d_scores.p, nullptr);
+    if (!r) JH_CUDA(cudaStreamSynchronize(m->st()));
+  } else r = run_viterbi(m, d, d_paths.p, d_scores.p, nullptr);
   timing_end(m);
   if (r) return r;
   if ((r = copy_paths_out(m, d, d_paths.p, paths, paths8))) return r;
@@ -1390,6 +1397,7 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   if ((r = d_post.alloc((size_t)m->S * L)) || (r = d_list.alloc(1))) return r;
   int32_t sid = (int32_t)seq_index;
   JH_CUDA(cudaMemcpyAsync(d_list.p, &sid, sizeof(int32_t), cudaMemcpyHostToDevice, m->st()));
+  if (m->m == 0) { jh_set_error("state posteriors of order-0 transitions (HigherOrderHMM.java:296-308) are not on the native path"); return JH_ERR_UNSUPPORTED; }
   if (m->has_silent) {  // general context graph: silent states score -inf (silentZero, HigherOrderHMM.java:316)
     jhg::WorkList W{d_list.p, nullptr, nullptr, 1};
     if ((r = run_general_posterior(m, d, W, L, d_post.p, nullptr, nullptr))) return r;
@@ -1487,6 +1495,7 @@ static int posterior_decode_impl(jh_model *m, jh_dataset *d, int32_t *paths, uin
   DevBuf<int32_t> d_paths;
   DevBuf<double> d_ll;
   if ((r = d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
+  if (m->m == 0) { jh_set_error("state posteriors of order-0 transitions (HigherOrderHMM.java:296-308) are not on the native path"); return JH_ERR_UNSUPPORTED; }
   timing_begin(m);
   if (m->has_silent) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
@@ -1660,7 +1669,7 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));  // resetStatistics (HOH:890-895)
   if (d->n_seq == 0) return JH_OK;
-  if (m->has_silent) {  // general context graph: one sequence per thread, reference order
+  if (general_model(m)) {  // general context graph: one sequence per thread, reference order
     cudaEventRecord(m->evk0, s);
     int r = mode == JH_MODE_VITERBI ? run_general_viterbi(m, d, nullptr, nullptr, nullptr, nullptr, m->d_stats.p) : run_general_estep(m, d);
     cudaEventRecord(m->evk1, s);

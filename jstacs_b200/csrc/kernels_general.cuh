@@ -117,7 +117,7 @@ __device__ __forceinline__ void bwd_last_layer(const DevModel &M, const GenModel
     const int e = M.ctx_elem[M.lc_ctx_ptr[lc] + c];
     const int p0 = M.elem_child_ptr[e], p1 = M.elem_child_ptr[e + 1];
     const int ls = M.ctx_last[M.lc_ctx_ptr[lc] + c];
-    const double val = (ls >= 0 && M.is_final[ls]) ? 0.0 : JH_NEG_INF;
+    const double val = (M.m == 0 || (ls >= 0 && M.is_final[ls])) ? 0.0 : JH_NEG_INF;
     int ns = 0;
     double off = JH_NEG_INF, mx = JH_NEG_INF;
     for (int p = p0; p < p1; p++) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void bwd_last_layer(const DevModel &M, const GenModel
       if (VITERBI) {
         res = fmax(val, mx);
         // trailing silent states of the trace (HOH:667-705): staying has distance (0 - bwd)^2 for a final state, inf otherwise
-        double dist = (ls >= 0 && M.is_final[ls]) ? dsub(0.0, res) : JH_NEG_INF;
+        double dist = (M.m == 0 || (ls >= 0 && M.is_final[ls])) ? dsub(0.0, res) : JH_NEG_INF;
         double best = dmul(dist, dist);
         for (int p = p0; p < p1; p++) {
           if (!X.silent[M.child_state[p]]) continue;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128) k_general_estep(DevModel M, GenModel X, D
       const int ncL = M.lc_ctx_ptr[lcL + 1] - M.lc_ctx_ptr[lcL];
       for (int i = 0; i < ncL; i++) {
         const int ls = M.ctx_last[M.lc_ctx_ptr[lcL] + i];
-        if (ls >= 0 && M.is_final[ls]) res = lse2(res, Fw.at(L, i));
+        if (M.m == 0 || (ls >= 0 && M.is_final[ls])) res = lse2(res, Fw.at(L, i));
       }
     }
     const bool counts = !isinf(res);

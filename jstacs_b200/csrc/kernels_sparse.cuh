@@ -568,15 +568,19 @@ __global__ void __launch_bounds__(256) k_sparse_pass1_cta(SparseDev F, DevData D
         ew[k] = T[(size_t)k * SP + j];
       }
     }
-    auto gather = [&](const double *v, const double (&w)[IND]) {
+    auto gather = [&](const double *v, const double (&w)[IND]) {  // NA independent accumulator chains (dependent FMAs are the critical path)
+      constexpr int NA = IND >= 16 ? 8 : IND >= 8 ? 4 : 2;
       const char *base = reinterpret_cast<const char *>(v);
-      double a0 = *reinterpret_cast<const double *>(base + eo[0]) * w[0], a1 = *reinterpret_cast<const double *>(base + eo[1]) * w[1];
+      double acc[NA];
 #pragma unroll
-      for (int k = 2; k < IND; k += 2) {
-        a0 = fma(*reinterpret_cast<const double *>(base + eo[k]), w[k], a0);
-        a1 = fma(*reinterpret_cast<const double *>(base + eo[k + 1]), w[k + 1], a1);
-      }
-      return a0 + a1;
+      for (int k = 0; k < NA; k++) acc[k] = *reinterpret_cast<const double *>(base + eo[k]) * w[k];
+#pragma unroll
+      for (int k = NA; k < IND; k++) acc[k % NA] = fma(*reinterpret_cast<const double *>(base + eo[k]), w[k], acc[k % NA]);
+#pragma unroll
+      for (int d = NA / 2; d >= 1; d >>= 1)
+#pragma unroll
+        for (int k = 0; k < d; k++) acc[k] += acc[k + d];
+      return acc[0];
     };
     // factor of a published maximum; false when it has left the safe range
     auto lazy_scale = [&](const unsigned *mb, double &v, long long &expo) {

@@ -42,7 +42,7 @@ def enumerate_paths(hmm, x):
 
     def rec(layer, ctx, logp, path, edges):
         last = tr.getLastContextState(layer, ctx)
-        if layer == L and last >= 0 and hmm.finalState[last]:
+        if layer == L and (tr.getMaximalMarkovOrder() == 0 or (last >= 0 and hmm.finalState[last])):  # HOH:498 'order 0' rule
             out.append((tuple(path), logp, list(edges)))
         for ch in range(tr.getNumberOfChildren(layer, ctx)):
             state, nxt, adv = tr.fillTransitionInformation(layer, ctx, ch)
@@ -116,6 +116,16 @@ def sparse_hmm(seed=3, ess=0.0):
         TransitionElement([2], [0, 2], [ess, ess]),
     ]
     hmm = HigherOrderHMM(pars, ["a", "b", "c"], em, *te)
+    hmm.setOutputStream(None)
+    return set_closed_form_parameters(hmm)
+
+
+def order0_hmm(ess=0.0, k=1):
+    """Transition order 0 (one transition element with the empty context: the states are drawn independently per position,
+    HigherOrderHMM.java:295-308, 498), unsorted child order, emission order k."""
+    pars = BaumWelchParameterSet(1, IterationCondition(3), 1)
+    em = [HigherOrderDiscreteEmission(DNA, ess, k) for _ in range(3)]
+    hmm = HigherOrderHMM(pars, ["a", "b", "c"], em, TransitionElement(None, [2, 0, 1], [ess] * 3))
     hmm.setOutputStream(None)
     return set_closed_form_parameters(hmm)
 

@@ -7,7 +7,7 @@ Every test runs the reference-order kernels (fast=0) and, where the model allows
 import numpy as np
 import pytest
 
-from helpers import dataset_of, ergodic_hmm, order2_hmm, random_dna, silent_hmm, sparse_hmm
+from helpers import dataset_of, ergodic_hmm, order0_hmm, order2_hmm, random_dna, silent_hmm, sparse_hmm
 from jstacs_b200 import (DNA, BaumWelchParameterSet, DataSet, DiscreteEmission, HigherOrderHMM, IterationCondition,
                          Sequence, SmallDifferenceOfFunctionEvaluationsCondition, TransitionElement, ViterbiParameterSet,
                          WrongAlphabetException)
@@ -333,6 +333,33 @@ def test_posterior_decoding_octets_ragged(nat, oracle_lib, fast, name):
         assert clear.mean() > 0.95
 
 
+def test_transition_order_zero(nat, oracle_lib):
+    """getMaximalMarkovOrder() == 0: one context for every layer, every context final (HigherOrderHMM.java:498, 1046-1058);
+    runs on the general context-graph kernels.  Scoring, windows, bit-exact Viterbi, counts, Baum-Welch and Viterbi training."""
+    hmm = order0_hmm(ess=2.0)
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(4, 40, lo=1, hi=60)
+    np.testing.assert_allclose(hmm.getLogScoreFor(data), om.loglik(data.codes, data.offsets), rtol=LL_RTOL)
+    res = hmm.getViterbiPathsFor(data)
+    rp, rs, _ = om.viterbi(data.codes, data.offsets)
+    for (p, s), p_ref, s_ref in zip(res, rp, rs):
+        assert np.array_equal(p, p_ref) and s == s_ref
+    eng, nd = hmm._engine(), hmm._data(data)
+    ts, es, sc = eng.estep(nd)
+    rts, res_, rsc = om.estep(data.codes, data.offsets)
+    np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+    np.testing.assert_allclose(es, res_, rtol=COUNT_TOL, atol=COUNT_TOL)
+    assert sc == pytest.approx(rsc, rel=LL_RTOL)
+    with pytest.raises(nat.NativeError):
+        hmm.decodePosteriorPathsFor(data)
+    hmm.trainingParameter = BaumWelchParameterSet(1, IterationCondition(4), 1)
+    hmm.train(data)
+    np.testing.assert_allclose(hmm.last_objectives[0], om.train(data.codes, data.offsets, max_iter=4), rtol=LL_RTOL)
+    for g, r in zip(hmm._engine().get_params(), om.get_params()):
+        fin = np.isfinite(r)
+        np.testing.assert_allclose(g[fin], r[fin], rtol=0, atol=PARAM_TOL)
+
+
 # ---- general context graph: silent states (profile-like HMM), one sequence per thread --------------------------
 def test_silent_states_loglik_viterbi_counts_training(nat, oracle_lib):
     """silent states + trailing silent states on the GPU, reference order (kernels_general.cuh)."""
@@ -458,8 +485,9 @@ def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, deg
         nat.check(nat.lib().jh_set_option(b"pass1_cta", 1))
 
 
+@pytest.mark.parametrize("cta", [0, 1], ids=["warp_per_sequence", "cta_per_sequence"])
 @pytest.mark.parametrize("name", ["erg_s2_k1", "sparse", "erg_s5_k2", "erg_s16_k1", "erg_s32_k3"])
-def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name):
+def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta):
     """The checkpointed warp-per-sequence path (taken for a few long sequences) also covers models with <= 32 states:
     forced here with fast_variant 4 and a tiny chunk length."""
     hmm = MODELS[name]()
@@ -469,6 +497,7 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name):
     data = dataset_of([random_dna(rng, int(L)) for L in lens])
     nat.check(nat.lib().jh_set_option(b"fast_variant", 4))
     nat.check(nat.lib().jh_set_option(b"chunk", 32))
+    nat.check(nat.lib().jh_set_option(b"pass1_cta", cta))
     try:
         ll_ref = om.loglik(data.codes, data.offsets)
         np.testing.assert_allclose(hmm.getLogScoreFor(data), ll_ref, rtol=LL_RTOL)
@@ -492,6 +521,7 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name):
     finally:
         nat.check(nat.lib().jh_set_option(b"fast_variant", 0))
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
+        nat.check(nat.lib().jh_set_option(b"pass1_cta", 1))
 
 
 def test_full_size_properties_cfg3_sample(nat):
