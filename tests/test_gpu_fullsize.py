@@ -126,5 +126,5 @@ def test_cfg5_shape_many_chunks_vs_oracle(nat, oracle_lib):
     # ~1e-8 at this length (observed difference 6.5e-9), the scaled recursion on the GPU ~1e-13.  1e-9 holds at 1 kb (above).
     np.testing.assert_allclose(ts, rts, rtol=5e-8, atol=COUNT_TOL)
     np.testing.assert_allclose(es, res, rtol=5e-8, atol=COUNT_TOL)
-    assert ts.sum() == pytest.approx(data.getNumberOfResidues(), rel=1e-12)  # ... while the scaled counts add up to 1e-12
+    assert ts.sum() == pytest.approx(data.getNumberOfResidues(), rel=1e-11)  # ... while the scaled counts add up to 1e-11
     assert sc == pytest.approx(rsc, rel=LL_RTOL)
