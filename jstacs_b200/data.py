@@ -185,11 +185,21 @@ class DataSet:
     def getNumberOfResidues(self) -> int:
         return int(self.offsets[-1])
 
-    def shard(self, rank: int, world: int) -> "DataSet":
-        """Contiguous shard balanced by RESIDUE count, not by sequence count like the
-        reference's thread partition (HigherOrderHMM.java:1241-1248)."""
-        from .parallel import shard_bounds
+    def shard(self, rank: int, world: int, policy: str = "contiguous") -> "DataSet":
+        """Shard balanced by RESIDUE count, not by sequence count like the reference's thread partition
+        (HigherOrderHMM.java:1241-1248).  policy "contiguous": a range of sequences; "lpt": longest-processing-time bin
+        packing (few very long sequences)."""
+        from .parallel import shard_bounds, shard_lpt
 
+        if policy == "lpt":
+            idx = shard_lpt(self.offsets, rank, world)
+            lens = np.diff(self.offsets)[idx]
+            off = np.zeros(idx.size + 1, dtype=np.int64)
+            np.cumsum(lens, out=off[1:])
+            codes = np.concatenate([self.codes[self.offsets[i]:self.offsets[i + 1]] for i in idx]) if idx.size else np.zeros(0, np.uint8)
+            return DataSet.from_packed(codes, off, self.con, f"{self.annotation}[lpt {rank}/{world}]")
+        if policy != "contiguous":
+            raise ValueError("unknown sharding policy")
         lo, hi = shard_bounds(self.offsets, rank, world)
         off = self.offsets[lo:hi + 1] - self.offsets[lo]
         return DataSet.from_packed(self.codes[self.offsets[lo]:self.offsets[hi]], off, self.con,

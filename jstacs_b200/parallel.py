@@ -26,6 +26,24 @@ def shard_bounds(offsets: np.ndarray, rank: int, world: int):
     return cuts[rank], cuts[rank + 1]
 
 
+def shard_lpt(offsets: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Sequence indices of `rank` under longest-processing-time bin packing by residue count (chromosome-scale
+    data — cfg5's 24 sequences of 47..248 Mb — cannot be balanced by a contiguous cut).  Deterministic: sequences by
+    decreasing length (ties by index) go to the currently lightest rank (ties by rank); indices are returned ascending."""
+    if not 0 <= rank < world:
+        raise ValueError("rank outside the world")
+    lens = np.diff(offsets)
+    order = np.lexsort((np.arange(lens.size), -lens))
+    load = [0] * world
+    mine = []
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += int(lens[i])
+        if r == rank:
+            mine.append(int(i))
+    return np.array(sorted(mine), dtype=np.int64)
+
+
 def allreduce_stats_(tensor, group=None):
     """In-place sum of the [transition | emission | score] statistics block over all ranks (torch.distributed;
     NCCL over NVLink on the GPU box, gloo in the CPU tests)."""

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from jstacs_b200.parallel import shard_bounds  # noqa: E402
+from jstacs_b200.parallel import shard_bounds, shard_lpt  # noqa: E402
 from jstacs_b200.workloads import ergodic_hmm, make_data, ragged_lengths  # noqa: E402
 
 
@@ -54,6 +54,25 @@ def test_shard_bounds_more_ranks_than_sequences():
     assert seen == [0, 1]
     with pytest.raises(ValueError):
         shard_bounds(offsets, 4, 4)
+
+
+def test_lpt_sharding_of_chromosome_scale_lengths():
+    """cfg5 (GRCh38 chromosome sizes in Mb): LPT bin packing is a partition and balances what a contiguous cut cannot."""
+    mb = np.array([248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57], np.int64)
+    offsets = np.zeros(mb.size + 1, np.int64)
+    np.cumsum(mb, out=offsets[1:])
+    for world in (1, 2, 4, 8):
+        parts = [shard_lpt(offsets, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(mb.size))
+        load = np.array([mb[p].sum() for p in parts])
+        assert load.max() <= max(mb.max(), 1.1 * mb.sum() / world)  # within 10 % of the mean, or one chromosome
+        cont = np.array([offsets[hi] - offsets[lo] for lo, hi in (shard_bounds(offsets, r, world) for r in range(world))])
+        assert load.max() <= cont.max()
+    data = make_data(5, [30, 10, 50, 20, 40])
+    a, b = data.shard(0, 2, policy="lpt"), data.shard(1, 2, policy="lpt")
+    assert a.getNumberOfResidues() + b.getNumberOfResidues() == 150 and abs(a.getNumberOfResidues() - b.getNumberOfResidues()) <= 10
+    i0 = shard_lpt(data.offsets, 0, 2)
+    assert np.array_equal(a.codes[:int(np.diff(data.offsets)[i0[0]])], data.getElementAt(int(i0[0])).codes)
 
 
 def _worker(rank, world, port, n_iter, out_dir):
