@@ -860,6 +860,12 @@ static int run_general_posterior(jh_model *m, jh_dataset *d, const jhg::WorkList
 // ---- sparse path (kernels_sparse.cuh): 33..256 states, chromosome-scale sequences ----------------------------------
 // One warp per sequence/chunk.  Models with more than 32 states always take it; smaller ones when the data set is a few long
 // sequences (the octet kernels need 8 sequences per warp to fill the GPU and (L+1) x 8 x G doubles of scratch per warp).
+// fast_variant in force for a model: the lane-per-state comparison kernels (1..3) keep the emission table in shared memory,
+// so models with a large table (e_global) always take the production mapping
+static int variant_of(const jh_model *m) {
+  return (m->fast.usable && m->fast.e_global && g_opt.fast_variant != 4) ? 0 : (int)g_opt.fast_variant;
+}
+
 static bool prefer_sparse(const jh_model *m, const jh_dataset *d) {
   if (!g_opt.fast || !m->sparse.usable) return false;
   if (m->S > 32 || g_opt.fast_variant == 4) return true;
@@ -1057,13 +1063,13 @@ static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
 
 // Octet scoring (kernels_mma.cuh): ONE launch over all octets (longest first, fetched dynamically: no scratch to size);
 // sequences the scaled recursion could not score are re-run by the log-space kernel.
-template <int NT>
-static int launch_mma_loglik(jh_model *m, jh_dataset *d, double *d_out) {
+template <int NT, bool EG>
+static int launch_mma_loglik_eg(jh_model *m, jh_dataset *d, double *d_out) {
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhm::k_mma_loglik<NT>;
+  auto kern = jhm::k_mma_loglik<NT, EG>;
   const int64_t n_oct = (int64_t)d->oct_hbase.size() - 1;
-  size_t smem = (size_t)F.H * F.G * sizeof(double);
+  size_t smem = EG ? 64 : (size_t)F.H * F.G * sizeof(double);
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
@@ -1080,19 +1086,24 @@ static int launch_mma_loglik(jh_model *m, jh_dataset *d, double *d_out) {
   return JH_OK;
 }
 
+template <int NT>
+static int launch_mma_loglik(jh_model *m, jh_dataset *d, double *d_out) {
+  return m->fast.e_global ? launch_mma_loglik_eg<NT, true>(m, d, d_out) : launch_mma_loglik_eg<NT, false>(m, d, d_out);
+}
+
 // Lane-per-sequence kernels for 2..4 states (kernels_lanes.cuh).  mode 1: E-step of bucket b; mode 0: scoring of all octets.
-template <int S, int MODE>
-static int launch_lanes(jh_model *m, jh_dataset *d, size_t b, double *d_out) {
+template <int S, int MODE, bool EG>
+static int launch_lanes_eg(jh_model *m, jh_dataset *d, size_t b, double *d_out) {
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhl::k_lanes<S, MODE>;
+  auto kern = jhl::k_lanes<S, MODE, EG>;
   const int64_t oct0 = MODE == 1 ? d->bucket_oct_ptr[b] : 0;
   const int64_t n_oct = MODE == 1 ? d->bucket_oct_ptr[b + 1] - oct0 : (int64_t)d->oct_hbase.size() - 1;
   const int64_t rows = MODE == 1 ? d->bucket_len[b] + 1 : 0;
   if (n_oct <= 0) return JH_OK;
   const int NT = 128, wpc = NT / 32, HS = F.H * S;
-  const int ec_smem = MODE == 1 && (size_t)HS * 32 * wpc * sizeof(double) <= 96 * 1024;
-  size_t smem = ((size_t)HS + (ec_smem ? (size_t)HS * 32 * wpc : 0)) * sizeof(double);
+  const int ec_smem = !EG && MODE == 1 && (size_t)HS * 32 * wpc * sizeof(double) <= 96 * 1024;
+  size_t smem = EG ? 64 : ((size_t)HS + (ec_smem ? (size_t)HS * 32 * wpc : 0)) * sizeof(double);
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -1127,6 +1138,11 @@ static int launch_lanes(jh_model *m, jh_dataset *d, size_t b, double *d_out) {
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
   return JH_OK;
+}
+
+template <int S, int MODE>
+static int launch_lanes(jh_model *m, jh_dataset *d, size_t b, double *d_out) {
+  return m->fast.e_global ? launch_lanes_eg<S, MODE, true>(m, d, b, d_out) : launch_lanes_eg<S, MODE, false>(m, d, b, d_out);
 }
 
 static int run_loglik_lanes(jh_model *m, jh_dataset *d, double *d_out) {
@@ -1171,8 +1187,8 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_loglik(m, d, W, d_out.p);
   } else if (prefer_sparse(m, d)) r = run_loglik_sparse(m, d, d_out.p);
-  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_loglik_octets(m, d, d_out.p);
-  else if (g_opt.fast && m->fast.usable && m->fast.G <= 4 && g_opt.fast_variant == 0) r = run_loglik_lanes(m, d, d_out.p);
+  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_loglik_octets(m, d, d_out.p);
+  else if (g_opt.fast && m->fast.usable && m->fast.G <= 4 && variant_of(m) == 0) r = run_loglik_lanes(m, d, d_out.p);
   else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
   else r = run_loglik_exact(m, d, d_out.p, nullptr, 0);
   timing_end(m);
@@ -1220,16 +1236,16 @@ extern "C" int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, cons
 static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
 
 // Lane-per-sequence Viterbi (kernels_viterbi.cuh): plain first-order models with sorted child lists; one launch per bucket.
-template <int S>
-static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_scores) {
+template <int S, bool EG>
+static int launch_viterbi_lanes_eg(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_scores) {
   using C = jhv::VitCfg<S>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhv::k_viterbi_lanes<S>;
+  auto kern = jhv::k_viterbi_lanes<S, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b];
   if (n_oct <= 0) return JH_OK;
   const int NT = 128, wpc = NT / 32;
-  size_t smem = ((size_t)S * S + S + (size_t)F.H * S) * sizeof(double);
+  size_t smem = ((size_t)S * S + S + (EG ? 0 : (size_t)F.H * S)) * sizeof(double);
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -1253,6 +1269,11 @@ static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, int32_t *d
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
   return JH_OK;
+}
+
+template <int S>
+static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_scores) {
+  return m->fast.e_global ? launch_viterbi_lanes_eg<S, true>(m, d, b, d_paths, d_scores) : launch_viterbi_lanes_eg<S, false>(m, d, b, d_paths, d_scores);
 }
 
 // One launch per length bucket so that the per-slot scratch follows the bucket's longest sequence.
@@ -1417,12 +1438,12 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
 }
 
 // Octet posterior decoding (kernels_mma.cuh), one launch per length bucket; long buckets chunked like the E-step.
-template <int NT, bool CHUNKED>
+template <int NT, bool CHUNKED, bool EG>
 static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem, int32_t *d_paths, double *d_ll) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhm::k_mma_decode<NT, CHUNKED>;
+  auto kern = jhm::k_mma_decode<NT, CHUNKED, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
   const int64_t CK = g_opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
@@ -1458,17 +1479,19 @@ static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, int32_t *d_pa
   jhf::FastTables &F = m->fast;
   const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b], rows = d->bucket_len[b] + 1;
   if (n_oct <= 0) return JH_OK;
-  const size_t smem = (size_t)F.H * C::G * sizeof(double) + (size_t)C::WARPS * C::RING * C::SLOTB;
-  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_decode<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const bool eg = F.e_global;
+  const size_t smem = (eg ? 0 : (size_t)F.H * C::G * sizeof(double)) + (size_t)C::WARPS * C::RING * C::SLOTB;
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_decode<NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_decode<NT, false>, C::NTHREADS, smem));
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_decode<NT, false, false>, C::NTHREADS, smem));
   if (per_sm < 1) { jh_set_error("octet decoding kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
   if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
   const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
   const bool chunked = g_opt.oct_chunk > 0 && rows > 2 * g_opt.oct_chunk &&
                        (g_opt.oct_chunk_force || grid * C::WARPS * per_slot > g_opt.scratch_mb * 1024 * 1024);
-  return chunked ? launch_mma_decode_impl<NT, true>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false>(m, d, b, grid, smem, d_paths, d_ll);
+  if (eg) return chunked ? launch_mma_decode_impl<NT, true, true>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, true>(m, d, b, grid, smem, d_paths, d_ll);
+  return chunked ? launch_mma_decode_impl<NT, true, false>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, false>(m, d, b, grid, smem, d_paths, d_ll);
 }
 
 static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) {
@@ -1502,7 +1525,7 @@ static int posterior_decode_impl(jh_model *m, jh_dataset *d, int32_t *paths, uin
     r = run_general_posterior(m, d, W, d->max_len, nullptr, d_paths.p, d_ll.p);
   } else
   if (prefer_sparse(m, d)) r = run_decode_sparse(m, d, d_paths.p, d_ll.p);
-  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && g_opt.fast_variant == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
+  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
   else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
   timing_end(m);
   if (r) return r;
@@ -1580,12 +1603,12 @@ static int ensure_octet_hashes(jh_model *m, jh_dataset *d) {
 // Octet E-step (kernels_mma.cuh): one launch per length bucket, 8 warps per CTA, one CTA per SM, octets fetched dynamically.
 // Buckets whose full forward rows would not leave scratch for the whole grid run the chunked variant (checkpoints every
 // `oct_chunk` positions, rows of one chunk per resident warp).
-template <int NT, bool CHUNKED>
+template <int NT, bool CHUNKED, bool EG>
 static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhm::k_mma_estep<NT, CHUNKED>;
+  auto kern = jhm::k_mma_estep<NT, CHUNKED, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
   const int64_t CK = g_opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
@@ -1621,24 +1644,26 @@ static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
   jhf::FastTables &F = m->fast;
   const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b], rows = d->bucket_len[b] + 1;
   if (n_oct <= 0) return JH_OK;
-  const size_t smem = C::smem_bytes(F.H);
+  const bool eg = F.e_global;
+  const size_t smem = C::smem_bytes(eg ? 0 : F.H);
   int per_sm = 0;
-  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_estep<NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_estep<NT, false>, C::NTHREADS, smem));
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_estep<NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_estep<NT, false, false>, C::NTHREADS, smem));
   if (per_sm < 1) { jh_set_error("octet E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
   if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
   const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
   const bool chunked = g_opt.oct_chunk > 0 && rows > 2 * g_opt.oct_chunk &&
                        (g_opt.oct_chunk_force || grid * C::WARPS * per_slot > g_opt.scratch_mb * 1024 * 1024);
-  return chunked ? launch_mma_estep_impl<NT, true>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false>(m, d, b, grid, smem);
+  if (eg) return chunked ? launch_mma_estep_impl<NT, true, true>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, b, grid, smem);
+  return chunked ? launch_mma_estep_impl<NT, true, false>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, false>(m, d, b, grid, smem);
 }
 
 static int run_estep_fast(jh_model *m, jh_dataset *d) {
   int r = JH_OK;
   JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * jhf::EC_REPLICAS * m->fast.H * m->fast.G, m->st()));
-  const bool octets = g_opt.fast_variant == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
-  const bool lanes = g_opt.fast_variant == 0 && m->fast.G <= 4;  // one sequence per lane
+  const bool octets = variant_of(m) == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
+  const bool lanes = variant_of(m) == 0 && m->fast.G <= 4;  // one sequence per lane
   for (size_t b = 0; lanes && b + 1 < d->bucket_ptr.size() && !r; b++) r = m->fast.G == 2 ? launch_lanes<2, 1>(m, d, b, nullptr) : launch_lanes<4, 1>(m, d, b, nullptr);
   for (size_t b = 0; octets && b + 1 < d->bucket_ptr.size() && !r; b++)
     r = m->fast.G == 8 ? launch_mma_estep<1>(m, d, b) : m->fast.G == 16 ? launch_mma_estep<2>(m, d, b) : launch_mma_estep<4>(m, d, b);
@@ -1684,7 +1709,7 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
     int32_t *flag = m->d_fallback.p + d->n_seq + 1;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
     JH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
-    if (!sparse && g_opt.fast_variant == 0 && (r = ensure_octet_hashes(m, d))) return r;
+    if (!sparse && variant_of(m) == 0 && (r = ensure_octet_hashes(m, d))) return r;
     cudaEventRecord(m->evk0, s);
     r = sparse ? run_estep_sparse(m, d) : run_estep_fast(m, d);
     cudaEventRecord(m->evk1, s);

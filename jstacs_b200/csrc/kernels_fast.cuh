@@ -54,7 +54,7 @@ struct FastDev {
 };
 
 struct FastTables {
-  bool usable = false;
+  bool usable = false, e_global = false;  // e_global: emission table too large for shared memory (> 64 KB)
   int S = 0, G = 0, a = 0, Kmax = 0, H = 0, n_child = 0, n_cond = 0;
   double *d_T = nullptr, *d_Tt = nullptr, *d_pi = nullptr, *d_E = nullptr, *d_fin = nullptr;
   int *d_korder = nullptr, *d_tstat = nullptr, *d_pistat = nullptr, *d_estat_tab = nullptr, *d_estat_mod = nullptr;
@@ -107,7 +107,8 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
   while (G < S) G *= 2;
   int64_t H = a;
   for (int i = 0; i < Kmax; i++) H *= a;
-  if (H * G * 8 > 64 * 1024) return JH_OK;
+  if (H > 65536 || H * G * 8 > ((int64_t)16 << 20)) return JH_OK;  // context hashes are uint16 records
+  F.e_global = H * G * 8 > 64 * 1024;  // the emission table stays in global memory (kernels with the EG flag)
   std::vector<int> tmap((size_t)G * G, -1), pimap(G, -1), tstat((size_t)G * G, -1), pistat(G, -1), korder(G, 0), etab(G, -1), emod(G, 1);
   std::vector<double> fin(G, 0.0);
   std::vector<char> seen(S, 0);

@@ -63,16 +63,17 @@ __device__ __forceinline__ void load_row(const double *src, double (&v)[S]) {
 
 // MODE 0: scoring only (out = log-likelihood per sequence); MODE 1: Baum-Welch E-step.
 // stats layout and fallback list as in kernels_mma.cuh.  ec_smem != 0: emission counts in the shared lane-private table.
-template <int S, int MODE>
+template <int S, int MODE, bool EG>
 __global__ void __launch_bounds__(128) k_lanes(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch, int *fexp_scratch, int64_t rows,
                                                double *stats, double *gEC, int32_t *fallback, double *out, int ec_smem) {
   extern __shared__ double sm[];
   const int HS = F.H * S;
-  double *sE = sm;
-  double *ecw = sE + HS + (size_t)(threadIdx.x >> 5) * HS * 32;  // [H*S][32 lanes], this warp's table
-  for (int i = threadIdx.x; i < HS; i += blockDim.x) sE[i] = F.E[i];
+  const double *sE = EG ? F.E : sm;  // EG: emission table too large for shared memory (then ec_smem == 0 as well)
+  double *ecw = sm + HS + (size_t)(threadIdx.x >> 5) * HS * 32;  // [H*S][32 lanes], this warp's table
+  if (!EG)
+    for (int i = threadIdx.x; i < HS; i += blockDim.x) sm[i] = F.E[i];
   if (MODE == 1 && ec_smem)
-    for (int i = threadIdx.x; i < HS * 32 * (int)(blockDim.x >> 5); i += blockDim.x) sE[HS + i] = 0;
+    for (int i = threadIdx.x; i < HS * 32 * (int)(blockDim.x >> 5); i += blockDim.x) sm[HS + i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;

@@ -252,7 +252,9 @@ struct OctChunks {
   int *ck_exp;
 };
 
-template <int NT, bool CHUNKED>
+// EG: the emission table (more than 64 KB: high emission orders) stays in global memory (L1/L2) instead of shared memory;
+// the fetch for position t+2 is issued at step t, so its latency stays off the recursion.
+template <int NT, bool CHUNKED, bool EG>
 __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch,
                                                       int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback,
                                                       OctChunks X) {
@@ -260,12 +262,14 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
   constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
   const int HG = F.H * G;
-  double *sE = sm, *sO = sE + HG, *sPi = sO + G * G;
+  const double *sE = EG ? F.E : sm;
+  double *sO = sm + (EG ? 0 : HG), *sPi = sO + G * G;
   char *swarp = reinterpret_cast<char *>(sPi + G) + (size_t)(threadIdx.x >> 5) * C::WARPB;
   char *const ring = swarp;                        // [RING][SLOTB]
   char *const bbuf = swarp + RING * SLOTB;         // [2][8*ROWB]
   int *const sbx = reinterpret_cast<int *>(bbuf + 2 * 8 * ROWB);  // [2][8]
-  for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
+  if (!EG)
+    for (int i = threadIdx.x; i < HG; i += blockDim.x) sm[i] = F.E[i];
   for (int i = threadIdx.x; i < G * G + G; i += blockDim.x) sO[i] = 0;
   __syncthreads();
   const int l = threadIdx.x & 31, r = l >> 2, q = l & 3;
@@ -546,13 +550,14 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 // Scoring (AbstractHMM.logProb, AbstractHMM.java:1049-1070: the value of bwd[0][0]) with the octet forward recursion;
 // nothing is stored.  A sequence whose scaled recursion came near the denormal range is listed in `fallback`
 // ([0] = count, then ids) and scored by the log-space kernel afterwards.
-template <int NT>
+template <int NT, bool EG>
 __global__ void __launch_bounds__(256) k_mma_loglik(FastDev F, OctData D, unsigned long long *counter, double *out, int32_t *fallback) {
   constexpr int G = 8 * NT, NV = 2 * NT;
   extern __shared__ double sm[];
   const int HG = F.H * G;
-  double *sE = sm;
-  for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
+  const double *sE = EG ? F.E : sm;
+  if (!EG)
+    for (int i = threadIdx.x; i < HG; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const int l = threadIdx.x & 31, r = l >> 2, q = l & 3;
   const unsigned FULL = 0xffffffffu;
@@ -595,16 +600,17 @@ __global__ void __launch_bounds__(256) k_mma_loglik(FastDev F, OctData D, unsign
 // E-step: forward rows through the HBM scratch and a cp.async ring, backward recursion on the FP64 MMA path, no count
 // product.  paths: int32 per residue (CSR by the data set offsets), loglik optional.
 // CHUNKED: as in k_mma_estep (checkpoint rows every CK positions, rows of one chunk per resident warp).
-template <int NT, bool CHUNKED>
+template <int NT, bool CHUNKED, bool EG>
 __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch, int *fexp_scratch,
                                                        int64_t rows, int32_t *paths, double *loglik, int32_t *fallback, OctChunks X) {
   using C = MmaCfg<NT>;
   constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
   const int HG = F.H * G;
-  double *sE = sm;
-  char *const ring = reinterpret_cast<char *>(sE + HG) + (size_t)(threadIdx.x >> 5) * (RING * SLOTB);
-  for (int i = threadIdx.x; i < HG; i += blockDim.x) sE[i] = F.E[i];
+  const double *sE = EG ? F.E : sm;
+  char *const ring = reinterpret_cast<char *>(sm + (EG ? 0 : HG)) + (size_t)(threadIdx.x >> 5) * (RING * SLOTB);
+  if (!EG)
+    for (int i = threadIdx.x; i < HG; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const int l = threadIdx.x & 31, r = l >> 2, q = l & 3;
   const unsigned FULL = 0xffffffffu;

@@ -55,16 +55,18 @@ __global__ void k_viterbi_prepare(jhf::FastDev F, const int *tmap, const int *pi
   }
 }
 
-template <int S>
+template <int S, bool EG>
 __global__ void __launch_bounds__(128) k_viterbi_lanes(VitTables V, OctData D, unsigned long long *counter, uint8_t *choice_scratch,
                                                        int64_t rows, int32_t *paths, double *scores) {
   using C = VitCfg<S>;
   constexpr int CB = C::CB, NW = C::NW;
   extern __shared__ double sm[];
-  double *sT = sm, *sPi = sT + S * S, *sE = sPi + S;
+  double *sT = sm, *sPi = sT + S * S;
+  const double *sE = EG ? V.E : sPi + S;  // EG: emission table too large for shared memory, read through L1/L2
   for (int i = threadIdx.x; i < S * S; i += blockDim.x) sT[i] = V.T[i];
   for (int i = threadIdx.x; i < S; i += blockDim.x) sPi[i] = V.pi[i];
-  for (int i = threadIdx.x; i < V.H * S; i += blockDim.x) sE[i] = V.E[i];
+  if (!EG)
+    for (int i = threadIdx.x; i < V.H * S; i += blockDim.x) sPi[S + i] = V.E[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;

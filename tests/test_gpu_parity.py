@@ -333,6 +333,38 @@ def test_posterior_decoding_octets_ragged(nat, oracle_lib, fast, name):
         assert clear.mean() > 0.95
 
 
+@pytest.mark.parametrize("states,order", [(32, 4), (8, 5), (16, 4), (4, 6), (2, 7)])
+def test_large_emission_tables_stay_on_the_fast_path(nat, oracle_lib, states, order):
+    """High emission orders: the [context hash][state] table exceeds 64 KB and is read from global memory (EG kernels)
+    instead of shared memory: scoring, bit-exact Viterbi, posterior decoding, E-step counts (ragged, weighted), training."""
+    hmm = ergodic_hmm(states, order, n_iter=3, ess=2.0)
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = ragged_data(order, 45, lo=1, hi=150)
+    np.testing.assert_allclose(hmm.getLogScoreFor(data), om.loglik(data.codes, data.offsets), rtol=LL_RTOL)
+    rp, rs, _ = om.viterbi(data.codes, data.offsets)
+    for (p, s), p_ref, s_ref in zip(hmm.getViterbiPathsFor(data), rp, rs):
+        assert np.array_equal(p, p_ref) and s == s_ref
+    eng, nd = hmm._engine(), hmm._data(data)
+    w = np.random.default_rng(order).random(data.getNumberOfElements()) + 0.5
+    for weights in (None, w):
+        nd.set_weights(weights)
+        ts, es, sc = eng.estep(nd)
+        rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+        np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+        np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+        assert sc == pytest.approx(rsc, rel=LL_RTOL)
+    nd.set_weights(None)
+    dec = hmm.decodePosteriorPathsFor(data)
+    for i in range(0, data.getNumberOfElements(), 5):
+        ref = om.posterior(data.getElementAt(i).codes)
+        path, _ = dec[i]
+        srt = np.sort(ref, axis=0)
+        clear = srt[-1] - srt[-2] > 1e-9
+        assert np.array_equal(path[clear], om.decode_posterior(ref)[clear])
+    hmm.train(data)
+    np.testing.assert_allclose(hmm.last_objectives[0], om.train(data.codes, data.offsets, max_iter=3), rtol=LL_RTOL)
+
+
 def test_transition_order_zero(nat, oracle_lib):
     """getMaximalMarkovOrder() == 0: one context for every layer, every context final (HigherOrderHMM.java:498, 1046-1058);
     runs on the general context-graph kernels.  Scoring, windows, bit-exact Viterbi, counts, Baum-Welch and Viterbi training."""
