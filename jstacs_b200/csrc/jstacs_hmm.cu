@@ -873,7 +873,15 @@ static bool prefer_sparse(const jh_model *m, const jh_dataset *d) {
   return d->n_seq <= 1024 && d->max_len >= 16384;
 }
 
-#define DISPATCH_SPARSE(P, ...)                                                             \
+#define DISPATCH_SPARSE(P, ...)                                   \
+  if ((P).e_global) {                                             \
+    constexpr bool EG_ = true;                                    \
+    DISPATCH_SPARSE_(P, __VA_ARGS__)                              \
+  } else {                                                        \
+    constexpr bool EG_ = false;                                   \
+    DISPATCH_SPARSE_(P, __VA_ARGS__)                              \
+  }
+#define DISPATCH_SPARSE_(P, ...)                                                            \
   switch ((P).SPL * 100 + (P).IND) {                                                        \
     case 104: { constexpr int SPL_ = 1, IND_ = 4; __VA_ARGS__; } break;                     \
     case 108: { constexpr int SPL_ = 1, IND_ = 8; __VA_ARGS__; } break;                     \
@@ -923,10 +931,12 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
   const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
   if (items == 0) return JH_OK;
   if (g_opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
-    const size_t smem_c = ((size_t)P.H * P.SP + 2 * (size_t)P.SP + 16) * sizeof(double);
+    const size_t smem_c = ((P.e_global ? 0 : (size_t)P.H * P.SP) + 2 * (size_t)P.SP + 16) * sizeof(double);
 #define JH_P1C(IND_)                                                                                                                     \
+  if (P.e_global) JH_P1C_(IND_, true) else JH_P1C_(IND_, false)
+#define JH_P1C_(IND_, EG_)                                                                                                               \
   {                                                                                                                                      \
-    auto kern = jhs::k_sparse_pass1_cta<IND_>;                                                                                           \
+    auto kern = jhs::k_sparse_pass1_cta<IND_, EG_>;                                                                                         \
     if (smem_c > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));               \
     kern<<<(int)items, P.SP, smem_c, s>>>(P.dev(), d->dev(), n_dir, (int)(d->chunk_len > 0 ? d->chunk_len : 1),                           \
                                           n_dir == 2 ? d->d_chunk_ptr.p : nullptr, n_dir == 2 ? m->d_ck_alpha.p : nullptr,               \
@@ -940,13 +950,14 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
       default: JH_P1C(32) break;
     }
 #undef JH_P1C
+#undef JH_P1C_
     JH_CUDA(cudaGetLastError());
     return JH_OK;
   }
   const int NT = items <= 2 * (int64_t)m->sm_count ? 32 : 128;  // few long sequences: one warp per SM
-  const size_t smem = ((size_t)P.H * P.SP + (size_t)(NT / 32) * 2 * P.SP) * sizeof(double);
+  const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)(NT / 32) * 2 * P.SP) * sizeof(double);
   DISPATCH_SPARSE(P, {
-    auto kern = jhs::k_sparse_pass1<SPL_, IND_>;
+    auto kern = jhs::k_sparse_pass1<SPL_, IND_, EG_>;
     if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -984,10 +995,10 @@ static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
   if ((r = m->d_ck_alpha.reserve((size_t)(d->n_chunks + 1) * P.SP)) || (r = m->d_ck_beta.reserve((size_t)(d->n_chunks + 1) * P.SP))) return r;
   if ((r = run_sparse_pass1(m, d, 2, d_ll))) return r;
   const int NT = 128, wpc = NT / 32;
-  const size_t smem = ((size_t)P.H * P.SP + (size_t)wpc * 2 * P.SP) * sizeof(double);
+  const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)wpc * 2 * P.SP) * sizeof(double);
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
   DISPATCH_SPARSE(P, {
-    auto kern = jhs::k_sparse_decode_chunks<SPL_, IND_>;
+    auto kern = jhs::k_sparse_decode_chunks<SPL_, IND_, EG_>;
     if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -1030,12 +1041,12 @@ static int run_estep_sparse(jh_model *m, jh_dataset *d) {
     if ((r = run_sparse_pass1(m, d, 2, nullptr, &X))) return r;
   }
   const int NT = 128, wpc = NT / 32;
-  const size_t smem = ((size_t)P.H * P.SP + (size_t)wpc * 2 * P.SP) * sizeof(double);
+  const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)wpc * 2 * P.SP) * sizeof(double);
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
   JH_CUDA(cudaMemsetAsync(P.d_ec, 0, sizeof(double) * jhs::EC_REPLICAS_SPARSE * P.H * P.SP, s));
   jhs::EstepTables ET{P.d_out_stat, P.d_pistat, (int)n_stats};
   DISPATCH_SPARSE(P, {
-    auto kern = jhs::k_sparse_estep_chunks<SPL_, IND_>;
+    auto kern = jhs::k_sparse_estep_chunks<SPL_, IND_, EG_>;
     if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));

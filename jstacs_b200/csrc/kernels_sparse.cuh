@@ -41,7 +41,7 @@ struct SparseDev {
 };
 
 struct SparseTables {
-  bool usable = false;
+  bool usable = false, e_global = false;
   int S = 0, SP = 0, SPL = 0, IND = 0, a = 0, Kmax = 0, H = 0;
   int *d_in_src = nullptr, *d_out_dst = nullptr, *d_in_p = nullptr, *d_out_p = nullptr, *d_pimap = nullptr, *d_korder = nullptr,
       *d_etab = nullptr, *d_emod = nullptr, *d_out_stat = nullptr, *d_pistat = nullptr;
@@ -89,7 +89,8 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
   const int SPL = S <= 32 ? 1 : S <= 64 ? 2 : S <= 128 ? 4 : 8, SP = 32 * SPL;
   int64_t H = a;
   for (int i = 0; i < Kmax; i++) H *= a;
-  if (H * SP * 8 > 96 * 1024) return JH_OK;
+  if (H * SP * 8 > ((int64_t)16 << 20)) return JH_OK;
+  F.e_global = H * SP * 8 > 96 * 1024;
   std::vector<std::vector<std::pair<int, int>>> in(S), out(S);  // (other state, child index)
   std::vector<char> seen(S, 0);
   for (int c = lc_ctx_ptr[1]; c < lc_ctx_ptr[2]; c++) {
@@ -377,14 +378,16 @@ struct Pass1Extra {        // E-step mode (all pointers null otherwise)
   double *score;             // += sum_n w_n log P(x_n) over the processed sequences
 };
 
-template <int SPL, int IND>
+// EG (all kernels below): the emission table (> 96 KB: high emission orders) is read from global memory (L1/L2) instead of shared memory
+template <int SPL, int IND, bool EG>
 __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, int n_dir, int CK, const int64_t *chunk_ptr, double *ck_alpha,
                                                       double *ck_beta, unsigned long long *counter, double *loglik, int32_t *fallback, Pass1Extra X) {
   extern __shared__ double sm[];
   const int SP = F.SP;
-  double *sE = sm;
-  double *vec = sE + (size_t)F.H * SP + (size_t)(threadIdx.x >> 5) * 2 * SP;  // two buffers per warp
-  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  const double *sE = EG ? F.E : sm;
+  double *vec = sm + (EG ? 0 : (size_t)F.H * SP) + (size_t)(threadIdx.x >> 5) * 2 * SP;  // two buffers per warp
+  if (!EG)
+    for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -517,16 +520,17 @@ __global__ void __launch_bounds__(128) k_sparse_pass1(SparseDev F, DevData D, in
 // bounded), so a rescale costs no barrier of its own.  Aligned 16-residue blocks run as straight-line code (no branches:
 // with four warps on the SM every taken branch is an exposed instruction fetch); blocks that contain a checkpoint, the
 // ragged ends and alphabets that are not a power of two go step by step.
-template <int IND>
+template <int IND, bool EG>
 __global__ void __launch_bounds__(256) k_sparse_pass1_cta(SparseDev F, DevData D, int n_dir, int CK, const int64_t *chunk_ptr, double *ck_alpha,
                                                           double *ck_beta, double *loglik, int32_t *fallback, Pass1Extra X) {
   extern __shared__ double sm[];
   const int SP = F.SP, j = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;  // blockDim.x == SP
-  double *sE = sm;
-  double *vbuf = sE + (size_t)F.H * SP;                              // [2][SP]
+  const double *sE = EG ? F.E : sm;
+  double *vbuf = sm + (EG ? 0 : (size_t)F.H * SP);          // [2][SP]
   unsigned *mbuf = reinterpret_cast<unsigned *>(vbuf + 2 * SP);     // [2][8] row maxima (high words) of the lazy rescale
   double *red = reinterpret_cast<double *>(mbuf + 16);              // [8]
-  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  if (!EG)
+    for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const unsigned FULL = 0xffffffffu;
   const int kord = F.korder[j], ash = F.ashift, Hm = F.H - 1, hpow = F.hpow, SPB = SP * 8;
@@ -793,15 +797,16 @@ __global__ void __launch_bounds__(256) k_sparse_pass1_cta(SparseDev F, DevData D
 }
 
 // Phase 2: posterior decoding of one chunk per warp.  chunk_seq / chunk_idx: the chunk list; rows: [warp slot][CK][SP].
-template <int SPL, int IND>
+template <int SPL, int IND, bool EG>
 __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int CK, int64_t n_chunks, const int32_t *chunk_seq,
                                                               const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
                                                               const double *ck_beta, unsigned long long *counter, double *rows, int32_t *paths) {
   extern __shared__ double sm[];
   const int SP = F.SP;
-  double *sE = sm;
-  double *vec = sE + (size_t)F.H * SP + (size_t)(threadIdx.x >> 5) * 2 * SP;
-  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  const double *sE = EG ? F.E : sm;
+  double *vec = sm + (EG ? 0 : (size_t)F.H * SP) + (size_t)(threadIdx.x >> 5) * 2 * SP;
+  if (!EG)
+    for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -933,7 +938,7 @@ struct EstepTables {
   int n_stats;             // index of the score entry
 };
 
-template <int SPL, int IND>
+template <int SPL, int IND, bool EG>
 __global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepTables ET, DevData D, int CK, int ROWS, int64_t n_chunks, const int32_t *chunk_seq,
                                                              const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
                                                              const double *ck_beta, const long long *ck_alpha_exp, const long long *ck_beta_exp,
@@ -941,9 +946,10 @@ __global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepT
                                                              double *rows, int *rexp, double *stats, double *gEC, int32_t *fallback) {
   extern __shared__ double sm[];
   const int SP = F.SP;
-  double *sE = sm;
-  double *vec = sE + (size_t)F.H * SP + (size_t)(threadIdx.x >> 5) * 2 * SP;
-  for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sE[i] = F.E[i];
+  const double *sE = EG ? F.E : sm;
+  double *vec = sm + (EG ? 0 : (size_t)F.H * SP) + (size_t)(threadIdx.x >> 5) * 2 * SP;
+  if (!EG)
+    for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;

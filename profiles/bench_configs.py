@@ -67,6 +67,10 @@ run("long_bw_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), "est
 run("cfg4_decode_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode")
 run("cfg2_viterbi_u8_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "viterbi_u8")
 run("cfg4_decode_u8_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode_u8")
+# emission tables larger than shared memory (EG kernels): 32 states order 4 = 256 KB, 8 states order 5 = 256 KB
+run("hiorder_bw_s32_k4", ergodic_hmm(32, 4, ess=4.0), make_data(n(1_000_000), 1000), "estep")
+run("hiorder_bw_s8_k5", ergodic_hmm(8, 5), make_data(n(1_000_000), 1000), "estep")
+run("hiorder_viterbi_u8_s8_k5", ergodic_hmm(8, 5), make_data(n(1_000_000), 1000), "viterbi_u8")
 # BASELINE configs[4] at FULL size (GRCh38 chromosome lengths in Mb, 3.085e9 residues); only when named explicitly
 GRCH38_MB = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
 _full5 = []

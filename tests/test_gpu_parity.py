@@ -473,7 +473,8 @@ def test_window_scoring_sees_the_residues_before_the_window(nat, oracle_lib, nam
 
 
 # ---- sparse path: 33..256 states, checkpointed chunk-parallel decoding (BASELINE cfg5 shape) ------------------------
-@pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0)])
+@pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0),
+                                                 (128, 4, 3), (40, 4, 5)])  # the last two: emission table in global memory
 @pytest.mark.parametrize("chunk", [16, 64, 2048])
 @pytest.mark.parametrize("cta", [0, 1], ids=["warp_per_sequence", "cta_per_sequence"])
 def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk, cta):
