@@ -30,6 +30,7 @@ struct Options {
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
+  int64_t overlap = 1;         // long-sequence path: per-sequence streams, a sequence's chunk pass starts when its checkpoint pass ends
   int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
   int64_t oct_chunk = 1024;    // positions per checkpoint of the chunked octet E-step (0: never chunk)
   int64_t oct_chunk_force = 0; // tests: chunk every bucket longer than 2 * oct_chunk
@@ -171,6 +172,10 @@ struct jh_model {
   DevBuf<long long> d_ck_exp, d_seq_AL;  // E-step: exponents of the checkpoints [2][n_chunks+1], of P(x) [n_seq]
   DevBuf<double> d_seq_sfin;             // E-step: mantissa of P(x) [n_seq]
   DevBuf<int> d_rexp;                    // E-step: exponents of the recomputed forward rows [slot][chunk]
+  DevBuf<unsigned long long> d_counters; // one work counter per concurrent chunk kernel
+  std::vector<cudaStream_t> seq_streams; // one stream per long sequence: its chunk pass starts when ITS checkpoint pass is done
+  std::vector<cudaEvent_t> seq_events;
+  cudaEvent_t ev_fork = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timed = false, ktimed = false;
@@ -231,6 +236,7 @@ struct jh_dataset {
   int hash_a = -1, hash_K = -1;
   // chunk list of the sparse decoding path (kernels_sparse.cuh), built per chunk length
   int64_t chunk_len = 0, n_chunks = 0, n_long = 0;
+  std::vector<int64_t> long_seg;  // [n_long+1] first chunk (in the chunk list) of the k-th long sequence; [n_long] = first single-chunk sequence
   DevBuf<int64_t> d_chunk_ptr;
   DevBuf<int32_t> d_chunk_seq, d_chunk_idx, d_long;  // d_long: sequences of more than one chunk, longest first
   DevData dev(int64_t first = 0, int64_t count = -1) const {
@@ -275,6 +281,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "fast_variant") g_opt.fast_variant = value;
   else if (n == "oct_chunk") g_opt.oct_chunk = value <= 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
   else if (n == "pass1_cta") g_opt.pass1_cta = value;
+  else if (n == "overlap") g_opt.overlap = value;
   else if (n == "oct_chunk_force") g_opt.oct_chunk_force = value;
   else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
     cudaMemPool_t pool;
@@ -518,6 +525,9 @@ extern "C" void jh_model_destroy(jh_model *m) {
   if (m->ev1) cudaEventDestroy(m->ev1);
   if (m->evk0) cudaEventDestroy(m->evk0);
   if (m->evk1) cudaEventDestroy(m->evk1);
+  for (cudaStream_t st : m->seq_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : m->seq_events) cudaEventDestroy(ev);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->stream) cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -902,10 +912,14 @@ static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK) {
   const int64_t n = ptr[d->n_seq];
   if (n > 0x7fffffff) { jh_set_error("too many chunks"); return JH_ERR_UNSUPPORTED; }
   std::vector<int32_t> cs(std::max<int64_t>(n, 1)), ci(std::max<int64_t>(n, 1)), lg;
+  std::vector<int64_t> seg;
   int64_t g = 0;
   for (int64_t k = 0; k < d->n_seq; k++) {  // longest sequences first
     const int32_t sid = d->order[k];
-    if (ptr[sid + 1] - ptr[sid] > 1) lg.push_back(sid);
+    if (ptr[sid + 1] - ptr[sid] > 1) {
+      lg.push_back(sid);
+      seg.push_back(g);
+    }
     for (int64_t c = 0; c < ptr[sid + 1] - ptr[sid]; c++, g++) { cs[g] = sid; ci[g] = (int32_t)c; }
   }
   cudaStream_t s = m->st();
@@ -915,23 +929,32 @@ static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK) {
   d->chunk_len = CK;
   d->n_chunks = n;
   d->n_long = (int64_t)lg.size();
+  seg.push_back(seg.empty() ? 0 : ptr[lg.back() + 1] - ptr[lg.back()] + seg.back());  // long sequences come first (decreasing length)
+  d->long_seg = seg;
   return JH_OK;
 }
 
 // phase 1: n_dir = 1 scoring only, n_dir = 2 forward and backward warps with checkpoints
-static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra *extra = nullptr) {
+static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra *extra = nullptr, cudaStream_t on = nullptr,
+                            bool reset_fallback = true) {
   jhs::SparseTables &P = m->sparse;
-  cudaStream_t s = m->st();
+  cudaStream_t s = on ? on : m->st();
   int r = m->d_fallback.reserve(d->n_seq + 2);
   if (r) return r;
   jhs::Pass1Extra X{};
   if (extra) X = *extra;
-  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
-  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  if (reset_fallback) JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  if (!on) JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));  // only the warp-per-sequence kernel uses it
   const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
   if (items == 0) return JH_OK;
   if (g_opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
-    const size_t smem_c = ((P.e_global ? 0 : (size_t)P.H * P.SP) + 2 * (size_t)P.SP + 16) * sizeof(double);
+    size_t smem_c = ((P.e_global ? 0 : (size_t)P.H * P.SP) + 2 * (size_t)P.SP + 16) * sizeof(double);
+    if (on) {  // overlapped with chunk kernels of other sequences: claim the SM's whole shared memory, so that no chunk CTA
+               // becomes co-resident and competes for the issue slots of this latency-bound CTA (measured: +25 % per step)
+      int optin = 0;
+      JH_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device));
+      smem_c = std::max<size_t>(smem_c, (size_t)optin);
+    }
 #define JH_P1C(IND_)                                                                                                                     \
   if (P.e_global) JH_P1C_(IND_, true) else JH_P1C_(IND_, false)
 #define JH_P1C_(IND_, EG_)                                                                                                               \
@@ -985,33 +1008,143 @@ static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
 
 static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, double *d_loglik, double *d_post, const int32_t *d_list, int64_t n_list);
 
-// posterior decoding in two exact phases: checkpoints every `chunk` positions, then all chunks in parallel
-static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) {
+// Long-sequence path (kernels_sparse.cuh), two exact phases: checkpoint pass over whole sequences (k_sparse_pass1 /
+// k_sparse_pass1_cta), then every chunk of `chunk` positions as an independent work item (posterior decisions:
+// k_sparse_decode_chunks; expected counts: k_sparse_estep_chunks).  Scratch per resident warp: one chunk of rows.
+//
+// With several long sequences of different lengths the checkpoint pass is as long as the LONGEST sequence while most SMs
+// idle (one CTA per sequence and direction).  With `overlap` every long sequence gets its own stream: checkpoint pass of the
+// sequence, then the chunk pass over ITS chunks — the chunk passes of the shorter sequences fill the SMs while the long
+// ones are still being swept.  Plain stream ordering, no device-side waiting.
+enum { SPARSE_DECODE = 0, SPARSE_ESTEP = 1 };
+
+static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d_paths, double *d_ll) {
   jhs::SparseTables &P = m->sparse;
   cudaStream_t s = m->st();
   const int64_t CK = g_opt.chunk;
   int r = ensure_chunks(m, d, CK);
   if (r) return r;
-  if ((r = m->d_ck_alpha.reserve((size_t)(d->n_chunks + 1) * P.SP)) || (r = m->d_ck_beta.reserve((size_t)(d->n_chunks + 1) * P.SP))) return r;
-  if ((r = run_sparse_pass1(m, d, 2, d_ll))) return r;
+  if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
+  const int64_t n_stats = m->n_stats();
+  if (d->n_long > 0 || what == SPARSE_DECODE) {
+    if ((r = m->d_ck_alpha.reserve((size_t)(d->n_chunks + 1) * P.SP)) || (r = m->d_ck_beta.reserve((size_t)(d->n_chunks + 1) * P.SP))) return r;
+  }
+  if (what == SPARSE_ESTEP && d->n_long > 0) {
+    if ((r = m->d_ck_exp.reserve((size_t)2 * (d->n_chunks + 1))) || (r = m->d_seq_sfin.reserve(d->n_seq)) || (r = m->d_seq_AL.reserve(d->n_seq))) return r;
+  }
+  jhs::Pass1Extra X{};
+  if (what == SPARSE_ESTEP) {
+    X.ck_alpha_exp = m->d_ck_exp.p; X.ck_beta_exp = m->d_ck_exp.p + d->n_chunks + 1; X.seq_sfin = m->d_seq_sfin.p; X.seq_AL = m->d_seq_AL.p;
+    X.score = m->d_stats.p + n_stats;
+  }
+  // ---- launch plan of the chunk pass: one launch, or one per long sequence (own stream) + one for the single-chunk sequences
+  const bool streamed = g_opt.overlap && g_opt.pass1_cta && d->n_long >= 2 && d->n_long <= 64;
+  const int64_t n_launch = streamed ? d->n_long + 1 : 1;
   const int NT = 128, wpc = NT / 32;
   const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)wpc * 2 * P.SP) * sizeof(double);
-  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  const int64_t rows = std::min<int64_t>(CK, d->max_len);
+  const int64_t per_slot = rows * (P.SP * (int64_t)sizeof(double) + (what == SPARSE_ESTEP ? (int64_t)sizeof(int) : 0));
+  int per_sm = 0;
   DISPATCH_SPARSE(P, {
-    auto kern = jhs::k_sparse_decode_chunks<SPL_, IND_, EG_>;
-    if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-    if (per_sm < 1) { jh_set_error("sparse decoding kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
-    int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);
-    const int64_t per_slot = CK * P.SP * (int64_t)sizeof(double);
-    grid = std::max<int64_t>(1, std::min<int64_t>(grid, g_opt.scratch_mb * 1024 * 1024 / per_slot / wpc));
-    if ((r = m->d_fwd.reserve((size_t)grid * wpc * CK * P.SP))) return r;
-    kern<<<(int)grid, NT, smem, s>>>(P.dev(), d->dev(), (int)CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_ck_alpha.p,
-                                     m->d_ck_beta.p, m->d_counter.p, m->d_fwd.p, d_paths);
-    JH_LAUNCHED();
+    if (what == SPARSE_ESTEP) {
+      auto kern = jhs::k_sparse_estep_chunks<SPL_, IND_, EG_>;
+      if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    } else {
+      auto kern = jhs::k_sparse_decode_chunks<SPL_, IND_, EG_>;
+      if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    }
   });
-  JH_CUDA(cudaGetLastError());
+  if (per_sm < 1) { jh_set_error("sparse chunk kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
+  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  const int64_t budget_slots = std::max<int64_t>(wpc, g_opt.scratch_mb * 1024 * 1024 / per_slot);
+  // streamed: every launch gets its own slice of the row scratch; one CTA per SM each (many of them are resident together)
+  const int64_t grid_cap = streamed ? std::max<int64_t>(1, std::min<int64_t>(m->sm_count, budget_slots / wpc / n_launch))
+                                    : std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, budget_slots / wpc));
+  std::vector<int64_t> first(n_launch), count(n_launch), grid(n_launch), slot0(n_launch);
+  int64_t total_slots = 0;
+  for (int64_t k = 0; k < n_launch; k++) {
+    first[k] = streamed ? d->long_seg[std::min<int64_t>(k, d->n_long)] : 0;
+    count[k] = streamed ? (k < d->n_long ? d->long_seg[k + 1] - d->long_seg[k] : d->n_chunks - d->long_seg[d->n_long]) : d->n_chunks;
+    grid[k] = std::max<int64_t>(1, std::min<int64_t>(grid_cap, (count[k] + wpc - 1) / wpc));
+    slot0[k] = total_slots;
+    total_slots += grid[k] * wpc;
+  }
+  if ((r = m->d_fwd.reserve((size_t)total_slots * rows * P.SP)) || (r = m->d_counters.reserve(n_launch))) return r;
+  if (what == SPARSE_ESTEP && (r = m->d_rexp.reserve((size_t)total_slots * rows))) return r;
+  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
+  JH_CUDA(cudaMemsetAsync(m->d_counters.p, 0, sizeof(unsigned long long) * n_launch, s));
+  jhs::EstepTables ET{P.d_out_stat, P.d_pistat, (int)n_stats};
+  if (what == SPARSE_ESTEP) JH_CUDA(cudaMemsetAsync(P.d_ec, 0, sizeof(double) * jhs::EC_REPLICAS_SPARSE * P.H * P.SP, s));
+  auto launch_chunks = [&](int64_t k, cudaStream_t st) -> int {
+    if (count[k] <= 0) return JH_OK;
+    double *rows_k = m->d_fwd.p + (size_t)slot0[k] * rows * P.SP;
+    DISPATCH_SPARSE(P, {
+      if (what == SPARSE_ESTEP) {
+        jhs::k_sparse_estep_chunks<SPL_, IND_, EG_><<<(int)grid[k], NT, smem, st>>>(
+            P.dev(), ET, d->dev(), (int)CK, (int)rows, count[k], d->d_chunk_seq.p + first[k], d->d_chunk_idx.p + first[k], d->d_chunk_ptr.p,
+            m->d_ck_alpha.p, m->d_ck_beta.p, m->d_ck_exp.p, m->d_ck_exp.p + d->n_chunks + 1, m->d_seq_sfin.p, m->d_seq_AL.p, m->d_counters.p + k,
+            rows_k, m->d_rexp.p + (size_t)slot0[k] * rows, m->d_stats.p, P.d_ec, m->d_fallback.p);
+      } else {
+        jhs::k_sparse_decode_chunks<SPL_, IND_, EG_><<<(int)grid[k], NT, smem, st>>>(
+            P.dev(), d->dev(), (int)CK, (int)rows, count[k], d->d_chunk_seq.p + first[k], d->d_chunk_idx.p + first[k], d->d_chunk_ptr.p,
+            m->d_ck_alpha.p, m->d_ck_beta.p, m->d_counters.p + k, rows_k, d_paths);
+      }
+      JH_LAUNCHED();
+    });
+    JH_CUDA(cudaGetLastError());
+    return JH_OK;
+  };
+  if (!streamed) {
+    if (what == SPARSE_DECODE) {
+      if ((r = run_sparse_pass1(m, d, 2, d_ll, nullptr, nullptr, false))) return r;
+    } else if (d->n_long > 0) {
+      X.list = d->d_long.p; X.n_list = d->n_long;
+      if ((r = run_sparse_pass1(m, d, 2, nullptr, &X, nullptr, false))) return r;
+    }
+    if ((r = launch_chunks(0, s))) return r;
+  } else {
+    while ((int64_t)m->seq_streams.size() < d->n_long) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      JH_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      m->seq_streams.push_back(st);
+      JH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      m->seq_events.push_back(ev);
+    }
+    if (!m->ev_fork) JH_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    JH_CUDA(cudaEventRecord(m->ev_fork, s));
+    // Issue order matters: the streams share a handful of hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) and a
+    // kernel that waits for its stream blocks the queue behind it.  So: all checkpoint passes first (longest first, they
+    // start at once), then the chunk passes in the order in which their sequences finish (shortest first).
+    for (int64_t k = 0; k < d->n_long; k++) {
+      cudaStream_t st = m->seq_streams[k];
+      JH_CUDA(cudaStreamWaitEvent(st, m->ev_fork, 0));
+      jhs::Pass1Extra Xk = X;
+      Xk.list = d->d_long.p + k; Xk.n_list = 1;
+      if ((r = run_sparse_pass1(m, d, 2, d_ll, &Xk, st, false))) return r;
+    }
+    for (int64_t k = d->n_long - 1; k >= 0; k--) {
+      if ((r = launch_chunks(k, m->seq_streams[k]))) return r;
+      JH_CUDA(cudaEventRecord(m->seq_events[k], m->seq_streams[k]));
+    }
+    // sequences of a single chunk: scoring pass for their log-likelihoods (decoding only), then their chunks, on the main stream
+    if (what == SPARSE_DECODE && d->n_seq > d->n_long) {
+      jhs::Pass1Extra Xs{};
+      Xs.list = d->d_order.p + d->n_long; Xs.n_list = d->n_seq - d->n_long;
+      if ((r = run_sparse_pass1(m, d, 2, d_ll, &Xs, nullptr, false))) return r;
+    }
+    if ((r = launch_chunks(d->n_long, s))) return r;
+    for (int64_t k = 0; k < d->n_long; k++) JH_CUDA(cudaStreamWaitEvent(s, m->seq_events[k], 0));
+  }
+  if (what == SPARSE_ESTEP) {
+    const int n = P.H * P.SP;
+    jhs::k_sparse_fold_ec<<<(n + 255) / 256, 256, 0, s>>>(P.dev(), P.d_etab, P.d_emod, m->n_child, P.d_ec, m->d_stats.p);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+    return JH_OK;
+  }
   int32_t n_fb = 0;
   JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   JH_CUDA(cudaStreamSynchronize(s));
@@ -1019,56 +1152,8 @@ static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
   return JH_OK;
 }
 
-// Baum-Welch E-step in two exact phases (kernels_sparse.cuh): sequences longer than a chunk get their checkpoints, P(x) and
-// the objective from k_sparse_pass1; then every chunk (and every sequence that is a single chunk) is an independent work item
-// of k_sparse_estep_chunks.  Scratch per resident warp: chunk x SP doubles, whatever the sequence length.
-static int run_estep_sparse(jh_model *m, jh_dataset *d) {
-  jhs::SparseTables &P = m->sparse;
-  cudaStream_t s = m->st();
-  const int64_t CK = g_opt.chunk;
-  int r = ensure_chunks(m, d, CK);
-  if (r) return r;
-  if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
-  JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
-  const int64_t n_stats = m->n_stats();
-  if (d->n_long > 0) {
-    if ((r = m->d_ck_alpha.reserve((size_t)(d->n_chunks + 1) * P.SP)) || (r = m->d_ck_beta.reserve((size_t)(d->n_chunks + 1) * P.SP)) ||
-        (r = m->d_ck_exp.reserve((size_t)2 * (d->n_chunks + 1))) || (r = m->d_seq_sfin.reserve(d->n_seq)) || (r = m->d_seq_AL.reserve(d->n_seq)))
-      return r;
-    jhs::Pass1Extra X{};
-    X.ck_alpha_exp = m->d_ck_exp.p; X.ck_beta_exp = m->d_ck_exp.p + d->n_chunks + 1; X.seq_sfin = m->d_seq_sfin.p; X.seq_AL = m->d_seq_AL.p;
-    X.list = d->d_long.p; X.n_list = d->n_long; X.score = m->d_stats.p + n_stats;
-    if ((r = run_sparse_pass1(m, d, 2, nullptr, &X))) return r;
-  }
-  const int NT = 128, wpc = NT / 32;
-  const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)wpc * 2 * P.SP) * sizeof(double);
-  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  JH_CUDA(cudaMemsetAsync(P.d_ec, 0, sizeof(double) * jhs::EC_REPLICAS_SPARSE * P.H * P.SP, s));
-  jhs::EstepTables ET{P.d_out_stat, P.d_pistat, (int)n_stats};
-  DISPATCH_SPARSE(P, {
-    auto kern = jhs::k_sparse_estep_chunks<SPL_, IND_, EG_>;
-    if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-    if (per_sm < 1) { jh_set_error("sparse E-step kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
-    if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
-    int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);
-    const int64_t rows = std::min<int64_t>(CK, d->max_len);
-    const int64_t per_slot = rows * (P.SP * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-    grid = std::max<int64_t>(1, std::min<int64_t>(grid, g_opt.scratch_mb * 1024 * 1024 / per_slot / wpc));
-    if ((r = m->d_fwd.reserve((size_t)grid * wpc * rows * P.SP)) || (r = m->d_rexp.reserve((size_t)grid * wpc * rows))) return r;
-    kern<<<(int)grid, NT, smem, s>>>(P.dev(), ET, d->dev(), (int)CK, (int)rows, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p,
-                                     m->d_ck_alpha.p, m->d_ck_beta.p, m->d_ck_exp.p, m->d_ck_exp.p + d->n_chunks + 1, m->d_seq_sfin.p, m->d_seq_AL.p,
-                                     m->d_counter.p, m->d_fwd.p, m->d_rexp.p, m->d_stats.p, P.d_ec, m->d_fallback.p);
-    JH_LAUNCHED();
-  });
-  JH_CUDA(cudaGetLastError());
-  const int n = P.H * P.SP;
-  jhs::k_sparse_fold_ec<<<(n + 255) / 256, 256, 0, s>>>(P.dev(), P.d_etab, P.d_emod, m->n_child, P.d_ec, m->d_stats.p);
-  JH_LAUNCHED();
-  JH_CUDA(cudaGetLastError());
-  return JH_OK;
-}
+static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) { return run_sparse_two_phase(m, d, SPARSE_DECODE, d_paths, d_ll); }
+static int run_estep_sparse(jh_model *m, jh_dataset *d) { return run_sparse_two_phase(m, d, SPARSE_ESTEP, nullptr, nullptr); }
 
 static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
 

@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(256) k_sparse_pass1_cta(SparseDev F, DevData D
 
 // Phase 2: posterior decoding of one chunk per warp.  chunk_seq / chunk_idx: the chunk list; rows: [warp slot][CK][SP].
 template <int SPL, int IND, bool EG>
-__global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int CK, int64_t n_chunks, const int32_t *chunk_seq,
+__global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int CK, int ROWS, int64_t n_chunks, const int32_t *chunk_seq,
                                                               const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
                                                               const double *ck_beta, unsigned long long *counter, double *rows, int32_t *paths) {
   extern __shared__ double sm[];
@@ -811,7 +811,7 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
   const int lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
   const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  double *const R = rows + (size_t)slot * CK * SP + SPL * lane;
+  double *const R = rows + (size_t)slot * ROWS * SP + SPL * lane;  // ROWS = min(CK, longest sequence)
   ResReader rd;
   SeqBlocks blocks;
   Edges<SPL, IND> Gin, Gout;

@@ -476,11 +476,13 @@ def test_window_scoring_sees_the_residues_before_the_window(nat, oracle_lib, nam
 @pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0),
                                                  (128, 4, 3), (40, 4, 5)])  # the last two: emission table in global memory
 @pytest.mark.parametrize("chunk", [16, 64, 2048])
-@pytest.mark.parametrize("cta", [0, 1], ids=["warp_per_sequence", "cta_per_sequence"])
-def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk, cta):
+@pytest.mark.parametrize("cta,overlap", [(0, 0), (1, 0), (1, 1)], ids=["warp_per_sequence", "cta_per_sequence", "cta_streams"])
+def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk, cta, overlap):
     """cta: the checkpoint pass as one warp per (sequence, direction) (many sequences) or one CTA with a state per thread
-    and the lazy rescale (few long sequences: latency mode)."""
+    and the lazy rescale (few long sequences: latency mode); overlap: one stream per long sequence, its chunk pass starts
+    when its own checkpoint pass is done."""
     nat.check(nat.lib().jh_set_option(b"pass1_cta", cta))
+    nat.check(nat.lib().jh_set_option(b"overlap", overlap))
     hmm = banded_hmm(states, degree, order)
     om = oracle_lib.OracleModel(hmm.ir())
     rng = np.random.default_rng(states + chunk)
@@ -516,6 +518,7 @@ def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, deg
     finally:
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
         nat.check(nat.lib().jh_set_option(b"pass1_cta", 1))
+        nat.check(nat.lib().jh_set_option(b"overlap", 1))
 
 
 @pytest.mark.parametrize("cta", [0, 1], ids=["warp_per_sequence", "cta_per_sequence"])
