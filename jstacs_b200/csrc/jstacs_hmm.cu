@@ -1059,15 +1059,19 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
   if (per_sm < 1) { jh_set_error("sparse chunk kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
   if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
   const int64_t budget_slots = std::max<int64_t>(wpc, g_opt.scratch_mb * 1024 * 1024 / per_slot);
-  // streamed: every launch gets its own slice of the row scratch; one CTA per SM each (many of them are resident together)
-  const int64_t grid_cap = streamed ? std::max<int64_t>(1, std::min<int64_t>(m->sm_count, budget_slots / wpc / n_launch))
-                                    : std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, budget_slots / wpc));
+  // streamed: every launch gets its own slice of the row scratch.  The longest sequences finish their checkpoint pass last
+  // and then have the GPU to themselves: they get full grids, the others a share of an SM's worth each (many are resident together).
+  const int64_t full_grid = (int64_t)m->sm_count * per_sm;
+  int64_t n_big = streamed ? std::min<int64_t>(3, d->n_long) : 0;
+  while (n_big > 0 && (budget_slots / wpc - n_big * full_grid) / (n_launch - n_big) < 16) n_big--;
+  const int64_t grid_cap = streamed ? std::max<int64_t>(1, std::min<int64_t>(m->sm_count, (budget_slots / wpc - n_big * full_grid) / (n_launch - n_big)))
+                                    : std::max<int64_t>(1, std::min<int64_t>(full_grid, budget_slots / wpc));
   std::vector<int64_t> first(n_launch), count(n_launch), grid(n_launch), slot0(n_launch);
   int64_t total_slots = 0;
   for (int64_t k = 0; k < n_launch; k++) {
     first[k] = streamed ? d->long_seg[std::min<int64_t>(k, d->n_long)] : 0;
     count[k] = streamed ? (k < d->n_long ? d->long_seg[k + 1] - d->long_seg[k] : d->n_chunks - d->long_seg[d->n_long]) : d->n_chunks;
-    grid[k] = std::max<int64_t>(1, std::min<int64_t>(grid_cap, (count[k] + wpc - 1) / wpc));
+    grid[k] = std::max<int64_t>(1, std::min<int64_t>(k < n_big ? full_grid : grid_cap, (count[k] + wpc - 1) / wpc));
     slot0[k] = total_slots;
     total_slots += grid[k] * wpc;
   }

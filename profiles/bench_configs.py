@@ -25,6 +25,7 @@ for kv in filter(None, os.environ.get("JH_OPTS", "").split(",")):  # library opt
 def run(name, hmm, data, what, reps=3):
     if (only and name not in only) or (name.startswith("full_") and not (only and name in only)):
         return
+    hmm = hmm()  # models and data are built lazily: only for the selected lines
     if callable(data):
         data = data()
     eng, nd = hmm._engine(), hmm._data(data)
@@ -50,27 +51,35 @@ def run(name, hmm, data, what, reps=3):
 
 
 n = lambda x: max(64, int(x * scale))
-run("cfg1_bw_s2_k1", ergodic_hmm(2, 1), make_data(10_000, 1000), "estep")
-run("cfg2_viterbi_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "viterbi")
-run("cfg2_bw_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "estep")
-run("cfg3_bw_s32_k3", ergodic_hmm(32, 3, ess=4.0), make_data(n(1_000_000), 1000), "estep")
-run("cfg3_loglik_s32_k3", ergodic_hmm(32, 3, ess=4.0), make_data(n(1_000_000), 1000), "loglik")
-run("cfg3_decode_s32_k3", ergodic_hmm(32, 3, ess=4.0), make_data(n(200_000), 1000), "decode")
-lens = ragged_lengths(n(100_000), seed=42)
-run("cfg4_loglik_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "loglik")
-run("cfg4_bw_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "estep")
-run("cfg5_loglik_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "loglik")
-run("long_decode_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), "decode")
-run("cfg5_decode_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "decode")
-run("cfg5_bw_s128_banded_1Mb", banded_hmm(128, 4, 0), make_data(24, 1_000_000), "estep")
-run("long_bw_s16_dense_8x2Mb", ergodic_hmm(16, 1), make_data(8, 2_000_000), "estep")
-run("cfg4_decode_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode")
-run("cfg2_viterbi_u8_s8_k2", ergodic_hmm(8, 2), make_data(n(1_000_000), 1000), "viterbi_u8")
-run("cfg4_decode_u8_s16_k1_ragged", ergodic_hmm(16, 1), make_data(lens.size, lens), "decode_u8")
+run("cfg1_bw_s2_k1", lambda: ergodic_hmm(2, 1), lambda: make_data(10_000, 1000), "estep")
+run("cfg2_viterbi_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "viterbi")
+run("cfg2_bw_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "estep")
+run("cfg3_bw_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(1_000_000), 1000), "estep")
+run("cfg3_loglik_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(1_000_000), 1000), "loglik")
+run("cfg3_decode_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(200_000), 1000), "decode")
+_lens = []
+
+
+def ragged():
+    if not _lens:
+        _lens.append(ragged_lengths(n(100_000), seed=42))
+    return _lens[0]
+
+
+run("cfg4_loglik_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_data(ragged().size, ragged()), "loglik")
+run("cfg4_bw_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_data(ragged().size, ragged()), "estep")
+run("cfg5_loglik_s128_banded_1Mb", lambda: banded_hmm(128, 4, 0), lambda: make_data(24, 1_000_000), "loglik")
+run("long_decode_s16_dense_8x2Mb", lambda: ergodic_hmm(16, 1), lambda: make_data(8, 2_000_000), "decode")
+run("cfg5_decode_s128_banded_1Mb", lambda: banded_hmm(128, 4, 0), lambda: make_data(24, 1_000_000), "decode")
+run("cfg5_bw_s128_banded_1Mb", lambda: banded_hmm(128, 4, 0), lambda: make_data(24, 1_000_000), "estep")
+run("long_bw_s16_dense_8x2Mb", lambda: ergodic_hmm(16, 1), lambda: make_data(8, 2_000_000), "estep")
+run("cfg4_decode_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_data(ragged().size, ragged()), "decode")
+run("cfg2_viterbi_u8_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "viterbi_u8")
+run("cfg4_decode_u8_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_data(ragged().size, ragged()), "decode_u8")
 # emission tables larger than shared memory (EG kernels): 32 states order 4 = 256 KB, 8 states order 5 = 256 KB
-run("hiorder_bw_s32_k4", ergodic_hmm(32, 4, ess=4.0), make_data(n(1_000_000), 1000), "estep")
-run("hiorder_bw_s8_k5", ergodic_hmm(8, 5), make_data(n(1_000_000), 1000), "estep")
-run("hiorder_viterbi_u8_s8_k5", ergodic_hmm(8, 5), make_data(n(1_000_000), 1000), "viterbi_u8")
+run("hiorder_bw_s32_k4", lambda: ergodic_hmm(32, 4, ess=4.0), lambda: make_data(n(1_000_000), 1000), "estep")
+run("hiorder_bw_s8_k5", lambda: ergodic_hmm(8, 5), lambda: make_data(n(1_000_000), 1000), "estep")
+run("hiorder_viterbi_u8_s8_k5", lambda: ergodic_hmm(8, 5), lambda: make_data(n(1_000_000), 1000), "viterbi_u8")
 # BASELINE configs[4] at FULL size (GRCh38 chromosome lengths in Mb, 3.085e9 residues); only when named explicitly
 GRCH38_MB = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156, 57]
 _full5 = []
@@ -82,6 +91,10 @@ def full5():
     return _full5[0]
 
 
-run("full_cfg5_loglik", banded_hmm(128, 4, 0), full5, "loglik", reps=1)
-run("full_cfg5_decode_u8", banded_hmm(128, 4, 0), full5, "decode_u8", reps=1)
-run("full_cfg5_bw", banded_hmm(128, 4, 0), full5, "estep", reps=1)
+mid5 = lambda: make_data(24, [mb * 20_000 for mb in GRCH38_MB])  # the same length profile at 1/50 (61.7e6 residues)
+run("full_mid_cfg5_loglik", lambda: banded_hmm(128, 4, 0), mid5, "loglik", reps=3)
+run("full_mid_cfg5_bw", lambda: banded_hmm(128, 4, 0), mid5, "estep", reps=3)
+run("full_mid_cfg5_decode_u8", lambda: banded_hmm(128, 4, 0), mid5, "decode_u8", reps=3)
+run("full_cfg5_loglik", lambda: banded_hmm(128, 4, 0), full5, "loglik", reps=1)
+run("full_cfg5_decode_u8", lambda: banded_hmm(128, 4, 0), full5, "decode_u8", reps=1)
+run("full_cfg5_bw", lambda: banded_hmm(128, 4, 0), full5, "estep", reps=1)
