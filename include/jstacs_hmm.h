@@ -175,9 +175,17 @@ int jh_viterbi_u8(jh_model *m, jh_dataset *d, uint8_t *paths, double *scores);
  * child could be chosen (the reference fails there). A safe capacity is L*(1+n_silent)+n_silent. */
 int jh_viterbi_paths(jh_model *m, jh_dataset *d, int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores);
 
+/* AbstractHMM.getViterbiPathFor(startPos, endPos, seq) (HigherOrderHMM.java:590-598) for MANY sub-sequences at once: window i
+ * decodes positions start[i]..end[i] (inclusive) of sequence seq_index[i]; like jh_loglik_windows the emissions keep their
+ * absolute positions.  paths / path_ptr / path_len / scores as in jh_viterbi_paths, indexed by the window. */
+int jh_viterbi_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start, const int64_t *end,
+                       int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores);
+
 /* AbstractHMM.getLogStatePosteriorMatrixFor(start,end,seq) (AbstractHMM.java:776-797):
  * out[S][L] row-major for sequence seq_index. */
 int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out);
+/* The same for positions start..end (inclusive) of the sequence: out[S][end-start+1]. */
+int jh_posterior_window(jh_model *m, jh_dataset *d, int64_t seq_index, int64_t start, int64_t end, double *out);
 /* AbstractHMM.decodeStatePosterior (:1125-1139) fused with the posterior: paths CSR like
  * jh_viterbi, loglik[n_seq] (may be NULL). */
 int jh_posterior_decode(jh_model *m, jh_dataset *d, int32_t *paths, double *loglik);

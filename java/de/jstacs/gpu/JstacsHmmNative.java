@@ -60,6 +60,8 @@ public final class JstacsHmmNative {
 	public static final MethodHandle jh_viterbi = h( "jh_viterbi", FunctionDescriptor.of( I, P, P, P, P ) );
 	public static final MethodHandle jh_viterbi_u8 = h( "jh_viterbi_u8", FunctionDescriptor.of( I, P, P, P, P ) );
 	public static final MethodHandle jh_viterbi_paths = h( "jh_viterbi_paths", FunctionDescriptor.of( I, P, P, P, P, P, P ) );
+	public static final MethodHandle jh_viterbi_windows = h( "jh_viterbi_windows", FunctionDescriptor.of( I, P, P, J, P, P, P, P, P, P, P ) );
+	public static final MethodHandle jh_posterior_window = h( "jh_posterior_window", FunctionDescriptor.of( I, P, P, J, J, J, P ) );
 	public static final MethodHandle jh_posterior = h( "jh_posterior", FunctionDescriptor.of( I, P, P, J, P ) );
 	public static final MethodHandle jh_posterior_decode = h( "jh_posterior_decode", FunctionDescriptor.of( I, P, P, P, P ) );
 	public static final MethodHandle jh_posterior_decode_u8 = h( "jh_posterior_decode_u8", FunctionDescriptor.of( I, P, P, P, P ) );

@@ -114,6 +114,8 @@ def lib():
         "jh_viterbi_paths": (C.c_int, [vp, vp, _P_I32, _P_I64, _P_I64, _P_F64]),
         "jh_loglik_windows": (C.c_int, [vp, vp, C.c_int64, _P_I64, _P_I64, _P_I64, _P_F64]),
         "jh_posterior": (C.c_int, [vp, vp, C.c_int64, _P_F64]),
+        "jh_posterior_window": (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int64, _P_F64]),
+        "jh_viterbi_windows": (C.c_int, [vp, vp, C.c_int64, _P_I64, _P_I64, _P_I64, _P_I32, _P_I64, _P_I64, _P_F64]),
         "jh_posterior_decode": (C.c_int, [vp, vp, _P_I32, _P_F64]),
         "jh_estep": (C.c_int, [vp, vp, C.c_int, _P_F64, _P_F64, _P_F64]),
         "jh_mstep": (C.c_int, [vp]),
@@ -253,6 +255,27 @@ class NativeModel:
         check(lib().jh_loglik_windows(self.h, data.h, si.size, si.ctypes.data_as(_P_I64), st.ctypes.data_as(_P_I64), en.ctypes.data_as(_P_I64),
                                       _f64(out)))
         return out[:si.size]
+
+    def viterbi_windows(self, data: NativeData, seq_index, start, end, n_silent: int = 0):
+        """getViterbiPathFor(startPos, endPos, seq) for many windows -> (list of paths, scores)."""
+        si, st, en = (np.ascontiguousarray(a, dtype=np.int64) for a in (seq_index, start, end))
+        if not (si.size == st.size == en.size):
+            raise ValueError("seq_index, start and end need the same length")
+        n = si.size
+        ptr = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(np.maximum(en - st + 1, 0) * (1 + n_silent) + n_silent, out=ptr[1:])
+        paths = np.full(max(int(ptr[-1]), 1), -1, dtype=np.int32)
+        plen = np.zeros(max(n, 1), dtype=np.int64)
+        scores = np.zeros(max(n, 1))
+        check(lib().jh_viterbi_windows(self.h, data.h, n, si.ctypes.data_as(_P_I64), st.ctypes.data_as(_P_I64), en.ctypes.data_as(_P_I64),
+                                       paths.ctypes.data_as(_P_I32), ptr.ctypes.data_as(_P_I64), plen.ctypes.data_as(_P_I64), _f64(scores)))
+        return [paths[ptr[i]:ptr[i] + max(plen[i], 0)] for i in range(n)], scores[:n], plen[:n]
+
+    def posterior_window(self, data: NativeData, index: int, start: int, end: int, n_states: int) -> np.ndarray:
+        length = end - start + 1
+        out = np.zeros(max(n_states * length, 1))
+        check(lib().jh_posterior_window(self.h, data.h, int(index), int(start), int(end), _f64(out)))
+        return out[:n_states * length].reshape(n_states, length)
 
     def posterior(self, data: NativeData, index: int, n_states: int, length: int) -> np.ndarray:
         out = np.zeros(max(n_states * length, 1))

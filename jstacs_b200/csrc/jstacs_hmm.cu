@@ -818,17 +818,18 @@ static int run_general_loglik(jh_model *m, jh_dataset *d, const jhg::WorkList &W
 }
 
 static int run_general_viterbi(jh_model *m, jh_dataset *d, int32_t *d_paths, const int64_t *d_path_ptr, int64_t *d_path_len, double *d_scores,
-                               double *d_stats) {
+                               double *d_stats, const jhg::WorkList *windows = nullptr) {
   if (m->max_children > 254) { jh_set_error("more than 254 children per context"); return JH_ERR_UNSUPPORTED; }
   int grid;
   int64_t nthreads;
   const int64_t layers = d->max_len + 1;
-  int r = plan_general(m, d->n_seq, (size_t)2 * m->Cmax * sizeof(double) + (size_t)layers * m->Cmax, &grid, &nthreads);
+  const jhg::WorkList W = windows ? *windows : jhg::WorkList{nullptr, nullptr, nullptr, d->n_seq};
+  int r = plan_general(m, W.n, (size_t)2 * m->Cmax * sizeof(double) + (size_t)layers * m->Cmax, &grid, &nthreads);
   if (r) return r;
   if ((r = m->d_rows.reserve((size_t)2 * m->Cmax * nthreads)) || (r = m->d_choice.reserve((size_t)layers * m->Cmax * nthreads))) return r;
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  jhg::k_general_viterbi<<<grid, 128, 0, s>>>(m->dev(), m->gen(), d->dev(), m->d_counter.p, m->d_rows.p, m->d_choice.p, layers, d_paths, d_path_ptr,
+  jhg::k_general_viterbi<<<grid, 128, 0, s>>>(m->dev(), m->gen(), d->dev(), W, m->d_counter.p, m->d_rows.p, m->d_choice.p, layers, d_paths, d_path_ptr,
                                              d_path_len, d_scores, d_stats);
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
@@ -1329,6 +1330,81 @@ extern "C" int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, cons
   if (r) return r;
   JH_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(double) * n_win, cudaMemcpyDeviceToHost, s));
   JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+
+// windows of sequences -> device work list (validated like the reference's range checks, AbstractHMM.java:985-998)
+struct DevWindows {
+  DevBuf<int32_t> sid;
+  DevBuf<int64_t> se;
+  jhg::WorkList W{nullptr, nullptr, nullptr, 0};
+  int64_t max_len = 0;
+};
+static int upload_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start, const int64_t *end, DevWindows &out) {
+  if (n_win < 0 || !seq_index || !start || !end) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  std::vector<int32_t> sid(std::max<int64_t>(n_win, 1));
+  for (int64_t i = 0; i < n_win; i++) {
+    if (seq_index[i] < 0 || seq_index[i] >= d->n_seq) { jh_set_error("window %lld: sequence index out of range", (long long)i); return JH_ERR_INVALID; }
+    const int64_t L = d->offsets[seq_index[i] + 1] - d->offsets[seq_index[i]];
+    if (start[i] < 0 || end[i] >= L || end[i] < start[i]) {
+      jh_set_error("window %lld: [%lld,%lld] is not inside a sequence of length %lld", (long long)i, (long long)start[i], (long long)end[i], (long long)L);
+      return JH_ERR_INVALID;
+    }
+    sid[i] = (int32_t)seq_index[i];
+    out.max_len = std::max(out.max_len, end[i] - start[i] + 1);
+  }
+  int r;
+  if ((r = out.sid.alloc(n_win)) || (r = out.se.alloc(2 * n_win))) return r;
+  cudaStream_t s = m->st();
+  if (n_win) {
+    JH_CUDA(cudaMemcpyAsync(out.sid.p, sid.data(), sizeof(int32_t) * n_win, cudaMemcpyHostToDevice, s));
+    JH_CUDA(cudaMemcpyAsync(out.se.p, start, sizeof(int64_t) * n_win, cudaMemcpyHostToDevice, s));
+    JH_CUDA(cudaMemcpyAsync(out.se.p + n_win, end, sizeof(int64_t) * n_win, cudaMemcpyHostToDevice, s));
+    JH_CUDA(cudaStreamSynchronize(s));  // `sid` is a local
+  }
+  out.W = jhg::WorkList{out.sid.p, out.se.p, out.se.p + n_win, n_win};
+  return JH_OK;
+}
+
+extern "C" int jh_viterbi_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start, const int64_t *end,
+                                  int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (n_win == 0) return JH_OK;
+  if (paths && !path_ptr) { jh_set_error("paths without path_ptr"); return JH_ERR_INVALID; }
+  DevWindows dw;
+  if ((r = upload_windows(m, d, n_win, seq_index, start, end, dw))) return r;
+  DevBuf<int32_t> d_paths;
+  DevBuf<int64_t> d_ptr, d_len;
+  DevBuf<double> d_scores;
+  cudaStream_t s = m->st();
+  const int64_t total = paths ? path_ptr[n_win] : 0;
+  if ((r = d_paths.alloc(total)) || (r = d_ptr.alloc(n_win + 1)) || (r = d_len.alloc(n_win)) || (r = d_scores.alloc(n_win))) return r;
+  if (paths) JH_CUDA(cudaMemcpyAsync(d_ptr.p, path_ptr, sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, s));
+  timing_begin(m);
+  r = run_general_viterbi(m, d, paths ? d_paths.p : nullptr, d_ptr.p, d_len.p, d_scores.p, nullptr, &dw.W);
+  timing_end(m);
+  if (r) return r;
+  if (paths && total) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+  if (path_len) JH_CUDA(cudaMemcpyAsync(path_len, d_len.p, sizeof(int64_t) * n_win, cudaMemcpyDeviceToHost, s));
+  if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * n_win, cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+
+extern "C" int jh_posterior_window(jh_model *m, jh_dataset *d, int64_t seq_index, int64_t start, int64_t end, double *out) {
+  int r = check_pair(m, d);
+  if (r) return r;
+  if (!out) { jh_set_error("null output"); return JH_ERR_INVALID; }
+  if (m->m == 0) { jh_set_error("state posteriors of order-0 transitions (HigherOrderHMM.java:296-308) are not on the native path"); return JH_ERR_UNSUPPORTED; }
+  DevWindows dw;
+  if ((r = upload_windows(m, d, 1, &seq_index, &start, &end, dw))) return r;
+  const int64_t L = end - start + 1;
+  DevBuf<double> d_post;
+  if ((r = d_post.alloc((size_t)m->S * L))) return r;
+  if ((r = run_general_posterior(m, d, dw.W, L, d_post.p, nullptr, nullptr))) return r;
+  JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
   return JH_OK;
 }
 

@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(128) k_general_loglik(DevModel M, GenModel X, 
 // HigherOrderHMM.viterbi (:617-708) for the general graph.  choice bytes: [(L+1) layers][Cmax][thread].
 // paths: CSR by path_ptr (capacity per sequence), path_len = number of states written, -1 if no child could be chosen.
 // stats != nullptr: Viterbi training (the sequence weight is added along the path instead of writing it).
-__global__ void __launch_bounds__(128) k_general_viterbi(DevModel M, GenModel X, DevData D, unsigned long long *counter, double *rows, uint8_t *choices,
-                                                         int64_t max_layers, int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores,
-                                                         double *stats) {
+__global__ void __launch_bounds__(128) k_general_viterbi(DevModel M, GenModel X, DevData D, WorkList W, unsigned long long *counter, double *rows,
+                                                         uint8_t *choices, int64_t max_layers, int32_t *paths, const int64_t *path_ptr,
+                                                         int64_t *path_len, double *scores, double *stats) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
   Rows B{rows + tid, nthreads, M.Cmax};
   uint8_t *const cbase = choices + tid;  // + (layer*Cmax + ctx)*nthreads
@@ -196,27 +196,32 @@ __global__ void __launch_bounds__(128) k_general_viterbi(DevModel M, GenModel X,
   double score_sum = 0;
   for (;;) {
     const long long it = (long long)atomicAdd(counter, 1ull);
-    if (it >= D.n_seq) break;
-    const int sid = D.order[it];
-    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    if (it >= W.n) break;
+    // work item: a whole sequence, or the window start..end of one (getViterbiPathFor(startPos, endPos, seq), HOH:590-598:
+    // layer 0 is the window start, the emissions keep their absolute positions); outputs are indexed by the work item then
+    const int sid = W.seq ? W.seq[it] : D.order[it];
+    const int64_t oid = W.seq ? it : sid;
+    const int64_t off = D.offsets[sid], Lseq = D.offsets[sid + 1] - off;
+    const int64_t s0 = W.start ? W.start[it] : 0, s1 = W.end ? W.end[it] : Lseq - 1;
+    const int64_t L = s1 - s0 + 1;
     const double w = D.weights ? D.weights[sid] : 1.0;
     rd.init(D.codes + off);
     bwd_last_layer<true>(M, X, L, B, L & 1, cbase + (size_t)L * M.Cmax * nthreads, nthreads);
-    int h = L > 0 ? jhx::hash_at(M, rd, L - 1) : 0;
+    int h = L > 0 ? jhx::hash_at(M, rd, s1) : 0;
     for (int64_t l = L - 1; l >= 0; --l) {
-      bwd_layer<true>(M, X, l, B, l & 1, (l + 1) & 1, l, h, cbase + (size_t)l * M.Cmax * nthreads, nthreads);
-      if (l > 0) h = jhx::hash_back(M, rd, h, l);
+      bwd_layer<true>(M, X, l, B, l & 1, (l + 1) & 1, s0 + l, h, cbase + (size_t)l * M.Cmax * nthreads, nthreads);
+      if (l > 0) h = jhx::hash_back(M, rd, h, s0 + l);
     }
     const double sc = B.at(0, 0);
-    if (scores) scores[sid] = sc;
+    if (scores) scores[oid] = sc;
     score_sum = dadd(score_sum, dmul(w, sc));
     // forward trace
-    int32_t *p_out = paths ? paths + path_ptr[sid] : nullptr;
-    const int64_t cap = paths ? path_ptr[sid + 1] - path_ptr[sid] : 0;
+    int32_t *p_out = paths ? paths + path_ptr[oid] : nullptr;
+    const int64_t cap = paths ? path_ptr[oid + 1] - path_ptr[oid] : 0;
     int64_t np = 0, layer = 0;
     int ctx = 0;
     bool bad = false;
-    int hh = (stats && L > 0) ? jhx::hash_at(M, rd, 0) : 0;
+    int hh = (stats && L > 0) ? jhx::hash_at(M, rd, s0) : 0;
     for (;;) {
       const int lc = lc_of(M, layer);
       const int ch = cbase[((size_t)layer * M.Cmax + ctx) * nthreads];
@@ -236,12 +241,12 @@ __global__ void __launch_bounds__(128) k_general_viterbi(DevModel M, GenModel X,
       np++;
       ctx = M.child_next[(size_t)lc * M.n_child + p];
       if (!sil) {
-        if (stats && layer + 1 < L) hh = jhx::hash_fwd(M, rd, hh, layer);
+        if (stats && layer + 1 < L) hh = jhx::hash_fwd(M, rd, hh, s0 + layer);
         layer++;
       }
       if (np > (L + 1) * (int64_t)(M.S + 1)) { bad = true; break; }  // cannot happen for a valid (acyclic silent) graph
     }
-    if (path_len) path_len[sid] = bad ? -1 : np;
+    if (path_len) path_len[oid] = bad ? -1 : np;
     if (paths && !bad)
       for (int64_t i = np; i < cap; i++) p_out[i] = -1;
   }
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(128) k_general_viterbi(DevModel M, GenModel X,
 
 // HOH:359-434 fillFwdMatrix in pull form: fwd[l][c] for l = 0..L.  Summand order of the reference's push form: emitting
 // in-edges from the previous layer by (source context, child), then silent in-edges of the same layer.
-__device__ __forceinline__ void general_forward(const DevModel &M, const GenModel &X, ResReader &rd, int64_t L, const Rows &Fw) {
+__device__ __forceinline__ void general_forward(const DevModel &M, const GenModel &X, ResReader &rd, int64_t L, const Rows &Fw, int64_t s0 = 0) {  // s0: window start
   int h = 0;  // context hash of position l-1 (emission of the children that entered layer l)
   for (int64_t l = 0; l <= L; l++) {
     const int lc = lc_of(M, l);
@@ -258,7 +263,7 @@ __device__ __forceinline__ void general_forward(const DevModel &M, const GenMode
     const int lcs = lc_of(M, l - 1);  // class of the source layer
     const int *ip = M.in_ptr + (size_t)lcs * (M.Cmax + 1), *isrc = M.in_src + (size_t)lcs * M.n_child, *ipp = M.in_p + (size_t)lcs * M.n_child;
     const int *sp = X.sin_ptr + (size_t)lc * (M.Cmax + 1), *ssrc = X.sin_src + (size_t)lc * M.n_child, *spp = X.sin_p + (size_t)lc * M.n_child;
-    if (l > 0) h = l == 1 ? jhx::hash_at(M, rd, 0) : jhx::hash_fwd(M, rd, h, l - 2);
+    if (l > 0) h = l == 1 ? jhx::hash_at(M, rd, s0) : jhx::hash_fwd(M, rd, h, s0 + l - 2);
     for (int c = 0; c < nc; c++) {
       double offm = JH_NEG_INF;
       int n = 0;
@@ -266,7 +271,7 @@ __device__ __forceinline__ void general_forward(const DevModel &M, const GenMode
       if (l > 0)
         for (int q = ip[c]; q < ip[c + 1]; q++) {
           const int p = ipp[q];
-          const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], l - 1, h)), M.tscore[p]);
+          const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], s0 + l - 1, h)), M.tscore[p]);
           if (v > offm) offm = v;
           n++;
         }
@@ -282,7 +287,7 @@ __device__ __forceinline__ void general_forward(const DevModel &M, const GenMode
         if (l > 0)
           for (int q = ip[c]; q < ip[c + 1]; q++) {
             const int p = ipp[q];
-            const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], l - 1, h)), M.tscore[p]);
+            const double v = dadd(dadd(Fw.at(l - 1, isrc[q]), emis_of(M, M.child_state[p], s0 + l - 1, h)), M.tscore[p]);
             sum = dadd(sum, exp(dsub(v, offm)));
           }
         for (int q = sp[c]; q < sp[c + 1]; q++) {
@@ -386,14 +391,16 @@ __global__ void __launch_bounds__(128) k_general_posterior(DevModel M, GenModel 
     const long long it = (long long)atomicAdd(counter, 1ull);
     if (it >= W.n) break;
     const int sid = W.seq ? W.seq[it] : D.order[it];
-    const int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    const int64_t off = D.offsets[sid], Lseq = D.offsets[sid + 1] - off;
+    const int64_t s0 = W.start ? W.start[it] : 0, s1 = W.end ? W.end[it] : Lseq - 1;  // window (layer 0 = position s0)
+    const int64_t L = s1 - s0 + 1;
     rd.init(D.codes + off);
-    general_forward(M, X, rd, L, Fw);
+    general_forward(M, X, rd, L, Fw, s0);
     bwd_last_layer<false>(M, X, L, B, L, nullptr, 0);
-    int h = L > 0 ? jhx::hash_at(M, rd, L - 1) : 0;
+    int h = L > 0 ? jhx::hash_at(M, rd, s1) : 0;
     for (int64_t l = L - 1; l >= 0; --l) {
-      bwd_layer<false>(M, X, l, B, l, l + 1, l, h, nullptr, 0);
-      if (l > 0) h = jhx::hash_back(M, rd, h, l);
+      bwd_layer<false>(M, X, l, B, l, l + 1, s0 + l, h, nullptr, 0);
+      if (l > 0) h = jhx::hash_back(M, rd, h, s0 + l);
     }
     const double lp = B.at(0, 0);
     if (loglik) loglik[sid] = lp;
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(128) k_general_posterior(DevModel M, GenModel 
         if (post_out) post_out[(size_t)st * L + (l - 1)] = v;
         if (bv < v) { bv = v; best = st; }
       }
-      if (paths) paths[off + l - 1] = best;
+      if (paths) paths[off + s0 + l - 1] = best;
     }
   }
 }

@@ -807,10 +807,17 @@ class HigherOrderHMM:
         """AbstractHMM.getViterbiPathFor (:879-881) / HigherOrderHMM.getViterbiPathFor (:590-598)."""
         if endPos is None:
             endPos = seq.getLength() - 1
-        if startPos != 0 and any(e.order > 0 for e in self.emission):
-            raise NotImplementedError("window decoding with higher-order emissions is not on the native path yet")
-        ds = DataSet("", Sequence(self.alphabets, seq.codes[startPos:endPos + 1]), con=self.alphabets)
-        return self.getViterbiPathsFor(ds)[0]
+        if startPos == 0 and endPos == seq.getLength() - 1:
+            return self.getViterbiPathsFor(DataSet("", seq, con=self.alphabets))[0]
+        # a window: the emissions see the residues before startPos (absolute positions, HigherOrderDiscreteEmission.java:138-146)
+        eng = self._engine()
+        self._push_params()
+        ds = DataSet("", seq, con=self.alphabets)
+        n_silent = sum(1 for i in self.emissionIdx if self.emission[i].order < 0)
+        paths, scores, plen = eng.viterbi_windows(self._data(ds), [0], [startPos], [endPos], n_silent)
+        if plen[0] < 0:
+            raise ValueError("Impossible path")
+        return paths[0], float(scores[0])
 
     def getLogStatePosteriorMatrixFor(self, seq_or_data, startPos: int = 0, endPos: int | None = None):
         """AbstractHMM.getLogStatePosteriorMatrixFor (:776-838) -> double[S][L] (list of them for a DataSet)."""
@@ -823,10 +830,10 @@ class HigherOrderHMM:
         seq = seq_or_data
         if endPos is None:
             endPos = seq.getLength() - 1
-        if startPos != 0 and any(e.order > 0 for e in self.emission):
-            raise NotImplementedError("window posterior with higher-order emissions is not on the native path yet")
-        ds = DataSet("", Sequence(self.alphabets, seq.codes[startPos:endPos + 1]), con=self.alphabets)
-        return eng.posterior(self._data(ds), 0, self.getNumberOfStates(), ds.getNumberOfResidues())
+        ds = DataSet("", seq, con=self.alphabets)
+        if startPos == 0 and endPos == seq.getLength() - 1:
+            return eng.posterior(self._data(ds), 0, self.getNumberOfStates(), ds.getNumberOfResidues())
+        return eng.posterior_window(self._data(ds), 0, startPos, endPos, self.getNumberOfStates())
 
     def getStatePosteriorMatrixFor(self, seq_or_data):
         """AbstractHMM.getStatePosteriorMatrixFor (:811-820)."""

@@ -49,6 +49,8 @@ def lib():
         L.jo_viterbi.restype = C.c_int
         L.jo_viterbi.argtypes = [vp, _P_U8, _P_I64, C.c_int64, _P_I32, _P_I64, _P_I64, _P_F64]
         L.jo_posterior.restype, L.jo_posterior.argtypes = C.c_int, [vp, _P_U8, C.c_int64, _P_F64]
+        L.jo_posterior_window.restype, L.jo_posterior_window.argtypes = C.c_int, [vp, _P_U8, C.c_int64, C.c_int64, _P_F64]
+        L.jo_viterbi_window.restype, L.jo_viterbi_window.argtypes = C.c_double, [vp, _P_U8, C.c_int64, C.c_int64, _P_I32, C.c_int64, _P_I64]
         L.jo_decode_posterior.restype, L.jo_decode_posterior.argtypes = None, [_P_F64, C.c_int, C.c_int64, _P_I32]
         L.jo_estep.restype = C.c_int
         L.jo_estep.argtypes = [vp, _P_U8, _P_I64, C.c_int64, _P_F64, C.c_int, C.c_int, _P_F64, _P_F64, _P_F64]
@@ -157,6 +159,21 @@ class OracleModel:
         if lib().jo_posterior(self.h, _u8(x), x.size, _f64(out)) != 0:
             raise ValueError("order-0 posterior not restated")
         return out
+
+    def posterior_window(self, x, start: int, end: int) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.uint8)
+        out = np.zeros((self.S, end - start + 1))
+        if lib().jo_posterior_window(self.h, _u8(x), start, end, _f64(out)) != 0:
+            raise ValueError("order-0 posterior not restated")
+        return out
+
+    def viterbi_window(self, x, start: int, end: int):
+        x = np.ascontiguousarray(x, np.uint8)
+        cap = (end - start + 1) * (1 + self.n_silent) + self.n_silent
+        path = np.zeros(max(cap, 1), np.int32)
+        plen = C.c_int64()
+        sc = lib().jo_viterbi_window(self.h, _u8(x), start, end, path.ctypes.data_as(_P_I32), cap, C.byref(plen))
+        return path[:max(plen.value, 0)], sc
 
     def decode_posterior(self, post) -> np.ndarray:
         post = np.ascontiguousarray(post, np.float64)

@@ -619,13 +619,26 @@ int jo_viterbi(const jo_model *m, const uint8_t *codes, const int64_t *off, int6
   return 0;
 }
 
-/* HOH:294-329 fillLogStatePosteriorMatrix(silentZero=true) + AHMM:790-797 (first column dropped).
- * out[S][L] row-major. */
-int jo_posterior(const jo_model *m, const uint8_t *x, int64_t L, double *out) {
+/* HOH:590-598 getViterbiPathFor(startPos, endPos, seq): emissions see the residues before startPos (absolute positions,
+ * HigherOrderDiscreteEmission.java:138-146). */
+double jo_viterbi_window(const jo_model *m, const uint8_t *x, int64_t start, int64_t end, int32_t *path, int64_t cap, int64_t *path_len) {
   jo_work w; work_init(&w);
+  long np = 0;
+  for (long k = 0; k < cap; k++) path[k] = -1;
+  double sc = viterbi(&w, m, x, (long)start, (long)end, 0, path, (long)cap, &np, NULL, NULL);
+  if (path_len) *path_len = np;
+  work_free(&w);
+  return sc;
+}
+
+/* HOH:294-329 fillLogStatePosteriorMatrix(silentZero=true) + AHMM:790-797 (first column dropped) for positions
+ * start..end of x (AHMM:776-797 getLogStatePosteriorMatrixFor(startPos, endPos, seq)).  out[S][L] row-major, L = end-start+1. */
+int jo_posterior_window(const jo_model *m, const uint8_t *x, int64_t start, int64_t end, double *out) {
+  jo_work w; work_init(&w);
+  const int64_t L = end - start + 1;
   if (m->m == 0) { work_free(&w); return -2; }
-  fill_fwd(&w, m, x, 0, (long)L - 1);
-  fill_bwd_or_viterbi(&w, m, TYPE_LIKELIHOOD, x, 0, (long)L - 1, 1, 0, NULL, NULL);
+  fill_fwd(&w, m, x, (long)start, (long)end);
+  fill_bwd_or_viterbi(&w, m, TYPE_LIKELIHOOD, x, (long)start, (long)end, 1, 0, NULL, NULL);
   double log_prob = BWD(&w, m, 0, 0);
   double *col = malloc(sizeof(double) * m->S);
   for (long l = 0; l <= L; l++) {
@@ -642,6 +655,8 @@ int jo_posterior(const jo_model *m, const uint8_t *x, int64_t L, double *out) {
   work_free(&w);
   return 0;
 }
+
+int jo_posterior(const jo_model *m, const uint8_t *x, int64_t L, double *out) { return jo_posterior_window(m, x, 0, L - 1, out); }
 
 /* AHMM:1125-1139 decodeStatePosterior: strict '<' => lowest index wins ties */
 void jo_decode_posterior(const double *post, int S, int64_t L, int32_t *path) {

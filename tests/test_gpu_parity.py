@@ -472,6 +472,36 @@ def test_window_scoring_sees_the_residues_before_the_window(nat, oracle_lib, nam
         hmm.getLogProbForWindows(data, [0], [5], [10_000])
 
 
+@pytest.mark.parametrize("name", ["erg_s3_k0_map", "erg_s5_k2", "erg_s32_k3", "order2_s3", "sparse", "silent"])
+def test_window_viterbi_and_posterior(nat, oracle_lib, name):
+    """getViterbiPathFor(startPos, endPos, seq) / getLogStatePosteriorMatrixFor(startPos, endPos, seq): layer 0 is the window
+    start, higher-order emissions see the residues before it (HigherOrderHMM.java:590-598, AbstractHMM.java:776-797)."""
+    hmm = silent_hmm() if name == "silent" else MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(17)
+    x = random_dna(rng, 90)
+    seq = Sequence(DNA, x)
+    for s0, s1 in [(0, 89), (5, 40), (37, 37), (60, 89), (1, 2)]:
+        path, score = hmm.getViterbiPathFor(seq, s0, s1)
+        rp, rs = om.viterbi_window(x, s0, s1)
+        assert np.array_equal(path, rp) and score == rs  # bit-exact, tie rule included
+        post = hmm.getLogStatePosteriorMatrixFor(seq, s0, s1)
+        ref = om.posterior_window(x, s0, s1)
+        fin = np.isfinite(ref)
+        assert post.shape == ref.shape and np.array_equal(np.isfinite(post), fin)
+        np.testing.assert_allclose(post[fin], ref[fin], rtol=1e-9, atol=1e-9)
+    # many windows in one call
+    eng, nd = hmm._engine(), hmm._data(dataset_of([x, x[::-1].copy()]))
+    si, st, en = [0, 1, 1, 0], [3, 0, 10, 80], [50, 89, 10, 89]
+    n_silent = sum(1 for i in hmm.emissionIdx if hmm.emission[i].order < 0)
+    paths, scores, plen = eng.viterbi_windows(nd, si, st, en, n_silent)
+    for k in range(4):
+        rp, rs = om.viterbi_window(x if si[k] == 0 else x[::-1].copy(), st[k], en[k])
+        assert np.array_equal(paths[k], rp) and scores[k] == rs
+    with pytest.raises(nat.NativeError):
+        eng.viterbi_windows(nd, [0], [10], [90], n_silent)  # window end outside the sequence
+
+
 # ---- sparse path: 33..256 states, checkpointed chunk-parallel decoding (BASELINE cfg5 shape) ------------------------
 @pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0),
                                                  (128, 4, 3), (40, 4, 5)])  # the last two: emission table in global memory
