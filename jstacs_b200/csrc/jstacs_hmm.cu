@@ -15,6 +15,7 @@
 #include "kernels_mma.cuh"
 #include "kernels_lanes.cuh"
 #include "kernels_sparse.cuh"
+#include "kernels_scan.cuh"
 #include "kernels_viterbi.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -30,6 +31,7 @@ struct Options {
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
+  int64_t scan = 1;            // small dense models: checkpoint pass parallel in the position (kernels_scan.cuh)
   int64_t overlap = 1;         // long-sequence path: per-sequence streams, a sequence's chunk pass starts when its checkpoint pass ends
   int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
   int64_t oct_chunk = 1024;    // positions per checkpoint of the chunked octet E-step (0: never chunk)
@@ -172,6 +174,8 @@ struct jh_model {
   DevBuf<long long> d_ck_exp, d_seq_AL;  // E-step: exponents of the checkpoints [2][n_chunks+1], of P(x) [n_seq]
   DevBuf<double> d_seq_sfin;             // E-step: mantissa of P(x) [n_seq]
   DevBuf<int> d_rexp;                    // E-step: exponents of the recomputed forward rows [slot][chunk]
+  DevBuf<double> d_scanR;                // chunk transfer rows of the parallel checkpoint pass (kernels_scan.cuh)
+  DevBuf<int> d_scanE;
   DevBuf<unsigned long long> d_counters; // one work counter per concurrent chunk kernel
   std::vector<cudaStream_t> seq_streams; // one stream per long sequence: its chunk pass starts when ITS checkpoint pass is done
   std::vector<cudaEvent_t> seq_events;
@@ -239,6 +243,7 @@ struct jh_dataset {
   std::vector<int64_t> long_seg;  // [n_long+1] first chunk (in the chunk list) of the k-th long sequence; [n_long] = first single-chunk sequence
   DevBuf<int64_t> d_chunk_ptr;
   DevBuf<int32_t> d_chunk_seq, d_chunk_idx, d_long;  // d_long: sequences of more than one chunk, longest first
+  DevBuf<int64_t> d_long_seg;
   DevData dev(int64_t first = 0, int64_t count = -1) const {
     DevData D;
     D.codes = d_codes.p; D.offsets = d_offsets.p; D.weights = has_weights ? d_weights.p : nullptr;
@@ -282,6 +287,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "oct_chunk") g_opt.oct_chunk = value <= 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
   else if (n == "pass1_cta") g_opt.pass1_cta = value;
   else if (n == "overlap") g_opt.overlap = value;
+  else if (n == "scan") g_opt.scan = value;
   else if (n == "oct_chunk_force") g_opt.oct_chunk_force = value;
   else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
     cudaMemPool_t pool;
@@ -926,6 +932,12 @@ static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK) {
   cudaStream_t s = m->st();
   int r;
   if ((r = d->d_chunk_ptr.upload(ptr, s)) || (r = d->d_chunk_seq.upload(cs, s)) || (r = d->d_chunk_idx.upload(ci, s)) || (r = d->d_long.upload(lg, s))) return r;
+  {
+    std::vector<int64_t> seg2 = seg;
+    seg2.push_back(seg.empty() ? 0 : ptr[lg.back() + 1] - ptr[lg.back()] + seg.back());
+    if ((r = d->d_long_seg.upload(seg2, s))) return r;
+    JH_CUDA(cudaStreamSynchronize(s));  // seg2 is a local
+  }
   JH_CUDA(cudaStreamSynchronize(s));
   d->chunk_len = CK;
   d->n_chunks = n;
@@ -1038,8 +1050,10 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
     X.ck_alpha_exp = m->d_ck_exp.p; X.ck_beta_exp = m->d_ck_exp.p + d->n_chunks + 1; X.seq_sfin = m->d_seq_sfin.p; X.seq_AL = m->d_seq_AL.p;
     X.score = m->d_stats.p + n_stats;
   }
+  // small dense models: the checkpoint pass of the long sequences runs parallel in the position (kernels_scan.cuh)
+  const bool scan = g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 16;
   // ---- launch plan of the chunk pass: one launch, or one per long sequence (own stream) + one for the single-chunk sequences
-  const bool streamed = g_opt.overlap && g_opt.pass1_cta && d->n_long >= 2 && d->n_long <= 64;
+  const bool streamed = !scan && g_opt.overlap && g_opt.pass1_cta && d->n_long >= 2 && d->n_long <= 64;
   const int64_t n_launch = streamed ? d->n_long + 1 : 1;
   const int NT = 128, wpc = NT / 32;
   const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)wpc * 2 * P.SP) * sizeof(double);
@@ -1101,7 +1115,40 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
     JH_CUDA(cudaGetLastError());
     return JH_OK;
   };
-  if (!streamed) {
+  if (scan) {
+    const jhf::FastTables &Ft = m->fast;
+    const int G = Ft.G;
+    const int64_t n_lc = d->long_seg[d->n_long];  // the chunks of the long sequences are the head of the chunk list
+    if ((r = m->d_scanR.reserve((size_t)n_lc * 2 * G * G)) || (r = m->d_scanE.reserve((size_t)n_lc * 2 * G))) return r;
+    const size_t smem_s = ((size_t)G * G + (size_t)Ft.H * G) * sizeof(double);
+    const int64_t items = n_lc * 2 * G;
+    const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((items + 127) / 128, (int64_t)m->sm_count * 16));
+    const int grid_b = (int)((2 * d->n_long + 3) / 4);
+#define JH_SCAN(GG)                                                                                                                       \
+  {                                                                                                                                       \
+    if (smem_s > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhp::k_scan_chunks<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
+    jhp::k_scan_chunks<GG><<<grid_a, 128, smem_s, s>>>(Ft.dev(), d->dev(), (int)CK, n_lc, d->d_chunk_seq.p, d->d_chunk_idx.p, m->d_scanR.p,  \
+                                                       m->d_scanE.p);                                                                    \
+    JH_LAUNCHED();                                                                                                                        \
+    jhp::k_scan_combine<GG><<<grid_b, 128, 0, s>>>(Ft.dev(), d->dev(), d->n_long, d->d_long.p, d->d_long_seg.p, d->d_chunk_ptr.p,           \
+                                                   m->d_scanR.p, m->d_scanE.p, P.SP, m->d_ck_alpha.p, m->d_ck_beta.p, d_ll, m->d_fallback.p, X); \
+    JH_LAUNCHED();                                                                                                                        \
+  }
+    switch (G) {
+      case 2: JH_SCAN(2) break;
+      case 4: JH_SCAN(4) break;
+      case 8: JH_SCAN(8) break;
+      default: JH_SCAN(16) break;
+    }
+#undef JH_SCAN
+    JH_CUDA(cudaGetLastError());
+    if (what == SPARSE_DECODE && d->n_seq > d->n_long) {  // log-likelihoods of the single-chunk sequences
+      jhs::Pass1Extra Xs{};
+      Xs.list = d->d_order.p + d->n_long; Xs.n_list = d->n_seq - d->n_long;
+      if ((r = run_sparse_pass1(m, d, 2, d_ll, &Xs, nullptr, false))) return r;
+    }
+    if ((r = launch_chunks(0, s))) return r;
+  } else if (!streamed) {
     if (what == SPARSE_DECODE) {
       if ((r = run_sparse_pass1(m, d, 2, d_ll, nullptr, nullptr, false))) return r;
     } else if (d->n_long > 0) {
