@@ -1007,11 +1007,64 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
   return JH_OK;
 }
 
+// Checkpoint pass parallel in the position (kernels_scan.cuh) for the long sequences of the data set: per-chunk transfer rows,
+// then one warp per (sequence, direction) combines them into checkpoints / P(x).  n_dir = 1: forward only (scoring).
+static bool scan_applies(const jh_model *m, const jh_dataset *d) {
+  return g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 16;
+}
+static int run_scan_checkpoints(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra &X) {
+  const jhf::FastTables &Ft = m->fast;
+  jhs::SparseTables &P = m->sparse;
+  cudaStream_t s = m->st();
+  const int G = Ft.G;
+  const int64_t CK = d->chunk_len;
+  const int64_t n_lc = d->long_seg[d->n_long];  // the chunks of the long sequences are the head of the chunk list
+  int r;
+  if ((r = m->d_scanR.reserve((size_t)n_lc * 2 * G * G)) || (r = m->d_scanE.reserve((size_t)n_lc * 2 * G))) return r;
+  const size_t smem_s = ((size_t)G * G + (size_t)Ft.H * G) * sizeof(double);
+  const int64_t items = n_lc * n_dir * G;
+  const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((items + 127) / 128, (int64_t)m->sm_count * 16));
+  const int grid_b = (int)((n_dir * d->n_long + 3) / 4);
+#define JH_SCAN(GG)                                                                                                                       \
+  {                                                                                                                                       \
+    if (smem_s > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhp::k_scan_chunks<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
+    jhp::k_scan_chunks<GG><<<grid_a, 128, smem_s, s>>>(Ft.dev(), d->dev(), (int)CK, n_lc, n_dir, d->d_chunk_seq.p, d->d_chunk_idx.p,         \
+                                                       m->d_scanR.p, m->d_scanE.p);                                                      \
+    JH_LAUNCHED();                                                                                                                        \
+    jhp::k_scan_combine<GG><<<grid_b, 128, 0, s>>>(Ft.dev(), d->dev(), d->n_long, n_dir, d->d_long.p, d->d_long_seg.p, d->d_chunk_ptr.p,     \
+                                                   m->d_scanR.p, m->d_scanE.p, P.SP, n_dir == 2 ? m->d_ck_alpha.p : nullptr,                \
+                                                   n_dir == 2 ? m->d_ck_beta.p : nullptr, d_ll, m->d_fallback.p, X);                       \
+    JH_LAUNCHED();                                                                                                                        \
+  }
+  switch (G) {
+    case 2: JH_SCAN(2) break;
+    case 4: JH_SCAN(4) break;
+    case 8: JH_SCAN(8) break;
+    default: JH_SCAN(16) break;
+  }
+#undef JH_SCAN
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
 static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int32_t *d_list, int64_t n_list);
 
 static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
-  int r = run_sparse_pass1(m, d, 1, d_out);
-  if (r) return r;
+  int r;
+  if (g_opt.scan && m->fast.usable && !m->fast.e_global && m->fast.G <= 16 && d->max_len > g_opt.chunk) {
+    if ((r = ensure_chunks(m, d, g_opt.chunk))) return r;
+  }
+  if (d->chunk_len == g_opt.chunk && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
+    if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
+    JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), m->st()));
+    jhs::Pass1Extra X{};
+    if ((r = run_scan_checkpoints(m, d, 1, d_out, X))) return r;
+    if (d->n_seq > d->n_long) {
+      X.list = d->d_order.p + d->n_long; X.n_list = d->n_seq - d->n_long;
+      if ((r = run_sparse_pass1(m, d, 1, d_out, &X, nullptr, false))) return r;
+    }
+  } else if ((r = run_sparse_pass1(m, d, 1, d_out)))
+    return r;
   int32_t n_fb = 0;
   JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, m->st()));
   JH_CUDA(cudaStreamSynchronize(m->st()));
@@ -1051,7 +1104,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
     X.score = m->d_stats.p + n_stats;
   }
   // small dense models: the checkpoint pass of the long sequences runs parallel in the position (kernels_scan.cuh)
-  const bool scan = g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 16;
+  const bool scan = scan_applies(m, d);
   // ---- launch plan of the chunk pass: one launch, or one per long sequence (own stream) + one for the single-chunk sequences
   const bool streamed = !scan && g_opt.overlap && g_opt.pass1_cta && d->n_long >= 2 && d->n_long <= 64;
   const int64_t n_launch = streamed ? d->n_long + 1 : 1;
@@ -1116,32 +1169,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
     return JH_OK;
   };
   if (scan) {
-    const jhf::FastTables &Ft = m->fast;
-    const int G = Ft.G;
-    const int64_t n_lc = d->long_seg[d->n_long];  // the chunks of the long sequences are the head of the chunk list
-    if ((r = m->d_scanR.reserve((size_t)n_lc * 2 * G * G)) || (r = m->d_scanE.reserve((size_t)n_lc * 2 * G))) return r;
-    const size_t smem_s = ((size_t)G * G + (size_t)Ft.H * G) * sizeof(double);
-    const int64_t items = n_lc * 2 * G;
-    const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((items + 127) / 128, (int64_t)m->sm_count * 16));
-    const int grid_b = (int)((2 * d->n_long + 3) / 4);
-#define JH_SCAN(GG)                                                                                                                       \
-  {                                                                                                                                       \
-    if (smem_s > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhp::k_scan_chunks<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
-    jhp::k_scan_chunks<GG><<<grid_a, 128, smem_s, s>>>(Ft.dev(), d->dev(), (int)CK, n_lc, d->d_chunk_seq.p, d->d_chunk_idx.p, m->d_scanR.p,  \
-                                                       m->d_scanE.p);                                                                    \
-    JH_LAUNCHED();                                                                                                                        \
-    jhp::k_scan_combine<GG><<<grid_b, 128, 0, s>>>(Ft.dev(), d->dev(), d->n_long, d->d_long.p, d->d_long_seg.p, d->d_chunk_ptr.p,           \
-                                                   m->d_scanR.p, m->d_scanE.p, P.SP, m->d_ck_alpha.p, m->d_ck_beta.p, d_ll, m->d_fallback.p, X); \
-    JH_LAUNCHED();                                                                                                                        \
-  }
-    switch (G) {
-      case 2: JH_SCAN(2) break;
-      case 4: JH_SCAN(4) break;
-      case 8: JH_SCAN(8) break;
-      default: JH_SCAN(16) break;
-    }
-#undef JH_SCAN
-    JH_CUDA(cudaGetLastError());
+    if ((r = run_scan_checkpoints(m, d, 2, d_ll, X))) return r;
     if (what == SPARSE_DECODE && d->n_seq > d->n_long) {  // log-likelihoods of the single-chunk sequences
       jhs::Pass1Extra Xs{};
       Xs.list = d->d_order.p + d->n_long; Xs.n_list = d->n_seq - d->n_long;

@@ -51,14 +51,14 @@ __device__ __forceinline__ int hash_direct(const FastDev &F, const uint8_t *x, i
 
 // R: [chunk][direction][start state][G] rows, RE: [chunk][direction][start state] exponents (ROW_ZERO / ROW_BAD)
 template <int G>
-__global__ void __launch_bounds__(128) k_scan_chunks(FastDev F, DevData D, int CK, int64_t n_lc, const int32_t *chunk_seq, const int32_t *chunk_idx,
-                                                     double *R, int *RE) {
+__global__ void __launch_bounds__(128) k_scan_chunks(FastDev F, DevData D, int CK, int64_t n_lc, int n_dir, const int32_t *chunk_seq,
+                                                     const int32_t *chunk_idx, double *R, int *RE) {
   extern __shared__ double sm[];
   double *sT = sm, *sE = sm + G * G;
   for (int i = threadIdx.x; i < G * G; i += blockDim.x) sT[i] = F.T[i];
   for (int i = threadIdx.x; i < F.H * G; i += blockDim.x) sE[i] = F.E[i];
   __syncthreads();
-  const int64_t n_items = n_lc * 2 * G;  // start state fastest, then the chunk, direction slowest: a warp runs one direction
+  const int64_t n_items = n_lc * n_dir * G;  // n_dir = 1: forward only (scoring); start state fastest, then the chunk, direction slowest: a warp runs one direction
   for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * blockDim.x) {
     const int i = (int)(item % G), dir = (int)(item / (n_lc * G));
     const int64_t g = (item / G) % n_lc;
@@ -167,15 +167,15 @@ __device__ __forceinline__ double pow2_neg(int k) {  // 2^k for k <= 0, 0 below 
 // One warp per (long sequence, direction), lane = state.  long_seg[k] = first chunk (in the chunk list) of the k-th long sequence.
 // Produces what k_sparse_pass1 produces: ck_alpha / ck_beta rows [chunk_ptr[seq] + c][SP] (+ exponents, P(x), objective in X).
 template <int G>
-__global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int64_t n_long, const int32_t *long_ids, const int64_t *long_seg,
+__global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int64_t n_long, int n_dir, const int32_t *long_ids, const int64_t *long_seg,
                                                       const int64_t *chunk_ptr, const double *R, const int *RE, int SP, double *ck_alpha,
                                                       double *ck_beta, double *loglik, int32_t *fallback, Pass1Extra X) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= 2 * n_long) return;
-  const int64_t k = w >> 1;
-  const int dir = (int)(w & 1);
+  if (w >= n_dir * n_long) return;
+  const int64_t k = w / n_dir;
+  const int dir = (int)(w % n_dir);
   const int sid = long_ids[k];
   const int64_t g0 = long_seg[k], nck = long_seg[k + 1] - g0, cbase = chunk_ptr[sid];
   const bool act = lane < G;
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int6
     bool alive = e0 > ROW_ZERO / 2;
     if (e0 == ROW_BAD) ok = false;
     for (int64_t c = 1; c < nck && alive; c++) {
-      if (lane < SP) ck_alpha[(size_t)(cbase + c) * SP + lane] = a;
+      if (ck_alpha && lane < SP) ck_alpha[(size_t)(cbase + c) * SP + lane] = a;
       if (X.ck_alpha_exp && lane == 0) X.ck_alpha_exp[cbase + c] = A;
       alive = apply(g0 + c, a, A);
     }
