@@ -1010,7 +1010,10 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
 // Checkpoint pass parallel in the position (kernels_scan.cuh) for the long sequences of the data set: per-chunk transfer rows,
 // then one warp per (sequence, direction) combines them into checkpoints / P(x).  n_dir = 1: forward only (scoring).
 static bool scan_applies(const jh_model *m, const jh_dataset *d) {
-  return g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 16;
+  if (!(g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global)) return false;
+  // 32 states: 32x the arithmetic of the sequential pass and 16 KB of transfer rows per chunk — only while those fit the scratch budget
+  const int64_t n_lc = d->long_seg.empty() ? 0 : d->long_seg[d->n_long];
+  return m->fast.G <= 16 || n_lc * 2 * 32 * 32 * 8 <= g_opt.scratch_mb * 1024 * 1024 / 2;
 }
 static int run_scan_checkpoints(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra &X) {
   const jhf::FastTables &Ft = m->fast;
@@ -1040,7 +1043,8 @@ static int run_scan_checkpoints(jh_model *m, jh_dataset *d, int n_dir, double *d
     case 2: JH_SCAN(2) break;
     case 4: JH_SCAN(4) break;
     case 8: JH_SCAN(8) break;
-    default: JH_SCAN(16) break;
+    case 16: JH_SCAN(16) break;
+    default: JH_SCAN(32) break;
   }
 #undef JH_SCAN
   JH_CUDA(cudaGetLastError());
@@ -1051,7 +1055,7 @@ static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int
 
 static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
   int r;
-  if (g_opt.scan && m->fast.usable && !m->fast.e_global && m->fast.G <= 16 && d->max_len > g_opt.chunk) {
+  if (g_opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > g_opt.chunk) {
     if ((r = ensure_chunks(m, d, g_opt.chunk))) return r;
   }
   if (d->chunk_len == g_opt.chunk && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
