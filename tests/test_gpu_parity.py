@@ -505,8 +505,8 @@ def test_window_viterbi_and_posterior(nat, oracle_lib, name):
 # ---- sparse path: 33..256 states, checkpointed chunk-parallel decoding (BASELINE cfg5 shape) ------------------------
 @pytest.mark.parametrize("states,degree,order", [(40, 4, 1), (128, 4, 0), (128, 4, 1), (64, 8, 0), (200, 3, 0),
                                                  (128, 4, 3), (40, 4, 5)])  # the last two: emission table in global memory
-@pytest.mark.parametrize("chunk", [16, 64, 2048])
-@pytest.mark.parametrize("cta,overlap", [(0, 0), (1, 0), (1, 1)], ids=["warp_per_sequence", "cta_per_sequence", "cta_streams"])
+@pytest.mark.parametrize("chunk,cta,overlap", [(16, 0, 0), (64, 0, 0), (16, 1, 0), (16, 1, 1), (64, 1, 1), (2048, 1, 1)],
+                         ids=["warp_16", "warp_64", "cta_16", "cta_streams_16", "cta_streams_64", "cta_streams_2048"])
 def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, degree, order, chunk, cta, overlap):
     """cta: the checkpoint pass as one warp per (sequence, direction) (many sequences) or one CTA with a state per thread
     and the lazy rescale (few long sequences: latency mode); overlap: one stream per long sequence, its chunk pass starts
