@@ -52,6 +52,8 @@ def run(name, hmm, data, what, reps=3):
 
 n = lambda x: max(64, int(x * scale))
 run("cfg1_bw_s2_k1", lambda: ergodic_hmm(2, 1), lambda: make_data(10_000, 1000), "estep")
+run("cfg1_decode_u8_s2_k1_100k", lambda: ergodic_hmm(2, 1), lambda: make_data(100_000, 1000), "decode_u8")
+run("cfg1_viterbi_u8_s2_k1_100k", lambda: ergodic_hmm(2, 1), lambda: make_data(100_000, 1000), "viterbi_u8")
 run("cfg2_viterbi_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "viterbi")
 run("cfg2_bw_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "estep")
 run("cfg3_bw_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(1_000_000), 1000), "estep")
