@@ -1291,8 +1291,8 @@ static int launch_lanes_eg(jh_model *m, jh_dataset *d, size_t b, double *d_out) 
   if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
   const int64_t n_quads = (n_oct + 3) / 4;
   int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_quads + wpc - 1) / wpc);
-  if (MODE == 1) {
-    const int64_t per_slot = rows * 32 * (S * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+  if constexpr (MODE == 1) {
+    const int64_t per_slot = std::max<int64_t>(1, rows * 32 * (S * (int64_t)sizeof(double) + (int64_t)sizeof(int)));
     const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
     if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
     grid = std::min(grid, max_slots / wpc);
