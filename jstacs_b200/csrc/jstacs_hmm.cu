@@ -1009,6 +1009,14 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
 
 // Checkpoint pass parallel in the position (kernels_scan.cuh) for the long sequences of the data set: per-chunk transfer rows,
 // then one warp per (sequence, direction) combines them into checkpoints / P(x).  n_dir = 1: forward only (scoring).
+// Positions per chunk of the long-sequence path.  Models of the parallel checkpoint pass (dense, <= 32 states: SP = 32) take
+// 4x longer chunks: their combination step walks over the chunks one by one, and their chunk scratch per resident warp is
+// a quarter of a 128-state model's at equal length.  (Tiny test chunk lengths are taken literally.)
+static int64_t chunk_len_for(const jh_model *m) {
+  const bool small_dense = g_opt.scan && m->fast.usable && !m->fast.e_global;
+  return small_dense && g_opt.chunk >= 1024 ? g_opt.chunk * 4 : g_opt.chunk;
+}
+
 static bool scan_applies(const jh_model *m, const jh_dataset *d) {
   if (!(g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global)) return false;
   // 32 states: 32x the arithmetic of the sequential pass and 16 KB of transfer rows per chunk — only while those fit the scratch budget
@@ -1055,10 +1063,10 @@ static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int
 
 static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
   int r;
-  if (g_opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > g_opt.chunk) {
-    if ((r = ensure_chunks(m, d, g_opt.chunk))) return r;
+  if (g_opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > chunk_len_for(m)) {
+    if ((r = ensure_chunks(m, d, chunk_len_for(m)))) return r;
   }
-  if (d->chunk_len == g_opt.chunk && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
+  if (d->chunk_len == chunk_len_for(m) && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
     if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), m->st()));
     jhs::Pass1Extra X{};
@@ -1091,7 +1099,7 @@ enum { SPARSE_DECODE = 0, SPARSE_ESTEP = 1 };
 static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d_paths, double *d_ll) {
   jhs::SparseTables &P = m->sparse;
   cudaStream_t s = m->st();
-  const int64_t CK = g_opt.chunk;
+  const int64_t CK = chunk_len_for(m);
   int r = ensure_chunks(m, d, CK);
   if (r) return r;
   if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;

@@ -180,9 +180,21 @@ __global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int6
   const int64_t g0 = long_seg[k], nck = long_seg[k + 1] - g0, cbase = chunk_ptr[sid];
   const bool act = lane < G;
   bool ok = true;
-  // v <- sum_i v[i] 2^(e_i - E) row_i of chunk g; returns false when nothing is left
-  auto apply = [&](int64_t g, double &v, long long &expo) {
-    const int my_e = act ? RE[(size_t)(g * 2 + dir) * G + lane] : ROW_ZERO;
+  // The walk over the chunks is one dependent chain; the rows and exponents of a chunk do not depend on it, so the next
+  // chunk's are fetched (into registers) while the current one is combined: the global-memory latency leaves the chain.
+  struct ChunkRows {
+    int e;          // exponent of row `lane`
+    double r[G];    // r[i] = row i, entry `lane`
+  };
+  auto fetch = [&](int64_t g, ChunkRows &C) {
+    C.e = act ? RE[(size_t)(g * 2 + dir) * G + lane] : ROW_ZERO;
+    const double *rows = R + (size_t)(g * 2 + dir) * G * G + lane;
+#pragma unroll
+    for (int i = 0; i < G; i++) C.r[i] = act ? rows[(size_t)i * G] : 0.0;
+  };
+  // v <- sum_i v[i] 2^(e_i - E) row_i; returns false when nothing is left
+  auto apply = [&](const ChunkRows &C, double &v, long long &expo) {
+    const int my_e = C.e;
     if (__any_sync(FULL, act && v > 0 && my_e == ROW_BAD)) ok = false;
     const bool valid = act && v > 0 && my_e > ROW_ZERO / 2;
     int emax = valid ? my_e : INT_MIN;
@@ -191,12 +203,8 @@ __global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int6
     double res = 0;
     if (emax != INT_MIN) {
       const double sc = valid ? v * pow2_neg(my_e - emax) : 0.0;
-      const double *rows = R + (size_t)(g * 2 + dir) * G * G + lane;
 #pragma unroll
-      for (int i = 0; i < G; i++) {
-        const double si = __shfl_sync(FULL, sc, i);
-        if (act && si != 0) res = fma(si, rows[(size_t)i * G], res);
-      }
+      for (int i = 0; i < G; i++) res = fma(__shfl_sync(FULL, sc, i), C.r[i], res);
       expo += emax;
     }
     v = res;
@@ -209,16 +217,20 @@ __global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int6
     ok &= (unsigned)(be - 81) < (0x7feu - 81u);
     return true;
   };
+  ChunkRows cur, nxt;
   if (dir == 0) {
     const int e0 = RE[(size_t)(g0 * 2) * G];
     double a = act ? R[(size_t)(g0 * 2) * G * G + lane] : 0.0;  // chunk 0, "row" 0: alpha at the end of chunk 0
     long long A = e0 > ROW_ZERO / 2 ? e0 : 0;
     bool alive = e0 > ROW_ZERO / 2;
     if (e0 == ROW_BAD) ok = false;
+    if (nck > 1) fetch(g0 + 1, nxt);
     for (int64_t c = 1; c < nck && alive; c++) {
+      cur = nxt;
+      if (c + 1 < nck) fetch(g0 + c + 1, nxt);
       if (ck_alpha && lane < SP) ck_alpha[(size_t)(cbase + c) * SP + lane] = a;
       if (X.ck_alpha_exp && lane == 0) X.ck_alpha_exp[cbase + c] = A;
-      alive = apply(g0 + c, a, A);
+      alive = apply(cur, a, A);
     }
     double sfin = act && alive ? a * F.fin[lane] : 0.0;
 #pragma unroll
@@ -243,11 +255,14 @@ __global__ void __launch_bounds__(128) k_scan_combine(FastDev F, DevData D, int6
     double b = act ? R[(size_t)(gl * 2 + 1) * G * G + lane] : 0.0;
     long long Bx = e0 > ROW_ZERO / 2 ? e0 : 0;
     bool alive = e0 > ROW_ZERO / 2;
+    if (nck > 2) fetch(g0 + nck - 2, nxt);
     for (int64_t c = nck - 2; c >= 0; c--) {  // ck_beta[c] = beta at the last position of chunk c
       if (lane < SP) ck_beta[(size_t)(cbase + c) * SP + lane] = alive ? b : 0.0;
       if (X.ck_beta_exp && lane == 0) X.ck_beta_exp[cbase + c] = Bx;
       if (c == 0) break;
-      if (alive) alive = apply(g0 + c, b, Bx);
+      cur = nxt;
+      if (c - 1 >= 1) fetch(g0 + c - 1, nxt);
+      if (alive) alive = apply(cur, b, Bx);
     }
   }
 }
