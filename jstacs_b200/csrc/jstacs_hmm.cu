@@ -16,6 +16,7 @@
 #include "kernels_lanes.cuh"
 #include "kernels_sparse.cuh"
 #include "kernels_scan.cuh"
+#include "kernels_lanechunks.cuh"
 #include "kernels_viterbi.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -31,6 +32,7 @@ struct Options {
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
+  int64_t lane_chunks = 1;     // 2..4 states: chunk pass with one chunk per lane (kernels_lanechunks.cuh)
   int64_t scan = 1;            // small dense models: checkpoint pass parallel in the position (kernels_scan.cuh)
   int64_t overlap = 1;         // long-sequence path: per-sequence streams, a sequence's chunk pass starts when its checkpoint pass ends
   int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
@@ -288,6 +290,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "pass1_cta") g_opt.pass1_cta = value;
   else if (n == "overlap") g_opt.overlap = value;
   else if (n == "scan") g_opt.scan = value;
+  else if (n == "lane_chunks") g_opt.lane_chunks = value;
   else if (n == "oct_chunk_force") g_opt.oct_chunk_force = value;
   else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
     cudaMemPool_t pool;
@@ -1187,7 +1190,41 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
       Xs.list = d->d_order.p + d->n_long; Xs.n_list = d->n_seq - d->n_long;
       if ((r = run_sparse_pass1(m, d, 2, d_ll, &Xs, nullptr, false))) return r;
     }
-    if ((r = launch_chunks(0, s))) return r;
+    if (g_opt.lane_chunks && m->fast.G <= 4) {  // tiny models: one chunk per lane instead of one state per lane
+      const jhf::FastTables &Ft = m->fast;
+      const int ec_smem = what == SPARSE_ESTEP && (size_t)Ft.H * Ft.G * 32 * wpc * sizeof(double) <= 96 * 1024;
+      const size_t smem_l = ((size_t)Ft.H * Ft.G + (ec_smem ? (size_t)Ft.H * Ft.G * 32 * wpc : 0)) * sizeof(double);
+      const int64_t per_warp = rows * 32 * (Ft.G * (int64_t)sizeof(double) + (what == SPARSE_ESTEP ? (int64_t)sizeof(int) : 0));
+      const int64_t warps = std::max<int64_t>(1, std::min<int64_t>((d->n_chunks + 31) / 32, std::min<int64_t>((int64_t)m->sm_count * 16, g_opt.scratch_mb * 1024 * 1024 / per_warp)));
+      const int grid_l = (int)((warps + wpc - 1) / wpc);
+      if ((r = m->d_fwd.reserve((size_t)grid_l * wpc * rows * 32 * Ft.G))) return r;
+      if (what == SPARSE_ESTEP && (r = m->d_rexp.reserve((size_t)grid_l * wpc * rows * 32))) return r;
+      if (what == SPARSE_ESTEP) JH_CUDA(cudaMemsetAsync(Ft.d_ec, 0, sizeof(double) * jhf::EC_REPLICAS * Ft.H * Ft.G, s));
+      jhc::LaneChunkIn In{(int)CK, (int)rows, P.SP, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_ck_alpha.p, m->d_ck_beta.p,
+                          m->d_ck_exp.p, m->d_ck_exp.p + d->n_chunks + 1, m->d_seq_sfin.p, m->d_seq_AL.p};
+#define JH_LC(GG)                                                                                                                        \
+  {                                                                                                                                      \
+    if (what == SPARSE_ESTEP) {                                                                                                          \
+      if (smem_l > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhc::k_lane_chunks<GG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
+      jhc::k_lane_chunks<GG, 1><<<grid_l, NT, smem_l, s>>>(Ft.dev(), d->dev(), In, m->d_counters.p, m->d_fwd.p, m->d_rexp.p, nullptr, m->d_stats.p, Ft.d_ec, m->d_fallback.p, ec_smem); \
+    } else {                                                                                                                             \
+      if (smem_l > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhc::k_lane_chunks<GG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
+      jhc::k_lane_chunks<GG, 0><<<grid_l, NT, smem_l, s>>>(Ft.dev(), d->dev(), In, m->d_counters.p, m->d_fwd.p, nullptr, d_paths, nullptr, Ft.d_ec, m->d_fallback.p, 0); \
+    }                                                                                                                                    \
+    JH_LAUNCHED();                                                                                                                       \
+  }
+      if (Ft.G == 2) JH_LC(2) else JH_LC(4)
+#undef JH_LC
+      JH_CUDA(cudaGetLastError());
+      if (what == SPARSE_ESTEP) {
+        const int nf = Ft.H * Ft.G;
+        jhf::k_fast_fold_ec<<<(nf + 255) / 256, 256, 0, s>>>(Ft.dev(), Ft.d_ec, m->d_stats.p);
+        JH_LAUNCHED();
+        JH_CUDA(cudaGetLastError());
+        return JH_OK;
+      }
+    } else if ((r = launch_chunks(0, s)))
+      return r;
   } else if (!streamed) {
     if (what == SPARSE_DECODE) {
       if ((r = run_sparse_pass1(m, d, 2, d_ll, nullptr, nullptr, false))) return r;

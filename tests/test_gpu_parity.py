@@ -552,9 +552,10 @@ def test_sparse_models_scoring_and_chunked_decoding(nat, oracle_lib, states, deg
         nat.check(nat.lib().jh_set_option(b"overlap", 1))
 
 
-@pytest.mark.parametrize("cta,scan", [(0, 0), (1, 0), (1, 1)], ids=["warp_per_sequence", "cta_per_sequence", "parallel_scan"])
+@pytest.mark.parametrize("cta,scan,lane", [(0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 1, 1)],
+                         ids=["warp_per_sequence", "cta_per_sequence", "parallel_scan", "parallel_scan_lane_chunks"])
 @pytest.mark.parametrize("name", ["erg_s2_k1", "sparse", "erg_s5_k2", "erg_s16_k1", "erg_s32_k3", "erg_s3_k0_map"])
-def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta, scan):
+def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta, scan, lane):
     """The checkpointed warp-per-sequence path (taken for a few long sequences) also covers models with <= 32 states:
     forced here with fast_variant 4 and a tiny chunk length."""
     hmm = MODELS[name]()
@@ -565,7 +566,10 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta, sca
     nat.check(nat.lib().jh_set_option(b"fast_variant", 4))
     nat.check(nat.lib().jh_set_option(b"chunk", 32))
     nat.check(nat.lib().jh_set_option(b"pass1_cta", cta))
-    nat.check(nat.lib().jh_set_option(b"scan", scan))  # checkpoint pass parallel in the position (kernels_scan.cuh, <= 16 states)
+    nat.check(nat.lib().jh_set_option(b"scan", scan))  # checkpoint pass parallel in the position (kernels_scan.cuh)
+    nat.check(nat.lib().jh_set_option(b"lane_chunks", lane))  # 2..4 states: chunk pass with one chunk per lane (kernels_lanechunks.cuh)
+    if lane and hmm.getNumberOfStates() > 4:
+        pytest.skip("one chunk per lane is for 2..4 states")
     try:
         ll_ref = om.loglik(data.codes, data.offsets)
         np.testing.assert_allclose(hmm.getLogScoreFor(data), ll_ref, rtol=LL_RTOL)
@@ -591,6 +595,7 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta, sca
         nat.check(nat.lib().jh_set_option(b"chunk", 2048))
         nat.check(nat.lib().jh_set_option(b"pass1_cta", 1))
         nat.check(nat.lib().jh_set_option(b"scan", 1))
+        nat.check(nat.lib().jh_set_option(b"lane_chunks", 1))
 
 
 def test_full_size_properties_cfg3_sample(nat):
