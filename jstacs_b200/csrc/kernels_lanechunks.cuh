@@ -185,28 +185,47 @@ __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneC
         }
         int hb = jhp::hash_direct(F, x, t1);
         bool okb = true;
-        for (int t = t1; t >= t0; t--) {
-          double e[G], at[G];
-          emis(hb, t, e);
-          const double *src = R + (size_t)(t - t0) * 32 * G;
+        // The rows come back from L2 / HBM: a rolling window keeps rows t, t-1, t-2 in registers and requests row t-3 at the
+        // top of step t, so a load has two steps to arrive (the row in front of the chunk is the checkpoint a0)
+        auto load_row = [&](int t, double (&r)[G], int &rx) {
+          if (t >= t0) {
+            const double *src = R + (size_t)(t - t0) * 32 * G;
 #pragma unroll
-          for (int j = 0; j < G; j++) at[j] = src[j];
+            for (int j = 0; j < G; j++) r[j] = src[j];
+            rx = MODE == 1 ? RX[(size_t)(t - t0) * 32] : 0;
+          } else {
+#pragma unroll
+            for (int j = 0; j < G; j++) r[j] = a0[j];
+            rx = 0;
+          }
+        };
+        double r0[G], r1[G], r2[G], r3[G];
+        int x0, x1, x2, x3 = 0;
+        load_row(t1, r0, x0);
+        load_row(t1 - 1, r1, x1);
+        load_row(t1 - 2, r2, x2);
+#pragma unroll
+        for (int j = 0; j < G; j++) r3[j] = 0;
+        for (int t = t1; t >= t0; t--) {
+          if (t - 3 >= t0 - 1) load_row(t - 3, r3, x3);
+          double e[G];
+          emis(hb, t, e);
           if (MODE == 0) {  // largest alpha_t[j] * beta_t[j], lowest index on ties
-            double best = at[0] * b[0];
+            double best = r0[0] * b[0];
             int arg = 0;
 #pragma unroll
             for (int j = 1; j < G; j++) {
-              const double gm = at[j] * b[j];
+              const double gm = r0[j] * b[j];
               if (gm > best) { best = gm; arg = j; }
             }
             paths[off + t] = arg;
           } else {
-            const long long At = A0 + RX[(size_t)(t - t0) * 32];
+            const long long At = A0 + x0;
             const double sg = pow2_any(At + Bx - AL) * winv;
             double *gdst = gECw + (size_t)hb * G;
 #pragma unroll
             for (int j = 0; j < G; j++) {
-              const double gm = at[j] * b[j] * sg;
+              const double gm = r0[j] * b[j] * sg;
               if (t >= F.Kmax || t >= F.korder[j]) {
                 if (ec_smem) ecw[(size_t)(hb * G + j) * 32 + lane] += gm;
                 else atomicAdd(gdst + j, gm);
@@ -215,26 +234,15 @@ __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneC
             }
           }
           if (t == 0) break;
-          // alpha_{t-1}: the previous row of the chunk, or the checkpoint in front of it
-          double ap[G];
-          long long Ap = A0;
-          if (t > t0) {
-            const double *srcp = R + (size_t)(t - 1 - t0) * 32 * G;
-#pragma unroll
-            for (int j = 0; j < G; j++) ap[j] = srcp[j];
-            if (MODE == 1) Ap = A0 + RX[(size_t)(t - 1 - t0) * 32];
-          } else {
-#pragma unroll
-            for (int j = 0; j < G; j++) ap[j] = a0[j];
-          }
+          // alpha_{t-1} = r1: the previous row of the chunk, or the checkpoint in front of it
           double xb[G], nb[G];
 #pragma unroll
           for (int j = 0; j < G; j++) xb[j] = e[j] * b[j];
           if (MODE == 1) {
-            const double sx = pow2_any(Ap + Bx - AL) * winv;
+            const double sx = pow2_any(A0 + x1 + Bx - AL) * winv;
 #pragma unroll
             for (int i = 0; i < G; i++) {
-              const double as = ap[i] * sx;
+              const double as = r1[i] * sx;
 #pragma unroll
               for (int j = 0; j < G; j++) O[i][j] = fma(as, xb[j], O[i][j]);
             }
@@ -248,7 +256,13 @@ __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneC
             nb[i] = s;
           }
 #pragma unroll
-          for (int j = 0; j < G; j++) b[j] = nb[j];
+          for (int j = 0; j < G; j++) {
+            b[j] = nb[j];
+            r0[j] = r1[j];
+            r1[j] = r2[j];
+            r2[j] = r3[j];
+          }
+          x0 = x1; x1 = x2; x2 = x3;
           if ((t & 7) == 0) rescale_lane<G>(b, Bx, okb);
           const int q = t - 1 - F.Kmax;
           hb = hb / F.a + F.hpow * (q >= 0 ? (int)__ldg(x + q) : 0);
