@@ -598,6 +598,43 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta, sca
         nat.check(nat.lib().jh_set_option(b"lane_chunks", 1))
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_parallel_checkpoint_pass_matches_the_sequential_one_randomized(nat, seed):
+    """Random models / chunk lengths / ragged long sequences: the position-parallel checkpoint pass (+ lane-per-chunk pass)
+    and the sequential pass are two evaluation orders of the same sums: scores, counts and decoded paths agree to 1e-11."""
+    rng = np.random.default_rng(100 + seed)
+    states = int(rng.choice([2, 3, 4, 6, 8, 13, 16, 27, 32]))
+    order = int(rng.integers(0, 3))
+    chunk = int(rng.choice([16, 24, 40, 128]))
+    hmm = ergodic_hmm(states, order, n_iter=2, ess=float(rng.choice([0.0, 3.0])))
+    lens = np.concatenate([rng.integers(1, 2 * chunk, 5), rng.integers(3 * chunk, 40 * chunk, 6), [chunk, chunk + 1, 7 * chunk]])
+    data = dataset_of([random_dna(rng, int(L)) for L in lens])
+    w = rng.random(lens.size) + 0.5
+    out = {}
+    try:
+        nat.check(nat.lib().jh_set_option(b"fast_variant", 4))
+        nat.check(nat.lib().jh_set_option(b"chunk", chunk))
+        for mode in (0, 1):
+            nat.check(nat.lib().jh_set_option(b"scan", mode))
+            nat.check(nat.lib().jh_set_option(b"lane_chunks", mode))
+            eng, nd = hmm._engine(), hmm._data(data)
+            nd.set_weights(w)
+            ts, es, sc = eng.estep(nd)
+            nd.set_weights(None)
+            paths, ll = eng.posterior_decode(nd)
+            out[mode] = (ts, es, sc, eng.loglik(nd), ll, paths)
+    finally:
+        for k, v in ((b"fast_variant", 0), (b"chunk", 2048), (b"scan", 1), (b"lane_chunks", 1)):
+            nat.check(nat.lib().jh_set_option(k, v))
+    a, b = out[0], out[1]
+    np.testing.assert_allclose(b[0], a[0], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(b[1], a[1], rtol=1e-11, atol=1e-11)
+    assert b[2] == pytest.approx(a[2], rel=1e-12)
+    np.testing.assert_allclose(b[3], a[3], rtol=1e-12)
+    np.testing.assert_allclose(b[4], a[4], rtol=1e-12)
+    assert (a[5] != b[5]).mean() < 1e-3  # decisions differ only where two posteriors tie to the last bits
+
+
 def test_full_size_properties_cfg3_sample(nat):
     """BASELINE cfg3 model (32 states, order-3 emissions) on 16k x 1 kb sequences: size-independent properties.
     Transition counts add up to the residues, emission counts to the residues with a full context, the score is the
