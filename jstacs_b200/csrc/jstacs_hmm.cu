@@ -32,7 +32,7 @@ struct Options {
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
-  int64_t lane_chunks = 1;     // 2..4 states: chunk pass with one chunk per lane (kernels_lanechunks.cuh)
+  int64_t lane_chunks = 1;     // 2..8 states: chunk pass with one chunk per lane (kernels_lanechunks.cuh)
   int64_t scan = 1;            // small dense models: checkpoint pass parallel in the position (kernels_scan.cuh)
   int64_t overlap = 1;         // long-sequence path: per-sequence streams, a sequence's chunk pass starts when its checkpoint pass ends
   int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
@@ -1190,7 +1190,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
       Xs.list = d->d_order.p + d->n_long; Xs.n_list = d->n_seq - d->n_long;
       if ((r = run_sparse_pass1(m, d, 2, d_ll, &Xs, nullptr, false))) return r;
     }
-    if (g_opt.lane_chunks && m->fast.G <= 4) {  // tiny models: one chunk per lane instead of one state per lane
+    if (g_opt.lane_chunks && m->fast.G <= 8) {  // small models: one chunk per lane instead of one state per lane
       const jhf::FastTables &Ft = m->fast;
       const int ec_smem = what == SPARSE_ESTEP && (size_t)Ft.H * Ft.G * 32 * wpc * sizeof(double) <= 96 * 1024;
       const size_t smem_l = ((size_t)Ft.H * Ft.G + (ec_smem ? (size_t)Ft.H * Ft.G * 32 * wpc : 0)) * sizeof(double);
@@ -1213,7 +1213,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
     }                                                                                                                                    \
     JH_LAUNCHED();                                                                                                                       \
   }
-      if (Ft.G == 2) JH_LC(2) else JH_LC(4)
+      if (Ft.G == 2) JH_LC(2) else if (Ft.G == 4) JH_LC(4) else JH_LC(8)
 #undef JH_LC
       JH_CUDA(cudaGetLastError());
       if (what == SPARSE_ESTEP) {

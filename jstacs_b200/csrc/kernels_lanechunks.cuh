@@ -1,4 +1,4 @@
-// kernels_lanechunks.cuh — chunk pass of the long-sequence path for TINY dense models (2..4 states after padding), ONE CHUNK
+// kernels_lanechunks.cuh — chunk pass of the long-sequence path for SMALL dense models (2..8 states after padding), ONE CHUNK
 // PER LANE.  The warp-per-chunk kernels of kernels_sparse.cuh keep one state per lane: for a 2-state model 30 of 32 lanes
 // idle.  Here a lane owns a whole chunk (like kernels_lanes.cuh owns a whole sequence): state vector, T and the S x S
 // count accumulators in registers, the chunk's forward rows in an HBM scratch laid out [position][lane][S] (coalesced

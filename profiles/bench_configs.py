@@ -82,6 +82,7 @@ run("cfg4_decode_u8_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_dat
 run("chr_cpg_bw_s2_k1_2x50Mb", lambda: ergodic_hmm(2, 1), lambda: make_data(2, 50_000_000), "estep")
 run("chr_cpg_decode_u8_s2_k1_2x50Mb", lambda: ergodic_hmm(2, 1), lambda: make_data(2, 50_000_000), "decode_u8")
 run("chr_cpg_loglik_s2_k1_2x50Mb", lambda: ergodic_hmm(2, 1), lambda: make_data(2, 50_000_000), "loglik")
+run("chr_decode_u8_s8_k2_4x25Mb", lambda: ergodic_hmm(8, 2), lambda: make_data(4, 25_000_000), "decode_u8")
 run("long_bw_s32_k3_dense_8x2Mb", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(8, 2_000_000), "estep")
 run("chr_bw_s8_k2_4x25Mb", lambda: ergodic_hmm(8, 2), lambda: make_data(4, 25_000_000), "estep")
 # emission tables larger than shared memory (EG kernels): 32 states order 4 = 256 KB, 8 states order 5 = 256 KB

@@ -568,8 +568,8 @@ def test_warp_per_sequence_path_for_small_models(nat, oracle_lib, name, cta, sca
     nat.check(nat.lib().jh_set_option(b"pass1_cta", cta))
     nat.check(nat.lib().jh_set_option(b"scan", scan))  # checkpoint pass parallel in the position (kernels_scan.cuh)
     nat.check(nat.lib().jh_set_option(b"lane_chunks", lane))  # 2..4 states: chunk pass with one chunk per lane (kernels_lanechunks.cuh)
-    if lane and hmm.getNumberOfStates() > 4:
-        pytest.skip("one chunk per lane is for 2..4 states")
+    if lane and hmm.getNumberOfStates() > 8:
+        pytest.skip("one chunk per lane is for 2..8 states")
     try:
         ll_ref = om.loglik(data.codes, data.offsets)
         np.testing.assert_allclose(hmm.getLogScoreFor(data), ll_ref, rtol=LL_RTOL)
