@@ -32,7 +32,8 @@ def run(name, hmm, data, what, reps=3):
     res, S = data.getNumberOfResidues(), hmm.getNumberOfStates()
     fn = {"estep": lambda: eng.estep(nd, fetch=False), "loglik": lambda: eng.loglik(nd), "viterbi": lambda: eng.viterbi(nd),
           "decode": lambda: eng.posterior_decode(nd), "viterbi_u8": lambda: eng.viterbi(nd, narrow=True),
-          "decode_u8": lambda: eng.posterior_decode(nd, narrow=True)}[what]
+          "decode_u8": lambda: eng.posterior_decode(nd, narrow=True),
+          "train": lambda: hmm.train(data)}[what]  # the whole HigherOrderHMM.train call (data set resident; parameters read back)
     if not name.startswith("full_"):
         fn()  # warm-up
     ms = []
@@ -41,7 +42,7 @@ def run(name, hmm, data, what, reps=3):
         fn()
         _native.check(_native.lib().jh_synchronize())
         wall = (time.perf_counter() - t0) * 1e3
-        ms.append((eng.last_main_kernel_ms() if what == "estep" else eng.last_kernel_ms(), wall))
+        ms.append((eng.last_main_kernel_ms() if what == "estep" else wall if what == "train" else eng.last_kernel_ms(), wall))
     k = float(np.median([m[0] for m in ms]))
     print(json.dumps({"config": name, "op": what, "states": S, "n_seq": data.getNumberOfElements(), "residues": res, "kernel_ms": round(k, 3),
                       "call_ms": round(float(np.median([m[1] for m in ms])), 3), "residues_states_per_s": res * S / (k * 1e-3),
@@ -52,6 +53,7 @@ def run(name, hmm, data, what, reps=3):
 
 n = lambda x: max(64, int(x * scale))
 run("cfg1_bw_s2_k1", lambda: ergodic_hmm(2, 1), lambda: make_data(10_000, 1000), "estep")
+run("cfg1_train10_s2_k1", lambda: ergodic_hmm(2, 1, n_iter=10), lambda: make_data(10_000, 1000), "train")
 run("cfg1_decode_u8_s2_k1_100k", lambda: ergodic_hmm(2, 1), lambda: make_data(100_000, 1000), "decode_u8")
 run("cfg1_viterbi_u8_s2_k1_100k", lambda: ergodic_hmm(2, 1), lambda: make_data(100_000, 1000), "viterbi_u8")
 run("cfg2_viterbi_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "viterbi")
