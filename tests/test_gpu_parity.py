@@ -142,6 +142,25 @@ def test_baum_welch_training_matches_oracle(nat, oracle_lib, fast, name, ess):
     np.testing.assert_array_equal(ir.emis_param, got[2])
 
 
+def test_multi_start_training_keeps_the_best_start(nat, oracle_lib):
+    """HigherOrderHMM.train with numberOfStarts > 1 (HigherOrderHMM.java:741-786): every start is initialised randomly, the
+    parameters of the start with the largest final objective are kept."""
+    hmm = ergodic_hmm(3, 1, n_iter=4)
+    hmm.setSkiptInit(False)
+    hmm.trainingParameter = BaumWelchParameterSet(4, IterationCondition(4), 1)
+    data = planted_dna(80, 120, n_states=3, seed=9)
+    best = hmm.train(data)
+    finals = [obj[-1] for obj in hmm.last_objectives]
+    assert len(finals) == 4 and len(set(finals)) > 1  # the starts really differ
+    assert best == max(finals)
+    # the model holds the parameters of the best start: the oracle, started from them, reports the same likelihood
+    om = oracle_lib.OracleModel(hmm.ir())
+    ll = om.loglik(data.codes, data.offsets).sum()
+    np.testing.assert_allclose(hmm.getLogScoreFor(data).sum(), ll, rtol=LL_RTOL)
+    # N E-steps and N-1 M-steps: the last objective was evaluated with exactly the parameters that are kept
+    assert ll + hmm.getLogPriorTerm() == pytest.approx(best, rel=1e-9)
+
+
 def test_small_difference_termination(nat, oracle_lib, fast):
     hmm = ergodic_hmm(3, 1)
     om = oracle_lib.OracleModel(hmm.ir())
