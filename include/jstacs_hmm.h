@@ -113,8 +113,9 @@ int jh_synchronize(void);
 /* Tuning / test switches: "fast" (1: scaled linear-space kernels where the model allows, 0: reference-order
  * log-space kernels only), "scratch_mb" (DP scratch budget), "blocks_per_sm", "fast_variant", "chunk" (positions per
  * checkpoint of the long-sequence path), "oct_chunk" / "oct_chunk_force" (checkpointed forward rows of the octet kernels),
- * "pass1_cta", "overlap", "scan" (mappings of the checkpoint pass: CTA per sequence, per-sequence streams, parallel in the
- * position; all on by default, switched off by the tests to reach the other kernels), "trim_pool" (return unused
+ * "pass1_cta", "overlap", "scan", "lane_chunks", "split_short" (mappings of the long-sequence path: CTA per sequence,
+ * per-sequence streams, checkpoint pass parallel in the position, one chunk per lane, short sequences of tiny models cut
+ * into chunks; all on by default, switched off by the tests to reach the other kernels), "trim_pool" (return unused
  * device-pool memory to the driver, keeping `value` bytes: device buffers are pooled so that per-call data sets do not
  * pay cudaMalloc/cudaFree). */
 int jh_set_option(const char *name, int64_t value);

@@ -32,6 +32,7 @@ struct Options {
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
+  int64_t split_short = 1;     // 2..4 states, few short sequences: cut them into chunks for the position-parallel path
   int64_t lane_chunks = 1;     // 2..8 states: chunk pass with one chunk per lane (kernels_lanechunks.cuh)
   int64_t scan = 1;            // small dense models: checkpoint pass parallel in the position (kernels_scan.cuh)
   int64_t overlap = 1;         // long-sequence path: per-sequence streams, a sequence's chunk pass starts when its checkpoint pass ends
@@ -291,6 +292,7 @@ extern "C" int jh_set_option(const char *name, int64_t value) {
   else if (n == "overlap") g_opt.overlap = value;
   else if (n == "scan") g_opt.scan = value;
   else if (n == "lane_chunks") g_opt.lane_chunks = value;
+  else if (n == "split_short") g_opt.split_short = value;
   else if (n == "oct_chunk_force") g_opt.oct_chunk_force = value;
   else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
     cudaMemPool_t pool;
@@ -886,11 +888,20 @@ static int variant_of(const jh_model *m) {
   return (m->fast.usable && m->fast.e_global && g_opt.fast_variant != 4) ? 0 : (int)g_opt.fast_variant;
 }
 
+// Tiny models (2..4 states) on a data set that is too small to fill the GPU with one sequence per lane (BASELINE configs[0]:
+// 10 000 sequences = 313 warps, each a dependent chain of 2 x 1000 positions): the sequences are cut into short chunks and
+// take the position-parallel checkpoint pass + the lane-per-chunk pass, which turns the chains into ~4x more, ~4x shorter
+// ones (cfg1 E-step 0.81 -> 0.53 ms, the whole 10-iteration train() call 9.1 -> 6.2 ms).
+static bool split_short_sequences(const jh_model *m, const jh_dataset *d) {
+  return g_opt.split_short && g_opt.scan && g_opt.lane_chunks && g_opt.fast_variant == 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 4 &&
+         d->n_seq < 32768 && d->n_res >= (1 << 20) && d->max_len >= 256 && d->max_len < 16384;
+}
+
 static bool prefer_sparse(const jh_model *m, const jh_dataset *d) {
   if (!g_opt.fast || !m->sparse.usable) return false;
   if (m->S > 32 || g_opt.fast_variant == 4) return true;
   if (g_opt.fast_variant != 0) return false;
-  return d->n_seq <= 1024 && d->max_len >= 16384;
+  return (d->n_seq <= 1024 && d->max_len >= 16384) || split_short_sequences(m, d);
 }
 
 #define DISPATCH_SPARSE(P, ...)                                   \
@@ -1015,7 +1026,11 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
 // Positions per chunk of the long-sequence path.  Models of the parallel checkpoint pass (dense, <= 32 states: SP = 32) take
 // 4x longer chunks: their combination step walks over the chunks one by one, and their chunk scratch per resident warp is
 // a quarter of a 128-state model's at equal length.  (Tiny test chunk lengths are taken literally.)
-static int64_t chunk_len_for(const jh_model *m) {
+static int64_t chunk_len_for(const jh_model *m, const jh_dataset *d) {
+  if (split_short_sequences(m, d)) {  // ~49 000 chunks (lanes) for the whole data set, at least 64 positions each
+    const int64_t ck = (d->n_res / 49152 + 15) / 16 * 16;
+    return std::max<int64_t>(64, std::min<int64_t>(ck, g_opt.chunk));
+  }
   const bool small_dense = g_opt.scan && m->fast.usable && !m->fast.e_global;
   return small_dense && g_opt.chunk >= 1024 ? g_opt.chunk * 4 : g_opt.chunk;
 }
@@ -1066,10 +1081,10 @@ static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int
 
 static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
   int r;
-  if (g_opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > chunk_len_for(m)) {
-    if ((r = ensure_chunks(m, d, chunk_len_for(m)))) return r;
+  if (g_opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > chunk_len_for(m, d)) {
+    if ((r = ensure_chunks(m, d, chunk_len_for(m, d)))) return r;
   }
-  if (d->chunk_len == chunk_len_for(m) && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
+  if (d->chunk_len == chunk_len_for(m, d) && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
     if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), m->st()));
     jhs::Pass1Extra X{};
@@ -1102,7 +1117,7 @@ enum { SPARSE_DECODE = 0, SPARSE_ESTEP = 1 };
 static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d_paths, double *d_ll) {
   jhs::SparseTables &P = m->sparse;
   cudaStream_t s = m->st();
-  const int64_t CK = chunk_len_for(m);
+  const int64_t CK = chunk_len_for(m, d);
   int r = ensure_chunks(m, d, CK);
   if (r) return r;
   if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;

@@ -654,6 +654,51 @@ def test_parallel_checkpoint_pass_matches_the_sequential_one_randomized(nat, see
     assert (a[5] != b[5]).mean() < 1e-3  # decisions differ only where two posteriors tie to the last bits
 
 
+@pytest.mark.parametrize("states,order", [(2, 1), (3, 0), (4, 2)])
+def test_short_sequences_of_tiny_models_are_split_into_chunks(nat, oracle_lib, states, order):
+    """2..4 states, a data set too small to fill the GPU with a sequence per lane (cfg1's shape): the library cuts the
+    sequences into chunks and runs the position-parallel path by itself (split_short).  Same results as the oracle, and as
+    the sequence-per-lane kernels with the rule switched off."""
+    hmm = ergodic_hmm(states, order, n_iter=3, ess=1.0)
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(states)
+    lens = rng.integers(300, 900, 1800)
+    lens[:3] = [1, 2, 64]
+    data = make_data(lens.size, lens)
+    assert data.getNumberOfResidues() >= 1 << 20
+    w = rng.random(lens.size) + 0.5
+    eng, nd = hmm._engine(), hmm._data(data)
+    res = {}
+    for split in (1, 0):
+        nat.check(nat.lib().jh_set_option(b"split_short", split))
+        try:
+            nd.set_weights(w)
+            ts, es, sc = eng.estep(nd)
+            nd.set_weights(None)
+            paths, ll = eng.posterior_decode(nd)
+            res[split] = (ts, es, sc, eng.loglik(nd), ll, paths)
+        finally:
+            nat.check(nat.lib().jh_set_option(b"split_short", 1))
+    rts, res_, rsc = om.estep(data.codes, data.offsets, w)
+    ll_ref = om.loglik(data.codes, data.offsets)
+    for split in (1, 0):
+        ts, es, sc, ll1, ll2, paths = res[split]
+        np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+        np.testing.assert_allclose(es, res_, rtol=COUNT_TOL, atol=COUNT_TOL)
+        assert sc == pytest.approx(rsc, rel=LL_RTOL)
+        np.testing.assert_allclose(ll1, ll_ref, rtol=LL_RTOL)
+        np.testing.assert_allclose(ll2, ll_ref, rtol=LL_RTOL)
+    assert (res[0][5] != res[1][5]).mean() < 1e-4  # decisions differ only where two posteriors tie to the last bits
+    off = data.offsets
+    for i in range(0, lens.size, 97):
+        ref = om.posterior(data.getElementAt(i).codes)
+        srt = np.sort(ref, axis=0)
+        clear = srt[-1] - srt[-2] > 1e-9
+        assert np.array_equal(res[1][5][off[i]:off[i + 1]][clear], om.decode_posterior(ref)[clear])
+    hmm.train(data)
+    np.testing.assert_allclose(hmm.last_objectives[0], om.train(data.codes, data.offsets, max_iter=3), rtol=LL_RTOL)
+
+
 def test_full_size_properties_cfg3_sample(nat):
     """BASELINE cfg3 model (32 states, order-3 emissions) on 16k x 1 kb sequences: size-independent properties.
     Transition counts add up to the residues, emission counts to the residues with a full context, the score is the
