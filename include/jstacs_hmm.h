@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define JH_ABI_VERSION 1
+#define JH_ABI_VERSION 2
 
 typedef enum jh_status {
   JH_OK = 0,
@@ -106,8 +106,9 @@ int jh_device_count(void);
 int jh_set_device(int device);
 /* Counts kernels launched by this library since load (bench.py: gpu_launches). */
 int64_t jh_kernel_launches(void);
-/* Use an existing CUDA stream (cudaStream_t as void*) for all subsequent work; NULL = the model's own stream.
- * The legacy default stream is addressed as cudaStreamLegacy ((void*)0x1). */
+/* Default CUDA stream (cudaStream_t as void*) of the handles on the current default device that have no stream of their
+ * own (jh_model_set_stream); NULL = every model works on its private stream.  The legacy default stream is addressed as
+ * cudaStreamLegacy ((void*)0x1). */
 int jh_set_stream(void *cuda_stream);
 int jh_synchronize(void);
 /* Tuning / test switches: "fast" (1: scaled linear-space kernels where the model allows, 0: reference-order
@@ -119,6 +120,10 @@ int jh_synchronize(void);
  * device-pool memory to the driver, keeping `value` bytes: device buffers are pooled so that per-call data sets do not
  * pay cudaMalloc/cudaFree). */
 int jh_set_option(const char *name, int64_t value);
+/* jh_set_option changes the DEFAULTS, which every handle follows unless it has its own value: device, stream and options
+ * live in the handle, so models on different devices or threads with different options do not interfere.
+ * Further switches: "graph" (replay the EM iteration as a CUDA graph, default 1), "stage" (pageable host memory is moved
+ * through the library's pinned double buffers, default 1), "vit_chunk" / "vit_chunk_force" (checkpointed Viterbi). */
 
 /* ---- model ------------------------------------------------------------- */
 /* Replaces the object graph built by HigherOrderHMM(...) / HMMFactory.createErgodicHMM
@@ -134,6 +139,10 @@ int jh_model_set_params(jh_model *m, const double *trans_param, const double *tr
 /* getCurrentParameterValues (:316-329) + the logNorm fields. Any pointer may be NULL. */
 int jh_model_get_params(jh_model *m, double *trans_param, double *trans_lognorm,
                         double *emis_param, double *emis_lognorm);
+/* Per-handle overrides of jh_set_option / jh_set_stream (a handle is bound to the device that was the default when it
+ * was created, jh_set_device). */
+int jh_model_set_option(jh_model *m, const char *name, int64_t value);
+int jh_model_set_stream(jh_model *m, void *cuda_stream);
 /* sizes: n_child_total, n_elem, n_cond_total*a, n_cond_total */
 int jh_model_sizes(const jh_model *m, int64_t sizes[4]);
 /* HigherOrderHMM.getLogPriorTerm (:253-259). */
@@ -147,6 +156,12 @@ int jh_model_log_prior(jh_model *m, double *out);
  * are in caller order. */
 int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_seq,
                       const double *weights, int32_t alphabet, jh_dataset **out);
+/* The same from 2-bit packed residues (alphabets of at most 4 symbols): four residues per byte, lowest bits first, every
+ * sequence starting on a byte boundary at packed[byte_ptr[n]] — the on-disk / in-memory form of genome-scale DNA, cf. the
+ * 32-symbols-per-long storage of de/jstacs/data/sequences/SparseSequence.java:59-73.  A quarter of the bytes cross PCIe;
+ * the device widens them to the uint8 codes the kernels read. */
+int jh_dataset_create_packed2(const uint8_t *packed, const int64_t *byte_ptr, const int64_t *offsets, int64_t n_seq,
+                              const double *weights, int32_t alphabet, jh_dataset **out);
 void jh_dataset_destroy(jh_dataset *d);
 /* Sequence weights of train(DataSet,double[]) (TrainableStatisticalModel.java:61-88); NULL = all 1. */
 int jh_dataset_set_weights(jh_dataset *d, const double *weights);
@@ -167,7 +182,9 @@ int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *
 
 /* AbstractHMM.getViterbiPathsFor(DataSet) (AbstractHMM.java:894-900) ==
  * HigherOrderHMM.viterbi (:617-708) per sequence.  paths: int32, CSR by the dataset offsets
- * (models without silent states emit exactly one state per residue); scores[n_seq]. */
+ * (models without silent states emit exactly one state per residue); scores[n_seq].
+ * A sequence without any state path of probability > 0 makes the reference throw "Impossible path" (:659): the call then
+ * returns JH_ERR_IMPOSSIBLE after filling the outputs (score -inf, states -1 / 255 for that sequence). */
 int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores);
 /* The same with ONE BYTE per residue (models with at most 255 states; 255 = "no state"): a quarter of the device->host
  * traffic, which dominates the call (cfg2: 1e9 residues = 4 GB of int32).  The shim widens to IntList on the host. */
@@ -225,6 +242,9 @@ typedef struct jh_train_opts {
  * (jh_comm_*) the statistics and the score are all-reduced over the ranks each iteration. */
 int jh_baum_welch(jh_model *m, jh_dataset *d, const jh_train_opts *opts,
                   double *objective, int32_t cap, int32_t *n_iter);
+/* Objective of the LAST iteration of the most recent jh_baum_welch of this model (what HigherOrderHMM.train compares
+ * between starts, :773-779), independent of the capacity of the history buffer. */
+int jh_last_objective(jh_model *m, double *out);
 
 /* ---- multi-GPU: one process per GPU, shards of the DataSet per rank ------ */
 /* The reference's joinStatistics + setParameters (HigherOrderHMM.java:1263-1288) is a sum over

@@ -21,7 +21,7 @@ public final class JstacsHmmNative {
 	public static final int JH_OK = 0, JH_ERR_INVALID = -1, JH_ERR_UNSUPPORTED = -2, JH_ERR_CUDA = -3, JH_ERR_ALPHABET = -4,
 			JH_ERR_NOMEM = -5, JH_ERR_IMPOSSIBLE = -6, JH_ERR_COMM = -7;
 	public static final int JH_MODE_VITERBI = 0, JH_MODE_BAUM_WELCH = 1, JH_TERM_ITERATIONS = 0, JH_TERM_SMALL_DIFFERENCE = 1;
-	public static final int JH_ABI_VERSION = 1;
+	public static final int JH_ABI_VERSION = 2;
 
 	private static final Linker LINKER = Linker.nativeLinker();
 	private static final SymbolLookup LIB;
@@ -68,6 +68,26 @@ public final class JstacsHmmNative {
 	public static final MethodHandle jh_estep = h( "jh_estep", FunctionDescriptor.of( I, P, P, I, P, P, P ) );
 	public static final MethodHandle jh_mstep = h( "jh_mstep", FunctionDescriptor.of( I, P ) );
 	public static final MethodHandle jh_baum_welch = h( "jh_baum_welch", FunctionDescriptor.of( I, P, P, P, P, I, P ) );
+	public static final MethodHandle jh_last_objective = h( "jh_last_objective", FunctionDescriptor.of( I, P, P ) );
+	public static final MethodHandle jh_model_log_prior = h( "jh_model_log_prior", FunctionDescriptor.of( I, P, P ) );
+	public static final MethodHandle jh_model_set_option = h( "jh_model_set_option", FunctionDescriptor.of( I, P, P, J ) );
+	public static final MethodHandle jh_model_set_stream = h( "jh_model_set_stream", FunctionDescriptor.of( I, P, P ) );
+	public static final MethodHandle jh_set_option = h( "jh_set_option", FunctionDescriptor.of( I, P, J ) );
+	public static final MethodHandle jh_dataset_create_packed2 = h( "jh_dataset_create_packed2", FunctionDescriptor.of( I, P, P, P, J, P, I, P ) );
+	public static final MethodHandle jh_dataset_info = h( "jh_dataset_info", FunctionDescriptor.of( I, P, P, P, P ) );
+
+	static {
+		try {
+			int v = (int) jh_abi_version.invokeExact();
+			if( v != JH_ABI_VERSION ) {
+				throw new UnsatisfiedLinkError( "libjstacs_hmm_b200 has ABI version " + v + ", this binding needs " + JH_ABI_VERSION );
+			}
+		} catch( Error e ) {
+			throw e;
+		} catch( Throwable t ) {
+			throw new UnsatisfiedLinkError( t.toString() );
+		}
+	}
 
 	/** Turns a jh_status into the exception type the reference throws at the same place (SURVEY.md §8b "Errors"). */
 	public static void check( int status ) throws Exception {

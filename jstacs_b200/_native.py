@@ -12,7 +12,7 @@ import numpy as np
 
 MODE_VITERBI, MODE_BAUM_WELCH = 0, 1
 TERM_ITERATIONS, TERM_SMALL_DIFFERENCE = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 COMM_ID_BYTES = 128
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libjstacs_hmm_b200.so")
@@ -130,6 +130,10 @@ def lib():
         "jh_probe_fp64": (C.c_int, [C.c_int, C.c_int, C.c_int, _P_F64]),
         "jh_probe_dmma": (C.c_int, [C.c_int, C.c_int, C.c_int, _P_F64]),
         "jh_last_main_kernel_ms": (C.c_int, [vp, _P_F64]),
+        "jh_model_set_option": (C.c_int, [vp, C.c_char_p, C.c_int64]),
+        "jh_model_set_stream": (C.c_int, [vp, vp]),
+        "jh_dataset_create_packed2": (C.c_int, [_P_U8, _P_I64, _P_I64, C.c_int64, _P_F64, C.c_int32, C.POINTER(vp)]),
+        "jh_last_objective": (C.c_int, [vp, _P_F64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -152,10 +156,14 @@ def _f64(a):
     return None if a is None else a.ctypes.data_as(_P_F64)
 
 
-class NativeData:
-    """jh_dataset handle: packed uint8 codes + int64 offsets (+ weights) resident on the device."""
+IMPOSSIBLE = -6  # JH_ERR_IMPOSSIBLE
 
-    def __init__(self, codes: np.ndarray, offsets: np.ndarray, weights, alphabet: int):
+
+class NativeData:
+    """jh_dataset handle: packed uint8 codes + int64 offsets (+ weights) resident on the device.
+    byte_ptr given: `codes` holds 2-bit packed residues (four per byte, every sequence on a byte boundary at byte_ptr[n])."""
+
+    def __init__(self, codes: np.ndarray, offsets: np.ndarray, weights, alphabet: int, byte_ptr=None):
         self.h = C.c_void_p()
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
@@ -163,7 +171,12 @@ class NativeData:
         self.n_res = int(offsets[-1])
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         cp = codes.ctypes.data_as(_P_U8) if codes.size else C.cast(None, _P_U8)
-        check(lib().jh_dataset_create(cp, offsets.ctypes.data_as(_P_I64), self.n_seq, _f64(w), int(alphabet), C.byref(self.h)))
+        if byte_ptr is None:
+            check(lib().jh_dataset_create(cp, offsets.ctypes.data_as(_P_I64), self.n_seq, _f64(w), int(alphabet), C.byref(self.h)))
+        else:
+            bp = np.ascontiguousarray(byte_ptr, dtype=np.int64)
+            check(lib().jh_dataset_create_packed2(cp, bp.ctypes.data_as(_P_I64), offsets.ctypes.data_as(_P_I64), self.n_seq, _f64(w),
+                                                  int(alphabet), C.byref(self.h)))
 
     def set_weights(self, weights):
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
@@ -200,6 +213,13 @@ class NativeModel:
             lib().jh_model_destroy(self.h)
             self.h = C.c_void_p()
 
+    def set_option(self, name: str, value: int):
+        """Per-handle override of a library option (jh_model_set_option)."""
+        check(lib().jh_model_set_option(self.h, name.encode(), int(value)))
+
+    def set_stream(self, cuda_stream):
+        check(lib().jh_model_set_stream(self.h, cuda_stream))
+
     def __del__(self):
         try:
             self.close()
@@ -225,15 +245,20 @@ class NativeModel:
         check(lib().jh_loglik(self.h, data.h, _f64(out)))
         return out[:data.n_seq]
 
-    def viterbi(self, data: NativeData, narrow: bool = False):
-        """narrow: one byte per residue (uint8 paths, 255 = no state) instead of int32."""
+    def viterbi(self, data: NativeData, narrow: bool = False, allow_impossible: bool = False, out=None):
+        """narrow: one byte per residue (uint8 paths, 255 = no state) instead of int32.
+        allow_impossible: sequences without a state path of probability > 0 come back with score -inf and states
+        -1 / 255 instead of raising JH_ERR_IMPOSSIBLE (the outputs are filled in both cases).
+        out: reuse a path buffer of a previous call."""
         scores = np.zeros(max(data.n_seq, 1))
         if narrow:
-            paths = np.empty(max(data.n_res, 1), dtype=np.uint8)
-            check(lib().jh_viterbi_u8(self.h, data.h, paths.ctypes.data_as(_P_U8), _f64(scores)))
+            paths = out if out is not None else np.empty(max(data.n_res, 1), dtype=np.uint8)
+            st = lib().jh_viterbi_u8(self.h, data.h, paths.ctypes.data_as(_P_U8), _f64(scores))
         else:
-            paths = np.zeros(max(data.n_res, 1), dtype=np.int32)
-            check(lib().jh_viterbi(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(scores)))
+            paths = out if out is not None else np.empty(max(data.n_res, 1), dtype=np.int32)
+            st = lib().jh_viterbi(self.h, data.h, paths.ctypes.data_as(_P_I32), _f64(scores))
+        if not (st == IMPOSSIBLE and allow_impossible):
+            check(st)
         return paths[:data.n_res], scores[:data.n_seq]
 
     def viterbi_paths(self, data: NativeData, capacity: np.ndarray):
@@ -311,7 +336,14 @@ class NativeModel:
         n_it = C.c_int32()
         opts = TrainOpts(mode, term_kind, max_iter, eps)
         check(lib().jh_baum_welch(self.h, data.h, C.byref(opts), _f64(obj), cap, C.byref(n_it)))
+        self.n_iterations = n_it.value
         return obj[:min(n_it.value, cap)]
+
+    def last_objective(self) -> float:
+        """Objective of the last iteration of the most recent baum_welch (the history may be capped)."""
+        v = C.c_double()
+        check(lib().jh_last_objective(self.h, C.byref(v)))
+        return v.value
 
     def stats_device(self):
         p, n = C.c_void_p(), C.c_int64()

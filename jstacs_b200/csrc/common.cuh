@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -24,8 +25,8 @@ void jh_set_error(const char *fmt, ...);
     }                                                                                              \
   } while (0)
 
-extern int64_t g_kernel_launches;
-#define JH_LAUNCHED() (++g_kernel_launches)
+extern std::atomic<int64_t> g_kernel_launches;
+#define JH_LAUNCHED() (g_kernel_launches.fetch_add(1, std::memory_order_relaxed))
 
 // ------------------------------------------------------------------------------------------------
 // Device view of the flattened model (all pointers are device memory, read-only during an E-step).
@@ -62,5 +63,24 @@ struct DevData {
   const int32_t *order;     // [n] sequence ids sorted by decreasing length (length bucketing)
   int64_t n_seq;
 };
+
+struct WorkList {   // sequences, or windows of sequences
+  const int32_t *seq;     // [n] sequence ids (nullptr: D.order)
+  const int64_t *start;   // [n] first position (nullptr: 0)
+  const int64_t *end;     // [n] last position inclusive (nullptr: L-1)
+  int64_t n;
+};
+
+// Sink of a state path: int32 per residue (IntList of the reference) or one byte per residue (255 = no state), decided by
+// the entry point (jh_viterbi / jh_viterbi_u8, ...): the kernels emit the narrow form directly, nothing is converted afterwards.
+struct PathOut {
+  void *p;
+  int u8;
+  __host__ __device__ explicit operator bool() const { return p != nullptr; }
+};
+__device__ __forceinline__ void path_store(const PathOut &o, int64_t idx, int v) {
+  if (o.u8) reinterpret_cast<uint8_t *>(o.p)[idx] = (uint8_t)v;  // -1 -> 255
+  else reinterpret_cast<int32_t *>(o.p)[idx] = v;
+}
 
 __device__ __forceinline__ double lse_finish(double offset, double sum) { return offset + log(sum); }

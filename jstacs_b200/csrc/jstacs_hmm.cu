@@ -5,7 +5,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <numeric>
+#include <thread>
 
 #include "common.cuh"
 #include "kernels_aux.cuh"
@@ -20,11 +24,16 @@
 #include "kernels_viterbi.cuh"
 
 // ------------------------------------------------------------------------------------------------
+// Process-wide state is limited to DEFAULTS for handles created afterwards (device, options) and to the launch counter;
+// everything a call works with (device, stream, options, scratch) lives in the handle, so two models on two devices,
+// or two threads with different options, do not interfere (a handle is still used by one thread at a time).
 static thread_local char g_err[1024] = "";
-int64_t g_kernel_launches = 0;
-static int g_device = 0;
-static cudaStream_t g_user_stream = nullptr;
+std::atomic<int64_t> g_kernel_launches{0};
+static std::atomic<int> g_default_device{0};
+static std::mutex g_mu;                      // guards the option defaults, the legacy stream default and the stagers
+static cudaStream_t g_user_stream = nullptr;  // jh_set_stream (legacy): default stream of handles on g_user_stream_device
 static bool g_have_user_stream = false;
+static int g_user_stream_device = 0;
 
 struct Options {
   int64_t fast = 1;            // use the scaled linear-space kernels where the model allows it
@@ -39,8 +48,35 @@ struct Options {
   int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
   int64_t oct_chunk = 1024;    // positions per checkpoint of the chunked octet E-step (0: never chunk)
   int64_t oct_chunk_force = 0; // tests: chunk every bucket longer than 2 * oct_chunk
+  int64_t graph = 1;           // jh_baum_welch with IterationCondition: replay the EM iteration as a CUDA graph
+  int64_t vit_chunk = 4096;    // positions per checkpoint of the chromosome-scale Viterbi
+  int64_t vit_chunk_force = 0; // tests: checkpointed Viterbi for every sequence longer than 2 * vit_chunk
+  int64_t stage = 1;           // host transfers of pageable caller memory through the library's pinned double buffers
 };
-static Options g_opt;
+static Options g_defaults;
+static std::atomic<uint64_t> g_opt_gen{1};
+
+// returns false for an unknown name
+static bool set_option_field(Options &o, const std::string &n, int64_t value) {
+  if (n == "fast") o.fast = value;
+  else if (n == "scratch_mb") o.scratch_mb = value;
+  else if (n == "blocks_per_sm") o.blocks_per_sm = value;
+  else if (n == "fast_variant") o.fast_variant = value;
+  else if (n == "oct_chunk") o.oct_chunk = value <= 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
+  else if (n == "pass1_cta") o.pass1_cta = value;
+  else if (n == "overlap") o.overlap = value;
+  else if (n == "scan") o.scan = value;
+  else if (n == "lane_chunks") o.lane_chunks = value;
+  else if (n == "split_short") o.split_short = value;
+  else if (n == "oct_chunk_force") o.oct_chunk_force = value;
+  else if (n == "chunk") o.chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
+  else if (n == "graph") o.graph = value;
+  else if (n == "vit_chunk") o.vit_chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
+  else if (n == "vit_chunk_force") o.vit_chunk_force = value;
+  else if (n == "stage") o.stage = value;
+  else return false;
+  return true;
+}
 
 void jh_set_error(const char *fmt, ...) {
   va_list ap;
@@ -52,47 +88,37 @@ void jh_set_error(const char *fmt, ...) {
 // Device buffers come from the device's stream-ordered memory pool with an unlimited release threshold: a data set that
 // is created and destroyed per call (the e2e path: pack -> upload -> train -> free) reuses the pool's memory instead of
 // paying cudaFree's unmap (measured: up to 360 ms for the 3 GB of a 1M x 1 kb data set).  Allocation and release are
-// synchronous like cudaMalloc / cudaFree (nothing in flight can touch a buffer that is handed out again).
-static cudaStream_t g_alloc_stream[64] = {};
-static cudaStream_t alloc_stream() {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  if (!g_alloc_stream[dev]) {
-    cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking);
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = UINT64_MAX;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+// ordered on the stream of the call that is running (tl_stream, set by the entry guard of every API function): nothing
+// waits for the device, and work of other handles on other streams is not stalled.
+static thread_local cudaStream_t tl_stream = nullptr;
+static thread_local bool tl_have_stream = false;
+static void pool_setup(int dev) {
+  static std::atomic<uint64_t> done{0};
+  if (dev < 0 || dev > 63 || (done.load() >> dev) & 1) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
-  return g_alloc_stream[dev];
-}
-static cudaError_t pool_alloc(void **p, size_t bytes) {
-  cudaStream_t s = alloc_stream();
-  cudaError_t e = cudaMallocAsync(p, bytes, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  return e;
-}
-static void pool_free(void *p) {
-  cudaDeviceSynchronize();
-  cudaFreeAsync(p, alloc_stream());
+  done.fetch_or(1ull << dev);
 }
 
 template <typename T>
 struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
+  cudaStream_t home = nullptr;  // stream the buffer was allocated on
   ~DevBuf() { release(); }
   void release() {
-    if (p) pool_free(p);
+    if (p) cudaFreeAsync(p, tl_have_stream ? tl_stream : home);  // ordered after the work already queued on that stream
     p = nullptr;
     n = 0;
   }
   int alloc(size_t count) {
     release();
     if (count == 0) count = 1;
-    if (pool_alloc((void **)&p, count * sizeof(T)) != cudaSuccess) {
+    home = tl_stream;
+    if (cudaMallocAsync((void **)&p, count * sizeof(T), home) != cudaSuccess) {
       cudaGetLastError();
       p = nullptr;
       jh_set_error("out of device memory allocating %zu bytes", count * sizeof(T));
@@ -109,6 +135,162 @@ struct DevBuf {
     return JH_OK;
   }
 };
+
+// ------------------------------------------------------------------------------------------------
+// Host transfers.  Callers hand over ordinary (pageable) memory — a Java off-heap segment, a numpy array — which the
+// driver would copy through its own small bounce buffer at ~5 GB/s (measured: 1 GB of byte paths = 210 ms).  The library
+// stages such transfers through its own PINNED double buffers: a few host threads copy slice k+1 between the caller's
+// memory and a pinned buffer while the DMA engine moves slice k, so the transfer runs at the host's memcpy rate or at
+// the PCIe rate, whichever is lower.  Memory that is already pinned (cudaHostAlloc / cudaHostRegister) is copied directly.
+class CopyPool {  // persistent helper threads for slice-parallel memcpy
+ public:
+  explicit CopyPool(int n) {
+    for (int i = 0; i < n; i++) th_.emplace_back([this, i] { run(i); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  void copy(void *dst, const void *src, size_t bytes) {
+    const int parts = (int)th_.size() + 1;
+    if (bytes < (size_t)1 << 20 || parts == 1) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t slice = ((bytes + parts - 1) / parts + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      dst_ = (char *)dst; src_ = (const char *)src; bytes_ = bytes; slice_ = slice;
+      pending_ = (int)th_.size();
+      gen_++;
+    }
+    cv_.notify_all();
+    const size_t o = slice * th_.size();  // the caller copies the last slice itself
+    if (o < bytes) memcpy((char *)dst + o, (const char *)src + o, bytes - o);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int i) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return gen_ != seen; });
+      seen = gen_;
+      if (stop_) return;
+      char *d = dst_;
+      const char *s = src_;
+      const size_t o = slice_ * i, n = o < bytes_ ? std::min(slice_, bytes_ - o) : 0;
+      lk.unlock();
+      if (n) memcpy(d + o, s + o, n);
+      lk.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+  char *dst_ = nullptr;
+  const char *src_ = nullptr;
+  size_t bytes_ = 0, slice_ = 0;
+  int pending_ = 0;
+};
+
+struct Stager {
+  static constexpr size_t CHUNK = (size_t)16 << 20;
+  static constexpr int NB = 3;
+  void *buf[NB] = {};
+  cudaEvent_t ev[NB] = {};
+  bool ready = false;
+  int init() {
+    if (ready) return JH_OK;
+    for (int i = 0; i < NB; i++) {
+      JH_CUDA(cudaHostAlloc(&buf[i], CHUNK, cudaHostAllocDefault));
+      JH_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    ready = true;
+    return JH_OK;
+  }
+};
+static Stager g_stager[64];
+static std::mutex g_stage_mu;
+static CopyPool &copy_pool() {
+  static CopyPool pool((int)std::min<unsigned>(7, std::max<unsigned>(1, std::thread::hardware_concurrency() / 2)) );
+  return pool;
+}
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+// host -> device; returns when the host buffer may be reused (the device copy is ordered on s)
+static int stage_h2d(void *dst, const void *src, size_t bytes, cudaStream_t s, int dev, bool stage) {
+  if (bytes == 0) return JH_OK;
+  if (!stage || bytes < ((size_t)4 << 20) || is_pinned(src)) {
+    JH_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    JH_CUDA(cudaStreamSynchronize(s));
+    return JH_OK;
+  }
+  std::lock_guard<std::mutex> g(g_stage_mu);
+  Stager &S = g_stager[dev & 63];
+  int r = S.init();
+  if (r) return r;
+  CopyPool &P = copy_pool();
+  size_t k = 0;
+  for (size_t o = 0; o < bytes; o += Stager::CHUNK, k++) {
+    const int b = (int)(k % Stager::NB);
+    const size_t n = std::min(Stager::CHUNK, bytes - o);
+    if (k >= Stager::NB) JH_CUDA(cudaEventSynchronize(S.ev[b]));
+    P.copy(S.buf[b], (const char *)src + o, n);
+    JH_CUDA(cudaMemcpyAsync((char *)dst + o, S.buf[b], n, cudaMemcpyHostToDevice, s));
+    JH_CUDA(cudaEventRecord(S.ev[b], s));
+  }
+  JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+// device -> host, ordered after the work queued on s; returns when dst holds the data
+static int stage_d2h(void *dst, const void *src, size_t bytes, cudaStream_t s, int dev, bool stage) {
+  if (bytes == 0) return JH_OK;
+  if (!stage || bytes < ((size_t)4 << 20) || is_pinned(dst)) {
+    JH_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+    JH_CUDA(cudaStreamSynchronize(s));
+    return JH_OK;
+  }
+  std::lock_guard<std::mutex> g(g_stage_mu);
+  Stager &S = g_stager[dev & 63];
+  int r = S.init();
+  if (r) return r;
+  CopyPool &P = copy_pool();
+  const size_t n_chunks = (bytes + Stager::CHUNK - 1) / Stager::CHUNK;
+  auto drain = [&](size_t k) -> int {  // chunk k: pinned -> caller memory
+    const int b = (int)(k % Stager::NB);
+    const size_t o = k * Stager::CHUNK, n = std::min(Stager::CHUNK, bytes - o);
+    JH_CUDA(cudaEventSynchronize(S.ev[b]));
+    P.copy((char *)dst + o, S.buf[b], n);
+    return JH_OK;
+  };
+  for (size_t k = 0; k < n_chunks; k++) {
+    const int b = (int)(k % Stager::NB);
+    const size_t o = k * Stager::CHUNK, n = std::min(Stager::CHUNK, bytes - o);
+    if (k >= Stager::NB && (r = drain(k - Stager::NB))) return r;  // frees buffer b
+    JH_CUDA(cudaMemcpyAsync(S.buf[b], (const char *)src + o, n, cudaMemcpyDeviceToHost, s));
+    JH_CUDA(cudaEventRecord(S.ev[b], s));
+  }
+  for (size_t k = n_chunks > Stager::NB ? n_chunks - Stager::NB : 0; k < n_chunks; k++)
+    if ((r = drain(k))) return r;
+  return JH_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 struct Id128 {  // ncclUniqueId (128 bytes, passed by value)
@@ -189,8 +371,35 @@ struct jh_model {
   int sm_count = 148;
   void *comm = nullptr;
   int n_ranks = 1, rank = 0;
+  // per-handle execution context
+  int device = 0;
+  cudaStream_t user_stream = nullptr;
+  bool have_user_stream = false;
+  Options opt;                                             // defaults (jh_set_option) + overrides (jh_model_set_option)
+  uint64_t opt_seen = 0;
+  std::vector<std::pair<std::string, int64_t>> overrides;
+  int failed = 0;                                          // multi-rank: error of this rank's E-step, returned after the collectives
+  char failed_msg[1024] = "";
+  bool capturing = false;                                  // stream capture of the EM iteration in progress: no timing events
+  double last_objective = JH_NEG_INF;                      // final objective of the last jh_baum_welch
+  DevBuf<int32_t> d_iter;                                  // device-side iteration counter of the graph-replayed EM loop
+  cudaGraphExec_t em_graph = nullptr;
+  const void *em_graph_data = nullptr;
+  int em_graph_mode = -1;
   int64_t n_stats() const { return (int64_t)n_child + (int64_t)n_cond * a; }
-  cudaStream_t st() const { return g_have_user_stream ? g_user_stream : stream; }
+  cudaStream_t st() const {
+    if (have_user_stream) return user_stream;
+    if (g_have_user_stream && g_user_stream_device == device) return g_user_stream;
+    return stream;
+  }
+  void refresh_options() {
+    const uint64_t gen = g_opt_gen.load();
+    if (gen == opt_seen) return;
+    std::lock_guard<std::mutex> g(g_mu);
+    opt = g_defaults;
+    for (auto &kv : overrides) set_option_field(opt, kv.first, kv.second);
+    opt_seen = gen;
+  }
   DevModel dev() const {
     DevModel M;
     M.S = S; M.a = a; M.m = m; M.Cmax = Cmax; M.n_elem = n_elem; M.n_child = n_child; M.n_ctx_total = n_ctx_total; M.n_cond = n_cond;
@@ -224,6 +433,9 @@ struct jh_model {
 struct jh_dataset {
   int64_t n_seq = 0, n_res = 0, max_len = 0, min_len = 0;
   int alphabet = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;   // uploads of this data set
+  cudaEvent_t ev_last = nullptr;   // recorded after every call that reads the data set: destroy waits for it, not for the device
   std::vector<int64_t> offsets;
   std::vector<int32_t> order;
   // length buckets over `order` (decreasing length): [bucket_ptr[b], bucket_ptr[b+1]) with max length bucket_len[b]
@@ -268,13 +480,15 @@ extern "C" int jh_device_count(void) {
 }
 extern "C" int jh_set_device(int device) {
   JH_CUDA(cudaSetDevice(device));
-  g_device = device;
+  g_default_device = device;
   return JH_OK;
 }
-extern "C" int64_t jh_kernel_launches(void) { return g_kernel_launches; }
+extern "C" int64_t jh_kernel_launches(void) { return g_kernel_launches.load(); }
 extern "C" int jh_set_stream(void *s) {
+  std::lock_guard<std::mutex> g(g_mu);
   g_user_stream = (cudaStream_t)s;
   g_have_user_stream = s != nullptr;
+  g_user_stream_device = g_default_device;
   return JH_OK;
 }
 extern "C" int jh_synchronize(void) {
@@ -283,39 +497,74 @@ extern "C" int jh_synchronize(void) {
 }
 extern "C" int jh_set_option(const char *name, int64_t value) {
   std::string n(name ? name : "");
-  if (n == "fast") g_opt.fast = value;
-  else if (n == "scratch_mb") g_opt.scratch_mb = value;
-  else if (n == "blocks_per_sm") g_opt.blocks_per_sm = value;
-  else if (n == "fast_variant") g_opt.fast_variant = value;
-  else if (n == "oct_chunk") g_opt.oct_chunk = value <= 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
-  else if (n == "pass1_cta") g_opt.pass1_cta = value;
-  else if (n == "overlap") g_opt.overlap = value;
-  else if (n == "scan") g_opt.scan = value;
-  else if (n == "lane_chunks") g_opt.lane_chunks = value;
-  else if (n == "split_short") g_opt.split_short = value;
-  else if (n == "oct_chunk_force") g_opt.oct_chunk_force = value;
-  else if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
+  if (n == "trim_pool") {  // give the unused memory of the device pool back to the driver (keep `value` bytes)
     cudaMemPool_t pool;
+    JH_CUDA(cudaSetDevice(g_default_device));
     JH_CUDA(cudaDeviceSynchronize());
-    JH_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+    JH_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_default_device));
     JH_CUDA(cudaMemPoolTrimTo(pool, (size_t)std::max<int64_t>(0, value)));
-  } else if (n == "chunk") g_opt.chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
-  else {
+    return JH_OK;
+  }
+  std::lock_guard<std::mutex> g(g_mu);
+  if (!set_option_field(g_defaults, n, value)) {
     jh_set_error("unknown option '%s'", n.c_str());
     return JH_ERR_INVALID;
   }
+  g_opt_gen++;
+  return JH_OK;
+}
+extern "C" int jh_model_set_option(jh_model *m, const char *name, int64_t value) {
+  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  std::string n(name ? name : "");
+  Options probe;
+  if (!set_option_field(probe, n, value)) {
+    jh_set_error("unknown option '%s'", n.c_str());
+    return JH_ERR_INVALID;
+  }
+  bool found = false;
+  for (auto &kv : m->overrides)
+    if (kv.first == n) { kv.second = value; found = true; }
+  if (!found) m->overrides.emplace_back(n, value);
+  m->opt_seen = 0;
+  return JH_OK;
+}
+extern "C" int jh_model_set_stream(jh_model *m, void *s) {
+  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  m->user_stream = (cudaStream_t)s;
+  m->have_user_stream = s != nullptr;
   return JH_OK;
 }
 
-static int ensure_device() {
+static int ensure_device(int device) {
   int n = jh_device_count();
   if (n <= 0) {
     if (n == 0) jh_set_error("no CUDA device visible (there is no CPU fallback)");
     return JH_ERR_CUDA;
   }
-  JH_CUDA(cudaSetDevice(g_device));
+  JH_CUDA(cudaSetDevice(device));
+  pool_setup(device);
   return JH_OK;
 }
+
+// Entry guard of every API call on a model: the handle's device becomes current, its options are refreshed, buffers that
+// the call allocates or frees are ordered on the handle's stream.
+struct Scope {
+  bool prev_have;
+  cudaStream_t prev;
+  Scope(int device, cudaStream_t s) : prev_have(tl_have_stream), prev(tl_stream) {
+    cudaSetDevice(device);
+    tl_stream = s;
+    tl_have_stream = true;
+  }
+  ~Scope() {
+    tl_stream = prev;
+    tl_have_stream = prev_have;
+  }
+};
+#define JH_ENTER(m)                                              \
+  if (!(m)) { jh_set_error("null model"); return JH_ERR_INVALID; } \
+  (m)->refresh_options();                                        \
+  Scope scope__((m)->device, (m)->st())
 
 // ------------------------------------------------------------------------------------------------
 static int prep_scores(jh_model *m) {
@@ -341,6 +590,28 @@ static int prep_scores(jh_model *m) {
   return JH_OK;
 }
 
+static void model_free(jh_model *m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->have_user_stream) cudaStreamSynchronize(m->user_stream);
+  for (cudaStream_t st : m->seq_streams) cudaStreamSynchronize(st);
+  Scope scope(m->device, cudaStreamPerThread);  // everything queued has finished: the buffers go back on a stream that outlives the handle
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  if (m->em_graph) cudaGraphExecDestroy(m->em_graph);
+  jhf::destroy(m->fast);
+  jhs::destroy(m->sparse);
+  if (m->ev0) cudaEventDestroy(m->ev0);
+  if (m->ev1) cudaEventDestroy(m->ev1);
+  if (m->evk0) cudaEventDestroy(m->evk0);
+  if (m->evk1) cudaEventDestroy(m->evk1);
+  for (cudaStream_t st : m->seq_streams) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : m->seq_events) cudaEventDestroy(ev);
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
 extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   if (!d || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
   if (d->abi_version != JH_ABI_VERSION) { jh_set_error("jh_model_desc.abi_version %d != %d", d->abi_version, JH_ABI_VERSION); return JH_ERR_INVALID; }
@@ -348,9 +619,12 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
     jh_set_error("invalid model sizes");
     return JH_ERR_INVALID;
   }
-  int r = ensure_device();
+  const int device = g_default_device;
+  int r = ensure_device(device);
   if (r) return r;
   jh_model *m = new jh_model();
+  m->device = device;
+  m->refresh_options();
   m->S = d->n_states; m->a = d->alphabet; m->m = d->max_order; m->n_elem = d->n_elem; m->n_emis = d->n_emis;
   m->lc_ctx_ptr.assign(d->lc_ctx_ptr, d->lc_ctx_ptr + m->m + 2);
   m->n_ctx_total = m->lc_ctx_ptr[m->m + 1];
@@ -371,7 +645,7 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   m->state_final.assign(d->state_final, d->state_final + m->S);
   auto fail = [&](int code, const char *msg) {
     jh_set_error("%s", msg);
-    delete m;
+    model_free(m);
     return code;
   };
   // validation (the reference checks these in BasicHigherOrderTransition.init and the AbstractHMM constructor)
@@ -486,8 +760,9 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   }
   // device ---------------------------------------------------------------------------------------
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, g_device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, m->device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(JH_ERR_CUDA, "cudaStreamCreate failed");
+  Scope scope(m->device, m->st());
   cudaEventCreate(&m->ev0);
   cudaEventCreate(&m->ev1);
   cudaEventCreate(&m->evk0);
@@ -497,7 +772,7 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   std::vector<double> tp(d->trans_param, d->trans_param + m->n_child), tl(d->trans_lognorm, d->trans_lognorm + m->n_elem),
       th(d->trans_hyper, d->trans_hyper + m->n_child), ep(d->emis_param, d->emis_param + (size_t)m->n_cond * m->a),
       el(d->emis_lognorm, d->emis_lognorm + m->n_cond), eh(d->emis_hyper, d->emis_hyper + (size_t)m->n_cond * m->a);
-#define UP(buf, vec) if ((r = m->buf.upload(vec, s)) != 0) { delete m; return r; }
+#define UP(buf, vec) if ((r = m->buf.upload(vec, s)) != 0) { model_free(m); return r; }
   UP(d_lc_ctx_ptr, m->lc_ctx_ptr) UP(d_ctx_elem, m->ctx_elem) UP(d_ctx_last, m->ctx_last) UP(d_elem_child_ptr, m->elem_child_ptr)
   UP(d_child_state, m->child_state) UP(d_child_next, m->child_next) UP(d_child_stat, m->child_stat) UP(d_in_ptr, m->in_ptr)
   UP(d_in_src, m->in_src) UP(d_in_p, m->in_p) UP(d_state_order, m->state_order) UP(d_state_tab, m->state_tab)
@@ -506,42 +781,27 @@ extern "C" int jh_model_create(const jh_model_desc *d, jh_model **out) {
   UP(d_emis_lognorm, el) UP(d_emis_hyper, eh)
 #undef UP
   if ((r = m->d_tscore.alloc(m->n_child)) || (r = m->d_escore.alloc((size_t)m->n_cond * m->a)) ||
-      (r = m->d_stats.alloc(m->n_stats() + 8)) || (r = m->d_counter.alloc(8)) || (r = m->d_objective.alloc(4096))) {
-    delete m;
+      (r = m->d_stats.alloc(m->n_stats() + 8)) || (r = m->d_counter.alloc(8)) || (r = m->d_objective.alloc(4096)) || (r = m->d_iter.alloc(4))) {
+    model_free(m);
     return r;
   }
   if ((r = jhf::build(m->fast, m->S, m->a, m->m, m->has_silent, m->Kmax, m->lc_ctx_ptr, m->ctx_elem, m->ctx_last, m->elem_child_ptr,
                       m->child_state, m->child_stat, m->state_order, m->state_tab, m->state_mod, m->state_final, m->n_child, m->n_cond, s)) != 0) {
-    delete m;
+    model_free(m);
     return r;
   }
   if ((r = jhs::build(m->sparse, m->S, m->a, m->m, m->has_silent, m->Kmax, m->lc_ctx_ptr, m->ctx_elem, m->ctx_last, m->elem_child_ptr, m->child_state,
                       m->child_stat, m->state_order, m->state_tab, m->state_mod, m->state_final, s)) != 0) {
-    delete m;
+    model_free(m);
     return r;
   }
-  if ((r = prep_scores(m)) != 0) { delete m; return r; }
+  if ((r = prep_scores(m)) != 0) { model_free(m); return r; }
   if (cudaStreamSynchronize(s) != cudaSuccess) return fail(JH_ERR_CUDA, "model upload failed");
   *out = m;
   return JH_OK;
 }
 
-extern "C" void jh_model_destroy(jh_model *m) {
-  if (!m) return;
-  cudaSetDevice(g_device);
-  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
-  jhf::destroy(m->fast);
-  jhs::destroy(m->sparse);
-  if (m->ev0) cudaEventDestroy(m->ev0);
-  if (m->ev1) cudaEventDestroy(m->ev1);
-  if (m->evk0) cudaEventDestroy(m->evk0);
-  if (m->evk1) cudaEventDestroy(m->evk1);
-  for (cudaStream_t st : m->seq_streams) cudaStreamDestroy(st);
-  for (cudaEvent_t ev : m->seq_events) cudaEventDestroy(ev);
-  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-  if (m->stream) cudaStreamDestroy(m->stream);
-  delete m;
-}
+extern "C" void jh_model_destroy(jh_model *m) { model_free(m); }
 
 extern "C" int jh_model_sizes(const jh_model *m, int64_t sizes[4]) {
   if (!m || !sizes) { jh_set_error("null argument"); return JH_ERR_INVALID; }
@@ -550,7 +810,7 @@ extern "C" int jh_model_sizes(const jh_model *m, int64_t sizes[4]) {
 }
 
 extern "C" int jh_model_set_params(jh_model *m, const double *tp, const double *tl, const double *ep, const double *el) {
-  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  JH_ENTER(m);
   cudaStream_t s = m->st();
   if (tp) JH_CUDA(cudaMemcpyAsync(m->d_trans_param.p, tp, sizeof(double) * m->n_child, cudaMemcpyHostToDevice, s));
   if (tl) JH_CUDA(cudaMemcpyAsync(m->d_trans_lognorm.p, tl, sizeof(double) * m->n_elem, cudaMemcpyHostToDevice, s));
@@ -569,7 +829,7 @@ extern "C" int jh_model_set_params(jh_model *m, const double *tp, const double *
 }
 
 extern "C" int jh_model_get_params(jh_model *m, double *tp, double *tl, double *ep, double *el) {
-  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  JH_ENTER(m);
   cudaStream_t s = m->st();
   if (tp) JH_CUDA(cudaMemcpyAsync(tp, m->d_trans_param.p, sizeof(double) * m->n_child, cudaMemcpyDeviceToHost, s));
   if (tl) JH_CUDA(cudaMemcpyAsync(tl, m->d_trans_lognorm.p, sizeof(double) * m->n_elem, cudaMemcpyDeviceToHost, s));
@@ -580,7 +840,8 @@ extern "C" int jh_model_get_params(jh_model *m, double *tp, double *tl, double *
 }
 
 extern "C" int jh_model_log_prior(jh_model *m, double *out) {
-  if (!m || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  JH_ENTER(m);
+  if (!out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
   jha::k_log_prior<<<1, 32, 0, m->st()>>>(m->params(), nullptr, m->d_objective.p + 4095);
   JH_LAUNCHED();
   JH_CUDA(cudaMemcpyAsync(out, m->d_objective.p + 4095, sizeof(double), cudaMemcpyDeviceToHost, m->st()));
@@ -589,15 +850,26 @@ extern "C" int jh_model_log_prior(jh_model *m, double *out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_seq, const double *weights,
-                                 int32_t alphabet, jh_dataset **out) {
-  if (!offsets || !out || n_seq < 0 || (n_seq > 0 && !codes)) { jh_set_error("null argument"); return JH_ERR_INVALID; }
-  if (n_seq > 0x7fffffff) { jh_set_error("more than 2^31-1 sequences"); return JH_ERR_UNSUPPORTED; }
-  int r = ensure_device();
-  if (r) return r;
+static void dataset_free(jh_dataset *d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->ev_last) cudaEventSynchronize(d->ev_last);  // the last call that read the data set, on whatever stream it ran
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  Scope scope(d->device, cudaStreamPerThread);
+  if (d->ev_last) cudaEventDestroy(d->ev_last);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+struct DatasetGuard {  // error paths of the constructors release everything
+  jh_dataset *d;
+  ~DatasetGuard() { dataset_free(d); }
+  jh_dataset *release() { jh_dataset *x = d; d = nullptr; return x; }
+};
+
+// host-side layout of a data set: length buckets (decreasing length), octets
+static int dataset_layout(jh_dataset *d, const int64_t *offsets, int64_t n_seq) {
   if (offsets[0] != 0) { jh_set_error("offsets[0] must be 0"); return JH_ERR_INVALID; }
-  jh_dataset *d = new jh_dataset();
-  d->n_seq = n_seq; d->alphabet = alphabet;
+  d->n_seq = n_seq;
   d->offsets.assign(offsets, offsets + n_seq + 1);
   d->n_res = offsets[n_seq];
   d->min_len = n_seq ? INT64_MAX : 0;
@@ -606,7 +878,6 @@ extern "C" int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, i
     int64_t L = offsets[i + 1] - offsets[i];
     if (L <= 0) {  // the reference fails on an empty sequence too (finalState[-1], HigherOrderHMM.java:498)
       jh_set_error("sequence %lld is empty", (long long)i);
-      delete d;
       return JH_ERR_INVALID;
     }
     if (i > 0 && L > offsets[i] - offsets[i - 1]) sorted = false;
@@ -630,66 +901,112 @@ extern "C" int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, i
     i = j;
   }
   d->bucket_oct_ptr.push_back(0);
-  {
-    int64_t rec = 0;
-    for (size_t b = 0; b + 1 < d->bucket_ptr.size(); b++) {
-      for (int64_t i = d->bucket_ptr[b]; i < d->bucket_ptr[b + 1]; i += 8) {
-        for (int64_t k = i; k < i + 8; k++) d->oct_seq.push_back(k < d->bucket_ptr[b + 1] ? d->order[k] : -1);
-        d->oct_hbase.push_back(rec);
-        rec += offsets[d->order[i] + 1] - offsets[d->order[i]];  // the first sequence of an octet is its longest
-      }
-      d->bucket_oct_ptr.push_back((int64_t)d->oct_hbase.size());
+  int64_t rec = 0;
+  for (size_t b = 0; b + 1 < d->bucket_ptr.size(); b++) {
+    for (int64_t i = d->bucket_ptr[b]; i < d->bucket_ptr[b + 1]; i += 8) {
+      for (int64_t k = i; k < i + 8; k++) d->oct_seq.push_back(k < d->bucket_ptr[b + 1] ? d->order[k] : -1);
+      d->oct_hbase.push_back(rec);
+      rec += offsets[d->order[i] + 1] - offsets[d->order[i]];  // the first sequence of an octet is its longest
     }
-    d->oct_hbase.push_back(rec);  // total number of records
+    d->bucket_oct_ptr.push_back((int64_t)d->oct_hbase.size());
   }
-  cudaStream_t s = g_have_user_stream ? g_user_stream : (cudaStream_t)0;
+  d->oct_hbase.push_back(rec);  // total number of records
+  return JH_OK;
+}
+
+// codes: uint8 per residue (packed2 == 0), or 2 bits per residue, four residues per byte, lowest bits first, every
+// sequence starting on a byte boundary at byte pack_ptr[n] (packed2 == 1; SparseSequence-style storage of DNA).
+static int dataset_create_impl(const uint8_t *codes, const int64_t *pack_ptr, int packed2, const int64_t *offsets, int64_t n_seq,
+                               const double *weights, int32_t alphabet, jh_dataset **out) {
+  if (!offsets || !out || n_seq < 0 || (n_seq > 0 && !codes)) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  if (n_seq > 0x7fffffff) { jh_set_error("more than 2^31-1 sequences"); return JH_ERR_UNSUPPORTED; }
+  if (packed2 && (alphabet > 4 || !pack_ptr)) { jh_set_error("2-bit packing needs an alphabet of at most 4 symbols and byte offsets"); return JH_ERR_INVALID; }
+  const int device = g_default_device;
+  int r = ensure_device(device);
+  if (r) return r;
+  DatasetGuard G{new jh_dataset()};
+  jh_dataset *d = G.d;
+  d->device = device;
+  d->alphabet = alphabet;
+  Options opt;
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    opt = g_defaults;
+  }
+  JH_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  JH_CUDA(cudaEventCreateWithFlags(&d->ev_last, cudaEventDisableTiming));
+  Scope scope(device, d->stream);
+  cudaStream_t s = d->stream;
+  if ((r = dataset_layout(d, offsets, n_seq))) return r;
   if ((r = d->d_codes.alloc((size_t)d->n_res + 64)) || (r = d->d_offsets.alloc(n_seq + 1)) || (r = d->d_order.alloc(n_seq)) ||
-      (r = d->d_weights.alloc(n_seq))) {
-    delete d;
+      (r = d->d_weights.alloc(n_seq)))
     return r;
-  }
-  cudaMemsetAsync(d->d_codes.p + d->n_res, 0, 64, s);
-  if (d->n_res) JH_CUDA(cudaMemcpyAsync(d->d_codes.p, codes, d->n_res, cudaMemcpyHostToDevice, s));
+  JH_CUDA(cudaMemsetAsync(d->d_codes.p + d->n_res, 0, 64, s));
   JH_CUDA(cudaMemcpyAsync(d->d_offsets.p, offsets, sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, s));
   if (n_seq) JH_CUDA(cudaMemcpyAsync(d->d_order.p, d->order.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, s));
   if (weights && n_seq) {
     JH_CUDA(cudaMemcpyAsync(d->d_weights.p, weights, sizeof(double) * n_seq, cudaMemcpyHostToDevice, s));
     d->has_weights = true;
   }
-  // alphabet check on the device (WrongAlphabetException, AbstractHMM.java:991-993)
-  unsigned int *d_mx = nullptr, h_mx = 0;
-  JH_CUDA(cudaMalloc(&d_mx, sizeof(unsigned int)));
-  cudaMemsetAsync(d_mx, 0, sizeof(unsigned int), s);
-  if (d->n_res) {
-    jha::k_max_code<<<592, 256, 0, s>>>(d->d_codes.p, d->n_res, d_mx);
+  DevBuf<unsigned int> d_mx;
+  if ((r = d_mx.alloc(1))) return r;
+  JH_CUDA(cudaMemsetAsync(d_mx.p, 0, sizeof(unsigned int), s));
+  if (d->n_res && !packed2) {
+    if ((r = stage_h2d(d->d_codes.p, codes, (size_t)d->n_res, s, device, opt.stage != 0))) return r;
+    // alphabet check on the device (WrongAlphabetException, AbstractHMM.java:991-993)
+    jha::k_max_code<<<592, 256, 0, s>>>(d->d_codes.p, d->n_res, d_mx.p);
     JH_LAUNCHED();
+  } else if (d->n_res) {  // 2 bits per residue over PCIe (a quarter of the bytes), widened on the device
+    DevBuf<uint8_t> d_pk;
+    DevBuf<int64_t> d_pp;
+    const int64_t pk_bytes = pack_ptr[n_seq];
+    if ((r = d_pk.alloc((size_t)pk_bytes + 16)) || (r = d_pp.alloc(n_seq + 1))) return r;
+    JH_CUDA(cudaMemcpyAsync(d_pp.p, pack_ptr, sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, s));
+    if ((r = stage_h2d(d_pk.p, codes, (size_t)pk_bytes, s, device, opt.stage != 0))) return r;
+    jha::k_unpack2<<<(int)std::min<int64_t>(n_seq, 148 * 32), 256, 0, s>>>(d_pk.p, d_pp.p, d->d_offsets.p, n_seq, d->d_codes.p, alphabet, d_mx.p);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+    JH_CUDA(cudaStreamSynchronize(s));  // d_pk / d_pp are locals
   }
-  cudaMemcpyAsync(&h_mx, d_mx, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+  unsigned int h_mx = 0;
+  JH_CUDA(cudaMemcpyAsync(&h_mx, d_mx.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
   cudaError_t e = cudaStreamSynchronize(s);
-  cudaFree(d_mx);
   if (e != cudaSuccess) {
     jh_set_error("CUDA error %s while uploading the data set", cudaGetErrorString(e));
-    delete d;
     return JH_ERR_CUDA;
   }
   if ((int)h_mx >= alphabet) {
     jh_set_error("The AlphabetContainer of the data set and the model do not match (code %u >= alphabet size %d).", h_mx, alphabet);
-    delete d;
     return JH_ERR_ALPHABET;
   }
-  *out = d;
+  *out = G.release();
   return JH_OK;
+}
+
+extern "C" int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_seq, const double *weights,
+                                 int32_t alphabet, jh_dataset **out) {
+  return dataset_create_impl(codes, nullptr, 0, offsets, n_seq, weights, alphabet, out);
+}
+
+extern "C" int jh_dataset_create_packed2(const uint8_t *packed, const int64_t *byte_ptr, const int64_t *offsets, int64_t n_seq,
+                                         const double *weights, int32_t alphabet, jh_dataset **out) {
+  return dataset_create_impl(packed, byte_ptr, 1, offsets, n_seq, weights, alphabet, out);
 }
 
 extern "C" int jh_dataset_set_weights(jh_dataset *d, const double *weights) {
   if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
   if (!weights) { d->has_weights = false; return JH_OK; }
-  if (d->n_seq) JH_CUDA(cudaMemcpy(d->d_weights.p, weights, sizeof(double) * d->n_seq, cudaMemcpyHostToDevice));
+  JH_CUDA(cudaSetDevice(d->device));
+  if (d->ev_last) JH_CUDA(cudaEventSynchronize(d->ev_last));  // a running E-step may still read the old weights
+  if (d->n_seq) {
+    JH_CUDA(cudaMemcpyAsync(d->d_weights.p, weights, sizeof(double) * d->n_seq, cudaMemcpyHostToDevice, d->stream));
+    JH_CUDA(cudaStreamSynchronize(d->stream));
+  }
   d->has_weights = true;
   return JH_OK;
 }
 
-extern "C" void jh_dataset_destroy(jh_dataset *d) { delete d; }
+extern "C" void jh_dataset_destroy(jh_dataset *d) { dataset_free(d); }
 
 extern "C" int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_res, int64_t *max_len) {
   if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
@@ -703,8 +1020,23 @@ extern "C" int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_r
 static int check_pair(jh_model *m, jh_dataset *d) {
   if (!m || !d) { jh_set_error("null handle"); return JH_ERR_INVALID; }
   if (d->alphabet != m->a) { jh_set_error("The AlphabetContainer of the data set and the model do not match."); return JH_ERR_ALPHABET; }
+  if (d->device != m->device) { jh_set_error("model (device %d) and data set (device %d) live on different devices", m->device, d->device); return JH_ERR_INVALID; }
   return JH_OK;
 }
+struct UseMark {  // the data set remembers the last work that reads it (jh_dataset_destroy / set_weights wait for it)
+  jh_dataset *d;
+  cudaStream_t s;
+  ~UseMark() {
+    if (d && d->ev_last) cudaEventRecord(d->ev_last, s);
+  }
+};
+#define JH_ENTER2(m, d)                       \
+  JH_ENTER(m);                                \
+  {                                           \
+    int r__ = check_pair(m, d);               \
+    if (r__) return r__;                      \
+  }                                           \
+  UseMark mark__{d, (m)->st()}
 // Models that run on the general context-graph kernels (kernels_general.cuh, one sequence per thread): silent states, and
 // transition order 0 (a single context for every layer: every context is final, HigherOrderHMM.java:498, 1046-1058).
 static bool general_model(const jh_model *m) { return m->has_silent || m->m == 0; }
@@ -724,7 +1056,7 @@ struct LaunchPlan {
 // grid = resident CTAs (multiple of the SM count) bounded by the work and by the scratch budget
 template <typename K>
 static int plan_launch(const jh_model *m, K kernel, int G, size_t extra_smem_doubles, int64_t work, size_t scratch_bytes_per_slot,
-                       LaunchPlan *pl) {
+                       LaunchPlan *pl, int64_t budget_bytes = 0) {
   pl->G = G; pl->threads = 256; pl->groups_per_cta = 256 / G;
   pl->smem = ((size_t)pl->groups_per_cta * (2 * m->Cmax + m->S) + extra_smem_doubles) * sizeof(double);
   if (pl->smem > 200 * 1024) { jh_set_error("model too large for the shared-memory layout (%zu bytes)", pl->smem); return JH_ERR_UNSUPPORTED; }
@@ -732,14 +1064,14 @@ static int plan_launch(const jh_model *m, K kernel, int G, size_t extra_smem_dou
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, pl->threads, pl->smem));
   if (per_sm < 1) { jh_set_error("kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   int64_t grid = (int64_t)m->sm_count * per_sm;
   int64_t need = (work + pl->groups_per_cta - 1) / pl->groups_per_cta;
   grid = std::max<int64_t>(1, std::min(grid, need));
   if (scratch_bytes_per_slot) {
-    int64_t budget = g_opt.scratch_mb * 1024 * 1024;
+    int64_t budget = budget_bytes > 0 ? budget_bytes : m->opt.scratch_mb * 1024 * 1024;
     int64_t max_slots = budget / (int64_t)scratch_bytes_per_slot;
-    if (max_slots < pl->groups_per_cta) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+    if (max_slots < pl->groups_per_cta) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
     grid = std::min<int64_t>(grid, max_slots / pl->groups_per_cta);
   }
   pl->grid = (int)grid;
@@ -800,16 +1132,16 @@ static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int
 static int plan_general(jh_model *m, int64_t work, size_t bytes_per_thread, int *grid, int64_t *nthreads) {
   const int NT = 128;
   int64_t n = std::min<int64_t>((int64_t)m->sm_count * 1024, (work + NT - 1) / NT * NT);
-  int64_t cap = g_opt.scratch_mb * 1024 * 1024 / (int64_t)std::max<size_t>(bytes_per_thread, 1);
+  int64_t cap = m->opt.scratch_mb * 1024 * 1024 / (int64_t)std::max<size_t>(bytes_per_thread, 1);
   cap = cap / 32 * 32;
-  if (cap < 32) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  if (cap < 32) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
   n = std::max<int64_t>(32, std::min(n, cap));
   *grid = (int)((n + NT - 1) / NT);
   *nthreads = (int64_t)*grid * NT;
   if (*nthreads > cap) {  // a partial last block is not possible: shrink to whole blocks or run one small block
     *grid = (int)std::max<int64_t>(1, cap / NT);
     *nthreads = (int64_t)*grid * NT;
-    if (*nthreads > cap) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+    if (*nthreads > cap) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
   }
   return JH_OK;
 }
@@ -863,7 +1195,7 @@ static int run_general_estep(jh_model *m, jh_dataset *d) {
 }
 
 // posterior matrix of one sequence (d_post) or posterior decoding of a work list with the thread-per-sequence kernel
-static int run_general_posterior(jh_model *m, jh_dataset *d, const jhg::WorkList &W, int64_t max_len, double *d_post, int32_t *d_paths, double *d_ll) {
+static int run_general_posterior(jh_model *m, jh_dataset *d, const jhg::WorkList &W, int64_t max_len, double *d_post, PathOut d_paths, double *d_ll) {
   int grid;
   int64_t nthreads;
   const int64_t layers = max_len + 1;
@@ -885,7 +1217,7 @@ static int run_general_posterior(jh_model *m, jh_dataset *d, const jhg::WorkList
 // fast_variant in force for a model: the lane-per-state comparison kernels (1..3) keep the emission table in shared memory,
 // so models with a large table (e_global) always take the production mapping
 static int variant_of(const jh_model *m) {
-  return (m->fast.usable && m->fast.e_global && g_opt.fast_variant != 4) ? 0 : (int)g_opt.fast_variant;
+  return (m->fast.usable && m->fast.e_global && m->opt.fast_variant != 4) ? 0 : (int)m->opt.fast_variant;
 }
 
 // Tiny models (2..4 states) on a data set that is too small to fill the GPU with one sequence per lane (BASELINE configs[0]:
@@ -893,14 +1225,14 @@ static int variant_of(const jh_model *m) {
 // take the position-parallel checkpoint pass + the lane-per-chunk pass, which turns the chains into ~4x more, ~4x shorter
 // ones (cfg1 E-step 0.81 -> 0.53 ms, the whole 10-iteration train() call 9.1 -> 6.2 ms).
 static bool split_short_sequences(const jh_model *m, const jh_dataset *d) {
-  return g_opt.split_short && g_opt.scan && g_opt.lane_chunks && g_opt.fast_variant == 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 4 &&
+  return m->opt.split_short && m->opt.scan && m->opt.lane_chunks && m->opt.fast_variant == 0 && m->fast.usable && !m->fast.e_global && m->fast.G <= 4 &&
          d->n_seq < 32768 && d->n_res >= (1 << 20) && d->max_len >= 256 && d->max_len < 16384;
 }
 
 static bool prefer_sparse(const jh_model *m, const jh_dataset *d) {
-  if (!g_opt.fast || !m->sparse.usable) return false;
-  if (m->S > 32 || g_opt.fast_variant == 4) return true;
-  if (g_opt.fast_variant != 0) return false;
+  if (!m->opt.fast || !m->sparse.usable) return false;
+  if (m->S > 32 || m->opt.fast_variant == 4) return true;
+  if (m->opt.fast_variant != 0) return false;
   return (d->n_seq <= 1024 && d->max_len >= 16384) || split_short_sequences(m, d);
 }
 
@@ -974,12 +1306,12 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
   if (!on) JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));  // only the warp-per-sequence kernel uses it
   const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
   if (items == 0) return JH_OK;
-  if (g_opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
+  if (m->opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
     size_t smem_c = ((P.e_global ? 0 : (size_t)P.H * P.SP) + 2 * (size_t)P.SP + 16) * sizeof(double);
     if (on) {  // overlapped with chunk kernels of other sequences: claim the SM's whole shared memory, so that no chunk CTA
                // becomes co-resident and competes for the issue slots of this latency-bound CTA (measured: +25 % per step)
       int optin = 0;
-      JH_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g_device));
+      JH_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
       smem_c = std::max<size_t>(smem_c, (size_t)optin);
     }
 #define JH_P1C(IND_)                                                                                                                     \
@@ -1029,17 +1361,17 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
 static int64_t chunk_len_for(const jh_model *m, const jh_dataset *d) {
   if (split_short_sequences(m, d)) {  // ~49 000 chunks (lanes) for the whole data set, at least 64 positions each
     const int64_t ck = (d->n_res / 49152 + 15) / 16 * 16;
-    return std::max<int64_t>(64, std::min<int64_t>(ck, g_opt.chunk));
+    return std::max<int64_t>(64, std::min<int64_t>(ck, m->opt.chunk));
   }
-  const bool small_dense = g_opt.scan && m->fast.usable && !m->fast.e_global;
-  return small_dense && g_opt.chunk >= 1024 ? g_opt.chunk * 4 : g_opt.chunk;
+  const bool small_dense = m->opt.scan && m->fast.usable && !m->fast.e_global;
+  return small_dense && m->opt.chunk >= 1024 ? m->opt.chunk * 4 : m->opt.chunk;
 }
 
 static bool scan_applies(const jh_model *m, const jh_dataset *d) {
-  if (!(g_opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global)) return false;
+  if (!(m->opt.scan && d->n_long > 0 && m->fast.usable && !m->fast.e_global)) return false;
   // 32 states: 32x the arithmetic of the sequential pass and 16 KB of transfer rows per chunk — only while those fit the scratch budget
   const int64_t n_lc = d->long_seg.empty() ? 0 : d->long_seg[d->n_long];
-  return m->fast.G <= 16 || n_lc * 2 * 32 * 32 * 8 <= g_opt.scratch_mb * 1024 * 1024 / 2;
+  return m->fast.G <= 16 || n_lc * 2 * 32 * 32 * 8 <= m->opt.scratch_mb * 1024 * 1024 / 2;
 }
 static int run_scan_checkpoints(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra &X) {
   const jhf::FastTables &Ft = m->fast;
@@ -1081,7 +1413,7 @@ static int run_loglik_exact(jh_model *m, jh_dataset *d, double *d_out, const int
 
 static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
   int r;
-  if (g_opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > chunk_len_for(m, d)) {
+  if (m->opt.scan && m->fast.usable && !m->fast.e_global && d->max_len > chunk_len_for(m, d)) {
     if ((r = ensure_chunks(m, d, chunk_len_for(m, d)))) return r;
   }
   if (d->chunk_len == chunk_len_for(m, d) && scan_applies(m, d)) {  // long sequences parallel in the position, the others one warp each
@@ -1102,7 +1434,8 @@ static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
   return JH_OK;
 }
 
-static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, double *d_loglik, double *d_post, const int32_t *d_list, int64_t n_list);
+static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, PathOut d_paths, double *d_loglik, double *d_post, const int32_t *d_list, int64_t n_list,
+                        const jhx::Cond &cond = jhx::Cond{}, int64_t budget_bytes = 0);
 
 // Long-sequence path (kernels_sparse.cuh), two exact phases: checkpoint pass over whole sequences (k_sparse_pass1 /
 // k_sparse_pass1_cta), then every chunk of `chunk` positions as an independent work item (posterior decisions:
@@ -1114,7 +1447,7 @@ static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, 
 // ones are still being swept.  Plain stream ordering, no device-side waiting.
 enum { SPARSE_DECODE = 0, SPARSE_ESTEP = 1 };
 
-static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d_paths, double *d_ll) {
+static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, PathOut d_paths, double *d_ll) {
   jhs::SparseTables &P = m->sparse;
   cudaStream_t s = m->st();
   const int64_t CK = chunk_len_for(m, d);
@@ -1136,7 +1469,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
   // small dense models: the checkpoint pass of the long sequences runs parallel in the position (kernels_scan.cuh)
   const bool scan = scan_applies(m, d);
   // ---- launch plan of the chunk pass: one launch, or one per long sequence (own stream) + one for the single-chunk sequences
-  const bool streamed = !scan && g_opt.overlap && g_opt.pass1_cta && d->n_long >= 2 && d->n_long <= 64;
+  const bool streamed = !scan && m->opt.overlap && m->opt.pass1_cta && d->n_long >= 2 && d->n_long <= 64;
   const int64_t n_launch = streamed ? d->n_long + 1 : 1;
   const int NT = 128, wpc = NT / 32;
   const size_t smem = ((P.e_global ? 0 : (size_t)P.H * P.SP) + (size_t)wpc * 2 * P.SP) * sizeof(double);
@@ -1155,8 +1488,8 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
     }
   });
   if (per_sm < 1) { jh_set_error("sparse chunk kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
-  const int64_t budget_slots = std::max<int64_t>(wpc, g_opt.scratch_mb * 1024 * 1024 / per_slot);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
+  const int64_t budget_slots = std::max<int64_t>(wpc, m->opt.scratch_mb * 1024 * 1024 / per_slot);
   // streamed: every launch gets its own slice of the row scratch.  The longest sequences finish their checkpoint pass last
   // and then have the GPU to themselves: they get full grids, the others a share of an SM's worth each (many are resident together).
   const int64_t full_grid = (int64_t)m->sm_count * per_sm;
@@ -1205,12 +1538,12 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
       Xs.list = d->d_order.p + d->n_long; Xs.n_list = d->n_seq - d->n_long;
       if ((r = run_sparse_pass1(m, d, 2, d_ll, &Xs, nullptr, false))) return r;
     }
-    if (g_opt.lane_chunks && m->fast.G <= 8) {  // small models: one chunk per lane instead of one state per lane
+    if (m->opt.lane_chunks && m->fast.G <= 8) {  // small models: one chunk per lane instead of one state per lane
       const jhf::FastTables &Ft = m->fast;
       const int ec_smem = what == SPARSE_ESTEP && (size_t)Ft.H * Ft.G * 32 * wpc * sizeof(double) <= 96 * 1024;
       const size_t smem_l = ((size_t)Ft.H * Ft.G + (ec_smem ? (size_t)Ft.H * Ft.G * 32 * wpc : 0)) * sizeof(double);
       const int64_t per_warp = rows * 32 * (Ft.G * (int64_t)sizeof(double) + (what == SPARSE_ESTEP ? (int64_t)sizeof(int) : 0));
-      const int64_t warps = std::max<int64_t>(1, std::min<int64_t>((d->n_chunks + 31) / 32, std::min<int64_t>((int64_t)m->sm_count * 16, g_opt.scratch_mb * 1024 * 1024 / per_warp)));
+      const int64_t warps = std::max<int64_t>(1, std::min<int64_t>((d->n_chunks + 31) / 32, std::min<int64_t>((int64_t)m->sm_count * 16, m->opt.scratch_mb * 1024 * 1024 / per_warp)));
       const int grid_l = (int)((warps + wpc - 1) / wpc);
       if ((r = m->d_fwd.reserve((size_t)grid_l * wpc * rows * 32 * Ft.G))) return r;
       if (what == SPARSE_ESTEP && (r = m->d_rexp.reserve((size_t)grid_l * wpc * rows * 32))) return r;
@@ -1221,7 +1554,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
   {                                                                                                                                      \
     if (what == SPARSE_ESTEP) {                                                                                                          \
       if (smem_l > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhc::k_lane_chunks<GG, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
-      jhc::k_lane_chunks<GG, 1><<<grid_l, NT, smem_l, s>>>(Ft.dev(), d->dev(), In, m->d_counters.p, m->d_fwd.p, m->d_rexp.p, nullptr, m->d_stats.p, Ft.d_ec, m->d_fallback.p, ec_smem); \
+      jhc::k_lane_chunks<GG, 1><<<grid_l, NT, smem_l, s>>>(Ft.dev(), d->dev(), In, m->d_counters.p, m->d_fwd.p, m->d_rexp.p, PathOut{nullptr, 0}, m->d_stats.p, Ft.d_ec, m->d_fallback.p, ec_smem); \
     } else {                                                                                                                             \
       if (smem_l > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhc::k_lane_chunks<GG, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l)); \
       jhc::k_lane_chunks<GG, 0><<<grid_l, NT, smem_l, s>>>(Ft.dev(), d->dev(), In, m->d_counters.p, m->d_fwd.p, nullptr, d_paths, nullptr, Ft.d_ec, m->d_fallback.p, 0); \
@@ -1296,8 +1629,8 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, int32_t *d
   return JH_OK;
 }
 
-static int run_decode_sparse(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) { return run_sparse_two_phase(m, d, SPARSE_DECODE, d_paths, d_ll); }
-static int run_estep_sparse(jh_model *m, jh_dataset *d) { return run_sparse_two_phase(m, d, SPARSE_ESTEP, nullptr, nullptr); }
+static int run_decode_sparse(jh_model *m, jh_dataset *d, PathOut d_paths, double *d_ll) { return run_sparse_two_phase(m, d, SPARSE_DECODE, d_paths, d_ll); }
+static int run_estep_sparse(jh_model *m, jh_dataset *d) { return run_sparse_two_phase(m, d, SPARSE_ESTEP, PathOut{nullptr, 0}, nullptr); }
 
 static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
 
@@ -1314,7 +1647,7 @@ static int launch_mma_loglik_eg(jh_model *m, jh_dataset *d, double *d_out) {
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
   if (per_sm < 1) { jh_set_error("octet scoring kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + 7) / 8));
   jhm::OctData D;
   D.oct_seq = d->d_oct_seq.p; D.oct_hbase = d->d_oct_hbase.p; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
@@ -1348,13 +1681,13 @@ static int launch_lanes_eg(jh_model *m, jh_dataset *d, size_t b, double *d_out) 
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) { jh_set_error("lane-per-sequence kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   const int64_t n_quads = (n_oct + 3) / 4;
   int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_quads + wpc - 1) / wpc);
   if constexpr (MODE == 1) {
     const int64_t per_slot = std::max<int64_t>(1, rows * 32 * (S * (int64_t)sizeof(double) + (int64_t)sizeof(int)));
-    const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
-    if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+    const int64_t max_slots = m->opt.scratch_mb * 1024 * 1024 / per_slot;
+    if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
     grid = std::min(grid, max_slots / wpc);
   }
   grid = std::max<int64_t>(1, grid);
@@ -1416,8 +1749,8 @@ static int run_loglik_octets(jh_model *m, jh_dataset *d, double *d_out) {
 }
 
 extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (d->n_seq == 0) return JH_OK;
   if (!out) { jh_set_error("null output"); return JH_ERR_INVALID; }
   DevBuf<double> d_out;
@@ -1427,9 +1760,9 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_loglik(m, d, W, d_out.p);
   } else if (prefer_sparse(m, d)) r = run_loglik_sparse(m, d, d_out.p);
-  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_loglik_octets(m, d, d_out.p);
-  else if (g_opt.fast && m->fast.usable && m->fast.G <= 4 && variant_of(m) == 0) r = run_loglik_lanes(m, d, d_out.p);
-  else if (g_opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
+  else if (m->opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_loglik_octets(m, d, d_out.p);
+  else if (m->opt.fast && m->fast.usable && m->fast.G <= 4 && variant_of(m) == 0) r = run_loglik_lanes(m, d, d_out.p);
+  else if (m->opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
   else r = run_loglik_exact(m, d, d_out.p, nullptr, 0);
   timing_end(m);
   if (r) return r;
@@ -1440,8 +1773,8 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
 
 extern "C" int jh_loglik_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start, const int64_t *end,
                                  double *out) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (n_win == 0) return JH_OK;
   if (n_win < 0 || !seq_index || !start || !end || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
   std::vector<int32_t> sid(n_win);
@@ -1505,10 +1838,171 @@ static int upload_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64
   return JH_OK;
 }
 
+extern "C" int jh_posterior_window(jh_model *m, jh_dataset *d, int64_t seq_index, int64_t start, int64_t end, double *out) {
+  JH_ENTER2(m, d);
+  int r = JH_OK;
+  if (!out) { jh_set_error("null output"); return JH_ERR_INVALID; }
+  DevWindows dw;
+  if ((r = upload_windows(m, d, 1, &seq_index, &start, &end, dw))) return r;
+  const int64_t L = end - start + 1;
+  DevBuf<double> d_post;
+  if ((r = d_post.alloc((size_t)m->S * L))) return r;
+  if ((r = run_general_posterior(m, d, dw.W, L, d_post.p, PathOut{nullptr, 0}, nullptr))) return r;
+  JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  return JH_OK;
+}
+
+// ---- Viterbi ------------------------------------------------------------------------------------
+static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
+
+// Lane-per-sequence Viterbi (kernels_viterbi.cuh): plain first-order models with sorted child lists; one launch per bucket.
+template <int S, bool EG, bool U8>
+static int launch_viterbi_lanes_eg(jh_model *m, jh_dataset *d, size_t b, PathOut paths, const int64_t *d_path_ptr, double *d_scores) {
+  using C = jhv::VitCfg<S>;
+  jhf::FastTables &F = m->fast;
+  cudaStream_t s = m->st();
+  auto kern = jhv::k_viterbi_lanes<S, EG, U8>;
+  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b];
+  if (n_oct <= 0) return JH_OK;
+  const int NT = 128, wpc = NT / 32;
+  size_t smem = ((size_t)S * S + S + (EG ? 0 : (size_t)F.H * S)) * sizeof(double);
+  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+  if (per_sm < 1) { jh_set_error("Viterbi kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
+  const int64_t n_quads = (n_oct + 3) / 4;
+  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_quads + wpc - 1) / wpc);
+  const int64_t per_slot = rows * 32 * C::CB;
+  const int64_t max_slots = m->opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  grid = std::max<int64_t>(1, std::min(grid, max_slots / wpc));
+  int r = m->d_choice.reserve((size_t)grid * wpc * per_slot);
+  if (r) return r;
+  jhv::VitTables V;
+  V.T = F.d_vT; V.pi = F.d_vpi; V.fin = F.d_vfin; V.E = F.d_vE; V.korder = F.d_korder; V.H = F.H; V.Kmax = F.Kmax; V.log_uniform = -log((double)F.a);
+  jhm::OctData D;
+  D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
+  D.weights = nullptr; D.n_oct = n_oct;
+  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+  kern<<<(int)grid, NT, smem, s>>>(V, D, m->d_counter.p, m->d_choice.p, rows, paths.p, d_path_ptr, d_scores);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+template <int S>
+static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, PathOut paths, const int64_t *d_path_ptr, double *d_scores) {
+  if (m->fast.e_global)
+    return paths.u8 ? launch_viterbi_lanes_eg<S, true, true>(m, d, b, paths, d_path_ptr, d_scores) : launch_viterbi_lanes_eg<S, true, false>(m, d, b, paths, d_path_ptr, d_scores);
+  return paths.u8 ? launch_viterbi_lanes_eg<S, false, true>(m, d, b, paths, d_path_ptr, d_scores) : launch_viterbi_lanes_eg<S, false, false>(m, d, b, paths, d_path_ptr, d_scores);
+}
+
+static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int64_t *d_path_ptr, double *d_scores, bool *handled) {
+  *handled = false;
+  return JH_OK;
+}
+
+// Models without silent states and with transition order >= 1.  One launch per length bucket so that the per-slot scratch
+// follows the bucket's longest sequence.  windows: sub-sequences (exact kernel only).
+static int run_viterbi(jh_model *m, jh_dataset *d, PathOut paths, const int64_t *d_path_ptr, double *d_scores, double *d_stats,
+                       const WorkList *windows = nullptr, int64_t win_max_len = 0) {
+  if (!d_stats && !windows) {  // chromosome-scale sequences: checkpointed sweep, choice bytes recomputed per chunk
+    bool handled = false;
+    int r = run_viterbi_long(m, d, paths, d_path_ptr, d_scores, &handled);
+    if (r || handled) return r;
+  }
+  if (!d_stats && !windows && m->opt.fast && m->fast.usable && m->fast.sorted_children) {  // decoding: one sequence per lane
+    int r = ensure_octet_hashes(m, d);
+    for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
+      switch (m->fast.G) {
+        case 2: r = launch_viterbi_lanes<2>(m, d, b, paths, d_path_ptr, d_scores); break;
+        case 4: r = launch_viterbi_lanes<4>(m, d, b, paths, d_path_ptr, d_scores); break;
+        case 8: r = launch_viterbi_lanes<8>(m, d, b, paths, d_path_ptr, d_scores); break;
+        case 16: r = launch_viterbi_lanes<16>(m, d, b, paths, d_path_ptr, d_scores); break;
+        default: r = launch_viterbi_lanes<32>(m, d, b, paths, d_path_ptr, d_scores); break;
+      }
+    }
+    return r;
+  }
+  if (m->max_children > 254) { jh_set_error("more than 254 children per context"); return JH_ERR_UNSUPPORTED; }
+  int G = group_size(m), r = JH_OK;
+  cudaStream_t s = m->st();
+  const size_t nb = windows ? 1 : d->bucket_ptr.size() - 1;
+  for (size_t b = 0; b < nb && !r; b++) {
+    int64_t first = windows ? 0 : d->bucket_ptr[b], count = windows ? windows->n : d->bucket_ptr[b + 1] - first;
+    int64_t rows = windows ? win_max_len : d->bucket_len[b];
+    const WorkList W = windows ? *windows : WorkList{nullptr, nullptr, nullptr, count};
+    JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
+    DISPATCH_G(G, {
+      LaunchPlan pl;
+      r = plan_launch(m, jhx::k_exact_viterbi<GG>, GG, 0, count, (size_t)rows * m->Cmax, &pl);
+      if (!r) r = m->d_choice.reserve((size_t)pl.slots * rows * m->Cmax);
+      if (!r) {
+        jhx::k_exact_viterbi<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(first, count), W, m->d_counter.p, m->d_choice.p, rows,
+                                                                    paths, d_path_ptr, d_scores, d_stats);
+        JH_LAUNCHED();
+      }
+    });
+  }
+  if (r) return r;
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
+// scores on the host: -inf = "Impossible path" (HigherOrderHMM.java:659) -> JH_ERR_IMPOSSIBLE (outputs stay filled)
+static int check_possible(const double *scores, int64_t n) {
+  if (!scores) return JH_OK;
+  for (int64_t i = 0; i < n; i++)
+    if (scores[i] == JH_NEG_INF) {
+      jh_set_error("Impossible path (sequence %lld has no state path with a probability > 0)", (long long)i);
+      return JH_ERR_IMPOSSIBLE;
+    }
+  return JH_OK;
+}
+
+extern "C" int jh_viterbi_paths(jh_model *m, jh_dataset *d, int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores) {
+  JH_ENTER2(m, d);
+  int r = JH_OK;
+  if (d->n_seq == 0) return JH_OK;
+  if (paths && !path_ptr) { jh_set_error("paths without path_ptr"); return JH_ERR_INVALID; }
+  DevBuf<int32_t> d_paths;
+  DevBuf<int64_t> d_ptr, d_len;
+  DevBuf<double> d_scores;
+  cudaStream_t s = m->st();
+  const int64_t total = paths ? path_ptr[d->n_seq] : 0;
+  if ((r = d_paths.alloc(total)) || (r = d_ptr.alloc(d->n_seq + 1)) || (r = d_len.alloc(d->n_seq)) || (r = d_scores.alloc(d->n_seq))) return r;
+  if (paths) JH_CUDA(cudaMemcpyAsync(d_ptr.p, path_ptr, sizeof(int64_t) * (d->n_seq + 1), cudaMemcpyHostToDevice, s));
+  timing_begin(m);
+  if (general_model(m)) {
+    r = run_general_viterbi(m, d, paths ? d_paths.p : nullptr, d_ptr.p, d_len.p, d_scores.p, nullptr);
+  } else {  // one state per residue: the data-set kernels (k_viterbi_lanes / k_exact_viterbi), then the variable-length bookkeeping
+    if (paths)
+      for (int64_t i = 0; i < d->n_seq; i++)
+        if (path_ptr[i + 1] - path_ptr[i] < d->offsets[i + 1] - d->offsets[i]) { jh_set_error("path capacity of sequence %lld is smaller than its length", (long long)i); return JH_ERR_INVALID; }
+    const bool same = paths && std::equal(path_ptr, path_ptr + d->n_seq + 1, d->offsets.begin());
+    r = run_viterbi(m, d, PathOut{paths ? d_paths.p : nullptr, 0}, same || !paths ? nullptr : d_ptr.p, d_scores.p, nullptr);
+    if (!r) {
+      jha::k_finish_paths<<<(int)std::min<int64_t>(d->n_seq, 148 * 8), 128, 0, s>>>(d_scores.p, d->d_offsets.p, nullptr, d->n_seq, paths ? d_paths.p : nullptr,
+                                                                                 same || !paths ? nullptr : d_ptr.p, d_len.p);
+      JH_LAUNCHED();
+      JH_CUDA(cudaGetLastError());
+    }
+  }
+  timing_end(m);
+  if (r) return r;
+  if (paths && total && (r = stage_d2h(paths, d_paths.p, sizeof(int32_t) * total, s, m->device, m->opt.stage != 0))) return r;
+  if (path_len) JH_CUDA(cudaMemcpyAsync(path_len, d_len.p, sizeof(int64_t) * d->n_seq, cudaMemcpyDeviceToHost, s));
+  if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  return JH_OK;
+}
+
 extern "C" int jh_viterbi_windows(jh_model *m, jh_dataset *d, int64_t n_win, const int64_t *seq_index, const int64_t *start, const int64_t *end,
                                   int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (n_win == 0) return JH_OK;
   if (paths && !path_ptr) { jh_set_error("paths without path_ptr"); return JH_ERR_INVALID; }
   DevWindows dw;
@@ -1521,184 +2015,82 @@ extern "C" int jh_viterbi_windows(jh_model *m, jh_dataset *d, int64_t n_win, con
   if ((r = d_paths.alloc(total)) || (r = d_ptr.alloc(n_win + 1)) || (r = d_len.alloc(n_win)) || (r = d_scores.alloc(n_win))) return r;
   if (paths) JH_CUDA(cudaMemcpyAsync(d_ptr.p, path_ptr, sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, s));
   timing_begin(m);
-  r = run_general_viterbi(m, d, paths ? d_paths.p : nullptr, d_ptr.p, d_len.p, d_scores.p, nullptr, &dw.W);
+  if (general_model(m)) {
+    r = run_general_viterbi(m, d, paths ? d_paths.p : nullptr, d_ptr.p, d_len.p, d_scores.p, nullptr, &dw.W);
+  } else {  // group-per-window kernel (k_exact_viterbi), bit-exact like the whole-sequence call
+    if (paths)
+      for (int64_t i = 0; i < n_win; i++)
+        if (path_ptr[i + 1] - path_ptr[i] < end[i] - start[i] + 1) { jh_set_error("path capacity of window %lld is smaller than its length", (long long)i); return JH_ERR_INVALID; }
+    if (!paths) {  // the kernel indexes its outputs through path_ptr
+      std::vector<int64_t> zero(n_win + 1, 0);
+      JH_CUDA(cudaMemcpyAsync(d_ptr.p, zero.data(), sizeof(int64_t) * (n_win + 1), cudaMemcpyHostToDevice, s));
+      JH_CUDA(cudaStreamSynchronize(s));
+    }
+    r = run_viterbi(m, d, PathOut{paths ? d_paths.p : nullptr, 0}, d_ptr.p, d_scores.p, nullptr, &dw.W, dw.max_len);
+    if (!r) {
+      jha::k_finish_paths<<<(int)std::min<int64_t>(n_win, 148 * 8), 128, 0, s>>>(d_scores.p, dw.se.p, dw.se.p + n_win, n_win, paths ? d_paths.p : nullptr,
+                                                                              paths ? d_ptr.p : nullptr, d_len.p);
+      JH_LAUNCHED();
+      JH_CUDA(cudaGetLastError());
+    }
+  }
   timing_end(m);
   if (r) return r;
-  if (paths && total) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+  if (paths && total && (r = stage_d2h(paths, d_paths.p, sizeof(int32_t) * total, s, m->device, m->opt.stage != 0))) return r;
   if (path_len) JH_CUDA(cudaMemcpyAsync(path_len, d_len.p, sizeof(int64_t) * n_win, cudaMemcpyDeviceToHost, s));
   if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * n_win, cudaMemcpyDeviceToHost, s));
   JH_CUDA(cudaStreamSynchronize(s));
   return JH_OK;
 }
 
-extern "C" int jh_posterior_window(jh_model *m, jh_dataset *d, int64_t seq_index, int64_t start, int64_t end, double *out) {
-  int r = check_pair(m, d);
-  if (r) return r;
-  if (!out) { jh_set_error("null output"); return JH_ERR_INVALID; }
-  if (m->m == 0) { jh_set_error("state posteriors of order-0 transitions (HigherOrderHMM.java:296-308) are not on the native path"); return JH_ERR_UNSUPPORTED; }
-  DevWindows dw;
-  if ((r = upload_windows(m, d, 1, &seq_index, &start, &end, dw))) return r;
-  const int64_t L = end - start + 1;
-  DevBuf<double> d_post;
-  if ((r = d_post.alloc((size_t)m->S * L))) return r;
-  if ((r = run_general_posterior(m, d, dw.W, L, d_post.p, nullptr, nullptr))) return r;
-  JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
-  JH_CUDA(cudaStreamSynchronize(m->st()));
-  return JH_OK;
-}
-
-// ---- Viterbi ------------------------------------------------------------------------------------
-static int ensure_octet_hashes(jh_model *m, jh_dataset *d);
-
-// Lane-per-sequence Viterbi (kernels_viterbi.cuh): plain first-order models with sorted child lists; one launch per bucket.
-template <int S, bool EG>
-static int launch_viterbi_lanes_eg(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_scores) {
-  using C = jhv::VitCfg<S>;
-  jhf::FastTables &F = m->fast;
-  cudaStream_t s = m->st();
-  auto kern = jhv::k_viterbi_lanes<S, EG>;
-  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, rows = d->bucket_len[b];
-  if (n_oct <= 0) return JH_OK;
-  const int NT = 128, wpc = NT / 32;
-  size_t smem = ((size_t)S * S + S + (EG ? 0 : (size_t)F.H * S)) * sizeof(double);
-  if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
-  if (per_sm < 1) { jh_set_error("Viterbi kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
-  const int64_t n_quads = (n_oct + 3) / 4;
-  int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_quads + wpc - 1) / wpc);
-  const int64_t per_slot = rows * 32 * C::CB;
-  const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
-  if (max_slots < wpc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
-  grid = std::max<int64_t>(1, std::min(grid, max_slots / wpc));
-  int r = m->d_choice.reserve((size_t)grid * wpc * per_slot);
-  if (r) return r;
-  jhv::VitTables V;
-  V.T = F.d_vT; V.pi = F.d_vpi; V.fin = F.d_vfin; V.E = F.d_vE; V.korder = F.d_korder; V.H = F.H; V.Kmax = F.Kmax; V.log_uniform = -log((double)F.a);
-  jhm::OctData D;
-  D.oct_seq = d->d_oct_seq.p + oct0 * 8; D.oct_hbase = d->d_oct_hbase.p + oct0; D.hashes = d->d_hashes.p; D.offsets = d->d_offsets.p;
-  D.weights = nullptr; D.n_oct = n_oct;
-  JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  kern<<<(int)grid, NT, smem, s>>>(V, D, m->d_counter.p, m->d_choice.p, rows, d_paths, d_scores);
-  JH_LAUNCHED();
-  JH_CUDA(cudaGetLastError());
-  return JH_OK;
-}
-
-template <int S>
-static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_scores) {
-  return m->fast.e_global ? launch_viterbi_lanes_eg<S, true>(m, d, b, d_paths, d_scores) : launch_viterbi_lanes_eg<S, false>(m, d, b, d_paths, d_scores);
-}
-
-// One launch per length bucket so that the per-slot scratch follows the bucket's longest sequence.
-static int run_viterbi(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_scores, double *d_stats) {
-  if (!d_stats && g_opt.fast && m->fast.usable && m->fast.sorted_children) {  // decoding: one sequence per lane
-    int r = ensure_octet_hashes(m, d);
-    for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
-      switch (m->fast.G) {
-        case 2: r = launch_viterbi_lanes<2>(m, d, b, d_paths, d_scores); break;
-        case 4: r = launch_viterbi_lanes<4>(m, d, b, d_paths, d_scores); break;
-        case 8: r = launch_viterbi_lanes<8>(m, d, b, d_paths, d_scores); break;
-        case 16: r = launch_viterbi_lanes<16>(m, d, b, d_paths, d_scores); break;
-        default: r = launch_viterbi_lanes<32>(m, d, b, d_paths, d_scores); break;
-      }
-    }
-    return r;
-  }
-  if (m->max_children > 254) { jh_set_error("more than 254 children per context"); return JH_ERR_UNSUPPORTED; }
-  int G = group_size(m), r = JH_OK;
-  cudaStream_t s = m->st();
-  for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
-    int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b];
-    JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-    DISPATCH_G(G, {
-      LaunchPlan pl;
-      r = plan_launch(m, jhx::k_exact_viterbi<GG>, GG, 0, count, (size_t)rows * m->Cmax, &pl);
-      if (!r) r = m->d_choice.reserve((size_t)pl.slots * rows * m->Cmax);
-      if (!r) {
-        jhx::k_exact_viterbi<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(first, count), m->d_counter.p, m->d_choice.p, rows,
-                                                                    d_paths, d_scores, d_stats);
-        JH_LAUNCHED();
-      }
-    });
-  }
-  if (r) return r;
-  JH_CUDA(cudaGetLastError());
-  return JH_OK;
-}
-
-extern "C" int jh_viterbi_paths(jh_model *m, jh_dataset *d, int32_t *paths, const int64_t *path_ptr, int64_t *path_len, double *scores) {
-  int r = check_pair(m, d);
-  if (r) return r;
-  if (d->n_seq == 0) return JH_OK;
-  if (paths && !path_ptr) { jh_set_error("paths without path_ptr"); return JH_ERR_INVALID; }
-  DevBuf<int32_t> d_paths;
-  DevBuf<int64_t> d_ptr, d_len;
-  DevBuf<double> d_scores;
-  cudaStream_t s = m->st();
-  const int64_t total = paths ? path_ptr[d->n_seq] : 0;
-  if ((r = d_paths.alloc(total)) || (r = d_ptr.alloc(d->n_seq + 1)) || (r = d_len.alloc(d->n_seq)) || (r = d_scores.alloc(d->n_seq))) return r;
-  if (paths) JH_CUDA(cudaMemcpyAsync(d_ptr.p, path_ptr, sizeof(int64_t) * (d->n_seq + 1), cudaMemcpyHostToDevice, s));
-  timing_begin(m);
-  r = run_general_viterbi(m, d, paths ? d_paths.p : nullptr, d_ptr.p, d_len.p, d_scores.p, nullptr);
-  timing_end(m);
-  if (r) return r;
-  if (paths && total) JH_CUDA(cudaMemcpyAsync(paths, d_paths.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
-  if (path_len) JH_CUDA(cudaMemcpyAsync(path_len, d_len.p, sizeof(int64_t) * d->n_seq, cudaMemcpyDeviceToHost, s));
-  if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, s));
-  JH_CUDA(cudaStreamSynchronize(s));
-  return JH_OK;
-}
-
-// paths as int32 (paths) or one byte per residue (paths8, 255 = no state), whichever is not null
-static int copy_paths_out(jh_model *m, jh_dataset *d, const int32_t *d_paths, int32_t *paths, uint8_t *paths8) {
-  cudaStream_t s = m->st();
-  if (paths) JH_CUDA(cudaMemcpyAsync(paths, d_paths, sizeof(int32_t) * d->n_res, cudaMemcpyDeviceToHost, s));
-  if (paths8) {
-    if (m->S > 255) { jh_set_error("byte paths need at most 255 states"); return JH_ERR_UNSUPPORTED; }
-    DevBuf<uint8_t> d8;
-    int r = d8.alloc((size_t)d->n_res + 16);
-    if (r) return r;
-    jha::k_narrow_paths<<<(int)std::min<int64_t>(148 * 8, (d->n_res + 4095) / 4096), 256, 0, s>>>(d_paths, d->n_res, d8.p);
-    JH_LAUNCHED();
-    JH_CUDA(cudaGetLastError());
-    JH_CUDA(cudaMemcpyAsync(paths8, d8.p, (size_t)d->n_res, cudaMemcpyDeviceToHost, s));
-    JH_CUDA(cudaStreamSynchronize(s));
-  }
-  return JH_OK;
-}
-
+// paths as int32 (paths) or one byte per residue (paths8, 255 = no state), whichever is not null: the kernels emit the
+// requested form directly
 static int viterbi_impl(jh_model *m, jh_dataset *d, int32_t *paths, uint8_t *paths8, double *scores) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (m->has_silent) { jh_set_error("models with silent states emit paths of variable length: use jh_viterbi_paths"); return JH_ERR_UNSUPPORTED; }
+  if (paths8 && m->S > 255) { jh_set_error("byte paths need at most 255 states"); return JH_ERR_UNSUPPORTED; }
   if (d->n_seq == 0) return JH_OK;
+  const bool u8 = paths8 != nullptr, want = paths || paths8;
   DevBuf<int32_t> d_paths;
+  DevBuf<uint8_t> d_paths8;
   DevBuf<double> d_scores;
-  if ((r = d_paths.alloc(d->n_res)) || (r = d_scores.alloc(d->n_seq))) return r;
+  if ((r = d_scores.alloc(d->n_seq))) return r;
   timing_begin(m);
   if (general_model(m)) {  // order 0: one state per residue, the data set offsets are the path pointers
     DevBuf<int64_t> d_len;
-    if ((r = d_len.alloc(d->n_seq))) return r;
+    if ((r = d_len.alloc(d->n_seq)) || (r = d_paths.alloc(d->n_res))) return r;
     r = run_general_viterbi(m, d, d_paths.p, d->d_offsets.p, d_len.p, d_scores.p, nullptr);
+    if (!r && u8) {
+      if ((r = d_paths8.alloc((size_t)d->n_res + 16))) return r;
+      jha::k_narrow_paths<<<(int)std::min<int64_t>(148 * 8, (d->n_res + 4095) / 4096), 256, 0, m->st()>>>(d_paths.p, d->n_res, d_paths8.p);
+      JH_LAUNCHED();
+      JH_CUDA(cudaGetLastError());
+    }
     if (!r) JH_CUDA(cudaStreamSynchronize(m->st()));
-  } else r = run_viterbi(m, d, d_paths.p, d_scores.p, nullptr);
+  } else {
+    if (want && (r = u8 ? d_paths8.alloc((size_t)d->n_res + 16) : d_paths.alloc(d->n_res))) return r;
+    r = run_viterbi(m, d, PathOut{want ? (u8 ? (void *)d_paths8.p : (void *)d_paths.p) : nullptr, u8 ? 1 : 0}, nullptr, d_scores.p, nullptr);
+  }
   timing_end(m);
   if (r) return r;
-  if ((r = copy_paths_out(m, d, d_paths.p, paths, paths8))) return r;
   if (scores) JH_CUDA(cudaMemcpyAsync(scores, d_scores.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
+  if (paths && (r = stage_d2h(paths, d_paths.p, sizeof(int32_t) * d->n_res, m->st(), m->device, m->opt.stage != 0))) return r;
+  if (paths8 && (r = stage_d2h(paths8, d_paths8.p, (size_t)d->n_res, m->st(), m->device, m->opt.stage != 0))) return r;
   JH_CUDA(cudaStreamSynchronize(m->st()));
-  return JH_OK;
+  return check_possible(scores, d->n_seq);
 }
 
 extern "C" int jh_viterbi(jh_model *m, jh_dataset *d, int32_t *paths, double *scores) { return viterbi_impl(m, d, paths, nullptr, scores); }
 extern "C" int jh_viterbi_u8(jh_model *m, jh_dataset *d, uint8_t *paths, double *scores) { return viterbi_impl(m, d, nullptr, paths, scores); }
 
 // ---- forward-backward family (exact) ----------------------------------------------------------
-static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, double *d_loglik, double *d_post,
-                        const int32_t *d_list, int64_t n_list) {
+// d_list with n_list < 0: the list is the device-side fallback list [count | ids...] (count read by the kernel).
+// cond: the launch does its work only if *cond.flag == cond.want (decided on the device, no host round trip).
+static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, PathOut d_paths, double *d_loglik, double *d_post,
+                        const int32_t *d_list, int64_t n_list, const jhx::Cond &cond, int64_t budget_bytes) {
   int G = group_size(m), r = JH_OK;
+  if (cond.n_list_dev) n_list = d->n_seq;  // upper bound for the grid; the kernel reads the real length
   cudaStream_t s = m->st();
   int64_t n_stats = m->n_stats();
   int stats_in_smem = mode == JHX_MODE_COUNTS && n_stats * 8 <= 96 * 1024;
@@ -1709,11 +2101,11 @@ static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, 
     JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
     DISPATCH_G(G, {
       LaunchPlan pl;
-      r = plan_launch(m, jhx::k_exact_fb<GG>, GG, stats_in_smem ? n_stats : 0, count, (size_t)rows * m->Cmax * sizeof(double), &pl);
+      r = plan_launch(m, jhx::k_exact_fb<GG>, GG, stats_in_smem ? n_stats : 0, count, (size_t)rows * m->Cmax * sizeof(double), &pl, budget_bytes);
       if (!r) r = m->d_fwd.reserve((size_t)pl.slots * rows * m->Cmax);
       if (!r) {
         jhx::k_exact_fb<GG><<<pl.grid, pl.threads, pl.smem, s>>>(m->dev(), d->dev(first, count), m->d_counter.p, m->d_fwd.p, rows, mode,
-                                                               m->d_stats.p, stats_in_smem, d_paths, d_loglik, d_post, d_list, n_list);
+                                                               m->d_stats.p, stats_in_smem, d_paths, d_loglik, d_post, d_list, n_list, cond);
         JH_LAUNCHED();
       }
     });
@@ -1724,8 +2116,8 @@ static int run_fb_exact(jh_model *m, jh_dataset *d, int mode, int32_t *d_paths, 
 }
 
 extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, double *out) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (seq_index < 0 || seq_index >= d->n_seq || !out) { jh_set_error("sequence index out of range"); return JH_ERR_INVALID; }
   int64_t L = d->offsets[seq_index + 1] - d->offsets[seq_index];
   DevBuf<double> d_post;
@@ -1733,10 +2125,9 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   if ((r = d_post.alloc((size_t)m->S * L)) || (r = d_list.alloc(1))) return r;
   int32_t sid = (int32_t)seq_index;
   JH_CUDA(cudaMemcpyAsync(d_list.p, &sid, sizeof(int32_t), cudaMemcpyHostToDevice, m->st()));
-  if (m->m == 0) { jh_set_error("state posteriors of order-0 transitions (HigherOrderHMM.java:296-308) are not on the native path"); return JH_ERR_UNSUPPORTED; }
-  if (m->has_silent) {  // general context graph: silent states score -inf (silentZero, HigherOrderHMM.java:316)
+  if (general_model(m)) {  // general context graph: silent states score -inf (silentZero, HigherOrderHMM.java:316); order 0: HOH:296-308
     jhg::WorkList W{d_list.p, nullptr, nullptr, 1};
-    if ((r = run_general_posterior(m, d, W, L, d_post.p, nullptr, nullptr))) return r;
+    if ((r = run_general_posterior(m, d, W, L, d_post.p, PathOut{nullptr, 0}, nullptr))) return r;
     JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
     JH_CUDA(cudaStreamSynchronize(m->st()));
     return JH_OK;
@@ -1744,7 +2135,7 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   // scratch sized for this sequence only
   int64_t saved = d->max_len;
   d->max_len = L;
-  r = run_fb_exact(m, d, JHX_MODE_POSTERIOR, nullptr, nullptr, d_post.p, d_list.p, 1);
+  r = run_fb_exact(m, d, JHX_MODE_POSTERIOR, PathOut{nullptr, 0}, nullptr, d_post.p, d_list.p, 1);
   d->max_len = saved;
   if (r) return r;
   JH_CUDA(cudaMemcpyAsync(out, d_post.p, sizeof(double) * m->S * L, cudaMemcpyDeviceToHost, m->st()));
@@ -1754,18 +2145,18 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
 
 // Octet posterior decoding (kernels_mma.cuh), one launch per length bucket; long buckets chunked like the E-step.
 template <int NT, bool CHUNKED, bool EG>
-static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem, int32_t *d_paths, double *d_ll) {
+static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem, PathOut d_paths, double *d_ll) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
   auto kern = jhm::k_mma_decode<NT, CHUNKED, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
-  const int64_t CK = g_opt.oct_chunk;
+  const int64_t CK = m->opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t per_slot = (rows + ck_rows) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-  const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
-  if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  const int64_t max_slots = m->opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
   grid = std::max<int64_t>(1, std::min(grid, max_slots / C::WARPS));
   const int64_t slots = grid * C::WARPS;
   int r = m->d_fwd.reserve((size_t)slots * (rows + ck_rows) * 8 * C::G);
@@ -1789,7 +2180,7 @@ static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t 
 }
 
 template <int NT>
-static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, int32_t *d_paths, double *d_ll) {
+static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, PathOut d_paths, double *d_ll) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b], rows = d->bucket_len[b] + 1;
@@ -1800,16 +2191,16 @@ static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, int32_t *d_pa
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_decode<NT, false, false>, C::NTHREADS, smem));
   if (per_sm < 1) { jh_set_error("octet decoding kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-  const bool chunked = g_opt.oct_chunk > 0 && rows > 2 * g_opt.oct_chunk &&
-                       (g_opt.oct_chunk_force || grid * C::WARPS * per_slot > g_opt.scratch_mb * 1024 * 1024);
+  const bool chunked = m->opt.oct_chunk > 0 && rows > 2 * m->opt.oct_chunk &&
+                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > m->opt.scratch_mb * 1024 * 1024);
   if (eg) return chunked ? launch_mma_decode_impl<NT, true, true>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, true>(m, d, b, grid, smem, d_paths, d_ll);
   return chunked ? launch_mma_decode_impl<NT, true, false>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, false>(m, d, b, grid, smem, d_paths, d_ll);
 }
 
-static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, double *d_ll) {
+static int run_decode_octets(jh_model *m, jh_dataset *d, PathOut d_paths, double *d_ll) {
   int r = ensure_octet_hashes(m, d);
   if (r) return r;
   if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
@@ -1827,25 +2218,29 @@ static int run_decode_octets(jh_model *m, jh_dataset *d, int32_t *d_paths, doubl
 }
 
 static int posterior_decode_impl(jh_model *m, jh_dataset *d, int32_t *paths, uint8_t *paths8, double *loglik) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (d->n_seq == 0) return JH_OK;
+  if (paths8 && m->S > 255) { jh_set_error("byte paths need at most 255 states"); return JH_ERR_UNSUPPORTED; }
+  const bool u8 = paths8 != nullptr;
   DevBuf<int32_t> d_paths;
+  DevBuf<uint8_t> d_paths8;
   DevBuf<double> d_ll;
-  if ((r = d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
-  if (m->m == 0) { jh_set_error("state posteriors of order-0 transitions (HigherOrderHMM.java:296-308) are not on the native path"); return JH_ERR_UNSUPPORTED; }
+  if ((r = u8 ? d_paths8.alloc((size_t)d->n_res + 16) : d_paths.alloc(d->n_res)) || (r = d_ll.alloc(d->n_seq))) return r;
+  const PathOut po{u8 ? (void *)d_paths8.p : (void *)d_paths.p, u8 ? 1 : 0};
   timing_begin(m);
-  if (m->has_silent) {
+  if (general_model(m)) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
-    r = run_general_posterior(m, d, W, d->max_len, nullptr, d_paths.p, d_ll.p);
+    r = run_general_posterior(m, d, W, d->max_len, nullptr, po, d_ll.p);
   } else
-  if (prefer_sparse(m, d)) r = run_decode_sparse(m, d, d_paths.p, d_ll.p);
-  else if (g_opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_decode_octets(m, d, d_paths.p, d_ll.p);
-  else r = run_fb_exact(m, d, JHX_MODE_DECODE, d_paths.p, d_ll.p, nullptr, nullptr, 0);
+  if (prefer_sparse(m, d)) r = run_decode_sparse(m, d, po, d_ll.p);
+  else if (m->opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_decode_octets(m, d, po, d_ll.p);
+  else r = run_fb_exact(m, d, JHX_MODE_DECODE, po, d_ll.p, nullptr, nullptr, 0);
   timing_end(m);
   if (r) return r;
-  if ((r = copy_paths_out(m, d, d_paths.p, paths, paths8))) return r;
   if (loglik) JH_CUDA(cudaMemcpyAsync(loglik, d_ll.p, sizeof(double) * d->n_seq, cudaMemcpyDeviceToHost, m->st()));
+  if (paths && (r = stage_d2h(paths, d_paths.p, sizeof(int32_t) * d->n_res, m->st(), m->device, m->opt.stage != 0))) return r;
+  if (paths8 && (r = stage_d2h(paths8, d_paths8.p, (size_t)d->n_res, m->st(), m->device, m->opt.stage != 0))) return r;
   JH_CUDA(cudaStreamSynchronize(m->st()));
   return JH_OK;
 }
@@ -1868,12 +2263,12 @@ static int launch_fast_estep(jh_model *m, jh_dataset *d, int64_t first, int64_t 
   int per_sm = 0;
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
   if (per_sm < 1) { jh_set_error("fast E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   const int spc = gpc * NS;  // sequences in flight per CTA
   int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (count + spc - 1) / spc);
   int64_t per_slot = rows * G * (int64_t)sizeof(double) + rows * (int64_t)sizeof(int);
-  int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
-  if (max_slots < spc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  int64_t max_slots = m->opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < spc) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
   grid = std::max<int64_t>(1, std::min(grid, max_slots / spc));
   int64_t slots = grid * spc;
   int r = m->d_fwd.reserve((size_t)slots * rows * G);
@@ -1925,12 +2320,12 @@ static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, size_t b, int64_t g
   cudaStream_t s = m->st();
   auto kern = jhm::k_mma_estep<NT, CHUNKED, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
-  const int64_t CK = g_opt.oct_chunk;
+  const int64_t CK = m->opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t per_slot = (rows + ck_rows) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-  const int64_t max_slots = g_opt.scratch_mb * 1024 * 1024 / per_slot;
-  if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)g_opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
+  const int64_t max_slots = m->opt.scratch_mb * 1024 * 1024 / per_slot;
+  if (max_slots < C::WARPS) { jh_set_error("sequence too long for the DP scratch budget (%lld MB)", (long long)m->opt.scratch_mb); return JH_ERR_UNSUPPORTED; }
   grid = std::max<int64_t>(1, std::min(grid, max_slots / C::WARPS));
   const int64_t slots = grid * C::WARPS;
   int r = m->d_fwd.reserve((size_t)slots * (rows + ck_rows) * 8 * C::G);
@@ -1965,11 +2360,11 @@ static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_estep<NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_estep<NT, false, false>, C::NTHREADS, smem));
   if (per_sm < 1) { jh_set_error("octet E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
-  if (g_opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)g_opt.blocks_per_sm);
+  if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-  const bool chunked = g_opt.oct_chunk > 0 && rows > 2 * g_opt.oct_chunk &&
-                       (g_opt.oct_chunk_force || grid * C::WARPS * per_slot > g_opt.scratch_mb * 1024 * 1024);
+  const bool chunked = m->opt.oct_chunk > 0 && rows > 2 * m->opt.oct_chunk &&
+                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > m->opt.scratch_mb * 1024 * 1024);
   if (eg) return chunked ? launch_mma_estep_impl<NT, true, true>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, b, grid, smem);
   return chunked ? launch_mma_estep_impl<NT, true, false>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, false>(m, d, b, grid, smem);
 }
@@ -1992,7 +2387,7 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
       case 8: r = JH_FE(8, 512, 2); break;
       case 16: r = JH_FE(16, 256, 2); break;
       default:  // fast_variant: 0 = octets on the FP64 MMA path (above); 3 = two sequences per warp in lock step, 1 = one sequence per warp, 2 = one sequence, 12 warps
-        r = g_opt.fast_variant == 1 ? JH_FE(32, 256, 1) : g_opt.fast_variant == 2 ? JH_FE(32, 384, 1) : JH_FE(32, 256, 2);
+        r = m->opt.fast_variant == 1 ? JH_FE(32, 256, 1) : m->opt.fast_variant == 2 ? JH_FE(32, 384, 1) : JH_FE(32, 256, 2);
         break;
     }
 #undef JH_FE
@@ -2010,44 +2405,57 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));  // resetStatistics (HOH:890-895)
   if (d->n_seq == 0) return JH_OK;
   if (general_model(m)) {  // general context graph: one sequence per thread, reference order
-    cudaEventRecord(m->evk0, s);
+    if (!m->capturing) cudaEventRecord(m->evk0, s);
     int r = mode == JH_MODE_VITERBI ? run_general_viterbi(m, d, nullptr, nullptr, nullptr, nullptr, m->d_stats.p) : run_general_estep(m, d);
-    cudaEventRecord(m->evk1, s);
+    if (!m->capturing) cudaEventRecord(m->evk1, s);
     m->ktimed = true;
     return r;
   }
-  if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, nullptr, nullptr, m->d_stats.p);
+  if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, PathOut{nullptr, 0}, nullptr, nullptr, m->d_stats.p);
   const bool sparse = prefer_sparse(m, d);
-  if (sparse || (g_opt.fast && m->fast.usable)) {
+  if (sparse || (m->opt.fast && m->fast.usable)) {
     int r = m->d_fallback.reserve(d->n_seq + 2);
     if (r) return r;
     int32_t *flag = m->d_fallback.p + d->n_seq + 1;
     JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
     JH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), s));
     if (!sparse && variant_of(m) == 0 && (r = ensure_octet_hashes(m, d))) return r;
-    cudaEventRecord(m->evk0, s);
+    if (!m->capturing) cudaEventRecord(m->evk0, s);
     r = sparse ? run_estep_sparse(m, d) : run_estep_fast(m, d);
-    cudaEventRecord(m->evk1, s);
+    if (!m->capturing) cudaEventRecord(m->evk1, s);
     m->ktimed = true;
     if (r) return r;
     int n = (int)m->n_stats() + 1;
     jhf::k_check_finite<<<(n + 255) / 256, 256, 0, s>>>(m->d_stats.p, n, flag);
     JH_LAUNCHED();
-    // sequences whose scaled recursion lost all mass are re-run by the reference-order kernels (still on the GPU)
+    // Sequences whose scaled recursion lost all mass are re-run by the reference-order kernels, and an E-step whose
+    // statistics are not finite (dynamic range exceeded) is redone entirely in log space — both decided ON THE DEVICE
+    // (kernels_exact.cuh: Cond), so E-step -> all-reduce -> M-step stays stream ordered.  The log-space kernels need
+    // (L+1) x Cmax forward rows per resident group; if those do not fit 1 GB of scratch (chromosome-scale sequences) the
+    // decision is taken on the host as before.
+    const int64_t fb_budget = (int64_t)1 << 30;
+    const int gpc = 256 / group_size(m);
+    if ((d->max_len + 1) * (int64_t)m->Cmax * 8 * gpc <= fb_budget) {
+      jha::k_zero_if<<<(n + 7 + 255) / 256, 256, 0, s>>>(flag, m->d_stats.p, n + 7);
+      JH_LAUNCHED();
+      jhx::Cond redo{flag, 1, nullptr}, listed{flag, 0, m->d_fallback.p};
+      if ((r = run_fb_exact(m, d, JHX_MODE_COUNTS, PathOut{nullptr, 0}, nullptr, nullptr, nullptr, 0, redo, fb_budget))) return r;
+      return run_fb_exact(m, d, JHX_MODE_COUNTS, PathOut{nullptr, 0}, nullptr, nullptr, m->d_fallback.p + 1, 0, listed, fb_budget);
+    }
     int32_t n_fb = 0, bad = 0;
     JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     JH_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     JH_CUDA(cudaStreamSynchronize(s));
     if (bad) {  // dynamic range exceeded: redo the whole E-step in log space
       JH_CUDA(cudaMemsetAsync(m->d_stats.p, 0, sizeof(double) * (m->n_stats() + 8), s));
-      return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, nullptr, 0);
+      return run_fb_exact(m, d, JHX_MODE_COUNTS, PathOut{nullptr, 0}, nullptr, nullptr, nullptr, 0);
     }
-    if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, m->d_fallback.p + 1, n_fb);
+    if (n_fb > 0) return run_fb_exact(m, d, JHX_MODE_COUNTS, PathOut{nullptr, 0}, nullptr, nullptr, m->d_fallback.p + 1, n_fb);
     return JH_OK;
   }
-  cudaEventRecord(m->evk0, s);
-  int r = run_fb_exact(m, d, JHX_MODE_COUNTS, nullptr, nullptr, nullptr, nullptr, 0);
-  cudaEventRecord(m->evk1, s);
+  if (!m->capturing) cudaEventRecord(m->evk0, s);
+  int r = run_fb_exact(m, d, JHX_MODE_COUNTS, PathOut{nullptr, 0}, nullptr, nullptr, nullptr, 0);
+  if (!m->capturing) cudaEventRecord(m->evk1, s);
   m->ktimed = true;
   return r;
 }
@@ -2069,14 +2477,20 @@ static int mstep_device(jh_model *m) {
   return prep_scores(m);
 }
 
+static int estep_collective(jh_model *m, jh_dataset *d, int mode);
+
 extern "C" int jh_estep(jh_model *m, jh_dataset *d, int mode, double *trans_stat, double *emis_stat, double *score) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (mode != JH_MODE_VITERBI && mode != JH_MODE_BAUM_WELCH) { jh_set_error("Training mode not available."); return JH_ERR_INVALID; }
   timing_begin(m);
-  r = estep_device(m, d, mode);
-  if (!r) r = allreduce_stats(m);
+  r = estep_collective(m, d, mode);
   timing_end(m);
+  if (!r && m->failed) {
+    r = m->failed;
+    m->failed = 0;
+    jh_set_error("%s", m->failed_msg);
+  }
   if (r) return r;
   cudaStream_t s = m->st();
   if (trans_stat) JH_CUDA(cudaMemcpyAsync(trans_stat, m->d_stats.p, sizeof(double) * m->n_child, cudaMemcpyDeviceToHost, s));
@@ -2087,7 +2501,7 @@ extern "C" int jh_estep(jh_model *m, jh_dataset *d, int mode, double *trans_stat
 }
 
 extern "C" int jh_mstep(jh_model *m) {
-  if (!m) { jh_set_error("null model"); return JH_ERR_INVALID; }
+  JH_ENTER(m);
   return mstep_device(m);
 }
 
@@ -2098,49 +2512,128 @@ extern "C" int jh_stats_device(jh_model *m, void **dev_ptr, int64_t *n_doubles) 
   return JH_OK;
 }
 
+// E-step + all-reduce.  With a communicator attached a rank whose local E-step fails must not leave its peers waiting in
+// the collective: it remembers the error (m->failed), poisons the score slot (NaN: every rank's objective becomes NaN, so the
+// peers notice) and keeps taking part in the collectives of the remaining iterations; its error is returned at the end.
+static int estep_collective(jh_model *m, jh_dataset *d, int mode) {
+  int r = m->failed ? m->failed : estep_device(m, d, mode);
+  if (r) {
+    if (!m->comm || m->n_ranks <= 1) return r;
+    if (!m->failed) snprintf(m->failed_msg, sizeof(m->failed_msg), "%s", g_err);
+    m->failed = r;
+    cudaGetLastError();
+    cudaMemsetAsync(m->d_stats.p + m->n_stats(), 0xff, sizeof(double), m->st());
+  }
+  return allreduce_stats(m);
+}
+
+// E-part of one EM iteration: E-step, count all-reduce, objective = getLogPriorTerm() + oneIteration() (HigherOrderHMM.java:762)
+// stored at objective[iteration % cap] by the device-side iteration counter (no host value enters: graph replayable).
+static int em_e_part(jh_model *m, jh_dataset *d, int mode, int obj_cap) {
+  cudaStream_t s = m->st();
+  int r;
+  if ((r = estep_collective(m, d, mode))) return r;
+  jha::k_log_prior<<<1, 32, 0, s>>>(m->params(), m->d_stats.p + m->n_stats(), m->d_objective.p + 4095);
+  JH_LAUNCHED();
+  jha::k_store_objective<<<1, 1, 0, s>>>(m->d_objective.p + 4095, m->d_objective.p, m->d_iter.p, obj_cap);
+  JH_LAUNCHED();
+  JH_CUDA(cudaGetLastError());
+  return JH_OK;
+}
+
 extern "C" int jh_baum_welch(jh_model *m, jh_dataset *d, const jh_train_opts *o, double *objective, int32_t cap, int32_t *n_iter) {
-  int r = check_pair(m, d);
-  if (r) return r;
+  JH_ENTER2(m, d);
+  int r = JH_OK;
   if (!o || !n_iter) { jh_set_error("null argument"); return JH_ERR_INVALID; }
   if (o->term_kind != JH_TERM_ITERATIONS && o->term_kind != JH_TERM_SMALL_DIFFERENCE) { jh_set_error("unknown termination condition"); return JH_ERR_INVALID; }
   cudaStream_t s = m->st();
   const int obj_cap = 4000;
   double old_value, new_value = JH_NEG_INF;
   int it = 0;
+  JH_CUDA(cudaMemsetAsync(m->d_iter.p, 0, sizeof(int32_t) * 4, s));
+  // history of the iterations [base, it) -> host (ring of obj_cap values on the device)
+  auto flush = [&](int upto) -> int {
+    const int base = ((upto - 1) / obj_cap) * obj_cap, cnt = upto - base;
+    if (objective && base < cap)
+      JH_CUDA(cudaMemcpyAsync(objective + base, m->d_objective.p, sizeof(double) * std::min(cnt, (int)cap - base), cudaMemcpyDeviceToHost, s));
+    JH_CUDA(cudaStreamSynchronize(s));
+    return JH_OK;
+  };
   timing_begin(m);
-  for (;;) {
-    old_value = new_value;
-    if ((r = estep_device(m, d, o->mode))) return r;
-    if ((r = allreduce_stats(m))) return r;
-    // objective = getLogPriorTerm() + oneIteration()   (HigherOrderHMM.java:762)
-    jha::k_log_prior<<<1, 32, 0, s>>>(m->params(), m->d_stats.p + m->n_stats(), m->d_objective.p + (it % obj_cap));
-    JH_LAUNCHED();
-    bool go_on;
-    if (o->term_kind == JH_TERM_ITERATIONS) {
-      it++;
-      go_on = it < o->max_iter;  // IterationCondition.java:83-86, no host round trip
-      if (it % obj_cap == 0 || !go_on) {
-        int base = ((it - 1) / obj_cap) * obj_cap, cnt = it - base;
-        if (objective && base < cap)
-          JH_CUDA(cudaMemcpyAsync(objective + base, m->d_objective.p, sizeof(double) * std::min(cnt, cap - base), cudaMemcpyDeviceToHost, s));
-        JH_CUDA(cudaStreamSynchronize(s));
+  if (o->term_kind == JH_TERM_ITERATIONS) {
+    // IterationCondition.java:83-86: N E-steps, N-1 M-steps, no host round trip.  From the second iteration on the
+    // (E-part + M-step) pair is replayed as a CUDA graph: cfg1-sized problems are bound by the ~15 launches per iteration.
+    const int N = std::max(1, o->max_iter);
+    if (m->opt.graph && N >= 6) {
+      if ((r = em_e_part(m, d, o->mode, obj_cap))) return r;
+      it = 1;
+      if ((r = mstep_device(m))) return r;
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+        m->capturing = true;
+        const int r1 = em_e_part(m, d, o->mode, obj_cap), r2 = r1 ? r1 : mstep_device(m);
+        m->capturing = false;
+        ok = cudaStreamEndCapture(s, &graph) == cudaSuccess && !r1 && !r2 && graph;
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
       }
-    } else {
+      cudaGetLastError();
+      if (ok) {
+        for (; it < N - 1; it++) {
+          if (cudaGraphLaunch(exec, s) != cudaSuccess) { ok = false; break; }
+          if ((it + 1) % obj_cap == 0 && (r = flush(it + 1))) break;
+        }
+      }
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+      if (r) return r;
+      if (!ok && it > 1) { jh_set_error("CUDA graph replay of the EM iteration failed: %s", cudaGetErrorString(cudaGetLastError())); return JH_ERR_CUDA; }
+    }
+    for (;;) {  // eager iterations (all of them without the graph; the last E-part with it)
+      if ((r = em_e_part(m, d, o->mode, obj_cap))) return r;
+      it++;
+      const bool go_on = it < N;
+      if (it % obj_cap == 0 || !go_on)
+        if ((r = flush(it))) return r;
+      if (!go_on) break;
+      if ((r = mstep_device(m))) return r;
+    }
+  } else {
+    for (;;) {
+      old_value = new_value;
+      if ((r = em_e_part(m, d, o->mode, obj_cap))) return r;
       JH_CUDA(cudaMemcpyAsync(&new_value, m->d_objective.p + (it % obj_cap), sizeof(double), cudaMemcpyDeviceToHost, s));
       JH_CUDA(cudaStreamSynchronize(s));
       if (objective && it < cap) objective[it] = new_value;
       it++;
-      go_on = o->eps <= fabs(old_value - new_value) && (o->max_iter <= 0 || it < o->max_iter);  // SmallDifference...java:86-89
-    }
-    if (go_on) {
+      const bool go_on = o->eps <= fabs(old_value - new_value) && (o->max_iter <= 0 || it < o->max_iter);  // SmallDifference...java:86-89
+      if (!go_on) break;
       if ((r = mstep_device(m))) return r;
-    } else {
-      break;
     }
   }
   timing_end(m);
+  JH_CUDA(cudaMemcpyAsync(&m->last_objective, m->d_objective.p + ((it - 1) % obj_cap), sizeof(double), cudaMemcpyDeviceToHost, s));
   JH_CUDA(cudaStreamSynchronize(s));
   *n_iter = it;
+  if (m->failed) {  // this rank's E-step failed; it only kept its peers' collectives company
+    r = m->failed;
+    m->failed = 0;
+    jh_set_error("%s", m->failed_msg);
+    return r;
+  }
+  if (m->comm && m->n_ranks > 1 && m->last_objective != m->last_objective) {
+    jh_set_error("the E-step of a peer rank failed (the all-reduced objective is NaN)");
+    return JH_ERR_COMM;
+  }
+  return JH_OK;
+}
+
+// Objective of the LAST iteration of the most recent jh_baum_welch on this model (the history buffer of that call may be
+// shorter than the run).
+extern "C" int jh_last_objective(jh_model *m, double *out) {
+  if (!m || !out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
+  *out = m->last_objective;
   return JH_OK;
 }
 
@@ -2160,7 +2653,7 @@ extern "C" int jh_comm_init(jh_model *m, const uint8_t id[JH_COMM_ID_BYTES], int
   if (!m || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) { jh_set_error("invalid communicator arguments"); return JH_ERR_INVALID; }
   int r = nccl_load();
   if (r) return r;
-  JH_CUDA(cudaSetDevice(g_device));
+  JH_CUDA(cudaSetDevice(m->device));
   Id128 u;
   memcpy(&u, id, JH_COMM_ID_BYTES);
   void *comm = nullptr;
@@ -2179,10 +2672,11 @@ extern "C" int jh_comm_destroy(jh_model *m) {
 
 // ---- measurement ---------------------------------------------------------------------------------
 extern "C" int jh_measure_fp64_peak(double *tflops) {
-  int r = ensure_device();
+  const int device = g_default_device;
+  int r = ensure_device(device);
   if (r) return r;
   cudaDeviceProp prop;
-  JH_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  JH_CUDA(cudaGetDeviceProperties(&prop, device));
   double *d_out;
   JH_CUDA(cudaMalloc(&d_out, 8));
   cudaEvent_t e0, e1;
@@ -2210,10 +2704,11 @@ extern "C" int jh_measure_fp64_peak(double *tflops) {
 // Probe (profiles/): DFMA rate in TFLOP/s with `chains` independent FMA chains per thread, `threads` per block and
 // `blocks_per_sm` resident blocks — used to size the ILP the E-step kernel needs at 8 warps per SM.
 extern "C" int jh_probe_fp64(int chains, int threads, int blocks_per_sm, double *tflops) {
-  int r = ensure_device();
+  const int device = g_default_device;
+  int r = ensure_device(device);
   if (r) return r;
   cudaDeviceProp prop;
-  JH_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  JH_CUDA(cudaGetDeviceProperties(&prop, device));
   double *d_out;
   JH_CUDA(cudaMalloc(&d_out, 8));
   cudaEvent_t e0, e1;
@@ -2246,10 +2741,11 @@ extern "C" int jh_probe_fp64(int chains, int threads, int blocks_per_sm, double 
 
 // Probe (profiles/): FP64 tensor-core (DMMA m8n8k4) rate in TFLOP/s — a measurement of the hardware ceiling only.
 extern "C" int jh_probe_dmma(int chains, int threads, int blocks_per_sm, double *tflops) {
-  int r = ensure_device();
+  const int device = g_default_device;
+  int r = ensure_device(device);
   if (r) return r;
   cudaDeviceProp prop;
-  JH_CUDA(cudaGetDeviceProperties(&prop, g_device));
+  JH_CUDA(cudaGetDeviceProperties(&prop, device));
   double *d_out;
   JH_CUDA(cudaMalloc(&d_out, 8));
   cudaEvent_t e0, e1;

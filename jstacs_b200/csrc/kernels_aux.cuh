@@ -133,7 +133,59 @@ __global__ void k_log_prior(DevParams P, const double *add, double *out) {
   out[0] = add ? __dadd_rn(res, add[0]) : res;
 }
 
-// int32 state paths -> one byte per residue (255 = no state: the int32 path holds -1), 16 residues per thread
+// 2-bit packed residues (four per byte, lowest bits first, every sequence on a byte boundary) -> uint8 codes; also the
+// largest code (alphabet check).  One block per sequence (grid-stride), a thread widens 4 packed bytes = 16 residues.
+__global__ void k_unpack2(const uint8_t *packed, const int64_t *byte_ptr, const int64_t *offsets, int64_t n_seq, uint8_t *codes, int alphabet,
+                          unsigned int *max_out) {
+  unsigned int mx = 0;
+  for (int64_t n = blockIdx.x; n < n_seq; n += gridDim.x) {
+    const uint8_t *src = packed + byte_ptr[n];
+    uint8_t *dst = codes + offsets[n];
+    const int64_t L = offsets[n + 1] - offsets[n];
+    for (int64_t i = (int64_t)threadIdx.x * 16; i < L; i += (int64_t)blockDim.x * 16) {
+      unsigned w[4] = {0, 0, 0, 0};
+      const int64_t nb = min((int64_t)4, (L - i + 3) / 4);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (k < nb) {
+          const unsigned b = src[i / 4 + k];
+          w[k] = (b & 3u) | ((b >> 2 & 3u) << 8) | ((b >> 4 & 3u) << 16) | ((b >> 6 & 3u) << 24);
+        }
+      }
+      if (i + 16 <= L && (((unsigned long long)(dst + i)) & 15ull) == 0) {
+        *reinterpret_cast<uint4 *>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (alphabet < 4)
+          for (int k = 0; k < 16; k++) mx = max(mx, (w[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+      } else {
+        for (int64_t k = 0; k < 16 && i + k < L; k++) {
+          const unsigned c = (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+          dst[i + k] = (uint8_t)c;
+          mx = max(mx, c);
+        }
+      }
+    }
+  }
+  if (alphabet < 4) {  // codes are < 4 by construction
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(max_out, mx);
+  }
+}
+
+// E-step whose statistics came out non-finite (flag set by k_check_finite): zero them before the log-space kernels redo
+// the whole E-step — decided on the device, the EM loop has no host round trip.
+__global__ void k_zero_if(const int32_t *flag, double *p, int n) {
+  if (*flag == 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
+}
+
+// objective of EM iteration *iter -> objective[*iter % cap]; increments the device-side iteration counter (graph replay)
+__global__ void k_store_objective(const double *value, double *objective, int32_t *iter, int cap) {
+  objective[*iter % cap] = *value;
+  *iter += 1;
+}
+
+// int32 state paths -> one byte per residue (255 = no state: the int32 path holds -1), 16 residues per thread; only the
+// thread-per-sequence kernels of the general context graph still produce int32 paths that have to be narrowed
 __global__ void k_narrow_paths(const int32_t *paths, int64_t n, uint8_t *out) {
   int64_t i = (int64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 16;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
@@ -149,6 +201,20 @@ __global__ void k_narrow_paths(const int32_t *paths, int64_t n, uint8_t *out) {
     } else {
       for (int64_t k = i; k < n; k++) out[k] = (uint8_t)(paths[k] & 0xff);
     }
+  }
+}
+
+// Fixed-length paths (models without silent states) behind the variable-length interface of jh_viterbi_paths /
+// jh_viterbi_windows: path_len[i] = L_i, or -1 when no path has a probability > 0 (the reference throws "Impossible
+// path", HigherOrderHMM.java:659); the unused capacity behind a path is filled with -1.
+// lens: a = offsets (b == nullptr: L_i = a[i+1] - a[i]) or a = start, b = end (L_i = b[i] - a[i] + 1).
+__global__ void k_finish_paths(const double *scores, const int64_t *a, const int64_t *b, int64_t n, int32_t *paths, const int64_t *path_ptr,
+                               int64_t *path_len) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const int64_t L = b ? b[i] - a[i] + 1 : a[i + 1] - a[i];
+    if (threadIdx.x == 0 && path_len) path_len[i] = isinf(scores[i]) ? -1 : L;
+    if (paths && path_ptr)
+      for (int64_t k = path_ptr[i] + L + threadIdx.x; k < path_ptr[i + 1]; k += blockDim.x) paths[k] = -1;
   }
 }
 

@@ -13,6 +13,15 @@
 
 namespace jhx {
 
+// Launch condition decided on the device: the scaled kernels hand sequences they cannot finish to these kernels through a
+// device-side list, and an E-step whose statistics are not finite is redone here — without a host round trip, so the EM
+// loop stays stream ordered (and graph capturable).  A launch whose condition does not hold exits at once.
+struct Cond {
+  const int32_t *flag = nullptr;        // work only if *flag == want (nullptr: always)
+  int want = 0;
+  const int32_t *n_list_dev = nullptr;  // length of seq_list, read on the device (nullptr: the n_list argument)
+};
+
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
@@ -211,9 +220,12 @@ __global__ void __launch_bounds__(256) k_exact_loglik(DevModel M, DevData D, uns
 // HigherOrderHMM.viterbi (:617-708): backward max sweep + forward trace.  The trace decision of the reference
 // depends only on (layer, context), so it is taken during the sweep and stored as one byte per (layer, context).
 // stats != nullptr: Viterbi training (path == null in the reference): `weight` is added along the path.
+// W.seq != nullptr: windows of sequences (getViterbiPathFor(startPos, endPos, seq), HOH:590-598): layer 0 is the window start,
+// the emissions keep their absolute positions; outputs are indexed by the window then.  path_ptr: CSR of the output paths
+// (nullptr: the data set offsets).
 template <int G>
-__global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, unsigned long long *counter, uint8_t *choice_scratch,
-                                                       int64_t scratch_rows, int32_t *paths, double *scores, double *stats) {
+__global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, WorkList W, unsigned long long *counter, uint8_t *choice_scratch,
+                                                       int64_t scratch_rows, PathOut paths, const int64_t *path_ptr, double *scores, double *stats) {
   extern __shared__ double smem[];
   Group<G> g = make_group<G>(M, smem);
   ResReader rd;
@@ -223,15 +235,19 @@ __global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, un
     long long it = 0;
     if (g.lane == 0) it = (long long)atomicAdd(counter, 1ull);
     it = g.bcast(it);
-    if (it >= D.n_seq) break;
-    int sid = D.order[it];
-    int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
+    if (it >= (W.seq ? W.n : D.n_seq)) break;
+    const int sid = W.seq ? W.seq[it] : D.order[it];
+    const int64_t oid = W.seq ? it : sid;
+    const int64_t off = D.offsets[sid], Lseq = D.offsets[sid + 1] - off;
+    const int64_t s0 = W.start ? W.start[it] : 0, s1 = W.end ? W.end[it] : Lseq - 1;
+    const int64_t L = s1 - s0 + 1;
+    const int64_t pbase = path_ptr ? path_ptr[oid] : off + s0;
     rd.init(D.codes + off);
     double *nxt = g.v0, *cur = g.v1;
     init_last_layer<G>(M, g, L, nxt);
-    int h = hash_at(M, rd, L - 1);
+    int h = hash_at(M, rd, s1);
     for (int64_t l = L - 1; l >= 0; --l) {
-      fill_em<G>(M, g, l, h);
+      fill_em<G>(M, g, s0 + l, h);
       g.sync();
       int lc = l < M.m ? (int)l : M.m;
       int nc = M.lc_ctx_ptr[lc + 1] - M.lc_ctx_ptr[lc];
@@ -242,32 +258,32 @@ __global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, un
       }
       g.sync();
       double *t = cur; cur = nxt; nxt = t;
-      if (l > 0) h = hash_back(M, rd, h, l);
+      if (l > 0) h = hash_back(M, rd, h, s0 + l);
     }
     if (g.lane == 0) {
       double sc = nxt[0];
-      if (scores) scores[sid] = sc;
+      if (scores) scores[oid] = sc;
       double w = D.weights ? D.weights[sid] : 1.0;
       score_sum = dadd(score_sum, dmul(w, sc));
       int ctx = 0;
       bool ok = true;
       int hh = 0;
-      if (stats) hh = hash_at(M, rd, 0);
+      if (stats) hh = hash_at(M, rd, s0);
       for (int64_t l = 0; l < L; l++) {
         int lc = l < M.m ? (int)l : M.m;
         int ch = ok ? choice[(size_t)l * M.Cmax + ctx] : 255;
         if (ch == 255) {
           ok = false;
-          if (paths) paths[off + l] = -1;
+          if (paths) path_store(paths, pbase + l, -1);
           continue;
         }
         int p = M.elem_child_ptr[M.ctx_elem[M.lc_ctx_ptr[lc] + ctx]] + ch;
         int st = M.child_state[p];
-        if (paths) paths[off + l] = st;
+        if (paths) path_store(paths, pbase + l, st);
         if (stats) {
           atomicAdd(&stats[M.child_stat[p]], w);
-          if (M.state_order[st] >= 0 && l >= M.state_order[st]) atomicAdd(&stats[M.n_child + emis_index(M, st, hh)], w);
-          if (l + 1 < L) hh = hash_fwd(M, rd, hh, l);
+          if (M.state_order[st] >= 0 && s0 + l >= M.state_order[st]) atomicAdd(&stats[M.n_child + emis_index(M, st, hh)], w);
+          if (l + 1 < L) hh = hash_fwd(M, rd, hh, s0 + l);
         }
         ctx = M.child_next[(size_t)lc * M.n_child + p];
       }
@@ -293,9 +309,11 @@ __global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, un
 template <int G>
 __global__ void __launch_bounds__(256) k_exact_fb(DevModel M, DevData D, unsigned long long *counter, double *fwd_scratch,
                                                   int64_t scratch_rows, int mode, double *stats_global, int stats_in_smem,
-                                                  int32_t *paths, double *loglik, double *post_out, const int32_t *seq_list,
-                                                  int64_t n_list) {
+                                                  PathOut paths, double *loglik, double *post_out, const int32_t *seq_list,
+                                                  int64_t n_list, Cond cond) {
   extern __shared__ double smem[];
+  if (cond.flag && *cond.flag != cond.want) return;
+  if (cond.n_list_dev) n_list = *cond.n_list_dev;
   const int n_stats = M.n_child + M.n_cond * M.a;
   double *sstats = smem;
   double *group_smem = smem + (stats_in_smem ? n_stats : 0);
@@ -414,7 +432,7 @@ __global__ void __launch_bounds__(256) k_exact_fb(DevModel M, DevData D, unsigne
             int os = __shfl_xor_sync(g.mask, best_s, d);
             if (ob > best || (ob == best && os < best_s)) { best = ob; best_s = os; }
           }
-          if (g.lane == 0) paths[off + l] = best_s == 0x7fffffff ? 0 : best_s;  // all -inf: index 0 (AHMM:1130-1137)
+          if (g.lane == 0) path_store(paths, off + l, best_s == 0x7fffffff ? 0 : best_s);  // all -inf: index 0 (AHMM:1130-1137)
         }
       }
       for (int c = g.lane; c < nc; c += G) {

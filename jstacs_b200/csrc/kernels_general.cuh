@@ -28,12 +28,7 @@ struct GenModel {            // additions to DevModel for silent states
   const int *sin_p;             // [(m+1)*n_child]
 };
 
-struct WorkList {   // sequences, or windows of sequences
-  const int32_t *seq;     // [n] sequence ids (nullptr: D.order)
-  const int64_t *start;   // [n] first position (nullptr: 0)
-  const int64_t *end;     // [n] last position inclusive (nullptr: L-1)
-  int64_t n;
-};
+using ::WorkList;
 
 struct Rows {  // per-thread DP rows in global memory, thread index fastest
   double *p;
@@ -382,7 +377,7 @@ __global__ void __launch_bounds__(128) k_general_estep(DevModel M, GenModel X, D
 // paths != nullptr: AbstractHMM.decodeStatePosterior (AHMM:1125-1139) per position, lowest index on ties.
 // col: [S][thread] scratch column.
 __global__ void __launch_bounds__(128) k_general_posterior(DevModel M, GenModel X, DevData D, WorkList W, unsigned long long *counter, double *fwd,
-                                                           double *bwd, double *col, double *post_out, int32_t *paths, double *loglik) {
+                                                           double *bwd, double *col, double *post_out, PathOut paths, double *loglik) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
   Rows Fw{fwd + tid, nthreads, M.Cmax}, B{bwd + tid, nthreads, M.Cmax};
   double *const cl = col + tid;  // + s*nthreads
@@ -395,6 +390,50 @@ __global__ void __launch_bounds__(128) k_general_posterior(DevModel M, GenModel 
     const int64_t s0 = W.start ? W.start[it] : 0, s1 = W.end ? W.end[it] : Lseq - 1;  // window (layer 0 = position s0)
     const int64_t L = s1 - s0 + 1;
     rd.init(D.codes + off);
+    if (M.m == 0) {
+      // Transition order 0 (HOH:296-308): every position stands alone, post[state][l] = (trans + em) - getLogSum over the
+      // children of the single element (child order).  The log-likelihood is the sum of the per-position normalisers only if
+      // every state is final, which order 0 implies (HOH:498): it is computed by the backward sweep as for every model.
+      const int e0 = M.ctx_elem[M.lc_ctx_ptr[0]];
+      const int p0 = M.elem_child_ptr[e0], p1 = M.elem_child_ptr[e0 + 1];
+      int h = L > 0 ? jhx::hash_at(M, rd, s0) : 0;
+      if (loglik) {
+        bwd_last_layer<false>(M, X, L, B, L & 1, nullptr, 0);
+        int hb = L > 0 ? jhx::hash_at(M, rd, s1) : 0;
+        for (int64_t l = L - 1; l >= 0; --l) {
+          bwd_layer<false>(M, X, l, B, l & 1, (l + 1) & 1, s0 + l, hb, nullptr, 0);
+          if (l > 0) hb = jhx::hash_back(M, rd, hb, s0 + l);
+        }
+        loglik[sid] = B.at(0, 0);
+      }
+      for (int64_t l = 0; l < L; l++) {
+        for (int st = 0; st < M.S; st++) cl[(size_t)st * nthreads] = 0.0;  // states that are no child keep the array's initial 0
+        double o = JH_NEG_INF;
+        for (int p = p0; p < p1; p++) {
+          const int st = M.child_state[p];
+          const double v = dadd(M.tscore[p], emis_of(M, st, s0 + l, h));
+          cl[(size_t)st * nthreads] = v;
+          if (v > o) o = v;
+        }
+        double dn = JH_NEG_INF;
+        if (!isinf(o)) {
+          double sum = 0;
+          for (int p = p0; p < p1; p++) sum = dadd(sum, exp(dsub(cl[(size_t)M.child_state[p] * nthreads], o)));
+          dn = dadd(o, log(sum));
+        }
+        int best = 0;
+        double bv = dsub(cl[0], dn);
+        if (post_out) post_out[l] = bv;
+        for (int st = 1; st < M.S; st++) {
+          const double v = dsub(cl[(size_t)st * nthreads], dn);
+          if (post_out) post_out[(size_t)st * L + l] = v;
+          if (bv < v) { bv = v; best = st; }
+        }
+        if (paths) path_store(paths, off + s0 + l, best);
+        if (l + 1 < L) h = jhx::hash_fwd(M, rd, h, s0 + l);
+      }
+      continue;
+    }
     general_forward(M, X, rd, L, Fw, s0);
     bwd_last_layer<false>(M, X, L, B, L, nullptr, 0);
     int h = L > 0 ? jhx::hash_at(M, rd, s1) : 0;
@@ -420,7 +459,7 @@ __global__ void __launch_bounds__(128) k_general_posterior(DevModel M, GenModel 
         if (post_out) post_out[(size_t)st * L + (l - 1)] = v;
         if (bv < v) { bv = v; best = st; }
       }
-      if (paths) paths[off + s0 + l - 1] = best;
+      if (paths) path_store(paths, off + s0 + l - 1, best);
     }
   }
 }

@@ -48,7 +48,7 @@ __device__ __forceinline__ double pow2_any(long long k) {  // 2^k, 0 below the n
 // rows: [slot][ROWS][32][G], rexp: [slot][ROWS][32] (MODE 1); gEC: [EC_REPLICAS][H][G]; stats as in kernels_mma.cuh
 template <int G, int MODE>
 __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneChunkIn I, unsigned long long *counter, double *rows, int *rexp,
-                                                     int32_t *paths, double *stats, double *gEC, int32_t *fallback, int ec_smem) {
+                                                     PathOut paths, double *stats, double *gEC, int32_t *fallback, int ec_smem) {
   extern __shared__ double sm[];
   double *sE = sm;
   const int HG = F.H * G;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneC
               const double gm = r0[j] * b[j];
               if (gm > best) { best = gm; arg = j; }
             }
-            paths[off + t] = arg;
+            path_store(paths, off + t, arg);
           } else {
             const long long At = A0 + x0;
             const double sg = pow2_any(At + Bx - AL) * winv;

@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) k_mma_loglik(FastDev F, OctData D, unsign
 // CHUNKED: as in k_mma_estep (checkpoint rows every CK positions, rows of one chunk per resident warp).
 template <int NT, bool CHUNKED, bool EG>
 __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch, int *fexp_scratch,
-                                                       int64_t rows, int32_t *paths, double *loglik, int32_t *fallback, OctChunks X) {
+                                                       int64_t rows, PathOut paths, double *loglik, int32_t *fallback, OctChunks X) {
   using C = MmaCfg<NT>;
   constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
@@ -713,7 +713,6 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
     int h1 = hrow[(size_t)(Lmax - 2) * 8];
     double e[NV];
     emis_rl<NT, true>(F, sE, q, e, h, Lmax - 1);
-    int32_t *const prow = paths + off;
     for (int c = n_ck - 1; c >= 0; --c) {
     const int t0 = CHUNKED ? c * CK : 0, t1 = CHUNKED ? min(t0 + CK, Lmax) - 1 : Lmax - 1;
     if (CHUNKED) {  // forward rows t0 .. t1 of the chunk -> scratch (row t0 first)
@@ -760,7 +759,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
         Fa[2 * tp + 1] = a2.y;
       }
       const int arg = best_state(Fa, beta);
-      if (q == 0 && act && good) prow[t] = arg;
+      if (q == 0 && act && good) path_store(paths, off + t, arg);
       __syncwarp();
       issue(t - 3);
       if (t > 0) {

@@ -787,7 +787,7 @@ __global__ void __launch_bounds__(256) k_sparse_pass1_cta(SparseDev F, DevData D
 template <int SPL, int IND, bool EG>
 __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevData D, int CK, int ROWS, int64_t n_chunks, const int32_t *chunk_seq,
                                                               const int32_t *chunk_idx, const int64_t *chunk_ptr, const double *ck_alpha,
-                                                              const double *ck_beta, unsigned long long *counter, double *rows, int32_t *paths) {
+                                                              const double *ck_beta, unsigned long long *counter, double *rows, PathOut paths) {
   extern __shared__ double sm[];
   const int SP = F.SP;
   const double *sE = EG ? F.E : sm;
@@ -868,7 +868,6 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
       load_vec<SPL>(ck_beta + (size_t)cb * SP + SPL * lane, b);
     }
     int hb = hash_at(F, rd, t1);
-    int32_t *const prow = paths + off;
     emis<SPL>(F, sE, lane, e, hmod_of(F, hb), t1);
     load_vec<SPL>(rdst, a);
     auto decide = [&](int t) {  // largest alpha_t[j] * beta_t[j], lowest state index on ties
@@ -885,7 +884,7 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
         const int oa = __shfl_xor_sync(FULL, arg, d);
         if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
       }
-      if (lane == 0) prow[t] = arg;
+      if (lane == 0) path_store(paths, off + t, arg);
     };
     auto bstep = [&](int p, int x) {  // t = p + K + 1 > t0: decision of position t, then beta_t -> beta_{t-1}
       const int t = p + K1;

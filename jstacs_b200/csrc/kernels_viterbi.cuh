@@ -55,9 +55,11 @@ __global__ void k_viterbi_prepare(jhf::FastDev F, const int *tmap, const int *pi
   }
 }
 
-template <int S, bool EG>
+// U8: the path leaves the kernel as one byte per residue (255 = no state), eight states per 64-bit store where the
+// sequence's bytes are aligned; otherwise int32 per residue.
+template <int S, bool EG, bool U8>
 __global__ void __launch_bounds__(128) k_viterbi_lanes(VitTables V, OctData D, unsigned long long *counter, uint8_t *choice_scratch,
-                                                       int64_t rows, int32_t *paths, double *scores) {
+                                                       int64_t rows, void *paths, const int64_t *path_ptr, double *scores) {
   using C = VitCfg<S>;
   constexpr int CB = C::CB, NW = C::NW;
   extern __shared__ double sm[];
@@ -170,9 +172,29 @@ __global__ void __launch_bounds__(128) k_viterbi_lanes(VitTables V, OctData D, u
     __syncwarp();  // the choice bytes of this warp are read back by the same lanes only, but keep the stores ordered
     // forward trace (HOH:627-664): the loads do not depend on the path
     if (paths && Lr > 0) {
-      int32_t *p = paths + off;
+      const int64_t pbase = path_ptr ? path_ptr[sid] : off;
+      int32_t *p = U8 ? nullptr : reinterpret_cast<int32_t *>(paths) + pbase;
+      uint8_t *p8 = U8 ? reinterpret_cast<uint8_t *>(paths) + pbase : nullptr;
+      unsigned long long acc = 0;  // U8: states of the current aligned 8-byte group, flushed when its last byte is known
+      int nacc = 0;
+      auto emit = [&](int l, unsigned st) {  // st: state or 255
+        if (!U8) {
+          p[l] = st == 255u ? -1 : (int32_t)st;
+          return;
+        }
+        acc |= (unsigned long long)st << (8 * nacc);
+        nacc++;
+        const bool last = l == Lr - 1;
+        if ((((unsigned long long)(p8 + l) + 1) & 7ull) == 0 || last) {
+          if (nacc == 8) *reinterpret_cast<unsigned long long *>(p8 + l - 7) = acc;
+          else
+            for (int k = 0; k < nacc; k++) p8[l - nacc + 1 + k] = (uint8_t)(acc >> (8 * k));
+          acc = 0;
+          nacc = 0;
+        }
+      };
       bool ok = ctx != 255u;
-      p[0] = ok ? (int32_t)ctx : -1;
+      emit(0, ok ? ctx : 255u);
       constexpr int TU = NW <= 2 ? 8 : (NW <= 4 ? 4 : 2);  // positions whose choice words are fetched together
       for (int l0 = 1; l0 < Lr; l0 += TU) {
         unsigned cw[TU][NW];
@@ -200,7 +222,7 @@ __global__ void __launch_bounds__(128) k_viterbi_lanes(VitTables V, OctData D, u
             const unsigned nxt = (word >> ((ctx & 3u) * 8u)) & 0xffu;
             ok = ok && nxt != 255u;
             ctx = ok ? nxt : 0u;
-            p[l0 + k] = ok ? (int32_t)ctx : -1;
+            emit(l0 + k, ok ? ctx : 255u);
           }
         }
       }

@@ -570,6 +570,12 @@ def flatten(transition: BasicHigherOrderTransition, emission, emissionIdx, final
     return ir
 
 
+def _native_error():
+    from . import _native
+
+    return _native.NativeError
+
+
 # --------------------------------------------------------------------------------------------------
 class _Stream:
     """SafeOutputStream (de/jstacs/utils/SafeOutputStream.java:41-61); None silences."""
@@ -745,7 +751,7 @@ class HigherOrderHMM:
                 self.sostream.writeln(f"{it}\t-\t{v}\t{v - old}")
                 old = v
             self.last_objectives.append(list(obj))
-            new_value = obj[-1] if len(obj) else NEG_INF
+            new_value = eng.last_objective()  # the history buffer may be shorter than the run
             if new_value > best:
                 best = new_value
                 if tp.getNumberOfStarts() > 1:
@@ -799,7 +805,12 @@ class HigherOrderHMM:
             if (plen < 0).any():
                 raise ValueError("Impossible path")
             return [(p, float(sc)) for p, sc in zip(paths, scores)]
-        paths, scores = eng.viterbi(self._data(data), narrow=narrow and self.getNumberOfStates() <= 255)
+        try:
+            paths, scores = eng.viterbi(self._data(data), narrow=narrow and self.getNumberOfStates() <= 255)
+        except _native_error() as e:
+            if e.status == -6:  # JH_ERR_IMPOSSIBLE
+                raise ValueError("Impossible path") from e  # IllegalArgumentException, HigherOrderHMM.java:659
+            raise
         off = data.offsets
         return [(paths[off[i]:off[i + 1]], float(scores[i])) for i in range(data.getNumberOfElements())]
 

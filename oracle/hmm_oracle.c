@@ -636,7 +636,22 @@ double jo_viterbi_window(const jo_model *m, const uint8_t *x, int64_t start, int
 int jo_posterior_window(const jo_model *m, const uint8_t *x, int64_t start, int64_t end, double *out) {
   jo_work w; work_init(&w);
   const int64_t L = end - start + 1;
-  if (m->m == 0) { work_free(&w); return -2; }
+  if (m->m == 0) { /* HOH:296-308: every position stands alone; statePosterior comes zero-initialised (AHMM:745-757) */
+    int c[3];
+    double *le = malloc(sizeof(double) * m->S);
+    for (long l = 0; l < L; l++) {
+      for (int s = 0; s < m->S; s++) out[(size_t)s * L + l] = 0.0;
+      for (int s = 0; s < m->S; s++) {
+        trans_info(m, 0, 0, s, c);
+        le[s] = out[(size_t)c[0] * L + l] = trans_score(m, 0, 0, s) + emis_score(m, c[0], x, (long)start + l);
+      }
+      double d = log_sum(0, m->S, le);
+      for (int s = 0; s < m->S; s++) out[(size_t)s * L + l] -= d;
+    }
+    free(le);
+    work_free(&w);
+    return 0;
+  }
   fill_fwd(&w, m, x, (long)start, (long)end);
   fill_bwd_or_viterbi(&w, m, TYPE_LIKELIHOOD, x, (long)start, (long)end, 1, 0, NULL, NULL);
   double log_prob = BWD(&w, m, 0, 0);
