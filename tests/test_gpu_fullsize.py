@@ -48,6 +48,7 @@ def test_cfg2_viterbi_full_size(nat, oracle_lib, million):
     om = oracle_lib.OracleModel(hmm.ir())
     eng, nd = hmm._engine(), hmm._data(million)
     paths, scores = eng.viterbi(nd, narrow=True)  # one byte per residue: 1 GB instead of 4 GB over PCIe
+    t_u8 = eng.last_kernel_ms()
     assert paths.size == 1_000_000_000 and paths.max() <= 7
     ll = eng.loglik(nd)
     assert np.isfinite(scores).all() and (scores <= ll + 1e-9).all()  # the best path cannot beat the sum over all paths
@@ -63,6 +64,15 @@ def test_cfg2_viterbi_full_size(nat, oracle_lib, million):
     rp, rs, _ = om.viterbi(sub.codes, sub.offsets)
     for k, i in enumerate(idx):
         assert np.array_equal(paths[off[i]:off[i + 1]], rp[k]) and scores[i] == rs[k]
+    # The general entry point the Java shim binds for silent-state models, jh_viterbi_paths, runs the SAME kernels for a
+    # model without silent states (it used to take the thread-per-sequence kernel): device time within
+    # 10 % of the byte route, identical paths.
+    paths2, scores2, plen = eng.viterbi_paths(nd, np.diff(off))
+    t_paths = eng.last_kernel_ms()
+    assert (plen == 1000).all() and np.array_equal(scores2, scores)
+    for i in rng.integers(0, 1_000_000, 2000):
+        assert np.array_equal(paths2[i], paths[off[i]:off[i + 1]])
+    assert t_paths <= 1.10 * t_u8 + 1.0, (t_paths, t_u8)
     nd.close()
     million._native = None
 
