@@ -254,6 +254,10 @@ int jh_last_objective(jh_model *m, double *out);
 #define JH_COMM_ID_BYTES 128
 int jh_comm_unique_id(uint8_t id[JH_COMM_ID_BYTES]);
 int jh_comm_init(jh_model *m, const uint8_t id[JH_COMM_ID_BYTES], int32_t n_ranks, int32_t rank);
+/* Rank 0's parameters -> every rank (ncclBroadcast).  jh_baum_welch does this itself at its start when a communicator is
+ * attached, so that ranks whose host side initialised randomly (HigherOrderHMM.initializeRandomly, :880-885, draws from an
+ * unseeded generator per process) still run the replicated M-step on identical parameters. */
+int jh_comm_broadcast_params(jh_model *m);
 int jh_comm_destroy(jh_model *m);
 /* Device pointer and length (doubles) of the contiguous [trans|emis|score] statistics block,
  * for callers that run their own collective (e.g. torch.distributed) between jh_estep and jh_mstep. */

@@ -123,6 +123,7 @@ def lib():
         "jh_comm_unique_id": (C.c_int, [_P_U8]),
         "jh_comm_init": (C.c_int, [vp, _P_U8, C.c_int32, C.c_int32]),
         "jh_comm_destroy": (C.c_int, [vp]),
+        "jh_comm_broadcast_params": (C.c_int, [vp]),
         "jh_stats_device": (C.c_int, [vp, C.POINTER(vp), _P_I64]),
         "jh_measure_fp64_peak": (C.c_int, [_P_F64]),
         "jh_last_kernel_ms": (C.c_int, [vp, _P_F64]),

@@ -22,6 +22,7 @@
 #include "kernels_scan.cuh"
 #include "kernels_lanechunks.cuh"
 #include "kernels_viterbi.cuh"
+#include "kernels_vitlong.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Process-wide state is limited to DEFAULTS for handles created afterwards (device, options) and to the launch counter;
@@ -301,6 +302,7 @@ struct NcclApi {
   int (*GetUniqueId)(void *) = nullptr;
   int (*CommInitRank)(void **, int, Id128, int) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*CommDestroy)(void *) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
@@ -319,6 +321,7 @@ static int nccl_load() {
   g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void **, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclBroadcast");
   g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) {
@@ -361,6 +364,8 @@ struct jh_model {
   DevBuf<int> d_rexp;                    // E-step: exponents of the recomputed forward rows [slot][chunk]
   DevBuf<double> d_scanR;                // chunk transfer rows of the parallel checkpoint pass (kernels_scan.cuh)
   DevBuf<int> d_scanE;
+  DevBuf<double> d_vit_ck;               // chromosome-scale Viterbi: rows bwd[c*CK] (kernels_vitlong.cuh)
+  DevBuf<uint8_t> d_vit_map, d_vit_entry, d_vit_nxt;
   DevBuf<unsigned long long> d_counters; // one work counter per concurrent chunk kernel
   std::vector<cudaStream_t> seq_streams; // one stream per long sequence: its chunk pass starts when ITS checkpoint pass is done
   std::vector<cudaEvent_t> seq_events;
@@ -577,6 +582,9 @@ static int prep_scores(jh_model *m) {
     int np = std::max(P.IND * P.SP, P.H * P.SP);
     jhs::k_sparse_prepare<<<(np + 255) / 256, 256, 0, m->st()>>>(P.dev(), P.IND, P.d_in_p, P.d_out_p, P.d_pimap, P.d_etab, P.d_emod, m->d_tscore.p,
                                                                m->d_escore.p, P.d_in_T, P.d_out_T, P.d_pi, P.d_E);
+    JH_LAUNCHED();
+    jhw::k_vitlong_prepare<<<(np + 255) / 256, 256, 0, m->st()>>>(P.dev(), P.IND, P.d_out_p, P.d_pimap, P.d_etab, P.d_emod, m->d_tscore.p, m->d_escore.p,
+                                                                P.d_out_lT, P.d_lpi, P.d_lE);
     JH_LAUNCHED();
     JH_CUDA(cudaGetLastError());
   }
@@ -1899,8 +1907,80 @@ static int launch_viterbi_lanes(jh_model *m, jh_dataset *d, size_t b, PathOut pa
   return paths.u8 ? launch_viterbi_lanes_eg<S, false, true>(m, d, b, paths, d_path_ptr, d_scores) : launch_viterbi_lanes_eg<S, false, false>(m, d, b, paths, d_path_ptr, d_scores);
 }
 
+static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK);
+
+// Chromosome-scale Viterbi (kernels_vitlong.cuh): taken when the choice bytes of the data set's longest sequence would not
+// leave scratch for a full grid of the ordinary kernels (one byte per (position, context) of every resident sequence), or
+// when forced (tests).  Exact: rows stored at chunk boundaries by a sequential sweep, decisions recomputed per chunk.
 static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int64_t *d_path_ptr, double *d_scores, bool *handled) {
   *handled = false;
+  jhs::SparseTables &P = m->sparse;
+  if (!P.usable || P.e_global || m->S > 255) return JH_OK;
+  const int64_t CK = m->opt.vit_chunk;
+  if (d->max_len <= 2 * CK) return JH_OK;
+  if (!m->opt.vit_chunk_force) {
+    // ordinary kernels: rows x Cmax bytes per resident group (k_exact_viterbi), rows x 32 x max(S,4) per warp (k_viterbi_lanes)
+    const int64_t budget = m->opt.scratch_mb * 1024 * 1024;
+    const bool lanes = m->opt.fast && m->fast.usable && m->fast.sorted_children;
+    const int64_t per_slot = lanes ? d->max_len * 32 * std::max(m->fast.G, 4) : d->max_len * m->Cmax;
+    const int64_t want = lanes ? (int64_t)m->sm_count * 4 : (int64_t)m->sm_count * (256 / group_size(m));
+    if (per_slot * std::min<int64_t>(want, lanes ? (d->n_seq + 31) / 32 : d->n_seq) <= budget) return JH_OK;
+  }
+  *handled = true;
+  cudaStream_t s = m->st();
+  int r = ensure_chunks(m, d, CK);
+  if (r) return r;
+  const int SP = P.SP;
+  if ((r = m->d_vit_ck.reserve((size_t)(d->n_chunks + 1) * SP)) || (r = m->d_vit_map.reserve((size_t)(d->n_chunks + 1) * SP)) ||
+      (r = m->d_vit_entry.reserve((size_t)d->n_chunks + 1)) || (r = m->d_counters.reserve(4)))
+    return r;
+  JH_CUDA(cudaMemsetAsync(m->d_counters.p, 0, sizeof(unsigned long long) * 4, s));
+  jhw::VitLongDev V{P.d_out_lT, P.d_lpi, P.d_pi_rank, P.d_lfin, P.d_lE, 0.0 + -log((double)m->a)};
+  const int NT = 128, wpc = NT / 32;
+  const size_t smem_c = (size_t)wpc * 2 * SP * sizeof(double), smem_s = (size_t)2 * SP * sizeof(double);
+  const int64_t rows = std::min<int64_t>(CK, d->max_len);
+  const int64_t per_warp = rows * SP;
+  int per_sm = 0;
+  int64_t grid = 0;
+#define JH_VL(SPL_, IND_)                                                                                                               \
+  {                                                                                                                                     \
+    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhw::k_vit_chunks<SPL_, IND_, 0>, NT, smem_c));                       \
+    if (per_sm < 1) { jh_set_error("Viterbi chunk kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }                          \
+    if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);                                              \
+    grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);                                               \
+    grid = std::max<int64_t>(1, std::min<int64_t>(grid, m->opt.scratch_mb * 1024 * 1024 / per_warp / wpc));                               \
+    if ((r = m->d_vit_nxt.reserve((size_t)grid * wpc * per_warp + 16))) return r;                                                        \
+    if (d->n_long > 0) {                                                                                                                \
+      jhw::k_vit_sweep<SPL_, IND_><<<(int)std::min<int64_t>(d->n_long, (int64_t)m->sm_count * 8), 32, smem_s, s>>>(                       \
+          P.dev(), V, d->dev(), (int)CK, d->d_long.p, d->n_long, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p, d_scores);              \
+      JH_LAUNCHED();                                                                                                                    \
+      jhw::k_vit_chunks<SPL_, IND_, 0><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->long_seg[d->n_long], d->d_chunk_seq.p, \
+                                                                    d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p + 1,  \
+                                                                    m->d_vit_nxt.p, m->d_vit_map.p, nullptr, PathOut{nullptr, 0}, nullptr, nullptr); \
+      JH_LAUNCHED();                                                                                                                    \
+      jhw::k_vit_compose<<<(int)((d->n_long + 63) / 64), 64, 0, s>>>(SP, (int)CK, d->d_long.p, d->n_long, d->d_offsets.p, d->d_chunk_ptr.p, \
+                                                                    m->d_vit_map.p, m->d_vit_entry.p);                                    \
+      JH_LAUNCHED();                                                                                                                    \
+    }                                                                                                                                   \
+    jhw::k_vit_chunks<SPL_, IND_, 1><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, \
+                                                                  d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p + 2, m->d_vit_nxt.p,         \
+                                                                  nullptr, m->d_vit_entry.p, paths, d_path_ptr, d_scores);                      \
+    JH_LAUNCHED();                                                                                                                      \
+  }
+  switch (P.SPL * 100 + P.IND) {
+    case 104: JH_VL(1, 4) break;
+    case 108: JH_VL(1, 8) break;
+    case 116: JH_VL(1, 16) break;
+    case 132: JH_VL(1, 32) break;
+    case 204: JH_VL(2, 4) break;
+    case 208: JH_VL(2, 8) break;
+    case 216: JH_VL(2, 16) break;
+    case 404: JH_VL(4, 4) break;
+    case 408: JH_VL(4, 8) break;
+    default: JH_VL(8, 4) break;
+  }
+#undef JH_VL
+  JH_CUDA(cudaGetLastError());
   return JH_OK;
 }
 
@@ -2470,6 +2550,22 @@ static int allreduce_stats(jh_model *m) {
   return JH_OK;
 }
 
+// Every rank has to start an EM run from the same parameters (the M-step is replicated, not broadcast): rank 0's
+// parameters go to all ranks — e.g. after a random initialisation drawn independently per process.
+static int broadcast_params(jh_model *m) {
+  if (!m->comm || m->n_ranks <= 1) return JH_OK;
+  if (!g_nccl.Broadcast) { jh_set_error("libnccl lacks ncclBroadcast"); return JH_ERR_COMM; }
+  cudaStream_t s = m->st();
+  struct { double *p; size_t n; } bufs[4] = {{m->d_trans_param.p, (size_t)m->n_child}, {m->d_trans_lognorm.p, (size_t)m->n_elem},
+                                             {m->d_emis_param.p, (size_t)m->n_cond * m->a}, {m->d_emis_lognorm.p, (size_t)m->n_cond}};
+  for (auto &b : bufs) {
+    if (b.n == 0) continue;
+    int rc = g_nccl.Broadcast(b.p, b.p, b.n, /*ncclDouble*/ 8, 0, m->comm, s);
+    if (rc != 0) { jh_set_error("ncclBroadcast failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return JH_ERR_COMM; }
+  }
+  return prep_scores(m);
+}
+
 static int mstep_device(jh_model *m) {
   jha::k_mstep<<<1, 256, 0, m->st()>>>(m->params(), m->d_stats.p, m->d_stats.p + m->n_child);
   JH_LAUNCHED();
@@ -2551,6 +2647,7 @@ extern "C" int jh_baum_welch(jh_model *m, jh_dataset *d, const jh_train_opts *o,
   double old_value, new_value = JH_NEG_INF;
   int it = 0;
   JH_CUDA(cudaMemsetAsync(m->d_iter.p, 0, sizeof(int32_t) * 4, s));
+  if ((r = broadcast_params(m))) return r;
   // history of the iterations [base, it) -> host (ring of obj_cap values on the device)
   auto flush = [&](int upto) -> int {
     const int base = ((upto - 1) / obj_cap) * obj_cap, cnt = upto - base;
@@ -2660,6 +2757,14 @@ extern "C" int jh_comm_init(jh_model *m, const uint8_t id[JH_COMM_ID_BYTES], int
   int rc = g_nccl.CommInitRank(&comm, n_ranks, u, rank);
   if (rc != 0) { jh_set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return JH_ERR_COMM; }
   m->comm = comm; m->n_ranks = n_ranks; m->rank = rank;
+  return JH_OK;
+}
+
+extern "C" int jh_comm_broadcast_params(jh_model *m) {
+  JH_ENTER(m);
+  int r = broadcast_params(m);
+  if (r) return r;
+  JH_CUDA(cudaStreamSynchronize(m->st()));
   return JH_OK;
 }
 

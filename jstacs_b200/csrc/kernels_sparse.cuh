@@ -46,6 +46,10 @@ struct SparseTables {
   int *d_in_src = nullptr, *d_out_dst = nullptr, *d_in_p = nullptr, *d_out_p = nullptr, *d_pimap = nullptr, *d_korder = nullptr,
       *d_etab = nullptr, *d_emod = nullptr, *d_out_stat = nullptr, *d_pistat = nullptr;
   double *d_in_T = nullptr, *d_out_T = nullptr, *d_pi = nullptr, *d_fin = nullptr, *d_E = nullptr, *d_ec = nullptr;
+  // log-space tables of the chromosome-scale Viterbi (kernels_vitlong.cuh) and band structure (kernels_band.cuh)
+  double *d_out_lT = nullptr, *d_lpi = nullptr, *d_lfin = nullptr, *d_lE = nullptr;
+  int *d_pi_rank = nullptr;
+  int band_lo = 0, band_hi = -1;  // every edge i -> j has (j - i) mod S in [band_lo, band_hi] (cyclic, |.| <= SPL); hi < lo: not banded
   SparseDev dev() const {
     SparseDev F;
     F.S = S; F.SP = SP; F.a = a; F.Kmax = Kmax; F.H = H;
@@ -61,7 +65,7 @@ struct SparseTables {
 
 inline void destroy(SparseTables &F) {
   void *ptrs[] = {F.d_in_src, F.d_out_dst, F.d_in_p, F.d_out_p, F.d_pimap, F.d_korder, F.d_etab, F.d_emod, F.d_out_stat, F.d_pistat,
-                  F.d_in_T,   F.d_out_T,   F.d_pi,   F.d_fin,   F.d_E,     F.d_ec};
+                  F.d_in_T,   F.d_out_T,   F.d_pi,   F.d_fin,   F.d_E,     F.d_ec,     F.d_out_lT, F.d_lpi, F.d_lfin, F.d_lE, F.d_pi_rank};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   F = SparseTables();
@@ -122,9 +126,28 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
       }
     }
   int e0 = ctx_elem[lc_ctx_ptr[0]];
+  std::vector<int> pi_rank(SP, 0x7fffffff);
+  std::vector<double> lfin(SP, -INFINITY);
   for (int p = elem_child_ptr[e0]; p < elem_child_ptr[e0 + 1]; p++) {
     pimap[child_state[p]] = p;
     pistat[child_state[p]] = child_stat[p];
+    pi_rank[child_state[p]] = p - elem_child_ptr[e0];
+  }
+  for (int j = 0; j < S; j++) lfin[j] = state_final[j] ? 0.0 : -INFINITY;
+  // band structure: all edges within SPL states (cyclically) of their source, S a multiple of 32
+  {
+    int lo = 0x7fffffff, hi = -0x7fffffff;
+    bool banded = S == SP;
+    for (int i = 0; i < S && banded; i++)
+      for (auto &ed : out[i]) {
+        int dlt = ((ed.first - i) % S + S) % S;
+        if (dlt > S / 2) dlt -= S;
+        if (dlt > SPL || dlt < -SPL) { banded = false; break; }
+        lo = std::min(lo, dlt);
+        hi = std::max(hi, dlt);
+      }
+    F.band_lo = banded && lo <= hi ? lo : 0;
+    F.band_hi = banded && lo <= hi ? hi : -1;
   }
   for (int j = 0; j < S; j++) {
     korder[j] = state_order[j];
@@ -138,7 +161,8 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
   if ((r = up(&F.d_in_src, in_src, s)) || (r = up(&F.d_out_dst, out_dst, s)) || (r = up(&F.d_in_p, in_p, s)) || (r = up(&F.d_out_p, out_p, s)) ||
       (r = up(&F.d_pimap, pimap, s)) || (r = up(&F.d_korder, korder, s)) || (r = up(&F.d_etab, etab, s)) || (r = up(&F.d_emod, emod, s)) ||
       (r = up(&F.d_fin, fin, s)) || (r = up(&F.d_in_T, zT, s)) || (r = up(&F.d_out_T, zT, s)) || (r = up(&F.d_pi, zp, s)) || (r = up(&F.d_E, zE, s)) ||
-      (r = up(&F.d_out_stat, out_stat, s)) || (r = up(&F.d_pistat, pistat, s)) || (r = up(&F.d_ec, zEC, s)))
+      (r = up(&F.d_out_stat, out_stat, s)) || (r = up(&F.d_pistat, pistat, s)) || (r = up(&F.d_ec, zEC, s)) || (r = up(&F.d_out_lT, zT, s)) ||
+      (r = up(&F.d_lpi, zp, s)) || (r = up(&F.d_lfin, lfin, s)) || (r = up(&F.d_lE, zE, s)) || (r = up(&F.d_pi_rank, pi_rank, s)))
     return r;
   F.usable = true;
   return JH_OK;

@@ -638,7 +638,7 @@ int jo_posterior_window(const jo_model *m, const uint8_t *x, int64_t start, int6
   const int64_t L = end - start + 1;
   if (m->m == 0) { /* HOH:296-308: every position stands alone; statePosterior comes zero-initialised (AHMM:745-757) */
     int c[3];
-    double *le = malloc(sizeof(double) * m->S);
+    double *le = calloc((size_t)m->S, sizeof(double));
     for (long l = 0; l < L; l++) {
       for (int s = 0; s < m->S; s++) out[(size_t)s * L + l] = 0.0;
       for (int s = 0; s < m->S; s++) {

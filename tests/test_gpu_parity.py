@@ -768,3 +768,61 @@ def test_full_size_properties_cfg1(nat, fast):
     assert (vs <= ll + 1e-9).all() and paths.min() >= 0 and paths.max() <= 1
     hmm.train(data)
     assert (np.diff(hmm.last_objectives[0]) >= -1e-6).all()
+
+
+# ---- chromosome-scale Viterbi: checkpointed sweep + per-chunk recomputation of the decisions (kernels_vitlong.cuh) ----
+@pytest.mark.parametrize("name,chunk", [("banded_s128", 64), ("banded_s128", 1024), ("sparse", 16), ("erg_s8_k2", 32), ("banded_s40", 48),
+                                        ("erg_s2_k1", 16), ("erg_s32_k3", 128)])
+def test_long_sequence_viterbi_is_bit_exact(nat, oracle_lib, name, chunk):
+    """HigherOrderHMM.viterbi (:617-708) without the (L+1) x C matrix: rows at chunk boundaries from one sequential sweep,
+    decisions recomputed per chunk, chunk entry states by composing per-chunk maps.  Paths and scores equal the oracle's bit
+    for bit, for chunk lengths that do and do not divide the sequence lengths, sequences of one chunk, of length 1, unsorted
+    child lists (tie rule in child order) and an impossible sequence."""
+    hmm = banded_hmm(128, 4, 1) if name == "banded_s128" else MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(7)
+    lens = [5 * chunk + 3, 1, chunk, chunk + 1, 2 * chunk, 7 * chunk - 1, 3, 12 * chunk + chunk // 2]
+    data = dataset_of([random_dna(rng, L) for L in lens])
+    eng, nd = hmm._engine(), hmm._data(data)
+    eng.set_option("vit_chunk", chunk)
+    eng.set_option("vit_chunk_force", 1)
+    rp, rs, _ = om.viterbi(data.codes, data.offsets)
+    for narrow in (False, True):
+        paths, scores = eng.viterbi(nd, narrow=narrow)
+        assert np.array_equal(scores, rs)
+        for i in range(len(lens)):
+            assert np.array_equal(paths[data.offsets[i]:data.offsets[i + 1]], rp[i]), f"sequence {i} (L={lens[i]})"
+    # the variable-length entry point of the Java shim takes the same route
+    p2, s2, plen = eng.viterbi_paths(nd, np.asarray(lens) + 2)
+    assert np.array_equal(s2, rs) and np.array_equal(plen, lens)
+    for i in range(len(lens)):
+        assert np.array_equal(p2[i], rp[i])
+    # ... and agrees with the ordinary kernels
+    eng.set_option("vit_chunk_force", 0)
+    paths0, scores0 = eng.viterbi(nd)
+    assert np.array_equal(scores0, rs) and np.array_equal(paths0, paths)
+
+
+def test_long_sequence_viterbi_impossible_path(nat, oracle_lib):
+    hmm = sparse_hmm()
+    for em in hmm.emission:
+        q = em.params.copy()
+        q[:, 0] = -np.inf
+        em.setLogProbabilities(q - np.log(np.exp(q).sum(1, keepdims=True)))
+    hmm._push_params()
+    rng = np.random.default_rng(1)
+    ok = rng.integers(1, 4, 200).astype(np.uint8)
+    bad = ok.copy()
+    bad[137] = 0
+    data = dataset_of([ok, bad, ok[:5]])
+    eng, nd = hmm._engine(), hmm._data(data)
+    eng.set_option("vit_chunk", 16)
+    eng.set_option("vit_chunk_force", 1)
+    paths, scores = eng.viterbi(nd, allow_impossible=True)
+    om = oracle_lib.OracleModel(hmm.ir())
+    rp, rs, _ = om.viterbi(np.concatenate([ok, ok[:5]]), np.array([0, 200, 205]))
+    assert scores[1] == -np.inf and scores[0] == rs[0] and scores[2] == rs[1]
+    assert np.array_equal(paths[:200], rp[0]) and np.array_equal(paths[400:], rp[1]) and (paths[200:400] == -1).all()
+    with pytest.raises(nat.NativeError) as ei:
+        eng.viterbi(nd)
+    assert ei.value.status == -6
