@@ -9,8 +9,18 @@ on rank 0.  A "step" is ONE EM iteration (E-step over the rank's shard, count al
   value    : whole-job residues*states/s, inputs resident in HBM, CUDA-event time, max over ranks
   e2e      : same metric through the public host API (HigherOrderHMM.train on HOST buffers): every step copies the
              packed residues host->device from pinned memory and reads the objective + parameters back
-  roofline : dominant kernel = the fused E-step kernel; bound = fp64 FMA pipe (no tensor cores on this path)
+             (reported twice: from pinned host memory, and from ordinary pageable memory, which the library stages
+             through its own pinned buffers)
+  roofline : dominant kernel = the fused E-step kernel k_mma_estep; bound = the FP64 rate.  The kernel issues its
+             products as FP64 tensor-core instructions (mma.sync.m8n8k4.f64 = SASS DMMA) — on B200 the DMMA and DFMA
+             peaks coincide, so the roofline denominator is the same FP64 peak either way (DESIGN.md 4.2a);
+             `dmma_pipe_frac` relates the DMMA work alone to the measured DMMA peak.  `traffic` comes from the ncu
+             capture listed in profiles/traffic_table.json for this (states, order, kernel).
   cpu_baseline : the C oracle (port of the Java path) on the host cores, bounded sample
+  multi_gpu_check (N > 1, outside the timed region): a small sharded EM run through the library's NCCL path against a
+             1-rank run over the union of the shards on rank 0.
+  --scaling strong: the TOTAL number of sequences is fixed (--total-seqs, default 8M = BASELINE configs[2] literally)
+             and divided over the ranks.
 """
 from __future__ import annotations
 
@@ -47,7 +57,13 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seqs", type=int, default=0, help="sequences of the CPU sample (0: 400 per core)")
     ap.add_argument("--set", action="append", default=[], metavar="NAME=VALUE", help="library tuning option (jh_set_option), repeatable")
-    return ap.parse_args()
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-seqs", type=int, default=8_000_000, help="--scaling strong: sequences of the whole job")
+    ap.add_argument("--no-multi-check", action="store_true")
+    args = ap.parse_args()
+    if args.scaling == "strong":
+        args.nseq = args.total_seqs // max(1, args.gpus)
+    return args
 
 
 class ClockSampler:
@@ -129,7 +145,7 @@ def run_reference(args):
     sample = f"{n} x {args.len} bp sequences per step (of {args.nseq * args.gpus}), one E-step + M-step, C port of HigherOrderHMM.baumWelch"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -143,6 +159,7 @@ def workload_config(args, world):
                         f"{args.nseq * world} x {args.len} bp java.util.Random sequences ({args.nseq} per GPU)",
             "states": args.states, "emission_order": args.order, "n_seq_per_gpu": args.nseq, "seq_len": args.len,
             "parallelism": f"dp{world} (sequences sharded, one NCCL all-reduce of the count block per iteration)",
+            "scaling": args.scaling,
             "l2": "inputs larger than L2 (residue buffer >= 1 GB per GPU; forward scratch > 1 GB)", "ess": 4.0}
 
 
@@ -253,32 +270,43 @@ def main():
         hmm.trainingParameter = BaumWelchParameterSet(1, IterationCondition(2), 1)
         from jstacs_b200.data import DataSet
 
-        def e2e_step():
-            ds = _packed(DataSet, codes_host, data.offsets)
-            hmm.train(ds)  # packs -> H2D, E-step, M-step, E-step(objective), reads objective + parameters back
-            ds._native.close()
+        def e2e_run(codes):
+            def e2e_step():
+                ds = _packed(DataSet, codes, data.offsets)
+                hmm.train(ds)  # packs -> H2D, E-step, M-step, E-step(objective), reads objective + parameters back
+                ds._native.close()
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 2))
-        for _ in range(n_e2e):
             e2e_step()
-        barrier()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        # IterationCondition(2) = 2 E-steps + 1 M-step per train() call: two passes over the data per step
-        e2e_val = 2 * total_units / float(dt.item())
+            barrier()
+            t0 = time.perf_counter()
+            n_e2e = max(1, min(args.steps, 2))
+            for _ in range(n_e2e):
+                e2e_step()
+            barrier()
+            dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            # IterationCondition(2) = 2 E-steps + 1 M-step per train() call: two passes over the data per step
+            return 2 * total_units / float(dt.item())
+
         n_par = sum(eng.sizes)
-        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(residues + 8 * (data.offsets.size + n_par)),
-               "d2h_bytes_per_step": int(8 * (n_par + 2)), "note": "HigherOrderHMM.train(DataSet) with IterationCondition(2): pack->H2D, 2 E-steps + 1 M-step, objective + parameters read back; wall clock incl. host work"}
+        e2e_pinned = e2e_run(codes_host)
+        e2e_pageable = e2e_run(data.codes)  # an ordinary numpy array: the library stages it through its pinned buffers
+        e2e = {"value": e2e_pinned, "unit": UNIT, "h2d_bytes_per_step": int(residues + 8 * (data.offsets.size + n_par)),
+               "d2h_bytes_per_step": int(8 * (n_par + 2)), "pinned": True,
+               "pageable": {"value": e2e_pageable, "pinned": False, "note": "same call from pageable host memory (library-side pinned staging)"},
+               "note": "HigherOrderHMM.train(DataSet) with IterationCondition(2): pack->H2D, 2 E-steps + 1 M-step, objective + parameters read back; wall clock incl. host work"}
+
+    # ---- multi-GPU correctness (outside every timed region): the library's NCCL path against a 1-rank run ----
+    multi_check = None
+    if world > 1 and not args.no_multi_check:
+        multi_check = multi_gpu_check(args, eng, hmm, world, rank, torch, dist, _native)
 
     if rank == 0:
+        import ctypes as C
+
         peak = None
         try:
-            import ctypes as C
-
             v = C.c_double()
             _native.check(L.jh_measure_fp64_peak(C.byref(v)))
             peak = v.value
@@ -295,11 +323,28 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # dram bytes per launch from the ncu --set full capture of this kernel (profiles/r1_estep_octets.md: 518 B per residue,
-        # forward rows written once and read once; lane-per-state kernel: 488 B per residue), scaled to this launch
-        traffic_per_res = 518.0 if (args.fast and args.variant == 0 and S >= 5) else (488.0 if args.fast else None)
+        # dram bytes per residue of this kernel on this shape: from the ncu --set full capture named in profiles/traffic_table.json
+        kernel = ("k_mma_estep" if args.variant == 0 and S >= 5 else "k_fast_estep") if args.fast else "k_exact_fb"
+        traffic_per_res, traffic_src = None, None
+        try:
+            for row in json.load(open(os.path.join(ROOT, "profiles", "traffic_table.json")))["rows"]:
+                if row["kernel"] == kernel and row["states"] == S and row["emission_order"] == args.order:
+                    traffic_per_res, traffic_src = float(row["dram_bytes_per_residue"]), row["source"]
+        except Exception:
+            pass
+        dmma_peak = None
+        try:
+            v = C.c_double()
+            _native.check(L.jh_probe_dmma(8, 256, 4, C.byref(v)))
+            dmma_peak = v.value
+        except Exception:
+            dmma_peak = None
+        # the three products of a position are 12 DMMA.8x8x4 per residue and 8 sequences = 12 * 512 flop per residue for S = 32
+        dmma_flop_per_res = 6.0 * S * S if kernel == "k_mma_estep" else 0.0
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if peak else None,
-                    "traffic": traffic_per_res * residues if traffic_per_res else None, "kernel": ("k_mma_estep" if args.variant == 0 and S >= 5 else "k_fast_estep") if args.fast else "k_exact_fb", "kernel_ms": k_ms,
+                    "traffic": traffic_per_res * residues if traffic_per_res else None, "traffic_source": traffic_src,
+                    "dmma_pipe_frac": (dmma_flop_per_res * residues / (k_ms * 1e-3) / 1e12 / dmma_peak) if (dmma_peak and dmma_flop_per_res) else None,
+                    "dmma_peak": dmma_peak, "kernel": kernel, "kernel_ms": k_ms,
                     "flop_per_residue": flop_per_res, "peak_source": "DFMA-chain microbenchmark measured live on this GPU (MEASURED_PEAKS.json has no fp64 entry)",
                     "nominal_reference_flop_per_residue": nominal_per_res,
                     "nominal_frac": nominal_per_res * residues / (k_ms * 1e-3) / 1e12 / peak if peak else None,
@@ -308,8 +353,8 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "multi_gpu_check": multi_check,
             "gpu_launches": int(launches2 - launches1), "roofline": roofline, "data_gen_s": t_gen,
         }
         if not args.no_cpu_baseline and world >= 1:
@@ -323,6 +368,40 @@ def main():
         _native.check(L.jh_comm_destroy(eng.h))
         dist.destroy_process_group()
     del launches0
+
+
+def multi_gpu_check(args, eng, hmm, world, rank, torch, dist, _native):
+    """A small sharded Baum-Welch run (4 iterations) through jh_baum_welch with the communicator attached, against the same
+    run over the UNION of the shards on rank 0 without a communicator: objectives <= 1e-12 relative, parameters <= 1e-10."""
+    from jstacs_b200.workloads import ergodic_hmm, make_data, set_closed_form_parameters
+
+    n_small, n_iter = 2048, 4
+    set_closed_form_parameters(hmm)  # back to the closed-form starting point (the timed steps and train() moved the parameters)
+    shard = make_data(n_small, 200, start_index=rank * n_small)
+    nd = _native.NativeData(shard.codes, shard.offsets, None, 4)
+    obj = eng.baum_welch(nd, _native.MODE_BAUM_WELCH, _native.TERM_ITERATIONS, n_iter, 0.0)
+    par = np.concatenate(eng.get_params())
+    nd.close()
+    # every rank must hold the same objective history and parameters (replicated M-step)
+    mine = torch.from_numpy(np.concatenate([obj, par])).cuda()
+    allr = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allr, mine)
+    agree = all(bool(torch.equal(allr[0], t)) for t in allr)
+    if rank != 0:
+        return None
+    ref = ergodic_hmm(args.states, args.order, n_iter=1, ess=4.0)
+    union = make_data(n_small * world, 200)
+    e2 = ref._engine()
+    nd2 = _native.NativeData(union.codes, union.offsets, None, 4)
+    obj1 = e2.baum_welch(nd2, _native.MODE_BAUM_WELCH, _native.TERM_ITERATIONS, n_iter, 0.0)
+    par1 = np.concatenate(e2.get_params())
+    nd2.close()
+    fin = np.isfinite(par1)
+    o_rel = float(np.max(np.abs(obj - obj1) / np.abs(obj1)))
+    p_abs = float(np.max(np.abs(par[fin] - par1[fin])))
+    return {"ok": bool(agree and o_rel <= 1e-12 and p_abs <= 1e-10 and np.array_equal(np.isfinite(par), fin)), "ranks_agree": agree,
+            "objective_rel": o_rel, "param_abs": p_abs, "iterations": n_iter, "sequences": n_small * world,
+            "what": "jh_baum_welch over NCCL on per-rank shards vs one rank over their union"}
 
 
 def _packed(DataSet, codes, offsets):

@@ -162,6 +162,16 @@ int jh_dataset_create(const uint8_t *codes, const int64_t *offsets, int64_t n_se
  * the device widens them to the uint8 codes the kernels read. */
 int jh_dataset_create_packed2(const uint8_t *packed, const int64_t *byte_ptr, const int64_t *offsets, int64_t n_seq,
                               const double *weights, int32_t alphabet, jh_dataset **out);
+/* Streamed construction for genome-scale inputs: the residues arrive shard by shard (e.g. memory-mapped files written by
+ * a streaming FASTA reader) and go straight to the device through the pinned staging buffers — the host never holds the
+ * whole data set.  create announces the totals; every append delivers the next `n_seq` whole sequences (lengths[n_seq])
+ * as uint8 codes (packed2 = 0, sum(lengths) bytes) or 2-bit packed, every sequence on a byte boundary (packed2 = 1,
+ * sum((lengths+3)/4) bytes); finish (which consumes the builder) yields the same handle jh_dataset_create would. */
+typedef struct jh_dataset_builder jh_dataset_builder;
+int jh_dataset_builder_create(int64_t n_seq, int64_t n_residues, int32_t alphabet, jh_dataset_builder **out);
+int jh_dataset_builder_append(jh_dataset_builder *b, const uint8_t *codes, const int64_t *lengths, int64_t n_seq, int32_t packed2);
+int jh_dataset_builder_finish(jh_dataset_builder *b, const double *weights, jh_dataset **out);
+void jh_dataset_builder_destroy(jh_dataset_builder *b);
 void jh_dataset_destroy(jh_dataset *d);
 /* Sequence weights of train(DataSet,double[]) (TrainableStatisticalModel.java:61-88); NULL = all 1. */
 int jh_dataset_set_weights(jh_dataset *d, const double *weights);

@@ -135,6 +135,10 @@ def lib():
         "jh_model_set_stream": (C.c_int, [vp, vp]),
         "jh_dataset_create_packed2": (C.c_int, [_P_U8, _P_I64, _P_I64, C.c_int64, _P_F64, C.c_int32, C.POINTER(vp)]),
         "jh_last_objective": (C.c_int, [vp, _P_F64]),
+        "jh_dataset_builder_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.POINTER(vp)]),
+        "jh_dataset_builder_append": (C.c_int, [vp, _P_U8, _P_I64, C.c_int64, C.c_int32]),
+        "jh_dataset_builder_finish": (C.c_int, [vp, _P_F64, C.POINTER(vp)]),
+        "jh_dataset_builder_destroy": (None, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -178,6 +182,29 @@ class NativeData:
             bp = np.ascontiguousarray(byte_ptr, dtype=np.int64)
             check(lib().jh_dataset_create_packed2(cp, bp.ctypes.data_as(_P_I64), offsets.ctypes.data_as(_P_I64), self.n_seq, _f64(w),
                                                   int(alphabet), C.byref(self.h)))
+
+    @classmethod
+    def from_shards(cls, shards, n_seq: int, n_res: int, weights, alphabet: int):
+        """Streamed construction (jh_dataset_builder_*): `shards` yields (codes, lengths, packed2) per shard — typically
+        numpy memmaps of shard files; nothing but one shard is ever resident on the host."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        self.n_seq, self.n_res = int(n_seq), int(n_res)
+        b = C.c_void_p()
+        check(lib().jh_dataset_builder_create(self.n_seq, self.n_res, int(alphabet), C.byref(b)))
+        try:
+            for codes, lengths, packed2 in shards:
+                lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+                codes = np.ascontiguousarray(codes, dtype=np.uint8)  # a memmap stays a memmap: no copy
+                cp = codes.ctypes.data_as(_P_U8) if codes.size else C.cast(None, _P_U8)
+                check(lib().jh_dataset_builder_append(b, cp, lengths.ctypes.data_as(_P_I64), lengths.size, 1 if packed2 else 0))
+            w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
+            check(lib().jh_dataset_builder_finish(b, _f64(w), C.byref(self.h)))
+            b = None
+        finally:
+            if b is not None:
+                lib().jh_dataset_builder_destroy(b)
+        return self
 
     def set_weights(self, weights):
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)

@@ -23,6 +23,7 @@
 #include "kernels_lanechunks.cuh"
 #include "kernels_viterbi.cuh"
 #include "kernels_vitlong.cuh"
+#include "kernels_band.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Process-wide state is limited to DEFAULTS for handles created afterwards (device, options) and to the launch counter;
@@ -53,6 +54,7 @@ struct Options {
   int64_t vit_chunk = 4096;    // positions per checkpoint of the chromosome-scale Viterbi
   int64_t vit_chunk_force = 0; // tests: checkpointed Viterbi for every sequence longer than 2 * vit_chunk
   int64_t stage = 1;           // host transfers of pageable caller memory through the library's pinned double buffers
+  int64_t band = 1;            // banded models: warp-resident whole-sequence passes (kernels_band.cuh)
 };
 static Options g_defaults;
 static std::atomic<uint64_t> g_opt_gen{1};
@@ -75,6 +77,7 @@ static bool set_option_field(Options &o, const std::string &n, int64_t value) {
   else if (n == "vit_chunk") o.vit_chunk = std::min<int64_t>(1 << 20, std::max<int64_t>(16, value));
   else if (n == "vit_chunk_force") o.vit_chunk_force = value;
   else if (n == "stage") o.stage = value;
+  else if (n == "band") o.band = value;
   else return false;
   return true;
 }
@@ -1001,6 +1004,133 @@ extern "C" int jh_dataset_create_packed2(const uint8_t *packed, const int64_t *b
   return dataset_create_impl(packed, byte_ptr, 1, offsets, n_seq, weights, alphabet, out);
 }
 
+// ---- streamed construction: the residues arrive shard by shard (memory-mapped files), never as one host array ----------
+struct jh_dataset_builder {
+  jh_dataset *d = nullptr;
+  int64_t n_seq_total = 0, n_res_total = 0, n_seq = 0, n_res = 0;
+  std::vector<int64_t> offsets;
+  DevBuf<unsigned int> d_mx;
+  Options opt;
+};
+
+extern "C" int jh_dataset_builder_create(int64_t n_seq, int64_t n_residues, int32_t alphabet, jh_dataset_builder **out) {
+  if (!out || n_seq < 0 || n_residues < 0) { jh_set_error("invalid builder arguments"); return JH_ERR_INVALID; }
+  if (n_seq > 0x7fffffff) { jh_set_error("more than 2^31-1 sequences"); return JH_ERR_UNSUPPORTED; }
+  const int device = g_default_device;
+  int r = ensure_device(device);
+  if (r) return r;
+  DatasetGuard G{new jh_dataset()};
+  jh_dataset *d = G.d;
+  d->device = device;
+  d->alphabet = alphabet;
+  JH_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  JH_CUDA(cudaEventCreateWithFlags(&d->ev_last, cudaEventDisableTiming));
+  Scope scope(device, d->stream);
+  std::unique_ptr<jh_dataset_builder> b(new jh_dataset_builder());
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    b->opt = g_defaults;
+  }
+  b->n_seq_total = n_seq; b->n_res_total = n_residues;
+  b->offsets.reserve(n_seq + 1);
+  b->offsets.push_back(0);
+  if ((r = d->d_codes.alloc((size_t)n_residues + 64)) || (r = b->d_mx.alloc(1))) return r;
+  JH_CUDA(cudaMemsetAsync(d->d_codes.p + n_residues, 0, 64, d->stream));
+  JH_CUDA(cudaMemsetAsync(b->d_mx.p, 0, sizeof(unsigned int), d->stream));
+  b->d = G.release();
+  *out = b.release();
+  return JH_OK;
+}
+
+extern "C" void jh_dataset_builder_destroy(jh_dataset_builder *b) {
+  if (!b) return;
+  if (b->d) {
+    Scope scope(b->d->device, b->d->stream);
+    b->d_mx.release();
+  }
+  dataset_free(b->d);
+  b->d = nullptr;
+  delete b;
+}
+
+extern "C" int jh_dataset_builder_append(jh_dataset_builder *b, const uint8_t *codes, const int64_t *lengths, int64_t n_seq, int32_t packed2) {
+  if (!b || !b->d || n_seq < 0 || (n_seq > 0 && (!codes || !lengths))) { jh_set_error("invalid append arguments"); return JH_ERR_INVALID; }
+  jh_dataset *d = b->d;
+  if (packed2 && d->alphabet > 4) { jh_set_error("2-bit packing needs an alphabet of at most 4 symbols"); return JH_ERR_INVALID; }
+  Scope scope(d->device, d->stream);
+  cudaStream_t s = d->stream;
+  int64_t res = 0, bytes = 0;
+  std::vector<int64_t> bp(n_seq + 1, 0), off(n_seq + 1, 0);
+  for (int64_t i = 0; i < n_seq; i++) {
+    if (lengths[i] <= 0) { jh_set_error("sequence %lld is empty", (long long)(b->n_seq + i)); return JH_ERR_INVALID; }
+    off[i] = b->n_res + res;
+    bp[i] = bytes;
+    res += lengths[i];
+    bytes += packed2 ? (lengths[i] + 3) / 4 : lengths[i];
+  }
+  off[n_seq] = b->n_res + res;
+  bp[n_seq] = bytes;
+  if (b->n_seq + n_seq > b->n_seq_total || b->n_res + res > b->n_res_total) { jh_set_error("more sequences or residues appended than announced"); return JH_ERR_INVALID; }
+  int r;
+  if (!packed2) {
+    if ((r = stage_h2d(d->d_codes.p + b->n_res, codes, (size_t)res, s, d->device, b->opt.stage != 0))) return r;
+    if (res) {
+      jha::k_max_code<<<592, 256, 0, s>>>(d->d_codes.p + b->n_res, res, b->d_mx.p);
+      JH_LAUNCHED();
+    }
+  } else if (n_seq) {
+    DevBuf<uint8_t> d_pk;
+    DevBuf<int64_t> d_pp, d_off;
+    if ((r = d_pk.alloc((size_t)bytes + 16)) || (r = d_pp.alloc(n_seq + 1)) || (r = d_off.alloc(n_seq + 1))) return r;
+    JH_CUDA(cudaMemcpyAsync(d_pp.p, bp.data(), sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, s));
+    JH_CUDA(cudaMemcpyAsync(d_off.p, off.data(), sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, s));
+    if ((r = stage_h2d(d_pk.p, codes, (size_t)bytes, s, d->device, b->opt.stage != 0))) return r;
+    jha::k_unpack2<<<(int)std::min<int64_t>(n_seq, 148 * 32), 256, 0, s>>>(d_pk.p, d_pp.p, d_off.p, n_seq, d->d_codes.p, d->alphabet, b->d_mx.p);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+    JH_CUDA(cudaStreamSynchronize(s));  // the packed staging buffers are locals
+  }
+  JH_CUDA(cudaStreamSynchronize(s));
+  for (int64_t i = 0; i < n_seq; i++) b->offsets.push_back(off[i + 1]);
+  b->n_seq += n_seq;
+  b->n_res += res;
+  return JH_OK;
+}
+
+extern "C" int jh_dataset_builder_finish(jh_dataset_builder *b, const double *weights, jh_dataset **out) {
+  if (!b || !b->d || !out) { jh_set_error("invalid finish arguments"); return JH_ERR_INVALID; }
+  if (b->n_seq != b->n_seq_total || b->n_res != b->n_res_total) {
+    jh_set_error("the builder holds %lld of %lld sequences and %lld of %lld residues", (long long)b->n_seq, (long long)b->n_seq_total, (long long)b->n_res,
+                 (long long)b->n_res_total);
+    return JH_ERR_INVALID;
+  }
+  jh_dataset *d = b->d;
+  Scope scope(d->device, d->stream);
+  cudaStream_t s = d->stream;
+  const int64_t n_seq = b->n_seq;
+  int r = dataset_layout(d, b->offsets.data(), n_seq);
+  if (r) return r;
+  if ((r = d->d_offsets.alloc(n_seq + 1)) || (r = d->d_order.alloc(n_seq)) || (r = d->d_weights.alloc(n_seq))) return r;
+  JH_CUDA(cudaMemcpyAsync(d->d_offsets.p, b->offsets.data(), sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, s));
+  if (n_seq) JH_CUDA(cudaMemcpyAsync(d->d_order.p, d->order.data(), sizeof(int32_t) * n_seq, cudaMemcpyHostToDevice, s));
+  if (weights && n_seq) {
+    JH_CUDA(cudaMemcpyAsync(d->d_weights.p, weights, sizeof(double) * n_seq, cudaMemcpyHostToDevice, s));
+    d->has_weights = true;
+  }
+  unsigned int h_mx = 0;
+  JH_CUDA(cudaMemcpyAsync(&h_mx, b->d_mx.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  JH_CUDA(cudaStreamSynchronize(s));
+  if ((int)h_mx >= d->alphabet) {
+    jh_set_error("The AlphabetContainer of the data set and the model do not match (code %u >= alphabet size %d).", h_mx, d->alphabet);
+    return JH_ERR_ALPHABET;
+  }
+  b->d_mx.release();
+  *out = d;
+  b->d = nullptr;
+  delete b;
+  return JH_OK;
+}
+
 extern "C" int jh_dataset_set_weights(jh_dataset *d, const double *weights) {
   if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
   if (!weights) { d->has_weights = false; return JH_OK; }
@@ -1301,6 +1431,32 @@ static int ensure_chunks(jh_model *m, jh_dataset *d, int64_t CK) {
   return JH_OK;
 }
 
+// Band template of a model (kernels_band.cuh): the smallest instantiated offset range that contains the model's band.
+// Returns false when the model is not banded or no instantiation covers it.
+struct BandSel { int spl, lo, hi; };
+static bool band_select(const jhs::SparseTables &P, BandSel *sel) {
+  if (P.band_hi < P.band_lo || P.e_global || (size_t)P.H * P.SP * sizeof(double) > 160 * 1024) return false;
+  static const BandSel cand[] = {{2, 0, 1}, {2, 0, 2}, {2, -1, 1}, {2, -2, 2}, {4, 0, 1}, {4, 0, 3}, {4, -1, 1}, {4, -4, 4},
+                                 {8, 0, 3}, {8, -1, 1}, {8, -3, 3}};
+  for (const BandSel &c : cand)
+    if (c.spl == P.SPL && c.lo <= P.band_lo && P.band_hi <= c.hi) { *sel = c; return true; }
+  return false;
+}
+#define JH_BAND_DISPATCH(sel, ...)                                                                        \
+  switch ((sel).spl * 10000 + ((sel).lo + 50) * 100 + (sel).hi) {                                            \
+    case 2 * 10000 + 50 * 100 + 1: { constexpr int SPL_ = 2, LO_ = 0, HI_ = 1; __VA_ARGS__; } break;       \
+    case 2 * 10000 + 50 * 100 + 2: { constexpr int SPL_ = 2, LO_ = 0, HI_ = 2; __VA_ARGS__; } break;       \
+    case 2 * 10000 + 49 * 100 + 1: { constexpr int SPL_ = 2, LO_ = -1, HI_ = 1; __VA_ARGS__; } break;      \
+    case 2 * 10000 + 48 * 100 + 2: { constexpr int SPL_ = 2, LO_ = -2, HI_ = 2; __VA_ARGS__; } break;      \
+    case 4 * 10000 + 50 * 100 + 1: { constexpr int SPL_ = 4, LO_ = 0, HI_ = 1; __VA_ARGS__; } break;       \
+    case 4 * 10000 + 50 * 100 + 3: { constexpr int SPL_ = 4, LO_ = 0, HI_ = 3; __VA_ARGS__; } break;       \
+    case 4 * 10000 + 49 * 100 + 1: { constexpr int SPL_ = 4, LO_ = -1, HI_ = 1; __VA_ARGS__; } break;      \
+    case 4 * 10000 + 46 * 100 + 4: { constexpr int SPL_ = 4, LO_ = -4, HI_ = 4; __VA_ARGS__; } break;      \
+    case 8 * 10000 + 50 * 100 + 3: { constexpr int SPL_ = 8, LO_ = 0, HI_ = 3; __VA_ARGS__; } break;       \
+    case 8 * 10000 + 49 * 100 + 1: { constexpr int SPL_ = 8, LO_ = -1, HI_ = 1; __VA_ARGS__; } break;      \
+    default: { constexpr int SPL_ = 8, LO_ = -3, HI_ = 3; __VA_ARGS__; } break;                             \
+  }
+
 // phase 1: n_dir = 1 scoring only, n_dir = 2 forward and backward warps with checkpoints
 static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll, const jhs::Pass1Extra *extra = nullptr, cudaStream_t on = nullptr,
                             bool reset_fallback = true) {
@@ -1314,6 +1470,24 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
   if (!on) JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));  // only the warp-per-sequence kernel uses it
   const int64_t items = (X.list ? X.n_list : d->n_seq) * n_dir;
   if (items == 0) return JH_OK;
+  BandSel bsel;
+  if (m->opt.band && items <= 8 * (int64_t)m->sm_count && band_select(P, &bsel)) {  // banded model: warp-resident, no shared-memory exchange
+    size_t smem_b = (size_t)P.H * P.SP * sizeof(double);
+    if (on) {  // overlapped with chunk kernels of other sequences: keep the SM to the latency-bound warp (see below)
+      int optin = 0;
+      JH_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+      smem_b = std::max<size_t>(smem_b, (size_t)optin);
+    }
+    JH_BAND_DISPATCH(bsel, {
+      auto kern = jhb::k_band_pass1<SPL_, LO_, HI_>;
+      if (smem_b > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      kern<<<(int)items, 32, smem_b, s>>>(P.dev(), P.IND, d->dev(), n_dir, (int)(d->chunk_len > 0 ? d->chunk_len : 1), n_dir == 2 ? d->d_chunk_ptr.p : nullptr,
+                                         n_dir == 2 ? m->d_ck_alpha.p : nullptr, n_dir == 2 ? m->d_ck_beta.p : nullptr, d_ll, m->d_fallback.p, X);
+      JH_LAUNCHED();
+    });
+    JH_CUDA(cudaGetLastError());
+    return JH_OK;
+  }
   if (m->opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
     size_t smem_c = ((P.e_global ? 0 : (size_t)P.H * P.SP) + 2 * (size_t)P.SP + 16) * sizeof(double);
     if (on) {  // overlapped with chunk kernels of other sequences: claim the SM's whole shared memory, so that no chunk CTA
@@ -1942,19 +2116,27 @@ static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int
   const int64_t per_warp = rows * SP;
   int per_sm = 0;
   int64_t grid = 0;
-#define JH_VL(SPL_, IND_)                                                                                                               \
+  BandSel bsel;
+  const bool banded = m->opt.band && band_select(P, &bsel);
+#define JH_VL(VS_, VI_)                                                                                                               \
   {                                                                                                                                     \
-    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhw::k_vit_chunks<SPL_, IND_, 0>, NT, smem_c));                       \
+    JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhw::k_vit_chunks<VS_, VI_, 0>, NT, smem_c));                       \
     if (per_sm < 1) { jh_set_error("Viterbi chunk kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }                          \
     if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);                                              \
     grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);                                               \
     grid = std::max<int64_t>(1, std::min<int64_t>(grid, m->opt.scratch_mb * 1024 * 1024 / per_warp / wpc));                               \
     if ((r = m->d_vit_nxt.reserve((size_t)grid * wpc * per_warp + 16))) return r;                                                        \
     if (d->n_long > 0) {                                                                                                                \
-      jhw::k_vit_sweep<SPL_, IND_><<<(int)std::min<int64_t>(d->n_long, (int64_t)m->sm_count * 8), 32, smem_s, s>>>(                       \
-          P.dev(), V, d->dev(), (int)CK, d->d_long.p, d->n_long, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p, d_scores);              \
+      if (banded) {                                                                                                                     \
+        JH_BAND_DISPATCH(bsel, {                                                                                                        \
+          jhb::k_band_vit_sweep<SPL_, LO_, HI_><<<(int)d->n_long, 32, 0, s>>>(P.dev(), V, P.IND, d->dev(), (int)CK, d->d_long.p, d->n_long,  \
+                                                                              d->d_chunk_ptr.p, m->d_vit_ck.p, d_scores);                  \
+        });                                                                                                                             \
+      } else                                                                                                                            \
+        jhw::k_vit_sweep<VS_, VI_><<<(int)std::min<int64_t>(d->n_long, (int64_t)m->sm_count * 8), 32, smem_s, s>>>(                     \
+            P.dev(), V, d->dev(), (int)CK, d->d_long.p, d->n_long, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p, d_scores);            \
       JH_LAUNCHED();                                                                                                                    \
-      jhw::k_vit_chunks<SPL_, IND_, 0><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->long_seg[d->n_long], d->d_chunk_seq.p, \
+      jhw::k_vit_chunks<VS_, VI_, 0><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->long_seg[d->n_long], d->d_chunk_seq.p, \
                                                                     d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p + 1,  \
                                                                     m->d_vit_nxt.p, m->d_vit_map.p, nullptr, PathOut{nullptr, 0}, nullptr, nullptr); \
       JH_LAUNCHED();                                                                                                                    \
@@ -1962,7 +2144,7 @@ static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int
                                                                     m->d_vit_map.p, m->d_vit_entry.p);                                    \
       JH_LAUNCHED();                                                                                                                    \
     }                                                                                                                                   \
-    jhw::k_vit_chunks<SPL_, IND_, 1><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, \
+    jhw::k_vit_chunks<VS_, VI_, 1><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, \
                                                                   d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p + 2, m->d_vit_nxt.p,         \
                                                                   nullptr, m->d_vit_entry.p, paths, d_path_ptr, d_scores);                      \
     JH_LAUNCHED();                                                                                                                      \

@@ -160,6 +160,14 @@ class DataSet:
             seqs.append(Sequence.create(con, "".join(cur)))
         return cls(path, *seqs, con=con)
 
+    @staticmethod
+    def from_fasta_stream(path: str, shard_dir: str, **kw):
+        """Genome-scale FASTA: streamed once into packed shard files (2 bits per residue by default) and used from there
+        (jstacs_b200/shards.py) — returns a ShardedDataSet."""
+        from .shards import fasta_to_shards
+
+        return fasta_to_shards(path, shard_dir, **kw)
+
     def getAlphabetContainer(self) -> AlphabetContainer:
         return self.con
 

@@ -651,6 +651,19 @@ class HigherOrderHMM:
     def getNumberOfStates(self) -> int:
         return len(self.name)
 
+    def toXML(self) -> str:
+        """AbstractHMM.toXML (:394-415) in the reference's XML dialect (jstacs_b200/xmlio.py)."""
+        from .xmlio import hmm_to_xml
+
+        return hmm_to_xml(self)
+
+    @staticmethod
+    def fromXML(xml: str) -> "HigherOrderHMM":
+        """AbstractHMM(StringBuffer xml) (:347-357, fromXML :424-465)."""
+        from .xmlio import hmm_from_xml
+
+        return hmm_from_xml(xml)
+
     def getAlphabetContainer(self):
         return self.alphabets
 
@@ -698,7 +711,10 @@ class HigherOrderHMM:
         if not data.getAlphabetContainer().checkConsistency(self.alphabets):
             raise WrongAlphabetException("The AlphabetContainer of the data set and the model do not match.")
         if data._native is None:
-            data._native = _native.NativeData(data.codes, data.offsets, None, self.alphabets.getAlphabetLengthAt(0))
+            if hasattr(data, "_make_native"):  # shard files: streamed to the device, never materialised on the host
+                data._native = data._make_native(self.alphabets.getAlphabetLengthAt(0))
+            else:
+                data._native = _native.NativeData(data.codes, data.offsets, None, self.alphabets.getAlphabetLengthAt(0))
         return data._native
 
     # ---- initialisation ------------------------------------------------------------------------

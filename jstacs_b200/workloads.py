@@ -47,13 +47,15 @@ def ergodic_hmm(n_states: int, emission_order: int, n_iter: int = 10, ess: float
     return set_closed_form_parameters(hmm)
 
 
-def banded_hmm(n_states: int = 128, out_degree: int = 4, emission_order: int = 0, ess: float = 0.0) -> HigherOrderHMM:
-    """cfg5: each state -> itself + the next out_degree-1 states (mod S), E = S*out_degree edges."""
+def banded_hmm(n_states: int = 128, out_degree: int = 4, emission_order: int = 0, ess: float = 0.0, offsets=None) -> HigherOrderHMM:
+    """cfg5: each state -> itself + the next out_degree-1 states (mod S), E = S*out_degree edges.
+    offsets: the children of state s are (s + d) mod S for d in offsets, in that (child) order, instead of 0..out_degree-1."""
     pars = BaumWelchParameterSet(1, IterationCondition(1), 1)
     em = [HigherOrderDiscreteEmission(DNA, ess, emission_order) for _ in range(n_states)]
     te = [TransitionElement(None, list(range(n_states)), [ess / n_states] * n_states)]
+    offsets = list(range(out_degree)) if offsets is None else list(offsets)
     for s in range(n_states):
-        te.append(TransitionElement([s], [(s + d) % n_states for d in range(out_degree)], [ess] * out_degree))
+        te.append(TransitionElement([s], [(s + d) % n_states for d in offsets], [ess] * len(offsets)))
     hmm = DifferentiableHigherOrderHMM(pars, [str(i) for i in range(n_states)], None, None, em, ess, *te)
     hmm.setOutputStream(None)
     return set_closed_form_parameters(hmm)

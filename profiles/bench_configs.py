@@ -77,6 +77,7 @@ run("long_decode_s16_dense_8x2Mb", lambda: ergodic_hmm(16, 1), lambda: make_data
 run("cfg5_decode_s128_banded_1Mb", lambda: banded_hmm(128, 4, 0), lambda: make_data(24, 1_000_000), "decode")
 run("cfg5_bw_s128_banded_1Mb", lambda: banded_hmm(128, 4, 0), lambda: make_data(24, 1_000_000), "estep")
 run("long_bw_s16_dense_8x2Mb", lambda: ergodic_hmm(16, 1), lambda: make_data(8, 2_000_000), "estep")
+run("cfg5_viterbi_u8_s128_banded_1Mb", lambda: banded_hmm(128, 4, 0), lambda: make_data(24, 1_000_000), "viterbi_u8")
 run("cfg4_decode_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_data(ragged().size, ragged()), "decode")
 run("cfg2_viterbi_u8_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "viterbi_u8")
 run("cfg4_decode_u8_s16_k1_ragged", lambda: ergodic_hmm(16, 1), lambda: make_data(ragged().size, ragged()), "decode_u8")
@@ -106,6 +107,9 @@ mid5 = lambda: make_data(24, [mb * 20_000 for mb in GRCH38_MB])  # the same leng
 run("full_mid_cfg5_loglik", lambda: banded_hmm(128, 4, 0), mid5, "loglik", reps=3)
 run("full_mid_cfg5_bw", lambda: banded_hmm(128, 4, 0), mid5, "estep", reps=3)
 run("full_mid_cfg5_decode_u8", lambda: banded_hmm(128, 4, 0), mid5, "decode_u8", reps=3)
+run("full_mid_cfg5_viterbi_u8", lambda: banded_hmm(128, 4, 0), mid5, "viterbi_u8", reps=3)
+run("full_cfg2_viterbi_u8_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(1_000_000, 1000), "viterbi_u8", reps=3)
+run("full_cfg5_viterbi_u8", lambda: banded_hmm(128, 4, 0), full5, "viterbi_u8", reps=1)
 run("full_cfg5_loglik", lambda: banded_hmm(128, 4, 0), full5, "loglik", reps=1)
 run("full_cfg5_decode_u8", lambda: banded_hmm(128, 4, 0), full5, "decode_u8", reps=1)
 run("full_cfg5_bw", lambda: banded_hmm(128, 4, 0), full5, "estep", reps=1)

@@ -826,3 +826,54 @@ def test_long_sequence_viterbi_impossible_path(nat, oracle_lib):
     with pytest.raises(nat.NativeError) as ei:
         eng.viterbi(nd)
     assert ei.value.status == -6
+
+
+# ---- banded models: warp-resident whole-sequence passes (kernels_band.cuh) ---------------------------------------------
+BAND_MODELS = {
+    "ring128_0to3": lambda: banded_hmm(128, 4, 1),                         # cfg5: SPL 4, band [0, 3]
+    "ring64_0to2": lambda: banded_hmm(64, 3, 0, ess=2.0),                  # SPL 2, band [0, 2]
+    "ring256_0to3": lambda: banded_hmm(256, 4, 1),                         # SPL 8
+    "ring128_pm1_unsorted": lambda: banded_hmm(128, 3, 1, offsets=[1, -1, 0]),  # band [-1, 1], children not in state order
+    "ring128_pm4_gaps": lambda: banded_hmm(128, 3, 0, offsets=[-4, 2, 4]),      # full window with gaps
+    "ring64_skip": lambda: banded_hmm(64, 2, 1, offsets=[2, 0]),            # no edge to the direct neighbour
+}
+
+
+@pytest.mark.parametrize("band", [1, 0], ids=["band", "general"])
+@pytest.mark.parametrize("name", list(BAND_MODELS))
+def test_banded_models_whole_sequence_passes(nat, oracle_lib, name, band):
+    """Scoring, posterior decoding, E-step and chromosome-style Viterbi of banded models with the shuffle exchange
+    (band = 1) and with the general shared-memory kernels (band = 0): both against the oracle."""
+    hmm = BAND_MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(3)
+    chunk = 48
+    lens = [7 * chunk + 5, 1, 2, chunk, chunk + 1, 3 * chunk, 11 * chunk - 1, 9]
+    data = dataset_of([random_dna(rng, L) for L in lens])
+    eng, nd = hmm._engine(), hmm._data(data)
+    for k, v in (("band", band), ("chunk", chunk), ("vit_chunk", chunk), ("vit_chunk_force", 1)):
+        eng.set_option(k, v)
+    ll_ref = om.loglik(data.codes, data.offsets)
+    np.testing.assert_allclose(eng.loglik(nd), ll_ref, rtol=LL_RTOL)
+    paths, ll = eng.posterior_decode(nd)
+    np.testing.assert_allclose(ll, ll_ref, rtol=LL_RTOL)
+    for i in range(len(lens)):
+        ref = om.posterior(data.getElementAt(i).codes)
+        srt = np.sort(ref, axis=0)
+        clear = srt[-1] - srt[-2] > 1e-9
+        assert np.array_equal(paths[data.offsets[i]:data.offsets[i + 1]][clear], om.decode_posterior(ref)[clear])
+    w = rng.uniform(0.5, 2.0, len(lens))
+    for weights in (None, w):
+        nd.set_weights(weights)
+        ts, es, sc = eng.estep(nd)
+        rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+        np.testing.assert_allclose(ts, rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+        np.testing.assert_allclose(es, res, rtol=COUNT_TOL, atol=COUNT_TOL)
+        assert sc == pytest.approx(rsc, rel=LL_RTOL)
+    nd.set_weights(None)
+    if hmm.getNumberOfStates() <= 255:
+        rp, rs, _ = om.viterbi(data.codes, data.offsets)
+        vp, vs = eng.viterbi(nd, narrow=True)
+        assert np.array_equal(vs, rs)
+        for i in range(len(lens)):
+            assert np.array_equal(vp[data.offsets[i]:data.offsets[i + 1]], rp[i])
