@@ -173,6 +173,16 @@ int jh_dataset_builder_append(jh_dataset_builder *b, const uint8_t *codes, const
 int jh_dataset_builder_finish(jh_dataset_builder *b, const double *weights, jh_dataset **out);
 void jh_dataset_builder_destroy(jh_dataset_builder *b);
 void jh_dataset_destroy(jh_dataset *d);
+/* Allowed states groups — semi-supervised training and constrained scoring / decoding (HigherOrderHMM.java:331-340, 795-835;
+ * AbstractHMM.java:146-228, AbstractHMM.AllowedStatesGroups :1198-1246).  The model declares groups of states
+ * (jh_model_set_states_groups = the constructor argument int[][] statesGroups); a data set carries, per position, the index
+ * of the group the state emitting that position has to belong to, or -1 (= the int[] of the sequence annotation
+ * AllowedStatesGroups.groups).  While both are set, jh_loglik (getLogProbFor(seq, start, end, statesGroups)), jh_viterbi*
+ * (getViterbiPathFor(..., allowedStatesGroup)), jh_estep and jh_baum_welch (doOneStep, :812-835) evaluate the constraint,
+ * on the reference-order kernels.  Posterior matrices ignore it, as in the reference.  Models without silent states and with
+ * transition order >= 1; groups == NULL detaches. */
+int jh_model_set_states_groups(jh_model *m, int32_t n_groups, const int32_t *group_ptr, const int32_t *group_states);
+int jh_dataset_set_groups(jh_dataset *d, const int32_t *groups);
 /* Sequence weights of train(DataSet,double[]) (TrainableStatisticalModel.java:61-88); NULL = all 1. */
 int jh_dataset_set_weights(jh_dataset *d, const double *weights);
 int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_residues, int64_t *max_len);

@@ -135,6 +135,8 @@ def lib():
         "jh_model_set_stream": (C.c_int, [vp, vp]),
         "jh_dataset_create_packed2": (C.c_int, [_P_U8, _P_I64, _P_I64, C.c_int64, _P_F64, C.c_int32, C.POINTER(vp)]),
         "jh_last_objective": (C.c_int, [vp, _P_F64]),
+        "jh_model_set_states_groups": (C.c_int, [vp, C.c_int32, _P_I32, _P_I32]),
+        "jh_dataset_set_groups": (C.c_int, [vp, _P_I32]),
         "jh_dataset_builder_create": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.POINTER(vp)]),
         "jh_dataset_builder_append": (C.c_int, [vp, _P_U8, _P_I64, C.c_int64, C.c_int32]),
         "jh_dataset_builder_finish": (C.c_int, [vp, _P_F64, C.POINTER(vp)]),
@@ -206,6 +208,16 @@ class NativeData:
                 lib().jh_dataset_builder_destroy(b)
         return self
 
+    def set_groups(self, groups):
+        """allowedStatesGroup of every position (int32, -1 = unconstrained), None detaches (jh_dataset_set_groups)."""
+        if groups is None:
+            check(lib().jh_dataset_set_groups(self.h, None))
+            return
+        g = np.ascontiguousarray(groups, dtype=np.int32)
+        if g.size != self.n_res:
+            raise ValueError("one group index per residue is needed")
+        check(lib().jh_dataset_set_groups(self.h, g.ctypes.data_as(_P_I32)))
+
     def set_weights(self, weights):
         w = None if weights is None else np.ascontiguousarray(weights, dtype=np.float64)
         if w is not None and w.size != self.n_seq:
@@ -240,6 +252,13 @@ class NativeModel:
         if self.h:
             lib().jh_model_destroy(self.h)
             self.h = C.c_void_p()
+
+    def set_states_groups(self, groups):
+        """statesGroups of the model constructor (AbstractHMM.java:173-228): a list of state-index lists."""
+        ptr = np.zeros(len(groups) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(g) for g in groups])
+        st = np.array([s for g in groups for s in g] or [0], np.int32)
+        check(lib().jh_model_set_states_groups(self.h, len(groups), ptr.ctypes.data_as(_P_I32), st.ctypes.data_as(_P_I32)))
 
     def set_option(self, name: str, value: int):
         """Per-handle override of a library option (jh_model_set_option)."""

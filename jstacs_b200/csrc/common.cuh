@@ -53,6 +53,9 @@ struct DevModel {
   const int *state_mod;       // [S] a^(order+1)
   const double *escore;       // [n_cond*a] (0 - logNorm[cond]) + params[cond][sym]
   const unsigned char *is_final;  // [S]
+  // allowed states groups (AbstractHMM.java:146-228): preComputedContext as a flag per (group, context of layer class m)
+  const unsigned char *allowed;   // [n_groups * Cmax] or nullptr
+  int n_groups;
 };
 
 // Device view of a packed data set.
@@ -62,7 +65,17 @@ struct DevData {
   const double *weights;    // [n] or nullptr
   const int32_t *order;     // [n] sequence ids sorted by decreasing length (length bucketing)
   int64_t n_seq;
+  const int32_t *groups;    // [n_res] allowedStatesGroup of every position (-1: unconstrained), nullptr: no constraint
 };
+
+// HigherOrderHMM.getAllowedContext (HigherOrderHMM.java:331-340) as a membership test: contexts of layer l (l >= m) whose
+// last state emitted the absolute position pos - 1 are restricted to preComputedContext[group[pos - 1]].
+// grp: groups of the sequence (indexed by absolute position) or nullptr.
+__device__ __forceinline__ bool ctx_allowed(const DevModel &M, const int32_t *grp, int64_t pos, int64_t layer, int c) {
+  if (!grp || !M.allowed || layer < M.m) return true;
+  const int g = grp[pos - 1];
+  return g < 0 || M.allowed[(size_t)g * M.Cmax + c] != 0;
+}
 
 struct WorkList {   // sequences, or windows of sequences
   const int32_t *seq;     // [n] sequence ids (nullptr: D.order)

@@ -349,7 +349,8 @@ struct jh_model {
   // device
   DevBuf<int> d_lc_ctx_ptr, d_ctx_elem, d_ctx_last, d_elem_child_ptr, d_child_state, d_child_next, d_child_stat, d_in_ptr,
       d_in_src, d_in_p, d_state_order, d_state_tab, d_state_mod, d_child_elem, d_trans_index, d_row_flag;
-  DevBuf<unsigned char> d_is_final, d_silent;
+  DevBuf<unsigned char> d_is_final, d_silent, d_allowed;
+  int n_groups = 0;
   DevBuf<int> d_sin_ptr, d_sin_src, d_sin_p;
   DevBuf<double> d_rows;       // rolling DP rows of the thread-per-sequence kernels
   DevBuf<double> d_trans_param, d_trans_lognorm, d_trans_hyper, d_emis_param, d_emis_lognorm, d_emis_hyper, d_tscore, d_escore;
@@ -421,6 +422,7 @@ struct jh_model {
     M.child_state = d_child_state.p; M.child_next = d_child_next.p; M.child_stat = d_child_stat.p; M.tscore = d_tscore.p;
     M.in_ptr = d_in_ptr.p; M.in_src = d_in_src.p; M.in_p = d_in_p.p; M.state_order = d_state_order.p; M.state_tab = d_state_tab.p;
     M.state_mod = d_state_mod.p; M.escore = d_escore.p; M.is_final = d_is_final.p;
+    M.allowed = n_groups > 0 ? d_allowed.p : nullptr; M.n_groups = n_groups;
     return M;
   }
   jhg::GenModel gen() const {
@@ -453,6 +455,8 @@ struct jh_dataset {
   DevBuf<int32_t> d_order;
   DevBuf<double> d_weights;
   bool has_weights = false;
+  DevBuf<int32_t> d_groups;   // allowedStatesGroup of every position (jh_dataset_set_groups)
+  bool has_groups = false;
   // octets: 8 consecutive sequences of a bucket advance in lock step through one warp (kernels_mma.cuh);
   // bucket b owns octets [bucket_oct_ptr[b], bucket_oct_ptr[b+1]); hash records are built lazily per (alphabet, Kmax)
   std::vector<int32_t> oct_seq;
@@ -471,6 +475,7 @@ struct jh_dataset {
     DevData D;
     D.codes = d_codes.p; D.offsets = d_offsets.p; D.weights = has_weights ? d_weights.p : nullptr;
     D.order = d_order.p + first; D.n_seq = count < 0 ? n_seq : count;
+    D.groups = has_groups ? d_groups.p : nullptr;
     return D;
   }
 };
@@ -1146,6 +1151,51 @@ extern "C" int jh_dataset_set_weights(jh_dataset *d, const double *weights) {
 
 extern "C" void jh_dataset_destroy(jh_dataset *d) { dataset_free(d); }
 
+static bool general_model(const jh_model *m);
+
+extern "C" int jh_dataset_set_groups(jh_dataset *d, const int32_t *groups) {
+  if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
+  if (!groups) { d->has_groups = false; return JH_OK; }
+  JH_CUDA(cudaSetDevice(d->device));
+  Scope scope(d->device, d->stream);
+  if (d->ev_last) JH_CUDA(cudaEventSynchronize(d->ev_last));
+  int r = d->d_groups.reserve((size_t)d->n_res + 1);
+  if (r) return r;
+  if ((r = stage_h2d(d->d_groups.p, groups, sizeof(int32_t) * (size_t)d->n_res, d->stream, d->device, true))) return r;
+  JH_CUDA(cudaStreamSynchronize(d->stream));
+  d->has_groups = true;
+  return JH_OK;
+}
+
+// AbstractHMM.fillPreComputedContext (AbstractHMM.java:173-228): a context of layer class m is allowed for group g if some
+// context of that class has a child whose state belongs to g and which leads to it.
+extern "C" int jh_model_set_states_groups(jh_model *m, int32_t n_groups, const int32_t *group_ptr, const int32_t *group_states) {
+  JH_ENTER(m);
+  if (n_groups < 0 || (n_groups > 0 && (!group_ptr || !group_states))) { jh_set_error("invalid states groups"); return JH_ERR_INVALID; }
+  if (n_groups > 0 && general_model(m)) { jh_set_error("allowed states groups with silent states or transition order 0 are not on the native path"); return JH_ERR_UNSUPPORTED; }
+  m->n_groups = 0;
+  if (n_groups == 0) return JH_OK;
+  std::vector<unsigned char> allowed((size_t)n_groups * m->Cmax, 0), in_group(m->S);
+  const int lc = m->m, c0 = m->lc_ctx_ptr[lc], nc = m->lc_ctx_ptr[lc + 1] - c0;
+  for (int g = 0; g < n_groups; g++) {
+    std::fill(in_group.begin(), in_group.end(), 0);
+    for (int k = group_ptr[g]; k < group_ptr[g + 1]; k++) {
+      if (group_states[k] < 0 || group_states[k] >= m->S) { jh_set_error("states group %d names an unknown state", g); return JH_ERR_INVALID; }
+      in_group[group_states[k]] = 1;
+    }
+    for (int c = 0; c < nc; c++) {
+      const int e = m->ctx_elem[c0 + c];
+      for (int p = m->elem_child_ptr[e]; p < m->elem_child_ptr[e + 1]; p++)
+        if (in_group[m->child_state[p]]) allowed[(size_t)g * m->Cmax + m->child_next[(size_t)lc * m->n_child + p]] = 1;
+    }
+  }
+  int r = m->d_allowed.upload(allowed, m->st());
+  if (r) return r;
+  JH_CUDA(cudaStreamSynchronize(m->st()));
+  m->n_groups = n_groups;
+  return JH_OK;
+}
+
 extern "C" int jh_dataset_info(const jh_dataset *d, int64_t *n_seq, int64_t *n_res, int64_t *max_len) {
   if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
   if (n_seq) *n_seq = d->n_seq;
@@ -1178,6 +1228,9 @@ struct UseMark {  // the data set remembers the last work that reads it (jh_data
 // Models that run on the general context-graph kernels (kernels_general.cuh, one sequence per thread): silent states, and
 // transition order 0 (a single context for every layer: every context is final, HigherOrderHMM.java:498, 1046-1058).
 static bool general_model(const jh_model *m) { return m->has_silent || m->m == 0; }
+// allowed states groups in force: the model declares groups and the data set carries the per-position constraints; only
+// the reference-order kernels (kernels_exact.cuh) evaluate them
+static bool groups_active(const jh_model *m, const jh_dataset *d) { return m->n_groups > 0 && d->has_groups; }
 
 static int group_size(const jh_model *m) {
   int g = 2;
@@ -1941,7 +1994,8 @@ extern "C" int jh_loglik(jh_model *m, jh_dataset *d, double *out) {
   if (general_model(m)) {
     jhg::WorkList W{nullptr, nullptr, nullptr, d->n_seq};
     r = run_general_loglik(m, d, W, d_out.p);
-  } else if (prefer_sparse(m, d)) r = run_loglik_sparse(m, d, d_out.p);
+  } else if (groups_active(m, d)) r = run_loglik_exact(m, d, d_out.p, nullptr, 0);
+  else if (prefer_sparse(m, d)) r = run_loglik_sparse(m, d, d_out.p);
   else if (m->opt.fast && m->fast.usable && m->fast.G >= 8 && variant_of(m) == 0) r = run_loglik_octets(m, d, d_out.p);
   else if (m->opt.fast && m->fast.usable && m->fast.G <= 4 && variant_of(m) == 0) r = run_loglik_lanes(m, d, d_out.p);
   else if (m->opt.fast && m->fast.usable) r = jhf::run_loglik(m->fast, m->dev(), d->dev(), d->n_seq, d->max_len, d_out.p, m->d_counter.p, m->sm_count, m->st());
@@ -2098,7 +2152,11 @@ static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int
     const bool lanes = m->opt.fast && m->fast.usable && m->fast.sorted_children;
     const int64_t per_slot = lanes ? d->max_len * 32 * std::max(m->fast.G, 4) : d->max_len * m->Cmax;
     const int64_t want = lanes ? (int64_t)m->sm_count * 4 : (int64_t)m->sm_count * (256 / group_size(m));
-    if (per_slot * std::min<int64_t>(want, lanes ? (d->n_seq + 31) / 32 : d->n_seq) <= budget) return JH_OK;
+    // ... and they need a sequence per lane / group to fill the GPU: a few long sequences are one dependent chain each
+    // there, while the chunk phases of this path run in parallel whatever the number of sequences
+    const bool enough = (lanes ? (d->n_seq + 31) / 32 : d->n_seq) >= want;
+    if (enough && per_slot * want <= budget) return JH_OK;
+    if (!enough && d->n_res < ((int64_t)1 << 22) && per_slot * std::max<int64_t>(1, lanes ? (d->n_seq + 31) / 32 : d->n_seq) <= budget) return JH_OK;  // small data: either way is fast
   }
   *handled = true;
   cudaStream_t s = m->st();
@@ -2170,12 +2228,13 @@ static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int
 // follows the bucket's longest sequence.  windows: sub-sequences (exact kernel only).
 static int run_viterbi(jh_model *m, jh_dataset *d, PathOut paths, const int64_t *d_path_ptr, double *d_scores, double *d_stats,
                        const WorkList *windows = nullptr, int64_t win_max_len = 0) {
-  if (!d_stats && !windows) {  // chromosome-scale sequences: checkpointed sweep, choice bytes recomputed per chunk
+  const bool grouped = groups_active(m, d);
+  if (!d_stats && !windows && !grouped) {  // chromosome-scale sequences: checkpointed sweep, choice bytes recomputed per chunk
     bool handled = false;
     int r = run_viterbi_long(m, d, paths, d_path_ptr, d_scores, &handled);
     if (r || handled) return r;
   }
-  if (!d_stats && !windows && m->opt.fast && m->fast.usable && m->fast.sorted_children) {  // decoding: one sequence per lane
+  if (!d_stats && !windows && !grouped && m->opt.fast && m->fast.usable && m->fast.sorted_children) {  // decoding: one sequence per lane
     int r = ensure_octet_hashes(m, d);
     for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++) {
       switch (m->fast.G) {
@@ -2675,7 +2734,7 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   }
   if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, PathOut{nullptr, 0}, nullptr, nullptr, m->d_stats.p);
   const bool sparse = prefer_sparse(m, d);
-  if (sparse || (m->opt.fast && m->fast.usable)) {
+  if (!groups_active(m, d) && (sparse || (m->opt.fast && m->fast.usable))) {
     int r = m->d_fallback.reserve(d->n_seq + 2);
     if (r) return r;
     int32_t *flag = m->d_fallback.p + d->n_seq + 1;

@@ -98,6 +98,10 @@ struct LazyScale {
 
 // Checkpoint pass / scoring for banded models: one WARP per (sequence, direction), one warp per CTA.  Interface and outputs
 // of jhs::k_sparse_pass1_cta.  The emission table lives in shared memory (models with larger tables keep the general kernels).
+// A lone warp cannot hide instruction fetches, so (like k_sparse_pass1_cta) aligned blocks of 16 residues run as
+// straight-line code without any branch — hash by shift/mask (power-of-two alphabets), no checkpoint inside, the rescale
+// at fixed places (probe after steps 5 and 13, applied after steps 7 and 15) — and everything else (ragged ends, the first
+// K positions, blocks that contain a checkpoint, other alphabets) goes through the general step.
 template <int SPL, int LO, int HI>
 __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData D, int n_dir, int CK, const int64_t *chunk_ptr, double *ck_alpha,
                                                    double *ck_beta, double *loglik, int32_t *fallback, Pass1Extra X) {
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
   for (int i = threadIdx.x; i < F.H * SP; i += blockDim.x) sm[i] = F.E[i];
   __syncthreads();
   const unsigned FULL = 0xffffffffu;
+  const int ash = F.ashift, Hm = F.H - 1, hpow = F.hpow;
+  const double *const sEl = sE + SPL * lane;  // + h * SP
   ResReader rd;
   SeqBlocks blocks;
   const long long items = (X.list ? X.n_list : D.n_seq) * n_dir;
@@ -120,27 +126,42 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
     const int L = (int)(D.offsets[sid + 1] - off);
     rd.init(D.codes + off);
     blocks.init(D.codes + off);
+    const int mis = blocks.mis;
+    const uint8_t *const bytes = reinterpret_cast<const uint8_t *>(blocks.base) + mis;  // residue t = bytes[t]
     const int64_t cbase = chunk_ptr ? chunk_ptr[sid] : 0;
     double w[SPL][W];
     LazyScale lz;
     if (!backward) {
       band_weights<SPL, LO, HI, double>(F.in_src, F.in_T, IND, SP, F.S, lane, -1, 0.0, w);
-      double f[SPL], e[SPL];
+      double f[SPL];
       long long A = 0;
       bool ok = true;
       int h = jhs::hash_at(F, rd, 0);
-      jhs::emis<SPL>(F, sE, lane, e, jhs::hmod_of(F, h), 0);
+      {
+        double e[SPL];
+        jhs::emis<SPL>(F, sE, lane, e, jhs::hmod_of(F, h), 0);
 #pragma unroll
-      for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+        for (int u = 0; u < SPL; u++) f[u] = F.pi[SPL * lane + u] * e[u];
+      }
       ok = jhs::rescale_warp<SPL>(f, A);
       int ck_left = CK;  // steps until the next checkpoint (the vector BEFORE chunk c = alpha_{c*CK-1}, stored in step t = c*CK)
       double *ck_dst = ck_alpha ? ck_alpha + (size_t)(cbase + 1) * SP + SPL * lane : nullptr;
       long long *cke_dst = X.ck_alpha_exp ? X.ck_alpha_exp + cbase + 1 : nullptr;
-      if (L > 1) {  // emission row of position 1, a step ahead from here on
-        h = jhs::roll_up(F, h, rd.get(1));
-        jhs::emis<SPL>(F, sE, lane, e, h, 1);
-      }
-      auto step = [&](int t, int xn) {  // alpha_{t-1} -> alpha_t; e = emission row of t; xn = x[t+1] (0 past the end)
+      auto advance = [&](const double (&e)[SPL]) {  // alpha_{t-1} -> alpha_t given the emission row of t
+        double c[3 * SPL];
+        exchange<SPL, FP, FN>(f, lane, c);
+#pragma unroll
+        for (int u = 0; u < SPL; u++) {
+          double a0 = 0;
+#pragma unroll
+          for (int x = 0; x < W; x++) a0 = fma(c[SPL + u - (x + LO)], w[u][x], a0);  // own values first for LO >= 0
+          f[u] = a0 * e[u];
+        }
+      };
+      auto step = [&](int t, int x) {
+        h = jhs::roll_up(F, h, x);
+        double e[SPL];
+        jhs::emis<SPL>(F, sE, lane, e, h, t);
         if (ck_dst && --ck_left == 0) {
           jhs::store_vec<SPL>(ck_dst, f);
           ck_dst += SP;
@@ -150,26 +171,43 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
             cke_dst++;
           }
         }
-        double c[3 * SPL];
-        exchange<SPL, FP, FN>(f, lane, c);
-        double en[SPL];
-        h = jhs::roll_up(F, h, xn);
-        jhs::emis<SPL>(F, sE, lane, en, h, t + 1);  // row of the next position: in flight during this step
-#pragma unroll
-        for (int u = 0; u < SPL; u++) {
-          double a0 = 0;
-#pragma unroll
-          for (int x = 0; x < W; x++) a0 = fma(c[SPL + u - (x + LO)], w[u][x], a0);  // own values first for LO >= 0
-          f[u] = a0 * e[u];
-        }
-        if ((t & 7) == 2) ok &= lz.apply<SPL>(f, A);
-        if ((t & 7) == 0) lz.probe<SPL>(f);
-#pragma unroll
-        for (int u = 0; u < SPL; u++) e[u] = en[u];
+        advance(e);
+        if ((t & 7) == 0) ok &= jhs::rescale_warp<SPL>(f, A);
       };
-      // the rescale cadence needs a probe before the first apply: t = 1 applies only after t = 8's probe
-      lz.hi = 1023u << 20;
-      jhs::for_residues_up(blocks, 2, L, [&](int tp, int x) { step(tp - 1, tp < L ? x : 0); });  // t = 1 .. L-1, x = x[t+1]
+      auto fast16 = [&](const uint4 blk) {  // 16 steps of an aligned block: positions > Kmax, no checkpoint inside
+        const unsigned wds[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int x = (int)((wds[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+          h = ((h << ash) | x) & Hm;
+          double e[SPL];
+          jhs::load_vec<SPL>(sEl + (size_t)h * SP, e);
+          advance(e);
+          if (k == 5 || k == 13) lz.probe<SPL>(f);
+          if (k == 7 || k == 15) ok &= lz.apply<SPL>(f, A);
+        }
+      };
+      int t = 1;
+      if (F.a_pow2) {
+#pragma unroll 1
+        for (; t <= L - 1 && ((((t + mis) & 15) != 0) || t <= F.Kmax); t++) step(t, (int)__ldg(bytes + t));
+        int blk = (t + mis) >> 4;
+        uint4 cur = t + 15 <= L - 1 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (; t + 15 <= L - 1; t += 16, blk++) {
+          const uint4 nxt = blocks.load(blk + 1);  // the code buffer is padded: one block past the end is readable
+          if (ck_dst && ck_left <= 16) {
+#pragma unroll 1
+            for (int k = 0; k < 16; k++) step(t + k, (int)__ldg(bytes + t + k));
+          } else {
+            fast16(cur);
+            ck_left -= 16;
+          }
+          cur = nxt;
+        }
+      }
+#pragma unroll 1
+      for (; t <= L - 1; t++) step(t, (int)__ldg(bytes + t));
       ok &= jhs::rescale_warp<SPL>(f, A);
       double sfin = 0;
 #pragma unroll
@@ -196,15 +234,28 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
       long long Bx = 0;
 #pragma unroll
       for (int u = 0; u < SPL; u++) b[u] = F.fin[SPL * lane + u];
-      int h = jhs::hash_at(F, rd, L - 1);
-      jhs::emis<SPL>(F, sE, lane, e, jhs::hmod_of(F, h), L - 1);
+      int h = jhs::hmod_of(F, jhs::hash_at(F, rd, L - 1));
+      jhs::emis<SPL>(F, sE, lane, e, h, L - 1);
       // checkpoints: beta at the last position of chunk c, t = (c+1)*CK - 1 < L - 1
       const int n_full = (L - 1) / CK;            // chunks that end before position L-1
       int ck_left = n_full > 0 ? (L - 1) - (n_full * CK - 1) : 0x7fffffff;  // steps until t reaches n_full*CK-1
       double *ck_dst = ck_beta + (size_t)(cbase + n_full - 1) * SP + SPL * lane;
       long long *cke_dst = X.ck_beta_exp ? X.ck_beta_exp + cbase + n_full - 1 : nullptr;
       const int K1 = F.Kmax + 1;
-      lz.hi = 1023u << 20;
+      auto advance = [&]() {  // beta_t -> beta_{t-1}: the exchanged vector is e_t * beta_t
+        double xb[SPL];
+#pragma unroll
+        for (int u = 0; u < SPL; u++) xb[u] = e[u] * b[u];
+        double c[3 * SPL];
+        exchange<SPL, BP, BN>(xb, lane, c);
+#pragma unroll
+        for (int u = 0; u < SPL; u++) {
+          double a0 = 0;
+#pragma unroll
+          for (int xo = 0; xo < W; xo++) a0 = fma(c[SPL + u + (xo + LO)], w[u][xo], a0);
+          b[u] = a0;
+        }
+      };
       auto step = [&](int p, int x) {  // t = p + K + 1: beta_t -> beta_{t-1}; x = x[t-1-K] completes the hash of t-1
         const int t = p + K1;
         if (ck_left == 0) {
@@ -217,36 +268,60 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
           }
         }
         --ck_left;
-        double xb[SPL];
-#pragma unroll
-        for (int u = 0; u < SPL; u++) xb[u] = e[u] * b[u];
-        double c[3 * SPL];
-        exchange<SPL, BP, BN>(xb, lane, c);
+        advance();
         h = jhs::roll_down(F, h, x);
-        jhs::emis<SPL>(F, sE, lane, e, h, t - 1);  // for the next step, in flight during the exchange
-#pragma unroll
-        for (int u = 0; u < SPL; u++) {
-          double a0 = 0;
-#pragma unroll
-          for (int xo = 0; xo < W; xo++) a0 = fma(c[SPL + u + (xo + LO)], w[u][xo], a0);
-          b[u] = a0;
-        }
-        if ((t & 7) == 2) lz.apply<SPL>(b, Bx);
-        if ((t & 7) == 0) lz.probe<SPL>(b);
+        jhs::emis<SPL>(F, sE, lane, e, h, t - 1);
+        if ((t & 7) == 0) jhs::rescale_warp<SPL>(b, Bx);
       };
-      jhs::for_residues_down(blocks, L - 2 - F.Kmax, -F.Kmax, step);  // t = L-1 .. 1
+      auto fast16 = [&](const uint4 blk) {  // 16 steps down an aligned block: p >= 0 (all positions >= Kmax), no checkpoint inside
+        const unsigned wds[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+        for (int k = 15; k >= 0; k--) {
+          const int x = (int)((wds[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+          advance();
+          h = (h >> ash) + hpow * x;
+          jhs::load_vec<SPL>(sEl + (size_t)h * SP, e);
+          if (k == 10 || k == 2) lz.probe<SPL>(b);
+          if (k == 8 || k == 0) lz.apply<SPL>(b, Bx);
+        }
+      };
+      int p = L - 2 - F.Kmax;
+      const int pa = -F.Kmax;
+      if (F.a_pow2) {
+#pragma unroll 1
+        for (; p >= pa && (((p + mis) & 15) != 15 || p < 15); p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+        int blk = (p + mis) >> 4;
+        uint4 cur = p >= 15 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (; p >= 15; p -= 16, blk--) {  // (p + mis) & 15 == 15: the block is bytes[p-15 .. p]
+          const uint4 nxt = blocks.load(blk - 1);
+          if (ck_left <= 16) {
+#pragma unroll 1
+            for (int k = 0; k < 16; k++) step(p - k, (int)__ldg(bytes + p - k));
+          } else {
+            fast16(cur);
+            ck_left -= 16;
+          }
+          cur = nxt;
+        }
+      }
+#pragma unroll 1
+      for (; p >= pa; p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
     }
     __syncwarp();
   }
 }
 
 // Phase A of the chromosome-scale Viterbi for banded models (jhw::k_vit_sweep with the shuffle exchange): bit-identical rows.
+// Same loop structure as k_band_pass1 (straight-line aligned blocks); the log emission table is read through L1.
 template <int SPL, int LO, int HI>
 __global__ void __launch_bounds__(32) k_band_vit_sweep(SparseDev F, jhw::VitLongDev V, int IND, DevData D, int CK, const int32_t *list, int64_t n_list,
                                                        const int64_t *chunk_ptr, double *ck_v, double *scores) {
   constexpr int W = HI - LO + 1;
   constexpr int BN = HI > 0 ? HI : 0, BP = LO < 0 ? -LO : 0;
   const int SP = F.SP, lane = threadIdx.x & 31;
+  const int ash = F.ashift, hpow = F.hpow;
+  const double *const lEl = V.lE + SPL * lane;  // + h * SP
   ResReader rd;
   SeqBlocks blocks;
   double w[SPL][W];
@@ -257,24 +332,23 @@ __global__ void __launch_bounds__(32) k_band_vit_sweep(SparseDev F, jhw::VitLong
     const int L = (int)(D.offsets[sid + 1] - off);
     rd.init(D.codes + off);
     blocks.init(D.codes + off);
+    const int mis = blocks.mis;
+    const uint8_t *const bytes = reinterpret_cast<const uint8_t *>(blocks.base) + mis;
     const int64_t cbase = chunk_ptr[sid];
     double b[SPL], e[SPL];
 #pragma unroll
     for (int u = 0; u < SPL; u++) b[u] = V.lfin[SPL * lane + u];
-    int h = jhs::hash_at(F, rd, L - 1);
-    jhw::lemis<SPL>(F, V, lane, e, jhs::hmod_of(F, h), L - 1);
+    int h = jhs::hmod_of(F, jhs::hash_at(F, rd, L - 1));
+    jhw::lemis<SPL>(F, V, lane, e, h, L - 1);
     const int K1 = F.Kmax + 1;
     int ck_left = (L - 1) % CK;
     double *ck_dst = ck_v + (size_t)(cbase + (L - 1) / CK) * SP + SPL * lane;
-    auto step = [&](int p, int x) {
-      const int t = p + K1;
+    auto advance = [&]() {  // bwd[t+1] -> bwd[t]
       double s[SPL];
 #pragma unroll
       for (int u = 0; u < SPL; u++) s[u] = __dadd_rn(b[u], e[u]);
       double c[3 * SPL];
       exchange<SPL, BP, BN>(s, lane, c);
-      h = jhs::roll_down(F, h, x);
-      jhw::lemis<SPL>(F, V, lane, e, h, t - 1);
 #pragma unroll
       for (int u = 0; u < SPL; u++) {
         double mx = JH_NEG_INF;
@@ -282,14 +356,51 @@ __global__ void __launch_bounds__(32) k_band_vit_sweep(SparseDev F, jhw::VitLong
         for (int xo = 0; xo < W; xo++) mx = fmax(mx, __dadd_rn(c[SPL + u + (xo + LO)], w[u][xo]));  // (bwd + em) + trans
         b[u] = mx;
       }
-      if (ck_left == 0) {
+    };
+    auto step = [&](int p, int x) {
+      const int t = p + K1;
+      advance();
+      h = jhs::roll_down(F, h, x);
+      jhw::lemis<SPL>(F, V, lane, e, h, t - 1);
+      if (ck_left == 0) {  // t is a multiple of CK: the row above chunk t/CK - 1
         jhs::store_vec<SPL>(ck_dst, b);
         ck_dst -= SP;
         ck_left = CK;
       }
       --ck_left;
     };
-    jhs::for_residues_down(blocks, L - 2 - F.Kmax, -F.Kmax, step);
+    auto fast16 = [&](const uint4 blk) {
+      const unsigned wds[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+      for (int k = 15; k >= 0; k--) {
+        const int x = (int)((wds[k >> 2] >> ((k & 3) * 8)) & 0xffu);
+        advance();
+        h = (h >> ash) + hpow * x;
+        jhs::load_vec<SPL>(lEl + (size_t)h * SP, e);
+      }
+    };
+    int p = L - 2 - F.Kmax;
+    const int pa = -F.Kmax;
+    if (F.a_pow2) {
+#pragma unroll 1
+      for (; p >= pa && (((p + mis) & 15) != 15 || p < 15); p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+      int blk = (p + mis) >> 4;
+      uint4 cur = p >= 15 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+      for (; p >= 15; p -= 16, blk--) {
+        const uint4 nxt = blocks.load(blk - 1);
+        if (ck_left < 16) {
+#pragma unroll 1
+          for (int k = 0; k < 16; k++) step(p - k, (int)__ldg(bytes + p - k));
+        } else {
+          fast16(cur);
+          ck_left -= 16;
+        }
+        cur = nxt;
+      }
+    }
+#pragma unroll 1
+    for (; p >= pa; p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
     double score;
     int st;
     jhw::start_choice<SPL>(F, V, lane, b, e, score, st);

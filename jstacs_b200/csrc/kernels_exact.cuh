@@ -170,13 +170,14 @@ __device__ __forceinline__ double lse2(double x, double y) {  // Normalisation.g
   return dadd(off, log(sum));
 }
 
+// grp / s0: allowed states groups of the sequence and the window start (layer L <-> absolute position s0 + L)
 template <int G>
-__device__ __forceinline__ void init_last_layer(const DevModel &M, const Group<G> &g, int64_t L, double *v) {
+__device__ __forceinline__ void init_last_layer(const DevModel &M, const Group<G> &g, int64_t L, double *v, const int32_t *grp = nullptr, int64_t s0 = 0) {
   int lc = L < M.m ? (int)L : M.m;  // bwd[L][c] = finalState[lastState(c)] ? 0 : -inf  (HOH:487-527 without silent states)
   int nc = M.lc_ctx_ptr[lc + 1] - M.lc_ctx_ptr[lc];
   for (int c = g.lane; c < nc; c += G) {
     int ls = M.ctx_last[M.lc_ctx_ptr[lc] + c];
-    v[c] = (ls >= 0 && M.is_final[ls]) ? 0.0 : JH_NEG_INF;
+    v[c] = (ls >= 0 && M.is_final[ls] && ctx_allowed(M, grp, s0 + L, L, c)) ? 0.0 : JH_NEG_INF;  // only allowed contexts are filled (HOH:493-496)
   }
 }
 
@@ -197,8 +198,9 @@ __global__ void __launch_bounds__(256) k_exact_loglik(DevModel M, DevData D, uns
     int sid = seq_list ? seq_list[it] : D.order[it];
     int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
     rd.init(D.codes + off);
+    const int32_t *grp = D.groups ? D.groups + off : nullptr;
     double *nxt = g.v0, *cur = g.v1;
-    init_last_layer<G>(M, g, L, nxt);
+    init_last_layer<G>(M, g, L, nxt, grp);
     int h = hash_at(M, rd, L - 1);
     for (int64_t l = L - 1; l >= 0; --l) {
       fill_em<G>(M, g, l, h);
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(256) k_exact_loglik(DevModel M, DevData D, uns
       int lc = l < M.m ? (int)l : M.m;
       int nc = M.lc_ctx_ptr[lc + 1] - M.lc_ctx_ptr[lc];
       double dummy;
-      for (int c = g.lane; c < nc; c += G) cur[c] = ctx_bwd_lse(M, lc, c, nxt, g.em, &dummy);
+      for (int c = g.lane; c < nc; c += G) cur[c] = ctx_allowed(M, grp, l, l, c) ? ctx_bwd_lse(M, lc, c, nxt, g.em, &dummy) : JH_NEG_INF;
       g.sync();
       double *t = cur; cur = nxt; nxt = t;
       if (l > 0) h = hash_back(M, rd, h, l);
@@ -243,8 +245,9 @@ __global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, Wo
     const int64_t L = s1 - s0 + 1;
     const int64_t pbase = path_ptr ? path_ptr[oid] : off + s0;
     rd.init(D.codes + off);
+    const int32_t *grp = D.groups ? D.groups + off : nullptr;
     double *nxt = g.v0, *cur = g.v1;
-    init_last_layer<G>(M, g, L, nxt);
+    init_last_layer<G>(M, g, L, nxt, grp, s0);
     int h = hash_at(M, rd, s1);
     for (int64_t l = L - 1; l >= 0; --l) {
       fill_em<G>(M, g, s0 + l, h);
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(256) k_exact_viterbi(DevModel M, DevData D, Wo
       for (int c = g.lane; c < nc; c += G) {
         int ch;
         cur[c] = ctx_bwd_max(M, lc, c, nxt, g.em, &ch);
+        if (!ctx_allowed(M, grp, s0 + l, l, c)) cur[c] = JH_NEG_INF;  // bwdMatrix stays -inf outside the allowed contexts (HOH:537, 567)
         choice[(size_t)l * M.Cmax + c] = (uint8_t)ch;
       }
       g.sync();
@@ -336,6 +340,9 @@ __global__ void __launch_bounds__(256) k_exact_fb(DevModel M, DevData D, unsigne
     int64_t off = D.offsets[sid], L = D.offsets[sid + 1] - off;
     double w = D.weights ? D.weights[sid] : 1.0;
     rd.init(D.codes + off);
+    // allowed states groups constrain training (baumWelch(..., allowedStatesGroup), HOH:723-726); the state posteriors of the
+    // reference are computed without them (fillLogStatePosteriorMatrix -> fillFwdMatrix(startPos, endPos, seq), HOH:309-310)
+    const int32_t *grp = (D.groups && mode == JHX_MODE_COUNTS) ? D.groups + off : nullptr;
     // ---------------- forward ----------------
     double *cur = g.v0, *nxt = g.v1;
     if (g.lane == 0) {
@@ -371,6 +378,7 @@ __global__ void __launch_bounds__(256) k_exact_fb(DevModel M, DevData D, unsigne
             r = dadd(offm, log(sum));
           }
         }
+        if (!ctx_allowed(M, grp, l + 1, l + 1, c)) r = JH_NEG_INF;  // fwdMatrix is only filled for the allowed contexts (HOH:386-388)
         nxt[c] = r;
         fwd[(size_t)(l + 1) * M.Cmax + c] = r;
       }
@@ -394,7 +402,7 @@ __global__ void __launch_bounds__(256) k_exact_fb(DevModel M, DevData D, unsigne
     // ---------------- backward ----------------
     double *bn = g.v0, *bc = g.v1;
     g.sync();
-    init_last_layer<G>(M, g, L, bn);
+    init_last_layer<G>(M, g, L, bn, grp);
     h = hash_at(M, rd, L - 1);
     g.sync();
     const bool counts = mode == JHX_MODE_COUNTS && !isinf(res);
@@ -438,6 +446,7 @@ __global__ void __launch_bounds__(256) k_exact_fb(DevModel M, DevData D, unsigne
       for (int c = g.lane; c < nc; c += G) {
         double offm;
         double b = ctx_bwd_lse(M, lc, c, bn, g.em, &offm);
+        if (!ctx_allowed(M, grp, l, l, c)) { b = JH_NEG_INF; offm = JH_NEG_INF; }
         bc[c] = b;
         if (counts && !isinf(offm)) {
           double f = fwd[(size_t)l * M.Cmax + c];

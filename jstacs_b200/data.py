@@ -124,6 +124,7 @@ class DataSet:
         np.cumsum(lens, out=self.offsets[1:])
         self.codes = (np.concatenate([s.codes for s in seqs]) if seqs else np.zeros(0, np.uint8)).astype(np.uint8, copy=False)
         self._native = None  # cached jh_dataset handle (owned by hmm._NativeData)
+        self.allowedStatesGroups = None  # int32 per residue, -1 = unconstrained (AbstractHMM.AllowedStatesGroups annotations)
 
     @classmethod
     def from_packed(cls, codes: np.ndarray, offsets: np.ndarray, con: AlphabetContainer | None = None,
@@ -134,6 +135,7 @@ class DataSet:
         ds.codes = np.ascontiguousarray(codes, dtype=np.uint8)
         ds.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         ds._native = None
+        ds.allowedStatesGroups = None
         if ds.offsets.ndim != 1 or ds.offsets.size < 1 or ds.offsets[0] != 0 or ds.offsets[-1] != ds.codes.size:
             raise ValueError("offsets must start at 0 and end at len(codes)")
         if ds.codes.size and int(ds.codes.max()) >= ds.con.getAlphabetLengthAt(0):

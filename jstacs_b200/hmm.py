@@ -596,7 +596,7 @@ class HigherOrderHMM:
     """
 
     def __init__(self, trainingParameterSet, name, emission, *te, emissionIdx=None, forward=None, transIndex=None,
-                 filter=None):
+                 filter=None, statesGroups=None, sequenceAnnotationType=None):
         if not trainingParameterSet.hasDefaultOrIsSet():
             raise ValueError("Please check the training parameters.")  # AbstractHMM.java:247-249
         self.trainingParameter = trainingParameterSet
@@ -633,6 +633,14 @@ class HigherOrderHMM:
         self.finalState = self.transition.isAbsorbing()
         if not any(self.finalState):
             self.finalState = [not s for s in isSilent]
+        # allowed states groups (HigherOrderHMM.java:183-187, AbstractHMM.java:173-228): groups of states that per-position
+        # annotations of the training data (DataSet.allowedStatesGroups, the reference's AllowedStatesGroups sequence
+        # annotation of type `sequenceAnnotationType`) can restrict the paths to
+        self.statesGroups = [] if statesGroups is None else [[int(s) for s in g] for g in statesGroups]
+        for g in self.statesGroups:
+            if any(not 0 <= s < n for s in g):
+                raise ValueError("states group names an unknown state")
+        self.type = sequenceAnnotationType
         self.sostream = _Stream(sys.stdout)
         self.skipInit = False
         self.threads = trainingParameterSet.getNumberOfThreads()
@@ -679,6 +687,8 @@ class HigherOrderHMM:
 
         if self._native is None:
             self._native = _native.NativeModel(self.ir())
+            if self.statesGroups:
+                self._native.set_states_groups(self.statesGroups)
         return self._native
 
     def _push_params(self):
@@ -705,7 +715,7 @@ class HigherOrderHMM:
             e.logNorm[...] = el[row:row + nc]
             row += nc
 
-    def _data(self, data: DataSet):
+    def _data(self, data: DataSet, groups=None):
         from . import _native
 
         if not data.getAlphabetContainer().checkConsistency(self.alphabets):
@@ -715,6 +725,7 @@ class HigherOrderHMM:
                 data._native = data._make_native(self.alphabets.getAlphabetLengthAt(0))
             else:
                 data._native = _native.NativeData(data.codes, data.offsets, None, self.alphabets.getAlphabetLengthAt(0))
+        data._native.set_groups(groups)  # None: unconstrained (what every reference method without a groups argument computes)
         return data._native
 
     # ---- initialisation ------------------------------------------------------------------------
@@ -747,7 +758,9 @@ class HigherOrderHMM:
         mode = _native.MODE_VITERBI if isinstance(tp, ViterbiParameterSet) else _native.MODE_BAUM_WELCH
         tc = tp.getTerminationCondition()
         eng = self._engine()
-        nd = self._data(data)
+        # semi-supervised training (doOneStep, HigherOrderHMM.java:812-820): sequences annotated with allowed states groups
+        groups = getattr(data, "allowedStatesGroups", None) if (self.type is not None and self.statesGroups) else None
+        nd = self._data(data, groups)
         nd.set_weights(weights)
         best, best_params = NEG_INF, None
         self.last_objectives = []
@@ -787,10 +800,17 @@ class HigherOrderHMM:
         self._push_params()
         return eng.loglik(self._data(data))
 
-    def getLogProbFor(self, sequence, startpos: int = 0, endpos: int | None = None):
-        """AbstractHMM.getLogProbFor (:985-998). A DataSet argument scores every element."""
+    def getLogProbFor(self, sequence, startpos: int = 0, endpos: int | None = None, statesGroups=None):
+        """AbstractHMM.getLogProbFor (:985-998; with statesGroups :989-998). A DataSet argument scores every element."""
         if isinstance(sequence, DataSet):
             return self.getLogScoreFor(sequence)
+        if statesGroups is not None:
+            if startpos != 0 or (endpos is not None and endpos != sequence.getLength() - 1):
+                raise NotImplementedError("allowed states groups on sub-sequences are outside the native path")
+            ds = DataSet("", sequence, con=self.alphabets)
+            eng = self._engine()
+            self._push_params()
+            return float(eng.loglik(self._data(ds, np.asarray(statesGroups, dtype=np.int32)))[0])
         if not sequence.getAlphabetContainer().checkConsistency(self.alphabets):
             raise WrongAlphabetException("The AlphabetContainer of the sequence and the model do not match.")
         if endpos is None:
@@ -830,10 +850,23 @@ class HigherOrderHMM:
         off = data.offsets
         return [(paths[off[i]:off[i + 1]], float(scores[i])) for i in range(data.getNumberOfElements())]
 
-    def getViterbiPathFor(self, seq: Sequence, startPos: int = 0, endPos: int | None = None):
-        """AbstractHMM.getViterbiPathFor (:879-881) / HigherOrderHMM.getViterbiPathFor (:590-598)."""
+    def getViterbiPathFor(self, seq: Sequence, startPos: int = 0, endPos: int | None = None, allowedStatesGroup=None):
+        """AbstractHMM.getViterbiPathFor (:879-881) / HigherOrderHMM.getViterbiPathFor (:590-598; with allowedStatesGroup :594-598)."""
         if endPos is None:
             endPos = seq.getLength() - 1
+        if allowedStatesGroup is not None:
+            if startPos != 0 or endPos != seq.getLength() - 1:
+                raise NotImplementedError("allowed states groups on sub-sequences are outside the native path")
+            ds = DataSet("", seq, con=self.alphabets)
+            eng = self._engine()
+            self._push_params()
+            try:
+                paths, scores = eng.viterbi(self._data(ds, np.asarray(allowedStatesGroup, dtype=np.int32)))
+            except _native_error() as e:
+                if e.status == -6:
+                    raise ValueError("Impossible path") from e
+                raise
+            return paths, float(scores[0])
         if startPos == 0 and endPos == seq.getLength() - 1:
             return self.getViterbiPathsFor(DataSet("", seq, con=self.alphabets))[0]
         # a window: the emissions see the residues before startPos (absolute positions, HigherOrderDiscreteEmission.java:138-146)

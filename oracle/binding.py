@@ -68,6 +68,8 @@ def lib():
         L.jo_train.restype = C.c_int
         L.jo_train.argtypes = [vp, _P_U8, _P_I64, C.c_int64, _P_F64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                _P_F64, C.c_int]
+        L.jo_model_set_groups.restype, L.jo_model_set_groups.argtypes = None, [vp, C.c_int, _P_I32, _P_I32]
+        L.jo_model_attach_groups.restype, L.jo_model_attach_groups.argtypes = None, [vp, _P_U8, _P_I32]
         L.jo_path_logprob.restype = C.c_double
         L.jo_path_logprob.argtypes = [vp, _P_U8, C.c_int64, _P_I32, C.c_int64]
         _lib = L
@@ -108,6 +110,24 @@ class OracleModel:
                 self.h = None
         except Exception:
             pass
+
+    def set_groups(self, groups):
+        """statesGroups (AbstractHMM.java:173-228): a list of state lists."""
+        ptr = np.zeros(len(groups) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(g) for g in groups])
+        st = np.array([s for g in groups for s in g] or [0], np.int32)
+        lib().jo_model_set_groups(self.h, len(groups), ptr.ctypes.data_as(_P_I32), st.ctypes.data_as(_P_I32))
+
+    def attach_groups(self, codes, groups):
+        """allowedStatesGroup of every position (-1 = unconstrained), aligned with `codes` (the SAME contiguous uint8 array
+        has to be passed to the following calls); None detaches."""
+        if groups is None:
+            self._g = None
+            lib().jo_model_attach_groups(self.h, None, None)
+            return
+        assert codes.dtype == np.uint8 and codes.flags.c_contiguous
+        self._g = (codes, np.ascontiguousarray(groups, np.int32))
+        lib().jo_model_attach_groups(self.h, _u8(codes), self._g[1].ctypes.data_as(_P_I32))
 
     @staticmethod
     def _pack(codes, offsets):

@@ -49,6 +49,11 @@ typedef struct jo_model {
   uint8_t *state_silent, *state_final;
   double log_uniform; /* ACDE:298  logUniform = -Math.log(a) */
   int max_children, max_in; /* helper sizes, HOH:189-203 */
+  /* allowed states groups (AHMM:146-228): preComputedContext as a flag per (group, context of layer class m) */
+  int n_groups;
+  uint8_t *allowed;              /* [n_groups * max_ctx] */
+  const uint8_t *groups_codes;   /* the code buffer the attached per-position groups are aligned with */
+  const int32_t *groups;         /* [n_res] group of every position, -1 = not constrained; NULL = no constraint at all */
 } jo_model;
 
 static void *dup_mem(const void *src, size_t bytes) {
@@ -189,14 +194,25 @@ static void work_reserve(jo_work *w, const jo_model *m, long len) {
 #define BWD(w, m, l, c) ((w)->bwd[(size_t)(l) * (m)->max_ctx + (c)])
 #define FINT(w, m, h, c) ((w)->f_int[h] + (size_t)(c) * ((m)->max_in + 1))
 
+/* HOH:331-340 getAllowedContext(pos, start, allowedStatesGroup, maxOrder) as a membership test: layer pos-start, the
+ * context's last state emitted position pos-1.  grp: the groups of the sequence x (indexed by position), or NULL. */
+static inline const int32_t *groups_of(const jo_model *m, const uint8_t *x) {
+  return m->groups ? m->groups + (x - m->groups_codes) : NULL;
+}
+static inline int ctx_allowed(const jo_model *m, const int32_t *grp, long pos, long start, int ctx) {
+  if (!grp || pos - start < m->m || grp[pos - 1] == -1) return 1; /* defContext[min(maxOrder, pos-start)]: every context */
+  return m->allowed[(size_t)grp[pos - 1] * m->max_ctx + ctx];     /* preComputedContext[group] */
+}
+
 static void fill_log_emission(jo_work *w, const jo_model *m, const uint8_t *x, long pos) { /* HOH:342-346 */
   for (int s = 0; s < m->S; s++) w->log_em[s] = emis_score(m, s, x, pos);
 }
 
-/* HOH:359-434 fillFwdMatrix (allowedStatesGroup == null, all filters accept) */
+/* HOH:359-434 fillFwdMatrix (all filters accept; allowedStatesGroup = the groups attached for x, if any) */
 static void fill_fwd(jo_work *w, const jo_model *m, const uint8_t *x, long start_pos, long end_pos) {
   long len = end_pos - start_pos + 1, l = 0, pos = start_pos;
   int c[3];
+  const int32_t *grp = groups_of(m, x);
   work_reserve(w, m, len);
   for (size_t i = 0; i < (size_t)(len + 1) * m->max_ctx; i++) w->fwd[i] = NEG_INF; /* AHMM:961-963 */
   memset(w->n_sum[0], 0, sizeof(int) * m->max_ctx);
@@ -208,6 +224,7 @@ static void fill_fwd(jo_work *w, const jo_model *m, const uint8_t *x, long start
     memset(w->n_sum[1 - h], 0, sizeof(int) * m->max_ctx);
     int nc = n_ctx(m, l);
     for (int ctx = 0; ctx < nc; ctx++) {
+      if (!ctx_allowed(m, grp, pos, start_pos, ctx)) continue; /* allContext = getAllowedContext(startPos, s, ...), HOH:386-388 */
       int n = n_children(m, l, ctx);
       if (w->n_sum[h][ctx] > 0) {
         FWD(w, m, l, ctx) = log_sum(0, w->n_sum[h][ctx], FINT(w, m, h, ctx));
@@ -228,6 +245,7 @@ static void fill_fwd(jo_work *w, const jo_model *m, const uint8_t *x, long start
   int h = (int)(l % 2);
   int nc = n_ctx(m, l);
   for (int ctx = 0; ctx < nc; ctx++) {
+    if (!ctx_allowed(m, grp, pos, start_pos, ctx)) continue; /* HOH:409 */
     int n = n_children(m, l, ctx);
     if (w->n_sum[h][ctx] > 0) {
       FWD(w, m, l, ctx) = log_sum(0, w->n_sum[h][ctx], FINT(w, m, h, ctx));
@@ -266,6 +284,7 @@ static void fill_bwd_or_viterbi(jo_work *w, const jo_model *m, int type, const u
   long l = end_pos - start_pos + 1;
   int c[3];
   double res, val, new_weight;
+  const int32_t *grp = groups_of(m, x);
   work_reserve(w, m, l);
   for (size_t i = 0; i < (size_t)(l + 1) * m->max_ctx; i++) w->bwd[i] = NEG_INF; /* provideMatrix(1,...) */
   if (add) {
@@ -278,6 +297,7 @@ static void fill_bwd_or_viterbi(jo_work *w, const jo_model *m, int type, const u
   int nc = n_ctx(m, l);
   for (int i = 0; i < m->max_ctx; i++) BWD(w, m, l, i) = zero ? 0 : NEG_INF;
   for (int ctx = nc - 1; ctx >= 0; ctx--) {
+    if (!ctx_allowed(m, grp, end_pos + 1, start_pos, ctx)) continue; /* getAllowedContext(endPos+1, startPos, ...), HOH:493 */
     int n = n_children(m, l, ctx), ns = 0;
     if (zero || m->state_final[last_state(m, l, ctx)]) val = 0; else val = NEG_INF;
     for (int ch = 0; ch < n; ch++) {
@@ -304,6 +324,7 @@ static void fill_bwd_or_viterbi(jo_work *w, const jo_model *m, int type, const u
     fill_log_emission(w, m, x, pos);
     nc = n_ctx(m, l);
     for (int ctx = nc - 1; ctx >= 0; ctx--) {
+      if (!ctx_allowed(m, grp, pos, start_pos, ctx)) continue; /* getAllowedContext(endPos, startPos, ...), HOH:537 */
       int n = n_children(m, l, ctx);
       if (n > 0) {
         for (int ch = 0; ch < n; ch++) {
@@ -449,8 +470,39 @@ jo_model *jo_model_create(const jh_model_desc *d) {
   return m;
 }
 
+/* AHMM:173-228 fillPreComputedContext: a context of layer class m is allowed for group g if some context of that class has a
+ * child whose state belongs to g and which leads to it.  group_ptr[n_groups+1], group_states: the states of every group. */
+void jo_model_set_groups(jo_model *m, int n_groups, const int32_t *group_ptr, const int32_t *group_states) {
+  free(m->allowed);
+  m->allowed = NULL;
+  m->n_groups = n_groups;
+  if (n_groups <= 0) return;
+  m->allowed = calloc((size_t)n_groups * m->max_ctx, 1);
+  int nc = n_ctx(m, m->m), c[3];
+  uint8_t *in_group = malloc(m->S);
+  for (int g = 0; g < n_groups; g++) {
+    memset(in_group, 0, m->S);
+    for (int k = group_ptr[g]; k < group_ptr[g + 1]; k++) in_group[group_states[k]] = 1;
+    for (int ctx = 0; ctx < nc; ctx++) {
+      int n = n_children(m, m->m, ctx);
+      for (int ch = 0; ch < n; ch++) {
+        trans_info(m, m->m, ctx, ch, c);
+        if (in_group[c[0]]) m->allowed[(size_t)g * m->max_ctx + c[1]] = 1;
+      }
+    }
+  }
+  free(in_group);
+}
+/* The allowedStatesGroup arrays of the sequences (HOH:812-820: one int per position, -1 = unconstrained), aligned with the
+ * code buffer of the following calls; NULL detaches (every call then behaves as with allowedStatesGroup == null). */
+void jo_model_attach_groups(jo_model *m, const uint8_t *codes, const int32_t *groups) {
+  m->groups_codes = codes;
+  m->groups = groups;
+}
+
 void jo_model_destroy(jo_model *m) {
   if (!m) return;
+  free(m->allowed);
   free(m->lc_ctx_ptr); free(m->ctx_elem); free(m->ctx_last_state); free(m->elem_child_ptr);
   free(m->child_state); free(m->child_desc); free(m->elem_ctx); free(m->trans_index);
   free(m->trans_param); free(m->trans_lognorm); free(m->trans_hyper); free(m->state_emis);
