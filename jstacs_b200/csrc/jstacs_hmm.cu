@@ -39,7 +39,7 @@ static int g_user_stream_device = 0;
 
 struct Options {
   int64_t fast = 1;            // use the scaled linear-space kernels where the model allows it
-  int64_t scratch_mb = 24576;  // upper bound of DP scratch memory
+  int64_t scratch_mb = 0;      // upper bound of DP scratch memory; 0 = automatic: 55 % of the free device memory, at most 96 GB
   int64_t blocks_per_sm = 0;   // 0 = occupancy API
   int64_t fast_variant = 0;
   int64_t chunk = 2048;        // positions per checkpoint of the sparse decoding path
@@ -55,6 +55,7 @@ struct Options {
   int64_t vit_chunk_force = 0; // tests: checkpointed Viterbi for every sequence longer than 2 * vit_chunk
   int64_t stage = 1;           // host transfers of pageable caller memory through the library's pinned double buffers
   int64_t band = 1;            // banded models: warp-resident whole-sequence passes (kernels_band.cuh)
+  int64_t oct_full_rows_mb = 24576;  // octet kernels: buckets whose full forward rows (whole grid) exceed this are chunked
 };
 static Options g_defaults;
 static std::atomic<uint64_t> g_opt_gen{1};
@@ -78,6 +79,7 @@ static bool set_option_field(Options &o, const std::string &n, int64_t value) {
   else if (n == "vit_chunk_force") o.vit_chunk_force = value;
   else if (n == "stage") o.stage = value;
   else if (n == "band") o.band = value;
+  else if (n == "oct_full_rows_mb") o.oct_full_rows_mb = value;
   else return false;
   return true;
 }
@@ -386,6 +388,7 @@ struct jh_model {
   bool have_user_stream = false;
   Options opt;                                             // defaults (jh_set_option) + overrides (jh_model_set_option)
   uint64_t opt_seen = 0;
+  int64_t auto_scratch_mb = 0;
   std::vector<std::pair<std::string, int64_t>> overrides;
   int failed = 0;                                          // multi-rank: error of this rank's E-step, returned after the collectives
   char failed_msg[1024] = "";
@@ -407,6 +410,15 @@ struct jh_model {
     std::lock_guard<std::mutex> g(g_mu);
     opt = g_defaults;
     for (auto &kv : overrides) set_option_field(opt, kv.first, kv.second);
+    if (opt.scratch_mb <= 0) {  // automatic budget, sized once per model from what the device has free (180 GB HBM3e on a B200)
+      if (auto_scratch_mb <= 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(device);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)32 << 30; }
+        auto_scratch_mb = std::max<int64_t>(1024, std::min<int64_t>(96 * 1024, (int64_t)(free_b >> 20) * 55 / 100));
+      }
+      opt.scratch_mb = auto_scratch_mb;
+    }
     opt_seen = gen;
   }
   DevModel dev() const {
@@ -2516,7 +2528,7 @@ static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, PathOut d_pat
   const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
   const bool chunked = m->opt.oct_chunk > 0 && rows > 2 * m->opt.oct_chunk &&
-                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > m->opt.scratch_mb * 1024 * 1024);
+                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > std::min<int64_t>(m->opt.scratch_mb, m->opt.oct_full_rows_mb) * 1024 * 1024);
   if (eg) return chunked ? launch_mma_decode_impl<NT, true, true>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, true>(m, d, b, grid, smem, d_paths, d_ll);
   return chunked ? launch_mma_decode_impl<NT, true, false>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, false>(m, d, b, grid, smem, d_paths, d_ll);
 }
@@ -2685,7 +2697,7 @@ static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
   const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
   const bool chunked = m->opt.oct_chunk > 0 && rows > 2 * m->opt.oct_chunk &&
-                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > m->opt.scratch_mb * 1024 * 1024);
+                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > std::min<int64_t>(m->opt.scratch_mb, m->opt.oct_full_rows_mb) * 1024 * 1024);
   if (eg) return chunked ? launch_mma_estep_impl<NT, true, true>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, b, grid, smem);
   return chunked ? launch_mma_estep_impl<NT, true, false>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, false>(m, d, b, grid, smem);
 }

@@ -7,6 +7,15 @@ so the parity tests read like Jstacs user code (cf. supplementary/cookbook/Cookb
 Everything numeric is done by libjstacs_hmm_b200.so through the C ABI of include/jstacs_hmm.h; this file only
 holds the model description (context graph construction = BasicHigherOrderTransition.init) and parameter
 bookkeeping.  There is no CPU fallback: without the CUDA library every compute method raises.
+
+WHAT IS A RESTATEMENT HERE (and not from-scratch product code): `BasicHigherOrderTransition._init` /
+`_add_and_topsort` follow BasicHigherOrderTransition.java:191-431 statement by statement (same variable names, same
+control flow), and `HMMFactory.createErgodicHMM` / `_addTransitions` follow HMMFactory.java:123-181.  They are the Python
+stand-in for the Java host side (the image has no JVM): the ORDER of the contexts inside a layer decides the summation
+order of the reference's log-sum-exp, so it has to be reproduced exactly for 1e-9 parity, and the hyper-parameters of the
+factory have to be the reference's.  In a Jstacs deployment this code does not exist — GpuTransitionExport.java reads
+Jstacs' own lookup tables.  tests/test_independent_ir.py checks the result against a first-principles construction that
+shares nothing with it.
 """
 from __future__ import annotations
 

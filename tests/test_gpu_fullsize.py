@@ -138,3 +138,79 @@ def test_cfg5_shape_many_chunks_vs_oracle(nat, oracle_lib):
     np.testing.assert_allclose(es, res, rtol=5e-8, atol=COUNT_TOL)
     assert ts.sum() == pytest.approx(data.getNumberOfResidues(), rel=1e-11)  # ... while the scaled counts add up to 1e-11
     assert sc == pytest.approx(rsc, rel=LL_RTOL)
+
+
+def test_cfg4_full_size_ragged(nat, oracle_lib):
+    """BASELINE configs[3] at FULL size: 100 000 sequences with log-uniform lengths 100 bp - 100 kb (1.45e9 residues),
+    16 states, order-1 emissions.  Scoring and one E-step over the whole data set; oracle parity on a sample of 64 sequences
+    that includes the longest one (chunked octets) and the shortest ones; size-independent properties on everything."""
+    from jstacs_b200.workloads import ragged_lengths
+
+    lens = ragged_lengths(100_000, seed=42)
+    assert lens.min() >= 100 and lens.max() <= 100_000 and 1.3e9 < lens.sum() < 1.6e9
+    data = make_data(lens.size, lens)
+    hmm = ergodic_hmm(16, 1)
+    om = oracle_lib.OracleModel(hmm.ir())
+    eng, nd = hmm._engine(), hmm._data(data)
+    ll = eng.loglik(nd)
+    assert np.isfinite(ll).all() and (ll < 0).all()
+    # longer sequences are less likely: the per-residue log-likelihood stays in a narrow band
+    per_res = ll / lens
+    assert per_res.min() > -1.5 and per_res.max() < -1.2
+    ts, es, sc = eng.estep(nd)
+    assert sc == pytest.approx(ll.sum(), rel=1e-11)
+    assert ts.sum() == pytest.approx(float(lens.sum()), rel=1e-10)            # one transition per residue (start element included)
+    assert es.sum() == pytest.approx(float(lens.sum() - lens.size), rel=1e-10)  # one emission count per residue from position 1 on
+    order = np.argsort(lens)
+    rng = np.random.default_rng(11)
+    idx = np.unique(np.concatenate([order[:8], order[-3:], rng.integers(0, lens.size, 53)]))
+    sub = subset(data, idx)
+    np.testing.assert_allclose(ll[idx], om.loglik(sub.codes, sub.offsets), rtol=LL_RTOL)
+    snd = hmm._data(sub)
+    w = rng.random(idx.size) + 0.5
+    snd.set_weights(w)
+    ts1, es1, sc1 = eng.estep(snd)
+    rts, res, rsc = om.estep(sub.codes, sub.offsets, w)
+    np.testing.assert_allclose(ts1, rts, rtol=2e-8, atol=COUNT_TOL)  # 100 kb sequences: see the note on the reference's own rounding below
+    np.testing.assert_allclose(es1, res, rtol=2e-8, atol=COUNT_TOL)
+    assert sc1 == pytest.approx(rsc, rel=LL_RTOL)
+    # posterior decoding of the sample, byte paths
+    paths, dll = eng.posterior_decode(snd, narrow=True)
+    np.testing.assert_allclose(dll, ll[idx], rtol=LL_RTOL)
+    k = int(np.argmin(np.diff(sub.offsets)))
+    ref = om.posterior(sub.getElementAt(k).codes)
+    srt = np.sort(ref, axis=0)
+    clear = srt[-1] - srt[-2] > 1e-9
+    assert np.array_equal(paths[sub.offsets[k]:sub.offsets[k + 1]][clear], om.decode_posterior(ref)[clear])
+    nd.close()
+    data._native = None
+
+
+def test_cfg5_shape_multi_megabase_vs_oracle(nat, oracle_lib):
+    """cfg5 shape beyond 5 Mb: a 5.2 Mb and a 1.1 Mb sequence, 128 states, banded (the warp-resident band kernels and the
+    chunk passes): log-likelihood and E-step against the oracle (which holds two 5.2M x 128 matrices = 10.6 GB here),
+    chromosome-scale Viterbi bit for bit on the 1.1 Mb sequence and through the path score on the long one."""
+    hmm = banded_hmm(128, 4, 0)
+    om = oracle_lib.OracleModel(hmm.ir())
+    data = make_data(2, [5_200_000, 1_100_000])
+    eng, nd = hmm._engine(), hmm._data(data)
+    ll = eng.loglik(nd)
+    ll_ref = om.loglik(data.codes, data.offsets)
+    np.testing.assert_allclose(ll, ll_ref, rtol=LL_RTOL)
+    ts, es, sc = eng.estep(nd)
+    assert sc == pytest.approx(ll_ref.sum(), rel=LL_RTOL)
+    assert ts.sum() == pytest.approx(data.getNumberOfResidues(), rel=1e-11) and es.sum() == pytest.approx(data.getNumberOfResidues(), rel=1e-11)
+    short = subset(data, [1])
+    rts, res, rsc = om.estep(short.codes, short.offsets)
+    ts1, es1, sc1 = eng.estep(hmm._data(short))
+    # the reference's log-space counts lose ~5e-7 at 1.1 Mb (|fwd|, |bwd| ~ 1.5e6: 1 ulp = 2e-10, accumulated over 1.1e6 positions;
+    # 6.5e-9 at 150 kb above); the scaled counts on the GPU add up to 1e-11 (checked above)
+    np.testing.assert_allclose(ts1, rts, rtol=3e-6, atol=COUNT_TOL)
+    np.testing.assert_allclose(es1, res, rtol=3e-6, atol=COUNT_TOL)
+    paths, scores = eng.viterbi(nd, narrow=True)
+    rp, rs, _ = om.viterbi(short.codes, short.offsets)
+    assert scores[1] == rs[0] and np.array_equal(paths[data.offsets[1]:], rp[0])
+    x, p = data.codes[:data.offsets[1]], paths[:data.offsets[1]]
+    assert om.path_logprob(x, p.astype(np.int32)) == pytest.approx(scores[0], rel=1e-12)  # the 5.2 Mb path really has its score
+    assert scores[0] <= ll[0]
+    nd.close()
