@@ -1758,7 +1758,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, PathOut d_
   JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
   JH_CUDA(cudaMemsetAsync(m->d_counters.p, 0, sizeof(unsigned long long) * n_launch, s));
   jhs::EstepTables ET{P.d_out_stat, P.d_pistat, (int)n_stats};
-  if (what == SPARSE_ESTEP) JH_CUDA(cudaMemsetAsync(P.d_ec, 0, sizeof(double) * jhs::EC_REPLICAS_SPARSE * P.H * P.SP, s));
+  if (what == SPARSE_ESTEP) JH_CUDA(cudaMemsetAsync(P.d_ec, 0, P.ec_bytes(), s));
   auto launch_chunks = [&](int64_t k, cudaStream_t st) -> int {
     if (count[k] <= 0) return JH_OK;
     double *rows_k = m->d_fwd.p + (size_t)slot0[k] * rows * P.SP;
@@ -1794,7 +1794,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, PathOut d_
       const int grid_l = (int)((warps + wpc - 1) / wpc);
       if ((r = m->d_fwd.reserve((size_t)grid_l * wpc * rows * 32 * Ft.G))) return r;
       if (what == SPARSE_ESTEP && (r = m->d_rexp.reserve((size_t)grid_l * wpc * rows * 32))) return r;
-      if (what == SPARSE_ESTEP) JH_CUDA(cudaMemsetAsync(Ft.d_ec, 0, sizeof(double) * jhf::EC_REPLICAS * Ft.H * Ft.G, s));
+      if (what == SPARSE_ESTEP) JH_CUDA(cudaMemsetAsync(Ft.d_ec, 0, Ft.ec_bytes(), s));
       jhc::LaneChunkIn In{(int)CK, (int)rows, P.SP, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_ck_alpha.p, m->d_ck_beta.p,
                           m->d_ck_exp.p, m->d_ck_exp.p + d->n_chunks + 1, m->d_seq_sfin.p, m->d_seq_AL.p};
 #define JH_LC(GG)                                                                                                                        \
@@ -1813,7 +1813,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, PathOut d_
       JH_CUDA(cudaGetLastError());
       if (what == SPARSE_ESTEP) {
         const int nf = Ft.H * Ft.G;
-        jhf::k_fast_fold_ec<<<(nf + 255) / 256, 256, 0, s>>>(Ft.dev(), Ft.d_ec, m->d_stats.p);
+        jhf::k_fast_fold_ec<<<(nf + 7) / 8, 256, 0, s>>>(Ft.dev(), Ft.d_ec, m->d_stats.p);
         JH_LAUNCHED();
         JH_CUDA(cudaGetLastError());
         return JH_OK;
@@ -1864,7 +1864,7 @@ static int run_sparse_two_phase(jh_model *m, jh_dataset *d, int what, PathOut d_
   }
   if (what == SPARSE_ESTEP) {
     const int n = P.H * P.SP;
-    jhs::k_sparse_fold_ec<<<(n + 255) / 256, 256, 0, s>>>(P.dev(), P.d_etab, P.d_emod, m->n_child, P.d_ec, m->d_stats.p);
+    jhs::k_sparse_fold_ec<<<(n + 7) / 8, 256, 0, s>>>(P.dev(), P.d_etab, P.d_emod, m->n_child, P.d_ec, m->d_stats.p);
     JH_LAUNCHED();
     JH_CUDA(cudaGetLastError());
     return JH_OK;
@@ -2476,14 +2476,49 @@ extern "C" int jh_posterior(jh_model *m, jh_dataset *d, int64_t seq_index, doubl
   return JH_OK;
 }
 
-// Octet posterior decoding (kernels_mma.cuh), one launch per length bucket; long buckets chunked like the E-step.
+// Launch groups of the octet kernels.  Octets are consumed longest first from ONE queue per launch, so a launch ends with a
+// tail as long as its last octets: with a launch per length bucket (about as many octets as warp slots each) that tail was
+// a second wave of half-length octets per bucket, 40 % of the E-step on ragged data (cfg4).  Consecutive buckets that agree
+// on chunked / full rows are therefore merged: normally one launch for the long (chunked) sequences and one for the rest,
+// whose queue ends with the shortest sequences of the data set.  Full-row groups are only merged while the rows of the
+// group's longest bucket for all its slots stay inside the budget.
+struct OctGroup {
+  size_t b0, b1;  // buckets [b0, b1)
+  bool chunked;
+};
+template <int NT>
+static std::vector<OctGroup> oct_groups(const jh_model *m, const jh_dataset *d, int64_t full_grid) {
+  using C = jhm::MmaCfg<NT>;
+  std::vector<OctGroup> out;
+  const int64_t budget = std::min<int64_t>(m->opt.scratch_mb, m->opt.oct_full_rows_mb) * 1024 * 1024;
+  auto slots_of = [&](int64_t n_oct) { return std::min<int64_t>(full_grid, (n_oct + C::WARPS - 1) / C::WARPS) * C::WARPS; };
+  auto per_slot_of = [&](size_t b) { return (d->bucket_len[b] + 1) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int)); };
+  for (size_t b = 0; b + 1 < d->bucket_ptr.size(); b++) {
+    const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b];
+    if (n_oct <= 0) continue;
+    const bool chunked = m->opt.oct_chunk > 0 && d->bucket_len[b] + 1 > 2 * m->opt.oct_chunk &&
+                         (m->opt.oct_chunk_force || slots_of(n_oct) * per_slot_of(b) > budget);
+    if (!out.empty() && out.back().chunked == chunked && out.back().b1 == b) {
+      const int64_t n_all = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[out.back().b0];
+      if (chunked || slots_of(n_all) * per_slot_of(out.back().b0) <= budget) {
+        out.back().b1 = b + 1;
+        continue;
+      }
+    }
+    out.push_back(OctGroup{b, b + 1, chunked});
+  }
+  return out;
+}
+
+// Octet posterior decoding (kernels_mma.cuh), one launch per group of length buckets; long buckets chunked like the E-step.
 template <int NT, bool CHUNKED, bool EG>
-static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem, PathOut d_paths, double *d_ll) {
+static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, OctGroup g, int64_t grid, size_t smem, PathOut d_paths, double *d_ll) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
   auto kern = jhm::k_mma_decode<NT, CHUNKED, EG>;
-  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
+  const int64_t oct0 = d->bucket_oct_ptr[g.b0], n_oct = d->bucket_oct_ptr[g.b1] - oct0, L = d->bucket_len[g.b0];
+  grid = std::min<int64_t>(grid, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t CK = m->opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2513,11 +2548,9 @@ static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, size_t b, int64_t 
 }
 
 template <int NT>
-static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, PathOut d_paths, double *d_ll) {
+static int launch_mma_decode(jh_model *m, jh_dataset *d, PathOut d_paths, double *d_ll) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
-  const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b], rows = d->bucket_len[b] + 1;
-  if (n_oct <= 0) return JH_OK;
   const bool eg = F.e_global;
   const size_t smem = (eg ? 0 : (size_t)F.H * C::G * sizeof(double)) + (size_t)C::WARPS * C::RING * C::SLOTB;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(jhm::k_mma_decode<NT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2525,12 +2558,14 @@ static int launch_mma_decode(jh_model *m, jh_dataset *d, size_t b, PathOut d_pat
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_decode<NT, false, false>, C::NTHREADS, smem));
   if (per_sm < 1) { jh_set_error("octet decoding kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
   if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
-  const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
-  const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-  const bool chunked = m->opt.oct_chunk > 0 && rows > 2 * m->opt.oct_chunk &&
-                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > std::min<int64_t>(m->opt.scratch_mb, m->opt.oct_full_rows_mb) * 1024 * 1024);
-  if (eg) return chunked ? launch_mma_decode_impl<NT, true, true>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, true>(m, d, b, grid, smem, d_paths, d_ll);
-  return chunked ? launch_mma_decode_impl<NT, true, false>(m, d, b, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, false>(m, d, b, grid, smem, d_paths, d_ll);
+  const int64_t grid = (int64_t)m->sm_count * per_sm;
+  int r = JH_OK;
+  for (const OctGroup &g : oct_groups<NT>(m, d, grid)) {
+    if (eg) r = g.chunked ? launch_mma_decode_impl<NT, true, true>(m, d, g, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, true>(m, d, g, grid, smem, d_paths, d_ll);
+    else r = g.chunked ? launch_mma_decode_impl<NT, true, false>(m, d, g, grid, smem, d_paths, d_ll) : launch_mma_decode_impl<NT, false, false>(m, d, g, grid, smem, d_paths, d_ll);
+    if (r) return r;
+  }
+  return JH_OK;
 }
 
 static int run_decode_octets(jh_model *m, jh_dataset *d, PathOut d_paths, double *d_ll) {
@@ -2539,9 +2574,8 @@ static int run_decode_octets(jh_model *m, jh_dataset *d, PathOut d_paths, double
   if ((r = m->d_fallback.reserve(d->n_seq + 2))) return r;
   cudaStream_t s = m->st();
   JH_CUDA(cudaMemsetAsync(m->d_fallback.p, 0, sizeof(int32_t), s));
-  for (size_t b = 0; b + 1 < d->bucket_ptr.size() && !r; b++)
-    r = m->fast.G == 8 ? launch_mma_decode<1>(m, d, b, d_paths, d_ll) : m->fast.G == 16 ? launch_mma_decode<2>(m, d, b, d_paths, d_ll)
-                                                                                        : launch_mma_decode<4>(m, d, b, d_paths, d_ll);
+  r = m->fast.G == 8 ? launch_mma_decode<1>(m, d, d_paths, d_ll) : m->fast.G == 16 ? launch_mma_decode<2>(m, d, d_paths, d_ll)
+                                                                                   : launch_mma_decode<4>(m, d, d_paths, d_ll);
   if (r) return r;
   int32_t n_fb = 0;
   JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -2647,12 +2681,13 @@ static int ensure_octet_hashes(jh_model *m, jh_dataset *d) {
 // Buckets whose full forward rows would not leave scratch for the whole grid run the chunked variant (checkpoints every
 // `oct_chunk` positions, rows of one chunk per resident warp).
 template <int NT, bool CHUNKED, bool EG>
-static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, size_t b, int64_t grid, size_t smem) {
+static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, OctGroup g, int64_t grid, size_t smem) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
   auto kern = jhm::k_mma_estep<NT, CHUNKED, EG>;
-  const int64_t oct0 = d->bucket_oct_ptr[b], n_oct = d->bucket_oct_ptr[b + 1] - oct0, L = d->bucket_len[b];
+  const int64_t oct0 = d->bucket_oct_ptr[g.b0], n_oct = d->bucket_oct_ptr[g.b1] - oct0, L = d->bucket_len[g.b0];
+  grid = std::min<int64_t>(grid, (n_oct + C::WARPS - 1) / C::WARPS);
   const int64_t CK = m->opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2682,11 +2717,9 @@ static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, size_t b, int64_t g
 }
 
 template <int NT>
-static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
+static int launch_mma_estep(jh_model *m, jh_dataset *d) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
-  const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b], rows = d->bucket_len[b] + 1;
-  if (n_oct <= 0) return JH_OK;
   const bool eg = F.e_global;
   const size_t smem = C::smem_bytes(eg ? 0 : F.H);
   int per_sm = 0;
@@ -2694,22 +2727,23 @@ static int launch_mma_estep(jh_model *m, jh_dataset *d, size_t b) {
   JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhm::k_mma_estep<NT, false, false>, C::NTHREADS, smem));
   if (per_sm < 1) { jh_set_error("octet E-step kernel does not fit on an SM (smem %zu)", smem); return JH_ERR_UNSUPPORTED; }
   if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
-  const int64_t grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (n_oct + C::WARPS - 1) / C::WARPS);
-  const int64_t per_slot = rows * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
-  const bool chunked = m->opt.oct_chunk > 0 && rows > 2 * m->opt.oct_chunk &&
-                       (m->opt.oct_chunk_force || grid * C::WARPS * per_slot > std::min<int64_t>(m->opt.scratch_mb, m->opt.oct_full_rows_mb) * 1024 * 1024);
-  if (eg) return chunked ? launch_mma_estep_impl<NT, true, true>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, b, grid, smem);
-  return chunked ? launch_mma_estep_impl<NT, true, false>(m, d, b, grid, smem) : launch_mma_estep_impl<NT, false, false>(m, d, b, grid, smem);
+  const int64_t grid = (int64_t)m->sm_count * per_sm;
+  int r = JH_OK;
+  for (const OctGroup &g : oct_groups<NT>(m, d, grid)) {
+    if (eg) r = g.chunked ? launch_mma_estep_impl<NT, true, true>(m, d, g, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, g, grid, smem);
+    else r = g.chunked ? launch_mma_estep_impl<NT, true, false>(m, d, g, grid, smem) : launch_mma_estep_impl<NT, false, false>(m, d, g, grid, smem);
+    if (r) return r;
+  }
+  return JH_OK;
 }
 
 static int run_estep_fast(jh_model *m, jh_dataset *d) {
   int r = JH_OK;
-  JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, sizeof(double) * jhf::EC_REPLICAS * m->fast.H * m->fast.G, m->st()));
+  JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, m->fast.ec_bytes(), m->st()));
   const bool octets = variant_of(m) == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
   const bool lanes = variant_of(m) == 0 && m->fast.G <= 4;  // one sequence per lane
   for (size_t b = 0; lanes && b + 1 < d->bucket_ptr.size() && !r; b++) r = m->fast.G == 2 ? launch_lanes<2, 1>(m, d, b, nullptr) : launch_lanes<4, 1>(m, d, b, nullptr);
-  for (size_t b = 0; octets && b + 1 < d->bucket_ptr.size() && !r; b++)
-    r = m->fast.G == 8 ? launch_mma_estep<1>(m, d, b) : m->fast.G == 16 ? launch_mma_estep<2>(m, d, b) : launch_mma_estep<4>(m, d, b);
+  if (octets) r = m->fast.G == 8 ? launch_mma_estep<1>(m, d) : m->fast.G == 16 ? launch_mma_estep<2>(m, d) : launch_mma_estep<4>(m, d);
   for (size_t b = 0; !octets && !lanes && b + 1 < d->bucket_ptr.size() && !r; b++) {
     int64_t first = d->bucket_ptr[b], count = d->bucket_ptr[b + 1] - first, rows = d->bucket_len[b] + 1;
     const bool p2 = (m->a & (m->a - 1)) == 0;
@@ -2727,7 +2761,7 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
   }
   if (r) return r;
   int n = m->fast.H * m->fast.G;
-  jhf::k_fast_fold_ec<<<(n + 255) / 256, 256, 0, m->st()>>>(m->fast.dev(), m->fast.d_ec, m->d_stats.p);
+  jhf::k_fast_fold_ec<<<(n + 7) / 8, 256, 0, m->st()>>>(m->fast.dev(), m->fast.d_ec, m->d_stats.p);
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
   return JH_OK;

@@ -33,13 +33,25 @@ struct DevBuf;
 
 namespace jhf {
 
-constexpr int EC_REPLICAS = 16;  // copies of the global emission-count table (spreads the fp64 reductions over L2 slices)
+// Copies of the global emission-count table [H][G].  The fp64 reductions of a position go to one copy, chosen by the warp
+// slot: the copies spread them over the L2 slices, and — what matters for small tables — over ADDRESSES: the L2 serialises
+// reductions to one address, and a 16-state model with first-order emissions (256 cells) on 16 copies spent two thirds of its
+// E-step waiting for them (same kernel, 4096 cells per copy: 11 ms instead of 37).  The number of copies is a power of two
+// chosen so that all copies together have about 2^19 cells (4 MB, L2 resident), at least 16, at most 2048.
+constexpr int EC_REPLICAS_MIN = 16, EC_REPLICAS_MAX = 2048;
+constexpr int64_t EC_CELLS_TARGET = (int64_t)1 << 19;
+inline int ec_replicas_for(int64_t cells) {
+  int r = EC_REPLICAS_MIN;
+  while (r < EC_REPLICAS_MAX && (int64_t)r * cells < EC_CELLS_TARGET) r *= 2;
+  return r;
+}
 
 using jhx::ResReader;
 
 struct FastDev {
   int S, G, a, Kmax, H;  // H = a^(Kmax+1) rows of the emission table
   int hpow, a_pow2, n_child, n_stats;
+  int ec_mask;          // number of emission-count table copies - 1 (a power of two)
   double inv_a;
   const double *T;      // [G*G] T[i*G+j] = P(i -> j)
   const double *Tt;     // [G*G] transposed
@@ -62,7 +74,9 @@ struct FastTables {
   bool sorted_children = false;               // every context lists its children in ascending state order (kernels_viterbi.cuh)
   double *d_vT = nullptr, *d_vpi = nullptr, *d_vfin = nullptr, *d_vE = nullptr;  // log-space dense tables of the lane-per-sequence Viterbi
   int *d_fexp = nullptr;                      // per-row exponent scratch
-  double *d_ec = nullptr;                     // [EC_REPLICAS][H*G] global emission-count tables
+  double *d_ec = nullptr;                     // [ec_replicas][H*G] global emission-count tables
+  int ec_replicas = EC_REPLICAS_MIN;
+  size_t ec_bytes() const { return sizeof(double) * (size_t)ec_replicas * H * G; }
   size_t fexp_n = 0;
   FastDev dev() const {
     FastDev F;
@@ -71,6 +85,7 @@ struct FastTables {
     for (int i = 0; i < Kmax; i++) pw *= a;
     F.hpow = pw; F.a_pow2 = (a & (a - 1)) == 0; F.n_child = n_child; F.n_stats = n_child + n_cond * a;
     F.inv_a = 1.0 / a;
+    F.ec_mask = ec_replicas - 1;
     F.T = d_T; F.Tt = d_Tt; F.pi = d_pi; F.E = d_E; F.fin = d_fin; F.korder = d_korder; F.tstat = d_tstat; F.pistat = d_pistat;
     F.estat_tab = d_estat_tab; F.estat_mod = d_estat_mod;
     return F;
@@ -143,7 +158,8 @@ inline int build(FastTables &F, int S, int a, int m, bool has_silent, int Kmax, 
   std::vector<double> z((size_t)std::max<int64_t>(H * G, (int64_t)G * G), 0.0);
   std::vector<double> zT((size_t)G * G, 0.0), zpi(G, 0.0), zE((size_t)H * G, 0.0);
   if ((r = up(&F.d_T, zT, s)) || (r = up(&F.d_Tt, zT, s)) || (r = up(&F.d_pi, zpi, s)) || (r = up(&F.d_E, zE, s))) return r;
-  std::vector<double> zEC((size_t)EC_REPLICAS * H * G, 0.0);
+  F.ec_replicas = ec_replicas_for((int64_t)H * G);
+  std::vector<double> zEC((size_t)F.ec_replicas * H * G, 0.0);
   if ((r = up(&F.d_ec, zEC, s))) return r;
   if ((r = up(&F.d_vT, zT, s)) || (r = up(&F.d_vpi, zpi, s)) || (r = up(&F.d_vfin, zpi, s)) || (r = up(&F.d_vE, zE, s))) return r;
   F.sorted_children = sorted;
@@ -690,13 +706,16 @@ __global__ void __launch_bounds__(NT, 1) k_fast_estep(FastDev F, DevData D, unsi
 }
 
 // emission-count table [H][G] -> emission statistics (several context hashes share a cell when a state's order < Kmax)
+// One warp per cell: the lanes stride over the copies, then a shuffle tree (a fixed summation order).
 __global__ void k_fast_fold_ec(FastDev F, const double *gEC, double *stats) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (i >= F.H * F.G) return;
-  int j = i % F.G, hh = i / F.G;
+  const int j = i % F.G, hh = i / F.G;
   double v = 0;
-  for (int rep = 0; rep < EC_REPLICAS; rep++) v += gEC[(size_t)rep * F.H * F.G + i];
-  if (v != 0 && F.estat_tab[j] >= 0) atomicAdd(&stats[F.n_child + F.estat_tab[j] + hh % F.estat_mod[j]], v);
+  for (int rep = lane; rep <= F.ec_mask; rep += 32) v += gEC[(size_t)rep * F.H * F.G + i];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if (lane == 0 && v != 0 && F.estat_tab[j] >= 0) atomicAdd(&stats[F.n_child + F.estat_tab[j] + hh % F.estat_mod[j]], v);
 }
 
 // NaN/Inf guard over the statistics block: a non-finite value makes the driver redo the E-step in log space.

@@ -11,7 +11,6 @@
 
 namespace jhc {
 
-using jhf::EC_REPLICAS;
 using jhf::FastDev;
 
 struct LaneChunkIn {
@@ -45,7 +44,7 @@ __device__ __forceinline__ double pow2_any(long long k) {  // 2^k, 0 below the n
   return __hiloint2double((1023 + kk) << 20, 0);
 }
 
-// rows: [slot][ROWS][32][G], rexp: [slot][ROWS][32] (MODE 1); gEC: [EC_REPLICAS][H][G]; stats as in kernels_mma.cuh
+// rows: [slot][ROWS][32][G], rexp: [slot][ROWS][32] (MODE 1); gEC: [copies][H][G]; stats as in kernels_mma.cuh
 template <int G, int MODE>
 __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneChunkIn I, unsigned long long *counter, double *rows, int *rexp,
                                                      PathOut paths, double *stats, double *gEC, int32_t *fallback, int ec_smem) {
@@ -64,7 +63,7 @@ __global__ void __launch_bounds__(128) k_lane_chunks(FastDev F, DevData D, LaneC
   const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   double *const R = rows + ((size_t)slot * I.ROWS * 32 + lane) * G;  // + r*32*G
   int *const RX = MODE == 1 ? rexp + (size_t)slot * I.ROWS * 32 + lane : nullptr;  // + r*32
-  double *const gECw = gEC + (size_t)(slot % EC_REPLICAS) * HG;
+  double *const gECw = gEC + (size_t)(slot & F.ec_mask) * HG;
   double T[G][G], fin[G];
 #pragma unroll
   for (int i = 0; i < G; i++) {

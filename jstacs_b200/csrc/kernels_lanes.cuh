@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) k_lanes(FastDev F, OctData D, unsigned lo
     for (int j = 0; j < S; j++) O[i][j] = 0;
   }
   double score = 0;
-  double *const gECw = gEC ? gEC + (size_t)(slot % jhf::EC_REPLICAS) * HS : nullptr;
+  double *const gECw = gEC ? gEC + (size_t)(slot & F.ec_mask) * HS : nullptr;
   auto ec_add = [&](int h, int j, double g) {
     if (ec_smem) ecw[(size_t)(h * S + j) * 32 + lane] += g;
     else atomicAdd(gECw + (size_t)h * S + j, g);

@@ -26,7 +26,6 @@
 
 namespace jhm {
 
-using jhf::EC_REPLICAS;
 
 using jhf::FastDev;
 
@@ -138,6 +137,10 @@ using GeneralStep = std::integral_constant<int, 2>;
 using UniformStep = std::integral_constant<int, 1>;
 using UniformStepNoRescale = std::integral_constant<int, 0>;
 constexpr int RS = 4;
+// Hash records are 16 bytes per position: every eighth position opens a new 128-byte line, and with small models a
+// position takes less time than a trip to L2 / HBM.  The line HPF positions ahead is prefetched into L1 once per RS steps.
+constexpr int HPF = 48;
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];\n" ::"l"(p)); }
 
 // Scaled forward recursion of one octet (lane (r,q) of the warp) over the rows t_from+1 .. t_to.  t_from < 0: the
 // recursion starts with the start element (row 0); otherwise A / Aexp hold row t_from on entry.  On return A holds row
@@ -213,6 +216,7 @@ __device__ __forceinline__ void octet_forward(const FastDev &F, const double *sE
       const int t_lo = min(max(kmin - 2, ts), te), t_hi = max(min(Lmin - 1, te), t_lo);
       for (; t < t_lo; t++) fstep(GeneralStep(), t);
       for (; t + RS <= t_hi; t += RS) {
+        prefetch_l1(hrow + (size_t)min(t + HPF, Lmax) * 8);
 #pragma unroll
         for (int u = 0; u < RS - 1; u++) fstep(UniformStepNoRescale(), t + u);
         fstep(UniformStep(), t + RS - 1);
@@ -226,7 +230,9 @@ template <int NT>
 struct MmaCfg {
   static constexpr int G = 8 * NT, NV = 2 * NT, WARPS = 8, NTHREADS = 256;
   static constexpr int ROWB = G * 8;              // bytes of one sequence's row of a tile (no padding: XOR swizzle below)
-  static constexpr int RING = 4;
+  // forward rows come back from the HBM scratch through a ring of RING slots, issued PD = RING - 1 positions ahead: the
+  // smaller the model the shorter a position, so the distance grows as the rows shrink (about 8 KB per warp for every NT)
+  static constexpr int RING = NT == 1 ? 16 : NT == 2 ? 8 : 4, PD = RING - 1;
   static constexpr int SLOTB = 8 * ROWB + 32;     // 8 rows + 8 exponents
   static constexpr int WARPB = RING * SLOTB + 2 * 8 * ROWB + 64;
   static size_t smem_bytes(int H) { return ((size_t)H * G + (size_t)G * G + G) * sizeof(double) + (size_t)WARPS * WARPB; }
@@ -278,9 +284,9 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
   double *const fw = fwd_scratch + (size_t)slot * rows * 8 * G + r * G + 2 * q;  // + t*8*G + 8*tp (+b)
   int *const fe = fexp_scratch + (size_t)slot * rows * 8;                       // + t*8 + row
   const int kmin = F.Kmax;  // positions below Kmax need the per-state order check
-  // emission-count table: EC_REPLICAS copies spread the fp64 reductions over the L2 slices (one 64 KB table kept a few
+  // emission-count table: the copies (kernels_fast.cuh) spread the fp64 reductions over the L2 slices (one 64 KB table kept a few
   // slices at 80 % atomic-unit load while the average was 28 %, profiles/r1_estep_octets.md); k_fast_fold_ec sums them
-  double *const gECw = gEC + (size_t)(slot % EC_REPLICAS) * HG;
+  double *const gECw = gEC + (size_t)(slot & F.ec_mask) * HG;
   // byte offsets inside a swizzled tile: RL chunk of (row r, tile tp), TL element of (row 4kk+q, state 8tp+r)
   int rl_off[NT], tl_off[2][NT];
 #pragma unroll
@@ -381,9 +387,8 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       };
       __syncwarp();
       if (!CHUNKED) {
-        issue(Lmax - 1);
-        issue(Lmax - 2);
-        issue(Lmax - 3);
+#pragma unroll
+        for (int u = 0; u < C::PD; u++) issue(Lmax - 1 - u);
       }
       int h = hrow[(size_t)(Lmax - 1) * 8];
       int h1 = hrow[(size_t)(Lmax - 2) * 8];  // hash of position t-1, loaded one step ahead of its use
@@ -402,9 +407,9 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 #pragma unroll
         for (int tp = 0; tp < NT; tp++) *reinterpret_cast<double2 *>(bb + rl_off[tp]) = make_double2(b[2 * tp], b[2 * tp + 1]);
         if (q == 0) sbx[par * 8 + r] = Bx - AL;
-        jhf::cp_async_wait<1>();  // rows t and t-1 have landed; row t-2 may still be in flight
+        jhf::cp_async_wait<C::PD - 2>();  // rows t and t-1 have landed; rows t-2 .. t-PD+1 may still be in flight
         __syncwarp();
-        issue(t - 3);  // two steps ahead of its first use; its slot held row t+1, last read before this __syncwarp
+        issue(t - C::PD);  // PD - 1 steps ahead of its first use; its slot held row t+1, last read before this __syncwarp
         const char *slt = ring + (size_t)(t & (RING - 1)) * SLOTB;
         const char *slp = ring + (size_t)((t - 1) & (RING - 1)) * SLOTB;
         // beta_{t-1}[n][i] = sum_j b[n][j] T[i][j]
@@ -484,15 +489,15 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
           bool ok2 = true;
           octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw - (int64_t)row_lo * 8 * G, fe - (int64_t)row_lo * 8, A, Aexp, ok2, t0 - 1, t1);
           __syncwarp();
-          issue(t1);
-          issue(t1 - 1);
-          issue(t1 - 2);
+#pragma unroll
+          for (int u = 0; u < C::PD; u++) issue(t1 - u);
         }
         // uniform steps: t < Lmin (all sequences running) and t-1 >= Kmax (no order checks)
         int t = t1;
         const int tl = max(t0, 1), t_hi = min(Lmin - 1, t1), t_lo = max(kmin + 1, tl);
         for (; t > t_hi && t >= tl; --t) bstep(GeneralStep(), t);
         for (; t - RS + 1 >= t_lo; t -= RS) {
+          prefetch_l1(hrow + (size_t)max(t - HPF, 0) * 8);
 #pragma unroll
           for (int u = 0; u < RS - 1; u++) bstep(UniformStepNoRescale(), t - u);
           bstep(UniformStep(), t - RS + 1);
@@ -705,9 +710,8 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
     };
     __syncwarp();
     if (!CHUNKED) {
-      issue(Lmax - 1);
-      issue(Lmax - 2);
-      issue(Lmax - 3);
+#pragma unroll
+      for (int u = 0; u < C::PD; u++) issue(Lmax - 1 - u);
     }
     int h = hrow[(size_t)(Lmax - 1) * 8];
     int h1 = hrow[(size_t)(Lmax - 2) * 8];
@@ -729,17 +733,17 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
       bool ok2 = true;
       octet_forward<NT, true>(F, sE, r, q, hrow, Lr, Lmax, Lmin, fw - (int64_t)row_lo * 8 * G, fe - (int64_t)row_lo * 8, A, Aexp, ok2, t0 - 1, t1);
       __syncwarp();
-      issue(t1);
-      issue(t1 - 1);
-      issue(t1 - 2);
+#pragma unroll
+      for (int u = 0; u < C::PD; u++) issue(t1 - u);
     }
     for (int t = t1; t >= t0; --t) {
+      if ((t & (RS - 1)) == 0) prefetch_l1(hrow + (size_t)max(t - HPF, 0) * 8);
       const int h2 = t >= 2 ? hrow[(size_t)(t - 2) * 8] : 0;
       const bool act = t < Lr;
       double b[NV];
 #pragma unroll
       for (int v = 0; v < NV; v++) b[v] = e[v] * beta[v];
-      jhf::cp_async_wait<2>();  // row t has landed
+      jhf::cp_async_wait<C::PD - 1>();  // row t has landed
       __syncwarp();
       const char *slt = ring + (size_t)(t & (RING - 1)) * SLOTB;
       double Dv[NV];
@@ -761,7 +765,7 @@ __global__ void __launch_bounds__(256, 1) k_mma_decode(FastDev F, OctData D, uns
       const int arg = best_state(Fa, beta);
       if (q == 0 && act && good) path_store(paths, off + t, arg);
       __syncwarp();
-      issue(t - 3);
+      issue(t - C::PD);
       if (t > 0) {
         int nbx = Bx;
         rescale_row<NV>(Dv, nbx);

@@ -25,10 +25,17 @@ namespace jhs {
 
 using jhx::ResReader;
 
-constexpr int EC_REPLICAS_SPARSE = 8;  // replicas of the emission-count table of the E-step (spread over the L2 slices)
+// copies of the emission-count table of the E-step: a power of two sized like jhf::ec_replicas_for (reductions to one address
+// are serialised by the L2: few cells need many copies), at least 8
+inline int ec_replicas_sparse_for(int64_t cells) {
+  int r = 8;
+  while (r < 2048 && (int64_t)r * cells < ((int64_t)1 << 19)) r *= 2;
+  return r;
+}
 
 struct SparseDev {
   int S, SP, a, Kmax, H, hpow, a_pow2, ashift;  // ashift = log2(a) when a is a power of two
+  int ec_mask;           // copies of the emission-count table - 1
   double inv_a;
   const int *in_src;     // [IND][SP] source state of in-edge k of state j (padding: j itself, weight 0)
   const double *in_T;    // [IND][SP] P(src -> j)
@@ -42,7 +49,8 @@ struct SparseDev {
 
 struct SparseTables {
   bool usable = false, e_global = false;
-  int S = 0, SP = 0, SPL = 0, IND = 0, a = 0, Kmax = 0, H = 0;
+  int S = 0, SP = 0, SPL = 0, IND = 0, a = 0, Kmax = 0, H = 0, ec_replicas = 8;
+  size_t ec_bytes() const { return sizeof(double) * (size_t)ec_replicas * H * SP; }
   int *d_in_src = nullptr, *d_out_dst = nullptr, *d_in_p = nullptr, *d_out_p = nullptr, *d_pimap = nullptr, *d_korder = nullptr,
       *d_etab = nullptr, *d_emod = nullptr, *d_out_stat = nullptr, *d_pistat = nullptr;
   double *d_in_T = nullptr, *d_out_T = nullptr, *d_pi = nullptr, *d_fin = nullptr, *d_E = nullptr, *d_ec = nullptr;
@@ -58,6 +66,7 @@ struct SparseTables {
     F.hpow = pw; F.a_pow2 = (a & (a - 1)) == 0; F.inv_a = 1.0 / a;
     F.ashift = 0;
     while ((1 << F.ashift) < a) F.ashift++;
+    F.ec_mask = ec_replicas - 1;
     F.in_src = d_in_src; F.in_T = d_in_T; F.out_dst = d_out_dst; F.out_T = d_out_T; F.pi = d_pi; F.fin = d_fin; F.E = d_E; F.korder = d_korder;
     return F;
   }
@@ -157,7 +166,8 @@ inline int build(SparseTables &F, int S, int a, int m, bool has_silent, int Kmax
   }
   F.S = S; F.SP = SP; F.SPL = SPL; F.IND = IND; F.a = a; F.Kmax = Kmax; F.H = (int)H;
   int r;
-  std::vector<double> zE((size_t)H * SP, 0.0), zT((size_t)IND * SP, 0.0), zp(SP, 0.0), zEC((size_t)EC_REPLICAS_SPARSE * H * SP, 0.0);
+  F.ec_replicas = ec_replicas_sparse_for((int64_t)H * SP);
+  std::vector<double> zE((size_t)H * SP, 0.0), zT((size_t)IND * SP, 0.0), zp(SP, 0.0), zEC((size_t)F.ec_replicas * H * SP, 0.0);
   if ((r = up(&F.d_in_src, in_src, s)) || (r = up(&F.d_out_dst, out_dst, s)) || (r = up(&F.d_in_p, in_p, s)) || (r = up(&F.d_out_p, out_p, s)) ||
       (r = up(&F.d_pimap, pimap, s)) || (r = up(&F.d_korder, korder, s)) || (r = up(&F.d_etab, etab, s)) || (r = up(&F.d_emod, emod, s)) ||
       (r = up(&F.d_fin, fin, s)) || (r = up(&F.d_in_T, zT, s)) || (r = up(&F.d_out_T, zT, s)) || (r = up(&F.d_pi, zp, s)) || (r = up(&F.d_E, zE, s)) ||
@@ -940,7 +950,7 @@ __global__ void __launch_bounds__(128) k_sparse_decode_chunks(SparseDev F, DevDa
 //   xi_t(i -> j)  = alpha_{t-1}[i] T[i][j] vb_t[j] 2^(A_{t-1} + B_t - AL) w / sfin,  vb_t = e_t * beta_t
 // accumulated per out-edge in registers (T is multiplied in at the end), with the values the beta recursion gathers anyway.
 // rows: [slot][ROWS][SP] doubles, rexp: [slot][ROWS] exponents relative to the chunk's base exponent (ROWS = min(CK, longest sequence)).
-// gEC: [EC_REPLICAS_SPARSE][H][SP] emission-count tables; stats: [transition | emission | score].
+// gEC: [copies][H][SP] emission-count tables; stats: [transition | emission | score].
 
 struct EstepTables {
   const int *out_stat;     // [IND][SP] statistics slot of out-edge k of state i, -1 for padding
@@ -966,7 +976,7 @@ __global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepT
   const int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   double *const R = rows + (size_t)slot * ROWS * SP + SPL * lane;
   int *const RX = rexp + (size_t)slot * ROWS;
-  double *const gECw = gEC + (size_t)(slot % EC_REPLICAS_SPARSE) * F.H * SP + SPL * lane;
+  double *const gECw = gEC + (size_t)(slot & F.ec_mask) * F.H * SP + SPL * lane;
   ResReader rd;
   SeqBlocks blocks;
   double O[IND][SPL], SC[SPL];
@@ -1172,14 +1182,16 @@ __global__ void __launch_bounds__(128) k_sparse_estep_chunks(SparseDev F, EstepT
 }
 
 // emission-count tables [replica][H][SP] -> emission statistics
+// (one warp per cell: the lanes stride over the copies, then a shuffle tree)
 __global__ void k_sparse_fold_ec(SparseDev F, const int *etab, const int *emod, int n_child, const double *gEC, double *stats) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (i >= F.H * F.SP) return;
-  const int hh = i / F.SP, c = i % F.SP;              // c = slot inside the row: lane-major [lane][u] as written by the lanes
+  const int hh = i / F.SP, j = i % F.SP;              // rows are written at SPL*lane + u == state index
   double v = 0;
-  for (int rep = 0; rep < EC_REPLICAS_SPARSE; rep++) v += gEC[(size_t)rep * F.H * F.SP + i];
-  const int j = c;                                    // rows are written at SPL*lane + u == state index
-  if (v != 0 && etab[j] >= 0) atomicAdd(&stats[n_child + etab[j] + hh % emod[j]], v);
+  for (int rep = lane; rep <= F.ec_mask; rep += 32) v += gEC[(size_t)rep * F.H * F.SP + i];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if (lane == 0 && v != 0 && etab[j] >= 0) atomicAdd(&stats[n_child + etab[j] + hh % emod[j]], v);
 }
 
 }  // namespace jhs

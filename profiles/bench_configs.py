@@ -22,6 +22,16 @@ for kv in filter(None, os.environ.get("JH_OPTS", "").split(",")):  # library opt
     _native.check(_native.lib().jh_set_option(k.encode(), int(v)))
 
 
+_bufs = {}
+
+
+def _buf(n):
+    if n not in _bufs:
+        _bufs.clear()
+        _bufs[n] = np.zeros(max(n, 1), dtype=np.uint8)
+    return _bufs[n]
+
+
 def run(name, hmm, data, what, reps=3):
     if (only and name not in only) or (name.startswith("full_") and not (only and name in only)):
         return
@@ -33,6 +43,8 @@ def run(name, hmm, data, what, reps=3):
     fn = {"estep": lambda: eng.estep(nd, fetch=False), "loglik": lambda: eng.loglik(nd), "viterbi": lambda: eng.viterbi(nd),
           "decode": lambda: eng.posterior_decode(nd), "viterbi_u8": lambda: eng.viterbi(nd, narrow=True),
           "decode_u8": lambda: eng.posterior_decode(nd, narrow=True),
+          # the caller's path buffer reused (already touched pages: no first-touch faults inside the call)
+          "viterbi_u8_reuse": lambda: eng.viterbi(nd, narrow=True, out=_buf(nd.n_res)),
           "train": lambda: hmm.train(data)}[what]  # the whole HigherOrderHMM.train call (data set resident; parameters read back)
     if not name.startswith("full_"):
         fn()  # warm-up
@@ -109,6 +121,7 @@ run("full_mid_cfg5_bw", lambda: banded_hmm(128, 4, 0), mid5, "estep", reps=3)
 run("full_mid_cfg5_decode_u8", lambda: banded_hmm(128, 4, 0), mid5, "decode_u8", reps=3)
 run("full_mid_cfg5_viterbi_u8", lambda: banded_hmm(128, 4, 0), mid5, "viterbi_u8", reps=3)
 run("full_cfg2_viterbi_u8_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(1_000_000, 1000), "viterbi_u8", reps=3)
+run("full_cfg2_viterbi_u8_reuse_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(1_000_000, 1000), "viterbi_u8_reuse", reps=4)
 run("full_cfg5_viterbi_u8", lambda: banded_hmm(128, 4, 0), full5, "viterbi_u8", reps=1)
 run("full_cfg5_loglik", lambda: banded_hmm(128, 4, 0), full5, "loglik", reps=1)
 run("full_cfg5_decode_u8", lambda: banded_hmm(128, 4, 0), full5, "decode_u8", reps=1)
