@@ -1,4 +1,3 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -q -m gpu -x -k "not multi_megabase and not cfg5" > gpurun_out/r2s_pytest.log 2>&1; echo rc=$?; tail -3 gpurun_out/r2s_pytest.log | cut -c1-300
-python profiles/bench_configs.py 1.0 cfg4_bw_s16_k1_ragged cfg4_decode_u8_s16_k1_ragged cfg4_loglik_s16_k1_ragged > gpurun_out/r2s_cfg.jsonl 2>gpurun_out/r2s_cfg.err; cut -c1-200 gpurun_out/r2s_cfg.jsonl; tail -2 gpurun_out/r2s_cfg.err
-JH_OPTS=oct_full_rows_mb=65536 python profiles/bench_configs.py 1.0 cfg4_bw_s16_k1_ragged cfg4_decode_u8_s16_k1_ragged > gpurun_out/r2s_cfg_b.jsonl 2>gpurun_out/r2s_cfg_b.err; cut -c1-200 gpurun_out/r2s_cfg_b.jsonl; tail -2 gpurun_out/r2s_cfg_b.err
-JH_OPTS=oct_chunk=256 python profiles/bench_configs.py 1.0 cfg4_bw_s16_k1_ragged cfg4_decode_u8_s16_k1_ragged > gpurun_out/r2s_cfg_c.jsonl 2>gpurun_out/r2s_cfg_c.err; cut -c1-200 gpurun_out/r2s_cfg_c.jsonl; tail -2 gpurun_out/r2s_cfg_c.err
+python -m pytest tests -q -m gpu --durations=6 > gpurun_out/r2v_pytest.log 2>&1; echo rc=$?; tail -14 gpurun_out/r2v_pytest.log | cut -c1-300
+python bench.py > gpurun_out/r2v_bench.json 2> gpurun_out/r2v_bench.err; cat gpurun_out/r2v_bench.json | cut -c1-2500; tail -3 gpurun_out/r2v_bench.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2v_bench_ref.json 2> gpurun_out/r2v_bench_ref.err; cat gpurun_out/r2v_bench_ref.json | cut -c1-800
