@@ -351,9 +351,12 @@ __global__ void __launch_bounds__(32) k_band_vit_sweep(SparseDev F, jhw::VitLong
       exchange<SPL, BP, BN>(s, lane, c);
 #pragma unroll
       for (int u = 0; u < SPL; u++) {
-        double mx = JH_NEG_INF;
+        double mx = __dadd_rn(c[SPL + u + LO], w[u][0]);  // (bwd + em) + trans; no NaN can occur (no +inf anywhere):
 #pragma unroll
-        for (int xo = 0; xo < W; xo++) mx = fmax(mx, __dadd_rn(c[SPL + u + (xo + LO)], w[u][xo]));  // (bwd + em) + trans
+        for (int xo = 1; xo < W; xo++) {                   // a plain compare-and-select instead of fmax's NaN handling
+          const double v = __dadd_rn(c[SPL + u + (xo + LO)], w[u][xo]);
+          mx = v > mx ? v : mx;
+        }
         b[u] = mx;
       }
     };

@@ -95,9 +95,12 @@ struct MaxEdges {  // the lane's out-edge lists in registers: byte offsets into 
     const char *base = reinterpret_cast<const char *>(vec);
 #pragma unroll
     for (int u = 0; u < SPL; u++) {
-      double mx = JH_NEG_INF;
+      double mx = __dadd_rn(*reinterpret_cast<const double *>(base + off[0][u]), w[0][u]);
 #pragma unroll
-      for (int k = 0; k < IND; k++) mx = fmax(mx, __dadd_rn(*reinterpret_cast<const double *>(base + off[k][u]), w[k][u]));
+      for (int k = 1; k < IND; k++) {  // compare-and-select: no NaN can occur (no +inf anywhere), fmax's handling is not needed
+        const double v = __dadd_rn(*reinterpret_cast<const double *>(base + off[k][u]), w[k][u]);
+        mx = v > mx ? v : mx;
+      }
       out[u] = mx;
     }
   }
