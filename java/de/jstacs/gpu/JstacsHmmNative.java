@@ -74,6 +74,8 @@ public final class JstacsHmmNative {
 	public static final MethodHandle jh_model_set_stream = h( "jh_model_set_stream", FunctionDescriptor.of( I, P, P ) );
 	public static final MethodHandle jh_set_option = h( "jh_set_option", FunctionDescriptor.of( I, P, J ) );
 	public static final MethodHandle jh_dataset_create_packed2 = h( "jh_dataset_create_packed2", FunctionDescriptor.of( I, P, P, P, J, P, I, P ) );
+	public static final MethodHandle jh_model_set_states_groups = h( "jh_model_set_states_groups", FunctionDescriptor.of( I, P, I, P, P ) );
+	public static final MethodHandle jh_dataset_set_groups = h( "jh_dataset_set_groups", FunctionDescriptor.of( I, P, P ) );
 	public static final MethodHandle jh_dataset_info = h( "jh_dataset_info", FunctionDescriptor.of( I, P, P, P, P ) );
 
 	static {

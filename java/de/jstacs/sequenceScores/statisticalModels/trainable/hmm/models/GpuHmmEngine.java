@@ -15,7 +15,10 @@ import de.jstacs.data.AlphabetContainer;
 import de.jstacs.data.DataSet;
 import de.jstacs.data.WrongAlphabetException;
 import de.jstacs.data.sequences.Sequence;
+import de.jstacs.data.sequences.annotation.SequenceAnnotation;
 import de.jstacs.gpu.JstacsHmmNative;
+import de.jstacs.results.StorableResult;
+import de.jstacs.sequenceScores.statisticalModels.trainable.hmm.AbstractHMM;
 import de.jstacs.sequenceScores.statisticalModels.trainable.hmm.states.State;
 import de.jstacs.sequenceScores.statisticalModels.trainable.hmm.states.emissions.Emission;
 import de.jstacs.sequenceScores.statisticalModels.trainable.hmm.states.emissions.discrete.GpuEmissionExport;
@@ -170,11 +173,9 @@ public final class GpuHmmEngine implements AutoCloseable {
 				throw new UnsupportedOperationException( "reverse-strand states are not on the native path" );
 			}
 		}
-		// "no groups" is an EMPTY array, never null (AbstractHMM.fillPreComputedContext, AbstractHMM.java:173-177)
-		int[][] groups = host.gpuStatesGroups();
-		if( groups != null && groups.length > 0 ) {
-			throw new UnsupportedOperationException( "allowed states groups are not on the native path of the Java shim" );
-		}
+		// allowed states groups: "no groups" is an EMPTY array, never null (AbstractHMM.fillPreComputedContext,
+		// AbstractHMM.java:173-177); declared groups go to the library in model() (jh_model_set_states_groups), which refuses
+		// them for models with silent states or transition order 0
 		AlphabetContainer con = host.getAlphabetContainer();
 		if( !con.isSimple() || !con.isDiscrete() ) {
 			throw new UnsupportedOperationException( "only simple discrete alphabets are on the native path" );
@@ -226,6 +227,19 @@ public final class GpuHmmEngine implements AutoCloseable {
 			MemorySegment out = arena.allocate( ValueLayout.ADDRESS );
 			JstacsHmmNative.check( (int) JstacsHmmNative.jh_model_create.invokeExact( d, out ) );
 			handles.model = out.get( ValueLayout.ADDRESS, 0 );
+			int[][] groups = host.gpuStatesGroups(); // the constructor argument int[][] statesGroups (AbstractHMM.java:154, 173-228)
+			if( groups != null && groups.length > 0 ) {
+				int[] ptr = new int[groups.length + 1];
+				for( int g = 0; g < groups.length; g++ ) {
+					ptr[g + 1] = ptr[g] + groups[g].length;
+				}
+				int[] members = new int[Math.max( ptr[groups.length], 1 )];
+				for( int g = 0; g < groups.length; g++ ) {
+					System.arraycopy( groups[g], 0, members, ptr[g], groups[g].length );
+				}
+				JstacsHmmNative.check( (int) JstacsHmmNative.jh_model_set_states_groups.invokeExact( handles.model, groups.length,
+						arena.allocateFrom( ValueLayout.JAVA_INT, ptr ), arena.allocateFrom( ValueLayout.JAVA_INT, members ) ) );
+			}
 		} catch( Exception ex ) {
 			throw ex;
 		} catch( Throwable th ) {
@@ -280,6 +294,9 @@ public final class GpuHmmEngine implements AutoCloseable {
 			MemorySegment w = weights == null ? MemorySegment.NULL : arena.allocateFrom( ValueLayout.JAVA_DOUBLE, weights );
 			if( cachedData.get() == data && !handles.dataset.equals( MemorySegment.NULL ) ) {
 				JstacsHmmNative.check( (int) JstacsHmmNative.jh_dataset_set_weights.invokeExact( handles.dataset, w ) );
+				// per-position groups are attached by train() only; every other call computes the unconstrained quantity,
+				// like the reference methods without an allowedStatesGroup argument
+				JstacsHmmNative.check( (int) JstacsHmmNative.jh_dataset_set_groups.invokeExact( handles.dataset, MemorySegment.NULL ) );
 				return handles.dataset;
 			}
 			if( !handles.dataset.equals( MemorySegment.NULL ) ) {
@@ -314,6 +331,40 @@ public final class GpuHmmEngine implements AutoCloseable {
 		}
 	}
 
+	/**
+	 * HigherOrderHMM.doOneStep (HigherOrderHMM.java:810-820): with a sequence annotation type, every sequence that carries an
+	 * annotation of that type is trained under its AllowedStatesGroups (one group index per position, -1 = unconstrained);
+	 * sequences without the annotation are unconstrained.  The per-position indices go to the data set handle.
+	 */
+	private void attachGroups( Arena arena, MemorySegment ds, DataSet data ) throws Throwable {
+		String type = host.gpuAnnotationType();
+		if( type == null ) {
+			return; // dataset() has detached whatever an earlier call attached
+		}
+		MemorySegment g = arena.allocate( ValueLayout.JAVA_INT, Math.max( cachedResidues, 1 ) );
+		long p = 0;
+		boolean any = false;
+		for( int n = 0; n < data.getNumberOfElements(); n++ ) {
+			Sequence seq = data.getElementAt( n );
+			int[] groups = null;
+			SequenceAnnotation sa = seq.getSequenceAnnotationByType( type, 0 );
+			if( sa != null ) {
+				StorableResult res = (StorableResult) sa.getResultAt( 0 );
+				groups = ( (AbstractHMM.AllowedStatesGroups) res.getResultInstance() ).groups;
+				if( groups.length != seq.getLength() ) {
+					throw new IllegalArgumentException( "AllowedStatesGroups of sequence " + n + " does not match its length." );
+				}
+				any = true;
+			}
+			for( int l = 0, len = seq.getLength(); l < len; l++, p++ ) {
+				g.setAtIndex( ValueLayout.JAVA_INT, p, groups == null ? -1 : groups[l] );
+			}
+		}
+		if( any ) {
+			JstacsHmmNative.check( (int) JstacsHmmNative.jh_dataset_set_groups.invokeExact( ds, g ) );
+		}
+	}
+
 	// ------------------------------------------------------------------------------------------------------------
 	/**
 	 * HigherOrderHMM.train (HigherOrderHMM.java:733-789): multi-start loop and best-of-starts stay here; the inner
@@ -332,9 +383,6 @@ public final class GpuHmmEngine implements AutoCloseable {
 			mode = JstacsHmmNative.JH_MODE_BAUM_WELCH;
 		} else {
 			throw new IllegalArgumentException( "Training mode not available." ); // HigherOrderHMM.java:805
-		}
-		if( host.gpuAnnotationType() != null ) {
-			throw new UnsupportedOperationException( "training with allowed states groups (sequence annotation type) is not on the native path of the Java shim" );
 		}
 		AbstractTerminationCondition tc = ( (MaxHMMTrainingParameterSet) trainingParameter ).getTerminationCondition();
 		int kind, maxIter = 0;
@@ -355,6 +403,7 @@ public final class GpuHmmEngine implements AutoCloseable {
 		Time time = Time.getTimeInstance( sostream );
 		MemorySegment model = model(), ds = dataset( data, weights );
 		try( Arena arena = Arena.ofConfined() ) {
+			attachGroups( arena, ds, data );
 			int cap = kind == JstacsHmmNative.JH_TERM_ITERATIONS ? Math.max( maxIter, 1 ) : 100000;
 			MemorySegment obj = arena.allocate( ValueLayout.JAVA_DOUBLE, cap ), nIt = arena.allocate( ValueLayout.JAVA_INT ),
 					last = arena.allocate( ValueLayout.JAVA_DOUBLE ), opts = arena.allocate( 24, 8 );

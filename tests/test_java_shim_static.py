@@ -253,6 +253,14 @@ def test_reference_semantics_the_shim_relies_on():
     # getAlphabetContainer / getLength are final in the model base class: the Host interface is satisfied by inheritance
     base = ref("de/jstacs/sequenceScores/statisticalModels/trainable/AbstractTrainableStatisticalModel.java")
     assert "public final AlphabetContainer getAlphabetContainer()" in base and "public final int getLength()" in base
+    # allowed states groups: what GpuHmmEngine.attachGroups reads (HigherOrderHMM.doOneStep :810-820 does the same)
+    assert "public SequenceAnnotation getSequenceAnnotationByType(String type, int idx)" in ref("de/jstacs/data/sequences/Sequence.java")
+    assert "public class SequenceAnnotation extends ResultSet" in ref("de/jstacs/data/sequences/annotation/SequenceAnnotation.java")
+    assert "public Result getResultAt(int index)" in ref("de/jstacs/results/ResultSet.java")
+    assert "public Storable getResultInstance()" in ref("de/jstacs/results/StorableResult.java")
+    assert re.search(r"public static class AllowedStatesGroups implements Storable \{\s*public int\[\] groups;", ahmm)
+    assert "protected String type;" in ref(f"{HMM}/models/HigherOrderHMM.java")
+    assert "attachGroups( arena, ds, data );" in eng and "jh_dataset_set_groups.invokeExact( handles.dataset, MemorySegment.NULL )" in eng
     # numerical training stays on the reference code path
     assert "if( trainingParameter instanceof NumericalHMMTrainingParameterSet )" in ref(f"{HMM}/models/DifferentiableHigherOrderHMM.java")
 
