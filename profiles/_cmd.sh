@@ -1,3 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 3 --warmup 3 --no-cpu-baseline --scaling strong --total-seqs 8000000 > gpurun_out/r2A_bench_n8_strong.json 2>gpurun_out/r2A_bench_n8_strong.err; echo rc=$?; cut -c1-400 gpurun_out/r2A_bench_n8_strong.json
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 profiles/cfg5_lpt.py 1.0 > gpurun_out/r2A_lpt_n8.json 2>gpurun_out/r2A_lpt_n8.err; echo rc=$?; cut -c1-1600 gpurun_out/r2A_lpt_n8.json; tail -2 gpurun_out/r2A_lpt_n8.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus 4 --steps 3 --warmup 3 --no-cpu-baseline --scaling strong --total-seqs 8000000 > gpurun_out/r2A_bench_n4_strong.json 2>gpurun_out/r2A_bench_n4_strong.err; echo rc=$?; cut -c1-400 gpurun_out/r2A_bench_n4_strong.json
+python -m pytest tests/test_shim_replay.py -q -m gpu > gpurun_out/r2B_pytest.log 2>&1; echo rc=$?; tail -8 gpurun_out/r2B_pytest.log | cut -c1-300

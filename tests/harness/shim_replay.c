@@ -93,6 +93,8 @@ static int (*p_posterior_decode)(jh_model *, jh_dataset *, int32_t *, double *);
 static int (*p_posterior_decode_u8)(jh_model *, jh_dataset *, uint8_t *, double *);
 static int (*p_baum_welch)(jh_model *, jh_dataset *, const jh_train_opts *, double *, int32_t, int32_t *);
 static int (*p_last_objective)(jh_model *, double *);
+static int (*p_model_set_states_groups)(jh_model *, int32_t, const int32_t *, const int32_t *);
+static int (*p_dataset_set_groups)(jh_dataset *, const int32_t *);
 
 #define BIND(var, sym)                                                 \
   do {                                                                 \
@@ -120,6 +122,7 @@ int main(int argc, char **argv) {
   BIND(p_loglik, "jh_loglik"); BIND(p_loglik_windows, "jh_loglik_windows"); BIND(p_viterbi_u8, "jh_viterbi_u8");
   BIND(p_viterbi_paths, "jh_viterbi_paths"); BIND(p_posterior, "jh_posterior"); BIND(p_posterior_decode, "jh_posterior_decode");
   BIND(p_posterior_decode_u8, "jh_posterior_decode_u8"); BIND(p_baum_welch, "jh_baum_welch"); BIND(p_last_objective, "jh_last_objective");
+  BIND(p_model_set_states_groups, "jh_model_set_states_groups"); BIND(p_dataset_set_groups, "jh_dataset_set_groups");
   load(argv[2]);
   out = fopen(argv[3], "wb");
   if (!out) { perror(argv[3]); return 2; }
@@ -139,6 +142,8 @@ int main(int argc, char **argv) {
   d.state_final = need("state_final");
   jh_model *model = NULL;
   CHECK(p_model_create(&d, &model));
+  if (find("group_ptr")) /* model(): the constructor's statesGroups, when there are any */
+    CHECK(p_model_set_states_groups(model, (int32_t)find("group_ptr")->count - 1, need("group_ptr"), need("group_states")));
   int64_t sz[4];
   CHECK(p_model_sizes(model, sz));
   /* the "Java objects": parameters as the host side currently holds them */
@@ -172,6 +177,9 @@ int main(int argc, char **argv) {
     } else {
       CHECK(p_dataset_set_weights(ds, w));
     }
+    /* per-position groups: attached by train() when the model has a sequence annotation type (record "seq_groups"),
+       detached for every other call (GpuHmmEngine.dataset / attachGroups) */
+    CHECK(p_dataset_set_groups(ds, is_train && find("seq_groups") ? (const int32_t *)find("seq_groups")->data : NULL));
     if (is_train) {
       int mode, kind, max_iter, starts;
       double eps;

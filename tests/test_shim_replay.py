@@ -198,6 +198,51 @@ def test_shim_multi_start_keeps_the_best_start(harness, tmp_path, oracle_lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["erg_s8_k2", "sparse_unsorted", "order2_s3"])
+def test_shim_semi_supervised_training_with_states_groups(harness, tmp_path, oracle_lib, name):
+    """A model built with statesGroups and a sequence annotation type (HigherOrderHMM.java:183-185): model() passes the
+    groups, train() attaches the per-position AllowedStatesGroups of the annotations (doOneStep :810-820), the scoring call
+    afterwards is unconstrained again — objectives, trained parameters and the final scores against the oracle."""
+    hmm = SHIM_MODELS[name]()
+    S = hmm.getNumberOfStates()
+    groups = [list(range(0, S, 2)), list(range(1, S, 2)), [0, S - 1]]
+    ir = hmm.ir()
+    data = ragged(21, 20, lo=5, hi=70)
+    rng = np.random.default_rng(2)
+    grp = rng.integers(0, len(groups), data.codes.size).astype(np.int32)
+    grp[rng.random(grp.size) < 0.7] = -1
+    lens = np.diff(data.offsets)
+    for i in range(0, len(lens), 3):  # every third sequence carries no annotation at all
+        grp[data.offsets[i]:data.offsets[i + 1]] = -1
+    om = oracle_lib.OracleModel(ir)
+    om.set_groups(groups)
+    om.attach_groups(data.codes, grp)
+    fin = np.isfinite(om.loglik(data.codes, data.offsets))
+    for i in np.flatnonzero(~fin):  # sequences that are impossible under their labels would stop the reference, too
+        grp[data.offsets[i]:data.offsets[i + 1]] = -1
+    om.attach_groups(data.codes, grp)
+    w = rng.random(len(lens)) + 0.5
+    recs = model_records(ir)
+    ptr = np.zeros(len(groups) + 1, np.int32)
+    ptr[1:] = np.cumsum([len(g) for g in groups])
+    recs.update(codes=data.codes, offsets=data.offsets, weights=w, group_ptr=ptr,
+                group_states=np.array([s for g in groups for s in g], np.int32), seq_groups=grp)
+    out, _ = run(harness, tmp_path, recs, ["train:1:0:4:0:1", "score"])
+    robj = om.train(data.codes, data.offsets, w, max_iter=4)
+    np.testing.assert_allclose(out["train_objective_start0"], robj, rtol=1e-9)
+    rtp, rtl, rep, rel_ = om.get_params()
+    for got, ref in ((out["trained_trans_param"], rtp), (out["trained_emis_param"], rep)):
+        f = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), f)
+        np.testing.assert_allclose(got[f], ref[f], rtol=0, atol=1e-6)
+    om.attach_groups(None, None)  # the score call is unconstrained: the shim detached the groups
+    np.testing.assert_allclose(out["loglik"], om.loglik(data.codes, data.offsets), rtol=1e-9)
+    # the constraint was really evaluated: training without it gives another objective
+    om2 = oracle_lib.OracleModel(ir)
+    assert abs(om2.train(data.codes, data.offsets, w, max_iter=4)[-1] - robj[-1]) > 1e-6 * abs(robj[-1])
+
+
+@pytest.mark.gpu
 def test_shim_impossible_path_is_an_error(harness, tmp_path):
     """A sequence without a state path of probability > 0: the reference throws IllegalArgumentException("Impossible path")
     (HigherOrderHMM.java:659); through the shim's route the library reports JH_ERR_IMPOSSIBLE."""
