@@ -48,7 +48,7 @@ struct Options {
   int64_t scan = 1;            // small dense models: checkpoint pass parallel in the position (kernels_scan.cuh)
   int64_t overlap = 1;         // long-sequence path: per-sequence streams, a sequence's chunk pass starts when its checkpoint pass ends
   int64_t pass1_cta = 1;       // few long sequences: one CTA per (sequence, direction) in the checkpoint pass
-  int64_t oct_chunk = 1024;    // positions per checkpoint of the chunked octet E-step (0: never chunk)
+  int64_t oct_chunk = -1;      // positions per checkpoint of the chunked octet kernels (0: never chunk; < 0: automatic, see oct_chunk_of)
   int64_t oct_chunk_force = 0; // tests: chunk every bucket longer than 2 * oct_chunk
   int64_t graph = 1;           // jh_baum_welch with IterationCondition: replay the EM iteration as a CUDA graph
   int64_t vit_chunk = 4096;    // positions per checkpoint of the chromosome-scale Viterbi
@@ -66,7 +66,7 @@ static bool set_option_field(Options &o, const std::string &n, int64_t value) {
   else if (n == "scratch_mb") o.scratch_mb = value;
   else if (n == "blocks_per_sm") o.blocks_per_sm = value;
   else if (n == "fast_variant") o.fast_variant = value;
-  else if (n == "oct_chunk") o.oct_chunk = value <= 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
+  else if (n == "oct_chunk") o.oct_chunk = value < 0 ? -1 : value == 0 ? 0 : std::min<int64_t>(1 << 20, std::max<int64_t>(8, value));
   else if (n == "pass1_cta") o.pass1_cta = value;
   else if (n == "overlap") o.overlap = value;
   else if (n == "scan") o.scan = value;
@@ -2486,6 +2486,18 @@ struct OctGroup {
   size_t b0, b1;  // buckets [b0, b1)
   bool chunked;
 };
+// Positions per chunk of the chunked octet kernels.  Automatic: the recomputed forward rows of ONE chunk per resident warp
+// (what the backward sweep re-reads at once) should stay in the 126 MB L2 instead of making an HBM round trip: about 80 MB for
+// all warp slots -> 64 positions for 16 states, 32 for 32 states (cfg4: E-step 135-141 -> 128 ms, decoding 131-144 -> 121 ms
+// against chunks of 1024 positions; below 32 positions the per-chunk overhead takes the gain back).
+template <int NT>
+static int64_t oct_chunk_of(const jh_model *m, int64_t full_grid) {
+  using C = jhm::MmaCfg<NT>;
+  if (m->opt.oct_chunk >= 0) return m->opt.oct_chunk;
+  const int64_t row_bytes = 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
+  const int64_t ck = ((int64_t)80 << 20) / (std::max<int64_t>(full_grid, 1) * C::WARPS * row_bytes);
+  return std::min<int64_t>(1024, std::max<int64_t>(16, ck & ~(int64_t)7));
+}
 template <int NT>
 static std::vector<OctGroup> oct_groups(const jh_model *m, const jh_dataset *d, int64_t full_grid) {
   using C = jhm::MmaCfg<NT>;
@@ -2493,10 +2505,11 @@ static std::vector<OctGroup> oct_groups(const jh_model *m, const jh_dataset *d, 
   const int64_t budget = std::min<int64_t>(m->opt.scratch_mb, m->opt.oct_full_rows_mb) * 1024 * 1024;
   auto slots_of = [&](int64_t n_oct) { return std::min<int64_t>(full_grid, (n_oct + C::WARPS - 1) / C::WARPS) * C::WARPS; };
   auto per_slot_of = [&](size_t b) { return (d->bucket_len[b] + 1) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int)); };
+  const int64_t CK = oct_chunk_of<NT>(m, full_grid);
   for (size_t b = 0; b + 1 < d->bucket_ptr.size(); b++) {
     const int64_t n_oct = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[b];
     if (n_oct <= 0) continue;
-    const bool chunked = m->opt.oct_chunk > 0 && d->bucket_len[b] + 1 > 2 * m->opt.oct_chunk &&
+    const bool chunked = CK > 0 && d->bucket_len[b] + 1 > 2 * CK &&
                          (m->opt.oct_chunk_force || slots_of(n_oct) * per_slot_of(b) > budget);
     if (!out.empty() && out.back().chunked == chunked && out.back().b1 == b) {
       const int64_t n_all = d->bucket_oct_ptr[b + 1] - d->bucket_oct_ptr[out.back().b0];
@@ -2518,8 +2531,8 @@ static int launch_mma_decode_impl(jh_model *m, jh_dataset *d, OctGroup g, int64_
   cudaStream_t s = m->st();
   auto kern = jhm::k_mma_decode<NT, CHUNKED, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[g.b0], n_oct = d->bucket_oct_ptr[g.b1] - oct0, L = d->bucket_len[g.b0];
+  const int64_t CK = oct_chunk_of<NT>(m, grid);
   grid = std::min<int64_t>(grid, (n_oct + C::WARPS - 1) / C::WARPS);
-  const int64_t CK = m->opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t per_slot = (rows + ck_rows) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));
@@ -2687,8 +2700,8 @@ static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, OctGroup g, int64_t
   cudaStream_t s = m->st();
   auto kern = jhm::k_mma_estep<NT, CHUNKED, EG>;
   const int64_t oct0 = d->bucket_oct_ptr[g.b0], n_oct = d->bucket_oct_ptr[g.b1] - oct0, L = d->bucket_len[g.b0];
+  const int64_t CK = oct_chunk_of<NT>(m, grid);
   grid = std::min<int64_t>(grid, (n_oct + C::WARPS - 1) / C::WARPS);
-  const int64_t CK = m->opt.oct_chunk;
   const int64_t rows = CHUNKED ? CK + 1 : L + 1, ck_rows = CHUNKED ? (L + CK - 1) / CK + 1 : 0;
   if (smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t per_slot = (rows + ck_rows) * 8 * (C::G * (int64_t)sizeof(double) + (int64_t)sizeof(int));

@@ -331,7 +331,7 @@ def test_chunked_octet_estep_matches_oracle(nat, oracle_lib, name, chunk):
             clear = srt[-1] - srt[-2] > 1e-9
             assert path.shape == ref_path.shape and np.array_equal(path[clear], ref_path[clear])
     finally:
-        nat.check(nat.lib().jh_set_option(b"oct_chunk", 1024))
+        nat.check(nat.lib().jh_set_option(b"oct_chunk", -1))
         nat.check(nat.lib().jh_set_option(b"oct_chunk_force", 0))
 
 
