@@ -870,7 +870,7 @@ extern "C" int jh_model_get_params(jh_model *m, double *tp, double *tl, double *
 extern "C" int jh_model_log_prior(jh_model *m, double *out) {
   JH_ENTER(m);
   if (!out) { jh_set_error("null argument"); return JH_ERR_INVALID; }
-  jha::k_log_prior<<<1, 32, 0, m->st()>>>(m->params(), nullptr, m->d_objective.p + 4095);
+  jha::k_log_prior<<<1, jha::LOG_PRIOR_THREADS, 0, m->st()>>>(m->params(), nullptr, m->d_objective.p + 4095);
   JH_LAUNCHED();
   JH_CUDA(cudaMemcpyAsync(out, m->d_objective.p + 4095, sizeof(double), cudaMemcpyDeviceToHost, m->st()));
   JH_CUDA(cudaStreamSynchronize(m->st()));
@@ -2929,7 +2929,7 @@ static int em_e_part(jh_model *m, jh_dataset *d, int mode, int obj_cap) {
   cudaStream_t s = m->st();
   int r;
   if ((r = estep_collective(m, d, mode))) return r;
-  jha::k_log_prior<<<1, 32, 0, s>>>(m->params(), m->d_stats.p + m->n_stats(), m->d_objective.p + 4095);
+  jha::k_log_prior<<<1, jha::LOG_PRIOR_THREADS, 0, s>>>(m->params(), m->d_stats.p + m->n_stats(), m->d_objective.p + 4095);
   JH_LAUNCHED();
   jha::k_store_objective<<<1, 1, 0, s>>>(m->d_objective.p + 4095, m->d_objective.p, m->d_iter.p, obj_cap);
   JH_LAUNCHED();

@@ -92,45 +92,108 @@ __global__ void k_mstep(DevParams P, double *trans_stat, double *emis_stat) {
   }
 }
 
-// HigherOrderHMM.getLogPriorTerm (:253-259): sequential, reference order. out[0] = prior (+ add[0] if add != nullptr).
-__global__ void k_log_prior(DevParams P, const double *add, double *out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double pt = 0;
-  for (int t = 0; t < P.n_elem; t++) {
-    if (P.trans_index[t] != t) continue;
-    int p0 = P.elem_child_ptr[t], n = P.elem_child_ptr[t + 1] - p0;
-    double term = 0;
-    if (n > 1) {
-      double r = 0, sh = 0;
-      for (int d = 0; d < n; d++) {
-        sh = __dadd_rn(sh, P.trans_hyper[p0 + d]);
-        r = __dadd_rn(r, __dmul_rn(P.trans_hyper[p0 + d], P.trans_param[p0 + d]));
+// HigherOrderHMM.getLogPriorTerm (:253-259): the sums run in the reference's order on ONE thread (the value is reproduced bit
+// for bit), but the operands are staged through shared memory by the whole block first — a lone thread chasing 18 000
+// global loads took 1.7 ms per EM iteration for BASELINE configs[2] (0.8 % of the step, more for higher emission orders).
+// out[0] = prior (+ add[0] if add != nullptr).  One block of LOG_PRIOR_THREADS threads, LOG_PRIOR_SMEM doubles of shared memory.
+constexpr int LOG_PRIOR_THREADS = 256, LOG_PRIOR_SMEM = 5120;  // 40 KB
+__global__ void __launch_bounds__(LOG_PRIOR_THREADS) k_log_prior(DevParams P, const double *add, double *out) {
+  __shared__ double sh[LOG_PRIOR_SMEM];
+  __shared__ double s_pt, s_res, s_r;
+  __shared__ int s_open;
+  const int tid = threadIdx.x, a = P.a;
+  // ---- transitions: children of the elements in tiles of whole elements ----
+  if (tid == 0) s_pt = 0;
+  for (int t0 = 0; t0 < P.n_elem;) {
+    int t1 = t0;
+    const int p_base = P.elem_child_ptr[t0];
+    while (t1 < P.n_elem && 2 * (P.elem_child_ptr[t1 + 1] - p_base) <= LOG_PRIOR_SMEM) t1++;
+    if (t1 == t0) {  // an element with more children than the tile holds: straight from global memory
+      if (tid == 0 && P.trans_index[t0] == t0) {
+        int p0 = P.elem_child_ptr[t0], n = P.elem_child_ptr[t0 + 1] - p0;
+        double r = 0, shy = 0;
+        for (int d = 0; d < n; d++) {
+          shy = __dadd_rn(shy, P.trans_hyper[p0 + d]);
+          r = __dadd_rn(r, __dmul_rn(P.trans_hyper[p0 + d], P.trans_param[p0 + d]));
+        }
+        s_pt = __dadd_rn(s_pt, n > 1 && shy != 0 ? __dsub_rn(r, __dmul_rn(shy, P.trans_lognorm[t0])) : 0.0);
       }
-      term = sh == 0 ? 0 : __dsub_rn(r, __dmul_rn(sh, P.trans_lognorm[t]));
+      t0++;
+      continue;
     }
-    pt = __dadd_rn(pt, term);
+    const int nn = P.elem_child_ptr[t1] - p_base;
+    __syncthreads();
+    for (int i = tid; i < nn; i += LOG_PRIOR_THREADS) {
+      sh[i] = P.trans_hyper[p_base + i];
+      sh[nn + i] = P.trans_param[p_base + i];
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double pt = s_pt;
+      for (int t = t0; t < t1; t++) {
+        if (P.trans_index[t] != t) continue;
+        const int p0 = P.elem_child_ptr[t] - p_base, n = P.elem_child_ptr[t + 1] - P.elem_child_ptr[t];
+        double term = 0;
+        if (n > 1) {
+          double r = 0, shy = 0;
+          for (int d = 0; d < n; d++) {
+            shy = __dadd_rn(shy, sh[p0 + d]);
+            r = __dadd_rn(r, __dmul_rn(sh[p0 + d], sh[nn + p0 + d]));
+          }
+          term = shy == 0 ? 0 : __dsub_rn(r, __dmul_rn(shy, P.trans_lognorm[t]));
+        }
+        pt = __dadd_rn(pt, term);
+      }
+      s_pt = pt;
+    }
+    t0 = t1;
   }
-  double res = pt, r = 0;
-  int a = P.a;
-  // rows are grouped by emission; the reference sums per emission and then adds to the total. Rows of one emission
-  // are contiguous, emission boundaries are not needed for the value except for the association order, which
-  // is restored with row_emitting[] == 2 marking the first row of each emission.
-  bool open = false;
-  for (int row = 0; row < P.n_cond; row++) {
-    if (P.row_emitting[row] == 2) {
-      if (open) res = __dadd_rn(res, r);
-      r = 0;
-      open = true;
+  __syncthreads();
+  // ---- emissions: rows are grouped by emission; the reference sums per emission and then adds to the total.  Rows of one
+  // emission are contiguous; row_emitting[] == 2 marks the first row of each emission (restores the association order).
+  if (tid == 0) { s_res = s_pt; s_r = 0; s_open = 0; }
+  const int per_row = 2 * a + 1;
+  const int tile = LOG_PRIOR_SMEM / per_row;  // rows per tile (tile == 0: alphabet too large for the tile, global path)
+  for (int row0 = 0; row0 < P.n_cond; row0 += max(tile, 1)) {
+    const int rows = min(max(tile, 1), P.n_cond - row0);
+    __syncthreads();
+    if (tile > 0) {
+      for (int i = tid; i < rows * a; i += LOG_PRIOR_THREADS) {
+        sh[i] = P.emis_hyper[(size_t)row0 * a + i];
+        sh[rows * a + i] = P.emis_param[(size_t)row0 * a + i];
+      }
+      for (int i = tid; i < rows; i += LOG_PRIOR_THREADS) sh[2 * rows * a + i] = P.emis_lognorm[row0 + i];
     }
-    double ess = 0;
-    for (int j = 0; j < a; j++) ess = __dadd_rn(ess, P.emis_hyper[(size_t)row * a + j]);
-    if (ess > 0) {
-      r = __dadd_rn(r, __dmul_rn(-ess, P.emis_lognorm[row]));
-      for (int j = 0; j < a; j++) r = __dadd_rn(r, __dmul_rn(P.emis_hyper[(size_t)row * a + j], P.emis_param[(size_t)row * a + j]));
+    __syncthreads();
+    if (tid == 0) {
+      double res = s_res, r = s_r;
+      bool open = s_open != 0;
+      for (int k = 0; k < rows; k++) {
+        const int row = row0 + k;
+        const double *hy = tile > 0 ? sh + (size_t)k * a : P.emis_hyper + (size_t)row * a;
+        const double *pa = tile > 0 ? sh + (size_t)rows * a + (size_t)k * a : P.emis_param + (size_t)row * a;
+        const double ln = tile > 0 ? sh[2 * rows * a + k] : P.emis_lognorm[row];
+        if (P.row_emitting[row] == 2) {
+          if (open) res = __dadd_rn(res, r);
+          r = 0;
+          open = true;
+        }
+        double ess = 0;
+        for (int j = 0; j < a; j++) ess = __dadd_rn(ess, hy[j]);
+        if (ess > 0) {
+          r = __dadd_rn(r, __dmul_rn(-ess, ln));
+          for (int j = 0; j < a; j++) r = __dadd_rn(r, __dmul_rn(hy[j], pa[j]));
+        }
+      }
+      s_res = res; s_r = r; s_open = open ? 1 : 0;
     }
   }
-  if (open) res = __dadd_rn(res, r);
-  out[0] = add ? __dadd_rn(res, add[0]) : res;
+  __syncthreads();
+  if (tid == 0) {
+    double res = s_res;
+    if (s_open) res = __dadd_rn(res, s_r);
+    out[0] = add ? __dadd_rn(res, add[0]) : res;
+  }
 }
 
 // 2-bit packed residues (four per byte, lowest bits first, every sequence on a byte boundary) -> uint8 codes; also the
