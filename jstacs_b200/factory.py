@@ -9,8 +9,9 @@ WHAT THIS FILE IS.  A statement-level Python restatement (not from-scratch produ
 order have to be the reference's so that parameters parsed from a HMMER file land in the right slots
 (DifferentiableHigherOrderHMM.setParameters, :339-344) — hence a restatement.  Nothing here is on the hot path: the
 builders produce the same HigherOrderHMM objects every other model goes through (context graph -> jh_model_desc ->
-kernels_general.cuh for models with silent states).  What is NOT mirrored: joining states (closeCircle), the sunflower
-HMM, reference-sequence / mismatch / phylogenetic emissions, uniform insert emissions.
+kernels_general.cuh for models with silent states).  Also restated: HMM/HMMFactory.java:270-400 createSunflowerHMM (a
+first-order model WITHOUT silent states: background state + motif chains, used by DeNovoSunflower).  What is NOT mirrored:
+joining states (closeCircle), reference-sequence / mismatch / phylogenetic emissions, uniform insert emissions.
 """
 from __future__ import annotations
 
@@ -243,6 +244,64 @@ def createProfileHMM(trainingParameterSet, hmm_type_or_initFromTo, order: int, n
         emissions.append(SilentEmission(con) if kind == "S" else DiscreteEmission(con, float(stateESS[i]) if i < len(stateESS) else 0.0))
     te = [TransitionElement(p.context, p.states, hyper[i]) for i, p in enumerate(lst)]  # createTransition (:1113-1120)
     hmm = DifferentiableHigherOrderHMM(trainingParameterSet, names, None, None, emissions, ess, *te)
+    hmm.setOutputStream(None)
+    return hmm
+
+
+def createSunflowerHMM(pars, con: AlphabetContainer | None, ess: float, expectedSequenceLength: int, startCentral: bool, motifLength,
+                       motifProb=None):
+    """HMMFactory.createSunflowerHMM (HMMFactory.java:291-400, without phylogenetic emissions): state 0 = background "bg",
+    then for every motif m a chain "motif m position p"; bg -> bg | first state of a motif, the last state of a motif -> bg.
+    The equivalent sample size is propagated over expectedSequenceLength positions exactly like :346-362."""
+    con = con or DNA
+    motifLength = [int(x) for x in motifLength]
+    M = len(motifLength)
+    motifProb = [0.1 / M] * M if motifProb is None else [float(x) for x in motifProb]
+    anz = 1
+    states = [0] * (1 + M)
+    for i in range(M):
+        states[1 + i] = anz
+        anz += motifLength[i]
+    hyperNext = [[0.0] * motifLength[i] for i in range(M)] + [[0.0]]
+    self_ = 1.0 - sum(motifProb)  # summed like the reference: self += motifProb[i]; self = 1 - self
+    stateESS = [list(r) for r in hyperNext]
+    if startCentral:
+        hyperNext[M][0] = ess
+        hyperParams = [ess]
+    else:
+        hyperNext[M][0] = ess * self_
+        hyperParams = [0.0] * anz
+        hyperParams[0] = hyperNext[M][0]
+        for i in range(M):
+            hyperNext[i] = [motifProb[i] * ess / len(hyperNext[i])] * len(hyperNext[i])
+            for k in range(states[1 + i], states[1 + i] + motifLength[i]):
+                hyperParams[k] = hyperNext[i][0]
+    te = [TransitionElement(None, [0] if startCentral else list(range(anz)), hyperParams)]
+    hyperParams = [0.0] * (M + 1)
+    for _ in range(int(expectedSequenceLength)):  # propagate ESS (:346-362)
+        d = 0.0
+        for i in range(M):
+            d += hyperNext[i][motifLength[i] - 1]
+            for j in range(motifLength[i] - 1, 0, -1):
+                stateESS[i][j] += hyperNext[i][j]
+                hyperNext[i][j] = hyperNext[i][j - 1]
+            stateESS[i][0] += hyperNext[i][0]
+            hyperNext[i][0] = motifProb[i] * hyperNext[M][0]
+            hyperParams[1 + i] += hyperNext[i][0]
+        stateESS[M][0] += hyperNext[M][0]
+        hyperParams[0] += self_ * hyperNext[M][0]
+        hyperNext[M][0] = d + self_ * hyperNext[M][0]
+    em = [DiscreteEmission(con, stateESS[M][0])]
+    name = ["bg"]
+    te.append(TransitionElement([0], states, hyperParams))  # transition to the petals
+    idx = 1
+    for m in range(M):
+        for p_ in range(motifLength[m]):
+            em.append(DiscreteEmission(con, stateESS[m][p_]))
+            name.append(f"motif {m} position {p_}")
+            te.append(TransitionElement([idx], [0] if p_ == motifLength[m] - 1 else [idx + 1], [ess]))  # "does not matter"
+            idx += 1
+    hmm = DifferentiableHigherOrderHMM(pars, name, None, None, em, ess, *te)
     hmm.setOutputStream(None)
     return hmm
 

@@ -1,1 +1,1 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_log_prior -c 4 --csv --log-file gpurun_out/r2K_prior.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --nseq 50000 > /dev/null 2>&1; tail -4 gpurun_out/r2K_prior.csv | awk -F'","' '{print $5, $NF}'
+python -m pytest tests/test_sunflower.py -q -m gpu > gpurun_out/r2M_pytest.log 2>&1; echo rc=$?; tail -25 gpurun_out/r2M_pytest.log | cut -c1-300

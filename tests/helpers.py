@@ -153,3 +153,17 @@ def silent_hmm(ess=0.0):
     hmm = HigherOrderHMM(pars, ["M1", "M2", "D1", "D2", "I", "E"], em, *te)
     hmm.setOutputStream(None)
     return set_closed_form_parameters(hmm)
+
+
+def sunflower_hmm(motifs=(2, 3), ess=0.0, start_central=True, seed=5, expected_length=30):
+    """HMMFactory.createSunflowerHMM (background + motif chains, no silent states) with random parameters."""
+    from jstacs_b200.factory import createSunflowerHMM
+    from jstacs_b200.hmm import BaumWelchParameterSet, IterationCondition
+
+    hmm = createSunflowerHMM(BaumWelchParameterSet(1, IterationCondition(4), 1), None, ess, expected_length, start_central, list(motifs))
+    rng = np.random.default_rng(seed)
+    for t in hmm.transition.transitions:
+        t.setLogProbabilities(np.log(rng.dirichlet(np.ones(len(t.states)))))
+    for e in hmm.emission:
+        e.setLogProbabilities(np.log(rng.dirichlet(np.ones(4), size=e.params.shape[0])))
+    return hmm

@@ -7,7 +7,7 @@ Every test runs the reference-order kernels (fast=0) and, where the model allows
 import numpy as np
 import pytest
 
-from helpers import dataset_of, ergodic_hmm, order0_hmm, order2_hmm, random_dna, silent_hmm, sparse_hmm
+from helpers import sunflower_hmm, dataset_of, ergodic_hmm, order0_hmm, order2_hmm, random_dna, silent_hmm, sparse_hmm
 from jstacs_b200 import (DNA, BaumWelchParameterSet, DataSet, DiscreteEmission, HigherOrderHMM, IterationCondition,
                          Sequence, SmallDifferenceOfFunctionEvaluationsCondition, TransitionElement, ViterbiParameterSet,
                          WrongAlphabetException)
@@ -54,6 +54,8 @@ MODELS = {
     "sparse": lambda: sparse_hmm(),
     "order2_s3": lambda: order2_hmm(3, 1),
     "banded_s40": lambda: banded_hmm(40, 4, 1),
+    "sunflower_12": lambda: sunflower_hmm((5, 6), ess=2.0),                       # HMMFactory.createSunflowerHMM: 12 states (octets)
+    "sunflower_41": lambda: sunflower_hmm((12, 9, 19), ess=0.0, start_central=False),  # 41 states (sparse tables)
 }
 
 

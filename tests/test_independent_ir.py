@@ -11,7 +11,7 @@ summation order."""
 import numpy as np
 import pytest
 
-from helpers import dataset_of, order2_hmm, random_dna, sparse_hmm
+from helpers import dataset_of, order2_hmm, random_dna, sparse_hmm, sunflower_hmm
 from jstacs_b200.hmm import ModelIR
 from jstacs_b200.workloads import banded_hmm, ergodic_hmm
 
@@ -93,6 +93,7 @@ MODELS = {
     "transition_order_3": lambda: ergodic_hmm(2, 1, transition_order=3),
     "banded_ring_40": lambda: banded_hmm(40, 4, 1),
     "ring_unsorted_offsets": lambda: banded_hmm(64, 3, 0, offsets=[1, -1, 0]),
+    "sunflower": lambda: sunflower_hmm((4, 7), ess=1.0, start_central=False),
 }
 
 
