@@ -1,2 +1,1 @@
-df -h /tmp | tail -1
-timeout 1200 python profiles/shards_scale.py 1.0 > gpurun_out/r2N_shards.json 2> gpurun_out/r2N_shards.err; echo rc=$?; cat gpurun_out/r2N_shards.json | cut -c1-1200; tail -3 gpurun_out/r2N_shards.err
+python profiles/windows_scan.py 200000 102 2>&1 | tail -2 | cut -c1-700
