@@ -123,7 +123,12 @@ int jh_set_option(const char *name, int64_t value);
 /* jh_set_option changes the DEFAULTS, which every handle follows unless it has its own value: device, stream and options
  * live in the handle, so models on different devices or threads with different options do not interfere.
  * Further switches: "graph" (replay the EM iteration as a CUDA graph, default 1), "stage" (pageable host memory is moved
- * through the library's pinned double buffers, default 1), "vit_chunk" / "vit_chunk_force" (checkpointed Viterbi). */
+ * through the library's pinned double buffers, default 1), "vit_chunk" / "vit_chunk_force" (checkpointed Viterbi),
+ * "band" (warp-resident passes of banded models, default 1), "oct_chunk" < 0 = automatic chunk length (default),
+ * "oct_full_rows_mb", "deterministic" (default 0; 1: Baum-Welch E-step in a fixed order — static work assignment,
+ * fixed-point emission counts, partial sums folded in slot order — so that statistics, objectives and trained parameters
+ * are bit-identical from run to run; covers the octet kernels, i.e. plain first-order models with 5..32 states on many
+ * sequences, anything else returns JH_ERR_UNSUPPORTED while the option is set). */
 
 /* ---- model ------------------------------------------------------------- */
 /* Replaces the object graph built by HigherOrderHMM(...) / HMMFactory.createErgodicHMM

@@ -56,6 +56,7 @@ struct Options {
   int64_t stage = 1;           // host transfers of pageable caller memory through the library's pinned double buffers
   int64_t band = 1;            // banded models: warp-resident whole-sequence passes (kernels_band.cuh)
   int64_t oct_full_rows_mb = 24576;  // octet kernels: buckets whose full forward rows (whole grid) exceed this are chunked
+  int64_t deterministic = 0;   // Baum-Welch E-step in a fixed order (bit-identical statistics run to run): octet kernels only (5..32 states)
 };
 static Options g_defaults;
 static std::atomic<uint64_t> g_opt_gen{1};
@@ -80,6 +81,7 @@ static bool set_option_field(Options &o, const std::string &n, int64_t value) {
   else if (n == "stage") o.stage = value;
   else if (n == "band") o.band = value;
   else if (n == "oct_full_rows_mb") o.oct_full_rows_mb = value;
+  else if (n == "deterministic") o.deterministic = value;
   else return false;
   return true;
 }
@@ -361,6 +363,7 @@ struct jh_model {
   DevBuf<double> d_fwd;        // forward scratch
   DevBuf<uint8_t> d_choice;    // Viterbi choice scratch
   DevBuf<unsigned long long> d_counter;
+  DevBuf<double> d_det;        // deterministic mode: per-slot partial sums + fold scratch
   DevBuf<int32_t> d_fallback;  // [1 + n] list of sequences the fast path handed to the exact kernels
   jhf::FastTables fast;        // linear-space tables of the fast path
   jhs::SparseTables sparse;    // edge lists of the sparse path (33..256 states)
@@ -467,6 +470,7 @@ struct jh_dataset {
   DevBuf<int32_t> d_order;
   DevBuf<double> d_weights;
   bool has_weights = false;
+  double weighted_total = 0;   // sum_n w_n * L_n of the current weights (host side; bounds every count cell)
   DevBuf<int32_t> d_groups;   // allowedStatesGroup of every position (jh_dataset_set_groups)
   bool has_groups = false;
   // octets: 8 consecutive sequences of a bucket advance in lock step through one warp (kernels_mma.cuh);
@@ -975,6 +979,8 @@ static int dataset_create_impl(const uint8_t *codes, const int64_t *pack_ptr, in
   if (weights && n_seq) {
     JH_CUDA(cudaMemcpyAsync(d->d_weights.p, weights, sizeof(double) * n_seq, cudaMemcpyHostToDevice, s));
     d->has_weights = true;
+    d->weighted_total = 0;
+    for (int64_t i = 0; i < n_seq; i++) d->weighted_total += fabs(weights[i]) * (double)(offsets[i + 1] - offsets[i]);
   }
   DevBuf<unsigned int> d_mx;
   if ((r = d_mx.alloc(1))) return r;
@@ -1133,6 +1139,8 @@ extern "C" int jh_dataset_builder_finish(jh_dataset_builder *b, const double *we
   if (weights && n_seq) {
     JH_CUDA(cudaMemcpyAsync(d->d_weights.p, weights, sizeof(double) * n_seq, cudaMemcpyHostToDevice, s));
     d->has_weights = true;
+    d->weighted_total = 0;
+    for (int64_t i = 0; i < n_seq; i++) d->weighted_total += fabs(weights[i]) * (double)(d->offsets[i + 1] - d->offsets[i]);
   }
   unsigned int h_mx = 0;
   JH_CUDA(cudaMemcpyAsync(&h_mx, b->d_mx.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
@@ -1151,6 +1159,8 @@ extern "C" int jh_dataset_builder_finish(jh_dataset_builder *b, const double *we
 extern "C" int jh_dataset_set_weights(jh_dataset *d, const double *weights) {
   if (!d) { jh_set_error("null data set"); return JH_ERR_INVALID; }
   if (!weights) { d->has_weights = false; return JH_OK; }
+  d->weighted_total = 0;
+  for (int64_t i = 0; i < d->n_seq; i++) d->weighted_total += fabs(weights[i]) * (double)(d->offsets[i + 1] - d->offsets[i]);
   JH_CUDA(cudaSetDevice(d->device));
   if (d->ev_last) JH_CUDA(cudaEventSynchronize(d->ev_last));  // a running E-step may still read the old weights
   if (d->n_seq) {
@@ -2693,12 +2703,20 @@ static int ensure_octet_hashes(jh_model *m, jh_dataset *d) {
 // Octet E-step (kernels_mma.cuh): one launch per length bucket, 8 warps per CTA, one CTA per SM, octets fetched dynamically.
 // Buckets whose full forward rows would not leave scratch for the whole grid run the chunked variant (checkpoints every
 // `oct_chunk` positions, rows of one chunk per resident warp).
-template <int NT, bool CHUNKED, bool EG>
+// fixed-point scale of the deterministic emission counts: the largest power of two that keeps sum_n w_n L_n below 2^62
+static double det_scale_of(const jh_dataset *d) {
+  const double total = std::max(1.0, d->has_weights ? d->weighted_total : (double)d->n_res);
+  int e = 0;
+  frexp(total, &e);  // total < 2^e
+  return ldexp(1.0, 62 - e);
+}
+
+template <int NT, bool CHUNKED, bool EG, bool DET = false>
 static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, OctGroup g, int64_t grid, size_t smem) {
   using C = jhm::MmaCfg<NT>;
   jhf::FastTables &F = m->fast;
   cudaStream_t s = m->st();
-  auto kern = jhm::k_mma_estep<NT, CHUNKED, EG>;
+  auto kern = jhm::k_mma_estep<NT, CHUNKED, EG, DET>;
   const int64_t oct0 = d->bucket_oct_ptr[g.b0], n_oct = d->bucket_oct_ptr[g.b1] - oct0, L = d->bucket_len[g.b0];
   const int64_t CK = oct_chunk_of<NT>(m, grid);
   grid = std::min<int64_t>(grid, (n_oct + C::WARPS - 1) / C::WARPS);
@@ -2723,8 +2741,19 @@ static int launch_mma_estep_impl(jh_model *m, jh_dataset *d, OctGroup g, int64_t
   D.weights = d->has_weights ? d->d_weights.p : nullptr; D.n_oct = n_oct;
   jhm::OctChunks X{(int)CK, ck_rows, m->d_fwd.p + (size_t)slots * rows * 8 * C::G, F.d_fexp + (size_t)slots * rows * 8};
   JH_CUDA(cudaMemsetAsync(m->d_counter.p, 0, sizeof(unsigned long long), s));
-  kern<<<(int)grid, C::NTHREADS, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, F.d_ec, m->d_fallback.p, X);
+  jhm::DetOut det{nullptr, 0.0};
+  const int64_t NC = (int64_t)C::G * C::G + C::G + 1;
+  if (DET) {
+    if ((r = m->d_det.reserve((size_t)(slots + 1) * NC + (size_t)C::G * F.H))) return r;
+    det.part = m->d_det.p;
+    det.scale = det_scale_of(d);
+  }
+  kern<<<(int)grid, C::NTHREADS, smem, s>>>(F.dev(), D, m->d_counter.p, m->d_fwd.p, F.d_fexp, rows, m->d_stats.p, F.d_ec, m->d_fallback.p, X, det);
   JH_LAUNCHED();
+  if (DET) {  // the launch's partial sums, added in slot order
+    jhm::k_det_fold_parts<<<1, 256, 0, s>>>(F.dev(), m->d_det.p, slots, m->d_det.p + (size_t)slots * NC, m->d_stats.p);
+    JH_LAUNCHED();
+  }
   JH_CUDA(cudaGetLastError());
   return JH_OK;
 }
@@ -2742,8 +2771,10 @@ static int launch_mma_estep(jh_model *m, jh_dataset *d) {
   if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);
   const int64_t grid = (int64_t)m->sm_count * per_sm;
   int r = JH_OK;
+  if (m->opt.deterministic && eg) { jh_set_error("deterministic mode: emission tables larger than shared memory are not covered"); return JH_ERR_UNSUPPORTED; }
   for (const OctGroup &g : oct_groups<NT>(m, d, grid)) {
-    if (eg) r = g.chunked ? launch_mma_estep_impl<NT, true, true>(m, d, g, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, g, grid, smem);
+    if (m->opt.deterministic) r = g.chunked ? launch_mma_estep_impl<NT, true, false, true>(m, d, g, grid, smem) : launch_mma_estep_impl<NT, false, false, true>(m, d, g, grid, smem);
+    else if (eg) r = g.chunked ? launch_mma_estep_impl<NT, true, true>(m, d, g, grid, smem) : launch_mma_estep_impl<NT, false, true>(m, d, g, grid, smem);
     else r = g.chunked ? launch_mma_estep_impl<NT, true, false>(m, d, g, grid, smem) : launch_mma_estep_impl<NT, false, false>(m, d, g, grid, smem);
     if (r) return r;
   }
@@ -2755,6 +2786,7 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
   JH_CUDA(cudaMemsetAsync(m->fast.d_ec, 0, m->fast.ec_bytes(), m->st()));
   const bool octets = variant_of(m) == 0 && m->fast.G >= 8;  // 8 sequences per warp on the FP64 MMA path
   const bool lanes = variant_of(m) == 0 && m->fast.G <= 4;  // one sequence per lane
+  if (m->opt.deterministic && !octets) { jh_set_error("deterministic mode covers the octet kernels (5..32 states, fast_variant 0)"); return JH_ERR_UNSUPPORTED; }
   for (size_t b = 0; lanes && b + 1 < d->bucket_ptr.size() && !r; b++) r = m->fast.G == 2 ? launch_lanes<2, 1>(m, d, b, nullptr) : launch_lanes<4, 1>(m, d, b, nullptr);
   if (octets) r = m->fast.G == 8 ? launch_mma_estep<1>(m, d) : m->fast.G == 16 ? launch_mma_estep<2>(m, d) : launch_mma_estep<4>(m, d);
   for (size_t b = 0; !octets && !lanes && b + 1 < d->bucket_ptr.size() && !r; b++) {
@@ -2774,6 +2806,13 @@ static int run_estep_fast(jh_model *m, jh_dataset *d) {
   }
   if (r) return r;
   int n = m->fast.H * m->fast.G;
+  if (m->opt.deterministic) {
+    jhm::k_det_fold_ec<<<1, 256, 0, m->st()>>>(m->fast.dev(), reinterpret_cast<const unsigned long long *>(m->fast.d_ec), 1.0 / det_scale_of(d),
+                                               m->d_det.p, m->d_stats.p);
+    JH_LAUNCHED();
+    JH_CUDA(cudaGetLastError());
+    return JH_OK;
+  }
   jhf::k_fast_fold_ec<<<(n + 7) / 8, 256, 0, m->st()>>>(m->fast.dev(), m->fast.d_ec, m->d_stats.p);
   JH_LAUNCHED();
   JH_CUDA(cudaGetLastError());
@@ -2793,6 +2832,10 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
   }
   if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, PathOut{nullptr, 0}, nullptr, nullptr, m->d_stats.p);
   const bool sparse = prefer_sparse(m, d);
+  if (m->opt.deterministic && (sparse || groups_active(m, d) || !(m->opt.fast && m->fast.usable))) {
+    jh_set_error("deterministic mode covers the octet kernels only (plain first-order models with 5..32 states, many sequences)");
+    return JH_ERR_UNSUPPORTED;
+  }
   if (!groups_active(m, d) && (sparse || (m->opt.fast && m->fast.usable))) {
     int r = m->d_fallback.reserve(d->n_seq + 2);
     if (r) return r;

@@ -258,12 +258,23 @@ struct OctChunks {
   int *ck_exp;
 };
 
+// DET (option "deterministic"): a fixed-order E-step — bit-identical statistics from run to run.  The three
+// sources of run-to-run differences are removed: octets are assigned to the warp slots statically (octet o -> slot o mod
+// slots, in increasing order) instead of through the work queue; emission counts are added as 64-bit FIXED-POINT integers
+// (integer reductions commute; scale = a power of two chosen from the weighted residue count so that no cell can overflow,
+// resolution comparable to an fp64 accumulator of that magnitude); transition / start counts and the score leave every
+// warp as a row of partial sums that k_det_fold_parts adds in slot order.  Costs the dynamic load balance on ragged data.
+struct DetOut {
+  double *part;   // [slots][G*G + G + 1]: O * T | start statistic | score
+  double scale;   // fixed-point scale of the emission counts
+};
+
 // EG: the emission table (more than 64 KB: high emission orders) stays in global memory (L1/L2) instead of shared memory;
 // the fetch for position t+2 is issued at step t, so its latency stays off the recursion.
-template <int NT, bool CHUNKED, bool EG>
+template <int NT, bool CHUNKED, bool EG, bool DET = false>
 __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsigned long long *counter, double *fwd_scratch,
                                                       int *fexp_scratch, int64_t rows, double *stats, double *gEC, int32_t *fallback,
-                                                      OctChunks X) {
+                                                      OctChunks X, DetOut det) {
   using C = MmaCfg<NT>;
   constexpr int G = C::G, NV = C::NV, ROWB = C::ROWB, RING = C::RING, SLOTB = C::SLOTB;
   extern __shared__ double sm[];
@@ -307,12 +318,21 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
 #pragma unroll
   for (int v = 0; v < NV; v++) SC[v] = 0;
   double score = 0;
-
+  auto ec_add = [&](double *p, double v) {  // emission statistic: fp64 reduction, or fixed point when the order must not matter
+    if (DET) atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__double2ll_rn(v * det.scale));
+    else atomicAdd(p, v);
+  };
+  long long o_static = slot;
 
   for (;;) {
     long long o = 0;
-    if (l == 0) o = (long long)atomicAdd(counter, 1ull);
-    o = __shfl_sync(FULL, o, 0);
+    if (DET) {
+      o = o_static;
+      o_static += (long long)gridDim.x * C::WARPS;
+    } else {
+      if (l == 0) o = (long long)atomicAdd(counter, 1ull);
+      o = __shfl_sync(FULL, o, 0);
+    }
     if (o >= D.n_oct) break;
     const int sid = D.oct_seq[o * 8 + r];
     int Lr = 0;
@@ -430,11 +450,11 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
             const double2 a2 = *reinterpret_cast<const double2 *>(slt + rl_off[tp]);
             const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
             if (!GEN || t >= kmin) {
-              atomicAdd(gdst + 8 * tp, g0);
-              atomicAdd(gdst + 8 * tp + 1, g1);
+              ec_add(gdst + 8 * tp, g0);
+              ec_add(gdst + 8 * tp + 1, g1);
             } else {
-              if (t >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
-              if (t >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);
+              if (t >= F.korder[8 * tp + 2 * q]) ec_add(gdst + 8 * tp, g0);
+              if (t >= F.korder[8 * tp + 2 * q + 1]) ec_add(gdst + 8 * tp + 1, g1);
             }
           }
         }
@@ -516,8 +536,8 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
         for (int tp = 0; tp < NT; tp++) {
           const double2 a2 = *reinterpret_cast<const double2 *>(sl0 + rl_off[tp]);
           const double g0 = a2.x * sc * beta[2 * tp], g1 = a2.y * sc * beta[2 * tp + 1];
-          if (0 >= F.korder[8 * tp + 2 * q]) atomicAdd(gdst + 8 * tp, g0);
-          if (0 >= F.korder[8 * tp + 2 * q + 1]) atomicAdd(gdst + 8 * tp + 1, g1);
+          if (0 >= F.korder[8 * tp + 2 * q]) ec_add(gdst + 8 * tp, g0);
+          if (0 >= F.korder[8 * tp + 2 * q + 1]) ec_add(gdst + 8 * tp + 1, g1);
           SC[2 * tp] += g0;
           SC[2 * tp + 1] += g1;
         }
@@ -525,6 +545,32 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
       __syncwarp();
     }
   }
+  if (DET) {  // ---------------- flush, fixed order: one row of partial sums per warp slot, added by k_det_fold_parts ----------------
+    double *const P = det.part + (size_t)slot * (G * G + G + 1);
+#pragma unroll
+    for (int ti = 0; ti < NT; ti++)
+#pragma unroll
+      for (int tj = 0; tj < NT; tj++)
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          const int i = 8 * ti + r, j = 8 * tj + 2 * q + b;
+          P[i * G + j] = O[ti][tj][b] * F.T[i * G + j];
+        }
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      double s = SC[v];
+      s += __shfl_xor_sync(FULL, s, 4);
+      s += __shfl_xor_sync(FULL, s, 8);
+      s += __shfl_xor_sync(FULL, s, 16);
+      if (r == 0) P[G * G + 8 * (v >> 1) + 2 * q + (v & 1)] = s;
+    }
+    double s = q == 0 ? score : 0.0;
+    s += __shfl_xor_sync(FULL, s, 4);
+    s += __shfl_xor_sync(FULL, s, 8);
+    s += __shfl_xor_sync(FULL, s, 16);
+    if (l == 0) P[G * G + G] = s;
+  }
+  if (!DET) {
   // ---------------- flush: T is multiplied in once; CTA-level reduction, then one atomic per cell ----------------
 #pragma unroll
   for (int ti = 0; ti < NT; ti++)
@@ -550,6 +596,51 @@ __global__ void __launch_bounds__(256, 1) k_mma_estep(FastDev F, OctData D, unsi
     if (sO[i] != 0 && F.tstat[i] >= 0) atomicAdd(&stats[F.tstat[i]], sO[i]);
   for (int i = threadIdx.x; i < G; i += blockDim.x)
     if (sPi[i] != 0 && F.pistat[i] >= 0) atomicAdd(&stats[F.pistat[i]], sPi[i]);
+  }
+}
+
+// Deterministic mode: rows of per-slot partial sums [slots][G*G + G + 1] -> statistics, in slot order per cell and in cell order
+// per statistics slot (tied transition elements share slots).  One block.
+__global__ void __launch_bounds__(256) k_det_fold_parts(FastDev F, const double *part, int64_t slots, double *tmp, double *stats) {
+  const int G = F.G, NC = G * G + G + 1;
+  for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+    double v = 0;
+    for (int64_t sl = 0; sl < slots; sl++) v += part[(size_t)sl * NC + c];
+    tmp[c] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < G * G; c++)
+      if (tmp[c] != 0 && F.tstat[c] >= 0) stats[F.tstat[c]] += tmp[c];
+    for (int c = 0; c < G; c++)
+      if (tmp[G * G + c] != 0 && F.pistat[c] >= 0) stats[F.pistat[c]] += tmp[G * G + c];
+    stats[F.n_stats] += tmp[G * G + G];
+  }
+}
+
+// Deterministic mode: fixed-point emission-count copies -> emission statistics.  Integer sums are exact, so the copies and
+// the context hashes that share a cell (state order < Kmax) can be added in any order; the cells are then added to the
+// statistics in a fixed order by one thread (states that share an emission share cells).  One block; tmp: [G * H] doubles.
+__global__ void __launch_bounds__(256) k_det_fold_ec(FastDev F, const unsigned long long *gEC, double inv_scale, double *tmp, double *stats) {
+  const int G = F.G, H = F.H;
+  for (int idx = threadIdx.x; idx < G * H; idx += blockDim.x) {
+    const int j = idx / H, ci = idx % H;
+    double v = 0;
+    if (F.estat_tab[j] >= 0 && ci < F.estat_mod[j]) {
+      long long tot = 0;
+      for (int hh = ci; hh < H; hh += F.estat_mod[j])
+        for (int rep = 0; rep <= F.ec_mask; rep++) tot += (long long)gEC[((size_t)rep * H + hh) * G + j];
+      v = (double)tot * inv_scale;
+    }
+    tmp[idx] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int j = 0; j < G; j++) {
+      if (F.estat_tab[j] < 0) continue;
+      for (int ci = 0; ci < F.estat_mod[j]; ci++)
+        if (tmp[j * H + ci] != 0) stats[F.n_child + F.estat_tab[j] + ci] += tmp[j * H + ci];
+    }
 }
 
 // Scoring (AbstractHMM.logProb, AbstractHMM.java:1049-1070: the value of bwd[0][0]) with the octet forward recursion;

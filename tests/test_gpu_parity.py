@@ -337,6 +337,56 @@ def test_chunked_octet_estep_matches_oracle(nat, oracle_lib, name, chunk):
         nat.check(nat.lib().jh_set_option(b"oct_chunk_force", 0))
 
 
+@pytest.mark.parametrize("chunked", [0, 1], ids=["full_rows", "chunked"])
+@pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
+def test_deterministic_estep_is_bit_identical_run_to_run(nat, oracle_lib, name, chunked):
+    """Option "deterministic" (a fixed-order E-step): static octet assignment, fixed-point emission counts,
+    per-slot partial sums folded in slot order.  Repeated E-steps and repeated EM runs give bit-identical statistics,
+    objectives and parameters, and still match the oracle; without the option the same calls are only equal to ~1e-13."""
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(23)
+    lens = rng.integers(20, 200, 800)
+    data = dataset_of([random_dna(rng, int(L)) for L in lens])
+    w = rng.random(lens.size) + 0.25
+    eng, nd = hmm._engine(), hmm._data(data)
+    eng.set_option("deterministic", 1)
+    if chunked:
+        eng.set_option("oct_chunk", 24)
+        eng.set_option("oct_chunk_force", 1)
+    for weights in (None, w):
+        nd.set_weights(weights)
+        runs = [eng.estep(nd) for _ in range(4)]
+        for ts, es, sc in runs[1:]:
+            assert np.array_equal(ts, runs[0][0]) and np.array_equal(es, runs[0][1]) and sc == runs[0][2]
+        rts, res, rsc = om.estep(data.codes, data.offsets, weights)
+        np.testing.assert_allclose(runs[0][0], rts, rtol=COUNT_TOL, atol=COUNT_TOL)
+        np.testing.assert_allclose(runs[0][1], res, rtol=COUNT_TOL, atol=COUNT_TOL)
+        assert runs[0][2] == pytest.approx(rsc, rel=LL_RTOL)
+    nd.set_weights(None)
+    p0 = eng.get_params()
+    objs, pars = [], []
+    for _ in range(3):
+        eng.set_params(*p0)
+        objs.append(eng.baum_welch(nd, nat.MODE_BAUM_WELCH, nat.TERM_ITERATIONS, 5, 0.0))
+        pars.append(eng.get_params())
+    for o, p in zip(objs[1:], pars[1:]):
+        assert np.array_equal(o, objs[0]) and all(np.array_equal(x, y) for x, y in zip(p, pars[0]))
+    np.testing.assert_allclose(objs[0], om.train(data.codes, data.offsets, max_iter=5), rtol=1e-9)
+
+
+def test_deterministic_mode_refuses_what_it_does_not_cover(nat):
+    """Small models (lane kernels) and the sparse / long-sequence path have no fixed-order variant: the option is an error there."""
+    hmm = ergodic_hmm(2, 1)
+    rng = np.random.default_rng(1)
+    data = dataset_of([random_dna(rng, 50) for _ in range(40)])
+    eng, nd = hmm._engine(), hmm._data(data)
+    eng.set_option("deterministic", 1)
+    with pytest.raises(nat.NativeError) as ei:
+        eng.estep(nd)
+    assert ei.value.status == -2 and "deterministic" in str(ei.value)
+
+
 @pytest.mark.parametrize("name", ["erg_s5_k2", "erg_s8_k2", "erg_s16_k1", "erg_s32_k3"])
 def test_posterior_decoding_octets_ragged(nat, oracle_lib, fast, name):
     """decodeStatePosterior(getStatePosteriorMatrixFor(seq)) fused on the device for a ragged data set (octets with
