@@ -2186,48 +2186,123 @@ static int run_viterbi_long(jh_model *m, jh_dataset *d, PathOut paths, const int
   if (r) return r;
   const int SP = P.SP;
   if ((r = m->d_vit_ck.reserve((size_t)(d->n_chunks + 1) * SP)) || (r = m->d_vit_map.reserve((size_t)(d->n_chunks + 1) * SP)) ||
-      (r = m->d_vit_entry.reserve((size_t)d->n_chunks + 1)) || (r = m->d_counters.reserve(4)))
+      (r = m->d_vit_entry.reserve((size_t)d->n_chunks + 1)))
     return r;
-  JH_CUDA(cudaMemsetAsync(m->d_counters.p, 0, sizeof(unsigned long long) * 4, s));
   jhw::VitLongDev V{P.d_out_lT, P.d_lpi, P.d_pi_rank, P.d_lfin, P.d_lE, 0.0 + -log((double)m->a)};
   const int NT = 128, wpc = NT / 32;
   const size_t smem_c = (size_t)wpc * 2 * SP * sizeof(double), smem_s = (size_t)2 * SP * sizeof(double);
   const int64_t rows = std::min<int64_t>(CK, d->max_len);
   const int64_t per_warp = rows * SP;
   int per_sm = 0;
-  int64_t grid = 0;
   BandSel bsel;
   const bool banded = m->opt.band && band_select(P, &bsel);
+  // With sequences of different lengths phase A lasts as long as the LONGEST sequence while most SMs idle, and phases B-D
+  // of everything would only start after it.  Like the E-step (run_sparse_two_phase) every long sequence gets its own
+  // stream: sweep of the sequence -> its chunks (B) -> its composition (C) -> its chunks again (D), so the chunk phases of
+  // the shorter sequences run while the long ones are still being swept.  Same issue-order rules as there.
+  const bool streamed = m->opt.overlap && d->n_long >= 2 && d->n_long <= 64;
+  const int64_t n_launch = streamed ? d->n_long + 1 : 1;
+  if ((r = m->d_counters.reserve(3 * n_launch + 4))) return r;
+  JH_CUDA(cudaMemsetAsync(m->d_counters.p, 0, sizeof(unsigned long long) * (3 * n_launch + 4), s));
+  if (streamed) {
+    while ((int64_t)m->seq_streams.size() < d->n_long) {
+      cudaStream_t st;
+      cudaEvent_t ev;
+      JH_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      m->seq_streams.push_back(st);
+      JH_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      m->seq_events.push_back(ev);
+    }
+    if (!m->ev_fork) JH_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  }
+  std::vector<int64_t> first(n_launch), count(n_launch), grid_k(n_launch), slot0(n_launch);
+  size_t smem_iso = 0;
+  if (streamed) {
+    int optin = 0;
+    JH_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
+    smem_iso = (size_t)optin;
+  }
 #define JH_VL(VS_, VI_)                                                                                                               \
   {                                                                                                                                     \
     JH_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jhw::k_vit_chunks<VS_, VI_, 0>, NT, smem_c));                       \
     if (per_sm < 1) { jh_set_error("Viterbi chunk kernel does not fit on an SM"); return JH_ERR_UNSUPPORTED; }                          \
     if (m->opt.blocks_per_sm > 0) per_sm = std::min<int>(per_sm, (int)m->opt.blocks_per_sm);                                              \
-    grid = std::min<int64_t>((int64_t)m->sm_count * per_sm, (d->n_chunks + wpc - 1) / wpc);                                               \
-    grid = std::max<int64_t>(1, std::min<int64_t>(grid, m->opt.scratch_mb * 1024 * 1024 / per_warp / wpc));                               \
-    if ((r = m->d_vit_nxt.reserve((size_t)grid * wpc * per_warp + 16))) return r;                                                        \
-    if (d->n_long > 0) {                                                                                                                \
+    const int64_t full_grid = (int64_t)m->sm_count * per_sm, budget_ctas = std::max<int64_t>(1, m->opt.scratch_mb * 1024 * 1024 / per_warp / wpc); \
+    int64_t n_big = streamed ? std::min<int64_t>(3, d->n_long) : 0;                                                                      \
+    while (n_big > 0 && (budget_ctas - n_big * full_grid) / (n_launch - n_big) < 16) n_big--;                                            \
+    const int64_t grid_cap = streamed ? std::max<int64_t>(1, std::min<int64_t>(m->sm_count, (budget_ctas - n_big * full_grid) / (n_launch - n_big))) \
+                                      : std::max<int64_t>(1, std::min<int64_t>(full_grid, budget_ctas));                                 \
+    int64_t total_ctas = 0;                                                                                                             \
+    for (int64_t k = 0; k < n_launch; k++) {                                                                                            \
+      first[k] = streamed ? d->long_seg[std::min<int64_t>(k, d->n_long)] : 0;                                                           \
+      count[k] = streamed ? (k < d->n_long ? d->long_seg[k + 1] - d->long_seg[k] : d->n_chunks - d->long_seg[d->n_long]) : d->n_chunks;  \
+      grid_k[k] = std::max<int64_t>(1, std::min<int64_t>(k < n_big ? full_grid : grid_cap, (count[k] + wpc - 1) / wpc));                 \
+      slot0[k] = total_ctas;                                                                                                            \
+      total_ctas += grid_k[k];                                                                                                          \
+    }                                                                                                                                   \
+    if ((r = m->d_vit_nxt.reserve((size_t)total_ctas * wpc * per_warp + 16))) return r;                                                  \
+    auto sweep = [&](int64_t k0, int64_t nk, cudaStream_t st, unsigned long long *ctr) -> int {  /* phase A of long sequences [k0, k0 + nk) */ \
+      /* streamed: the latency-bound warp claims the SM's whole shared memory, so that no chunk CTA becomes co-resident */              \
+      const size_t iso = streamed ? smem_iso : 0;                                                                                       \
       if (banded) {                                                                                                                     \
         JH_BAND_DISPATCH(bsel, {                                                                                                        \
-          jhb::k_band_vit_sweep<SPL_, LO_, HI_><<<(int)d->n_long, 32, 0, s>>>(P.dev(), V, P.IND, d->dev(), (int)CK, d->d_long.p, d->n_long,  \
-                                                                              d->d_chunk_ptr.p, m->d_vit_ck.p, d_scores);                  \
+          auto kern = jhb::k_band_vit_sweep<SPL_, LO_, HI_>;                                                                            \
+          if (iso > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)iso));              \
+          kern<<<(int)nk, 32, iso, st>>>(P.dev(), V, P.IND, d->dev(), (int)CK, d->d_long.p + k0, nk, d->d_chunk_ptr.p, m->d_vit_ck.p, d_scores); \
         });                                                                                                                             \
-      } else                                                                                                                            \
-        jhw::k_vit_sweep<VS_, VI_><<<(int)std::min<int64_t>(d->n_long, (int64_t)m->sm_count * 8), 32, smem_s, s>>>(                     \
-            P.dev(), V, d->dev(), (int)CK, d->d_long.p, d->n_long, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p, d_scores);            \
+      } else {                                                                                                                          \
+        auto kern = jhw::k_vit_sweep<VS_, VI_>;                                                                                         \
+        const size_t sm_ = std::max(smem_s, iso);                                                                                       \
+        if (sm_ > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_));                \
+        kern<<<(int)std::min<int64_t>(nk, (int64_t)m->sm_count * 8), 32, sm_, st>>>(P.dev(), V, d->dev(), (int)CK, d->d_long.p + k0, nk,  \
+                                                                                    d->d_chunk_ptr.p, m->d_vit_ck.p, ctr, d_scores);     \
+      }                                                                                                                                 \
       JH_LAUNCHED();                                                                                                                    \
-      jhw::k_vit_chunks<VS_, VI_, 0><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->long_seg[d->n_long], d->d_chunk_seq.p, \
-                                                                    d->d_chunk_idx.p, d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p + 1,  \
-                                                                    m->d_vit_nxt.p, m->d_vit_map.p, nullptr, PathOut{nullptr, 0}, nullptr, nullptr); \
+      return JH_OK;                                                                                                                     \
+    };                                                                                                                                  \
+    auto chunks_b = [&](int64_t k, int64_t c0, int64_t nc, cudaStream_t st, unsigned long long *ctr) {  /* phase B */                     \
+      jhw::k_vit_chunks<VS_, VI_, 0><<<(int)grid_k[k], NT, smem_c, st>>>(P.dev(), V, d->dev(), (int)CK, nc, d->d_chunk_seq.p + c0,        \
+                                                                        d->d_chunk_idx.p + c0, d->d_chunk_ptr.p, m->d_vit_ck.p, ctr,    \
+                                                                        m->d_vit_nxt.p + (size_t)slot0[k] * wpc * per_warp, m->d_vit_map.p, \
+                                                                        nullptr, PathOut{nullptr, 0}, nullptr, nullptr);                  \
       JH_LAUNCHED();                                                                                                                    \
-      jhw::k_vit_compose<<<(int)((d->n_long + 63) / 64), 64, 0, s>>>(SP, (int)CK, d->d_long.p, d->n_long, d->d_offsets.p, d->d_chunk_ptr.p, \
-                                                                    m->d_vit_map.p, m->d_vit_entry.p);                                    \
+    };                                                                                                                                  \
+    auto chunks_d = [&](int64_t k, int64_t c0, int64_t nc, cudaStream_t st, unsigned long long *ctr) {  /* phase D */                     \
+      if (nc <= 0) return;                                                                                                              \
+      jhw::k_vit_chunks<VS_, VI_, 1><<<(int)grid_k[k], NT, smem_c, st>>>(P.dev(), V, d->dev(), (int)CK, nc, d->d_chunk_seq.p + c0,        \
+                                                                        d->d_chunk_idx.p + c0, d->d_chunk_ptr.p, m->d_vit_ck.p, ctr,    \
+                                                                        m->d_vit_nxt.p + (size_t)slot0[k] * wpc * per_warp, nullptr,     \
+                                                                        m->d_vit_entry.p, paths, d_path_ptr, d_scores);                  \
       JH_LAUNCHED();                                                                                                                    \
+    };                                                                                                                                  \
+    auto compose = [&](int64_t k0, int64_t nk, cudaStream_t st) {  /* phase C */                                                         \
+      jhw::k_vit_compose<<<(int)((nk + 63) / 64), 64, 0, st>>>(SP, (int)CK, d->d_long.p + k0, nk, d->d_offsets.p, d->d_chunk_ptr.p,       \
+                                                              m->d_vit_map.p, m->d_vit_entry.p);                                        \
+      JH_LAUNCHED();                                                                                                                    \
+    };                                                                                                                                  \
+    if (!streamed) {                                                                                                                    \
+      if (d->n_long > 0) {                                                                                                              \
+        if ((r = sweep(0, d->n_long, s, m->d_counters.p))) return r;                                                                    \
+        chunks_b(0, 0, d->long_seg[d->n_long], s, m->d_counters.p + 1);                                                                 \
+        compose(0, d->n_long, s);                                                                                                       \
+      }                                                                                                                                 \
+      chunks_d(0, 0, d->n_chunks, s, m->d_counters.p + 2);                                                                              \
+    } else {                                                                                                                            \
+      JH_CUDA(cudaEventRecord(m->ev_fork, s));                                                                                          \
+      for (int64_t k = 0; k < d->n_long; k++) {  /* all sweeps first, longest first */                                                   \
+        JH_CUDA(cudaStreamWaitEvent(m->seq_streams[k], m->ev_fork, 0));                                                                 \
+        if ((r = sweep(k, 1, m->seq_streams[k], m->d_counters.p + 3 * k))) return r;                                                    \
+      }                                                                                                                                 \
+      for (int64_t k = d->n_long - 1; k >= 0; k--) {  /* chunk phases in the order in which the sweeps finish */                         \
+        cudaStream_t st = m->seq_streams[k];                                                                                            \
+        chunks_b(k, first[k], count[k], st, m->d_counters.p + 3 * k + 1);                                                               \
+        compose(k, 1, st);                                                                                                              \
+        chunks_d(k, first[k], count[k], st, m->d_counters.p + 3 * k + 2);                                                               \
+        JH_CUDA(cudaEventRecord(m->seq_events[k], st));                                                                                 \
+      }                                                                                                                                 \
+      chunks_d(d->n_long, first[d->n_long], count[d->n_long], s, m->d_counters.p + 3 * d->n_long);  /* single-chunk sequences */         \
+      for (int64_t k = 0; k < d->n_long; k++) JH_CUDA(cudaStreamWaitEvent(s, m->seq_events[k], 0));                                      \
     }                                                                                                                                   \
-    jhw::k_vit_chunks<VS_, VI_, 1><<<(int)grid, NT, smem_c, s>>>(P.dev(), V, d->dev(), (int)CK, d->n_chunks, d->d_chunk_seq.p, d->d_chunk_idx.p, \
-                                                                  d->d_chunk_ptr.p, m->d_vit_ck.p, m->d_counters.p + 2, m->d_vit_nxt.p,         \
-                                                                  nullptr, m->d_vit_entry.p, paths, d_path_ptr, d_scores);                      \
-    JH_LAUNCHED();                                                                                                                      \
   }
   switch (P.SPL * 100 + P.IND) {
     case 104: JH_VL(1, 4) break;
