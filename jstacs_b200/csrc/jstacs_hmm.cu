@@ -56,6 +56,7 @@ struct Options {
   int64_t stage = 1;           // host transfers of pageable caller memory through the library's pinned double buffers
   int64_t band = 1;            // banded models: warp-resident whole-sequence passes (kernels_band.cuh)
   int64_t oct_full_rows_mb = 24576;  // octet kernels: buckets whose full forward rows (whole grid) exceed this are chunked
+  int64_t band_meet = 1;       // banded models, scoring of long sequences: forward and backward chains meet in the middle
   int64_t deterministic = 0;   // Baum-Welch E-step in a fixed order (bit-identical statistics run to run): octet kernels only (5..32 states)
 };
 static Options g_defaults;
@@ -82,6 +83,7 @@ static bool set_option_field(Options &o, const std::string &n, int64_t value) {
   else if (n == "band") o.band = value;
   else if (n == "oct_full_rows_mb") o.oct_full_rows_mb = value;
   else if (n == "deterministic") o.deterministic = value;
+  else if (n == "band_meet") o.band_meet = value;
   else return false;
   return true;
 }
@@ -364,6 +366,9 @@ struct jh_model {
   DevBuf<uint8_t> d_choice;    // Viterbi choice scratch
   DevBuf<unsigned long long> d_counter;
   DevBuf<double> d_det;        // deterministic mode: per-slot partial sums + fold scratch
+  DevBuf<double> d_meet_vec;   // scoring that meets in the middle: [n][2][SP] vectors, [n][2] exponents and flags
+  DevBuf<long long> d_meet_exp;
+  DevBuf<int32_t> d_meet_ok;
   DevBuf<int32_t> d_fallback;  // [1 + n] list of sequences the fast path handed to the exact kernels
   jhf::FastTables fast;        // linear-space tables of the fast path
   jhs::SparseTables sparse;    // edge lists of the sparse path (33..256 states)
@@ -1553,16 +1558,24 @@ static int run_sparse_pass1(jh_model *m, jh_dataset *d, int n_dir, double *d_ll,
       JH_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device));
       smem_b = std::max<size_t>(smem_b, (size_t)optin);
     }
+    const bool ck = n_dir == 2 && !X.meet_vec;  // checkpoints: not when the two directions only meet in the middle (scoring)
     JH_BAND_DISPATCH(bsel, {
       auto kern = jhb::k_band_pass1<SPL_, LO_, HI_>;
       if (smem_b > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
-      kern<<<(int)items, 32, smem_b, s>>>(P.dev(), P.IND, d->dev(), n_dir, (int)(d->chunk_len > 0 ? d->chunk_len : 1), n_dir == 2 ? d->d_chunk_ptr.p : nullptr,
-                                         n_dir == 2 ? m->d_ck_alpha.p : nullptr, n_dir == 2 ? m->d_ck_beta.p : nullptr, d_ll, m->d_fallback.p, X);
+      kern<<<(int)items, 32, smem_b, s>>>(P.dev(), P.IND, d->dev(), n_dir, ck ? (int)(d->chunk_len > 0 ? d->chunk_len : 1) : 0x3fffffff,
+                                         ck ? d->d_chunk_ptr.p : nullptr, ck ? m->d_ck_alpha.p : nullptr, ck ? m->d_ck_beta.p : nullptr, d_ll,
+                                         m->d_fallback.p, X);
       JH_LAUNCHED();
     });
+    if (X.meet_vec) {
+      const int64_t n = items / 2;
+      jhb::k_band_meet<<<(int)((n + 3) / 4), 128, 0, s>>>(P.SP, d->dev(), X.list, n, X.meet_vec, X.meet_exp, X.meet_ok, d_ll, m->d_fallback.p);
+      JH_LAUNCHED();
+    }
     JH_CUDA(cudaGetLastError());
     return JH_OK;
   }
+  if (X.meet_vec) { jh_set_error("internal: meet-in-the-middle scoring outside the band kernels"); return JH_ERR_INVALID; }
   if (m->opt.pass1_cta && items <= (int64_t)m->sm_count) {  // few long sequences: latency mode, one CTA per (sequence, direction)
     size_t smem_c = ((P.e_global ? 0 : (size_t)P.H * P.SP) + 2 * (size_t)P.SP + 16) * sizeof(double);
     if (on) {  // overlapped with chunk kernels of other sequences: claim the SM's whole shared memory, so that no chunk CTA
@@ -1682,8 +1695,37 @@ static int run_loglik_sparse(jh_model *m, jh_dataset *d, double *d_out) {
       X.list = d->d_order.p + d->n_long; X.n_list = d->n_seq - d->n_long;
       if ((r = run_sparse_pass1(m, d, 1, d_out, &X, nullptr, false))) return r;
     }
-  } else if ((r = run_sparse_pass1(m, d, 1, d_out)))
-    return r;
+  } else {
+    // banded models, few long sequences: the forward chain over the first half and the backward chain over the second half
+    // of a sequence run at the same time and meet in the middle (kernels_band.cuh: k_band_meet) — half the dependent chain
+    BandSel bsel;
+    int64_t n_meet = 0;
+    if (m->opt.band && m->opt.band_meet && band_select(m->sparse, &bsel)) {
+      const int64_t min_len = 4096;
+      int64_t lo = 0, hi = d->n_seq;  // d->order: decreasing length
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) / 2;
+        if (d->offsets[d->order[mid] + 1] - d->offsets[d->order[mid]] >= min_len) lo = mid + 1;
+        else hi = mid;
+      }
+      if (lo > 0 && 2 * lo <= (int64_t)m->sm_count) n_meet = lo;  // worth it (and possible) only while every chain has an SM of its own
+    }
+    if (n_meet > 0) {
+      const size_t SP = (size_t)m->sparse.SP;
+      if ((r = m->d_meet_vec.reserve((size_t)n_meet * 2 * SP)) || (r = m->d_meet_exp.reserve((size_t)n_meet * 2)) || (r = m->d_meet_ok.reserve((size_t)n_meet * 2)))
+        return r;
+      jhs::Pass1Extra Xm{};
+      Xm.list = d->d_order.p; Xm.n_list = n_meet;
+      Xm.meet_vec = m->d_meet_vec.p; Xm.meet_exp = m->d_meet_exp.p; Xm.meet_ok = m->d_meet_ok.p;
+      if ((r = run_sparse_pass1(m, d, 2, d_out, &Xm))) return r;
+      if (d->n_seq > n_meet) {
+        jhs::Pass1Extra Xs{};
+        Xs.list = d->d_order.p + n_meet; Xs.n_list = d->n_seq - n_meet;
+        if ((r = run_sparse_pass1(m, d, 1, d_out, &Xs, nullptr, false))) return r;
+      }
+    } else if ((r = run_sparse_pass1(m, d, 1, d_out)))
+      return r;
+  }
   int32_t n_fb = 0;
   JH_CUDA(cudaMemcpyAsync(&n_fb, m->d_fallback.p, sizeof(int32_t), cudaMemcpyDeviceToHost, m->st()));
   JH_CUDA(cudaStreamSynchronize(m->st()));

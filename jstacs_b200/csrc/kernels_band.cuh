@@ -187,14 +187,16 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
           if (k == 7 || k == 15) ok &= lz.apply<SPL>(f, A);
         }
       };
+      const int mid = L >> 1;                        // meeting point of the two directions (X.meet_vec)
+      const int t_end = X.meet_vec ? mid : L - 1;    // last position of the forward recursion
       int t = 1;
       if (F.a_pow2) {
 #pragma unroll 1
-        for (; t <= L - 1 && ((((t + mis) & 15) != 0) || t <= F.Kmax); t++) step(t, (int)__ldg(bytes + t));
+        for (; t <= t_end && ((((t + mis) & 15) != 0) || t <= F.Kmax); t++) step(t, (int)__ldg(bytes + t));
         int blk = (t + mis) >> 4;
-        uint4 cur = t + 15 <= L - 1 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+        uint4 cur = t + 15 <= t_end ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-        for (; t + 15 <= L - 1; t += 16, blk++) {
+        for (; t + 15 <= t_end; t += 16, blk++) {
           const uint4 nxt = blocks.load(blk + 1);  // the code buffer is padded: one block past the end is readable
           if (ck_dst && ck_left <= 16) {
 #pragma unroll 1
@@ -207,8 +209,18 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
         }
       }
 #pragma unroll 1
-      for (; t <= L - 1; t++) step(t, (int)__ldg(bytes + t));
+      for (; t <= t_end; t++) step(t, (int)__ldg(bytes + t));
       ok &= jhs::rescale_warp<SPL>(f, A);
+      if (X.meet_vec) {  // alpha_mid, its exponent and the flag; k_band_meet finishes the sequence
+        const size_t slot = (size_t)(it / n_dir) * 2;
+        jhs::store_vec<SPL>(X.meet_vec + slot * SP + SPL * lane, f);
+        if (lane == 0) {
+          X.meet_exp[slot] = A;
+          X.meet_ok[slot] = ok ? 1 : 0;
+        }
+        __syncwarp();
+        continue;
+      }
       double sfin = 0;
 #pragma unroll
       for (int u = 0; u < SPL; u++) sfin += f[u] * F.fin[SPL * lane + u];
@@ -286,14 +298,16 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
         }
       };
       int p = L - 2 - F.Kmax;
-      const int pa = -F.Kmax;
+      // the last step goes from t = p + Kmax + 1 to t - 1: down to position 0, or to the meeting point L/2 (X.meet_vec)
+      const int pa = X.meet_vec ? (L >> 1) - F.Kmax : -F.Kmax;
+      const int pb = pa > 0 ? pa : 0;  // blocks must not reach below the last step
       if (F.a_pow2) {
 #pragma unroll 1
-        for (; p >= pa && (((p + mis) & 15) != 15 || p < 15); p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+        for (; p >= pa && (((p + mis) & 15) != 15 || p - 15 < pb); p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
         int blk = (p + mis) >> 4;
-        uint4 cur = p >= 15 ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
+        uint4 cur = p - 15 >= pb ? blocks.load(blk) : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-        for (; p >= 15; p -= 16, blk--) {  // (p + mis) & 15 == 15: the block is bytes[p-15 .. p]
+        for (; p - 15 >= pb; p -= 16, blk--) {  // (p + mis) & 15 == 15: the block is bytes[p-15 .. p]
           const uint4 nxt = blocks.load(blk - 1);
           if (ck_left <= 16) {
 #pragma unroll 1
@@ -307,8 +321,43 @@ __global__ void __launch_bounds__(32) k_band_pass1(SparseDev F, int IND, DevData
       }
 #pragma unroll 1
       for (; p >= pa; p--) step(p, p >= 0 ? (int)__ldg(bytes + p) : 0);
+      if (X.meet_vec) {  // beta_mid
+        const bool okb = jhs::rescale_warp<SPL>(b, Bx);
+        const size_t slot = (size_t)(it / n_dir) * 2 + 1;
+        jhs::store_vec<SPL>(X.meet_vec + slot * SP + SPL * lane, b);
+        if (lane == 0) {
+          X.meet_exp[slot] = Bx;
+          X.meet_ok[slot] = okb ? 1 : 0;
+        }
+      }
     }
     __syncwarp();
+  }
+}
+
+// Scoring that meets in the middle: P(x) = sum_i alpha_mid[i] beta_mid[i].  The forward chain over [0, L/2] and the backward
+// chain over [L/2, L) of a sequence run at the same time on two warps (k_band_pass1 with X.meet_vec), which halves the
+// dependent chain that a long sequence costs (cfg5: 248e6 -> 124e6 steps for scoring).  One warp per sequence finishes it;
+// outputs as in the forward-only pass (loglik, fallback list).  The value differs from the one-directional pass only by
+// the association of the sums.
+__global__ void __launch_bounds__(128) k_band_meet(int SP, DevData D, const int32_t *list, int64_t n_list, const double *meet_vec,
+                                                   const long long *meet_exp, const int32_t *meet_ok, double *loglik, int32_t *fallback) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_list) return;
+  const int sid = list ? list[i] : D.order[i];
+  const double *a = meet_vec + (size_t)i * 2 * SP, *b = a + SP;
+  double s = 0;
+  for (int j = lane; j < SP; j += 32) s += a[j] * b[j];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0) {
+    const bool good = meet_ok[i * 2] && meet_ok[i * 2 + 1] && s > 0;
+    if (loglik) loglik[sid] = good ? log(s) + (double)(meet_exp[i * 2] + meet_exp[i * 2 + 1]) * 0.6931471805599453094 : JH_NEG_INF;
+    if (!good) {
+      int pos = atomicAdd(fallback, 1);
+      fallback[1 + pos] = sid;
+    }
   }
 }
 

@@ -410,6 +410,11 @@ struct Pass1Extra {        // E-step mode (all pointers null otherwise)
   const int32_t *list;       // sequences to process (nullptr: all, in D.order)
   int64_t n_list;
   double *score;             // += sum_n w_n log P(x_n) over the processed sequences
+  // scoring that meets in the middle (kernels_band.cuh): the forward warp stops at position L/2 and the backward warp at
+  // the same position; both leave their vector, its exponent and their "ok" flag here, indexed by (list position, direction)
+  double *meet_vec;          // [n_list][2][SP]
+  long long *meet_exp;       // [n_list][2]
+  int32_t *meet_ok;          // [n_list][2]
 };
 
 // EG (all kernels below): the emission table (> 96 KB: high emission orders) is read from global memory (L1/L2) instead of shared memory

@@ -880,6 +880,32 @@ def test_long_sequence_viterbi_impossible_path(nat, oracle_lib):
     assert ei.value.status == -6
 
 
+@pytest.mark.parametrize("name", ["ring128_0to3", "ring64_0to2", "ring128_pm1_unsorted", "ring256_0to3", "ring128_pm4_gaps"])
+def test_band_scoring_meets_in_the_middle(nat, oracle_lib, name):
+    """Scoring of long sequences of banded models: forward chain over the first half, backward chain over the second half,
+    P(x) = sum_i alpha_mid[i] beta_mid[i] (k_band_pass1 with meet buffers + k_band_meet) — against the oracle and against
+    the one-directional pass; sequences below 4096 positions in the same data set keep the forward-only pass."""
+    hmm = BAND_MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(29)
+    lens = [4096, 4097, 5000, 12345, 100, 8191, 20000, 1, 4095, 6002]
+    data = dataset_of([random_dna(rng, L) for L in lens])
+    ll_ref = om.loglik(data.codes, data.offsets)
+    got, launches = {}, {}
+    for meet in (1, 0):
+        eng, nd = hmm._engine(), hmm._data(data)
+        eng.set_option("band_meet", meet)
+        n0 = nat.lib().jh_kernel_launches()
+        got[meet] = eng.loglik(nd)
+        launches[meet] = nat.lib().jh_kernel_launches() - n0
+        np.testing.assert_allclose(got[meet], ll_ref, rtol=LL_RTOL)
+    # two-directional pass + k_band_meet + forward-only pass for the short sequences, against one forward-only pass
+    assert launches == {1: 3, 0: 1}
+    # log P ~ -5e3 has an ulp of 1e-12: the different association of the sums (1e-15 relative in P) usually vanishes in it
+    np.testing.assert_allclose(got[1], got[0], rtol=1e-12)
+    assert np.array_equal(got[1][[4, 7, 8]], got[0][[4, 7, 8]])  # the short sequences took the same pass
+
+
 # ---- banded models: warp-resident whole-sequence passes (kernels_band.cuh) ---------------------------------------------
 BAND_MODELS = {
     "ring128_0to3": lambda: banded_hmm(128, 4, 1),                         # cfg5: SPL 4, band [0, 3]
