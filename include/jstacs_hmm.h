@@ -124,7 +124,8 @@ int jh_set_option(const char *name, int64_t value);
  * live in the handle, so models on different devices or threads with different options do not interfere.
  * Further switches: "graph" (replay the EM iteration as a CUDA graph, default 1), "stage" (pageable host memory is moved
  * through the library's pinned double buffers, default 1), "vit_chunk" / "vit_chunk_force" (checkpointed Viterbi),
- * "band" (warp-resident passes of banded models, default 1), "oct_chunk" < 0 = automatic chunk length (default),
+ * "band" (warp-resident passes of banded models, default 1), "band_meet" (scoring of long sequences of banded models with
+ * a forward and a backward chain that meet in the middle, default 1), "oct_chunk" < 0 = automatic chunk length (default),
  * "oct_full_rows_mb", "deterministic" (default 0; 1: Baum-Welch E-step in a fixed order — static work assignment,
  * fixed-point emission counts, partial sums folded in slot order — so that statistics, objectives and trained parameters
  * are bit-identical from run to run; covers the octet kernels, i.e. plain first-order models with 5..32 states on many
