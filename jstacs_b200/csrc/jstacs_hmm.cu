@@ -56,6 +56,7 @@ struct Options {
   int64_t stage = 1;           // host transfers of pageable caller memory through the library's pinned double buffers
   int64_t band = 1;            // banded models: warp-resident whole-sequence passes (kernels_band.cuh)
   int64_t oct_full_rows_mb = 24576;  // octet kernels: buckets whose full forward rows (whole grid) exceed this are chunked
+  int64_t vit_train_fast = 1;  // Viterbi training: decode with the fast kernels, then count along the paths (0: reference-order kernel)
   int64_t band_meet = 1;       // banded models, scoring of long sequences: forward and backward chains meet in the middle
   int64_t deterministic = 0;   // Baum-Welch E-step in a fixed order (bit-identical statistics run to run): octet kernels only (5..32 states)
 };
@@ -84,6 +85,7 @@ static bool set_option_field(Options &o, const std::string &n, int64_t value) {
   else if (n == "oct_full_rows_mb") o.oct_full_rows_mb = value;
   else if (n == "deterministic") o.deterministic = value;
   else if (n == "band_meet") o.band_meet = value;
+  else if (n == "vit_train_fast") o.vit_train_fast = value;
   else return false;
   return true;
 }
@@ -366,6 +368,8 @@ struct jh_model {
   DevBuf<uint8_t> d_choice;    // Viterbi choice scratch
   DevBuf<unsigned long long> d_counter;
   DevBuf<double> d_det;        // deterministic mode: per-slot partial sums + fold scratch
+  DevBuf<uint8_t> d_vt_paths;  // Viterbi training on the fast decoders: byte paths and scores of the data set
+  DevBuf<double> d_vt_scores;
   DevBuf<double> d_meet_vec;   // scoring that meets in the middle: [n][2][SP] vectors, [n][2] exponents and flags
   DevBuf<long long> d_meet_exp;
   DevBuf<int32_t> d_meet_ok;
@@ -2947,7 +2951,33 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
     m->ktimed = true;
     return r;
   }
-  if (mode == JH_MODE_VITERBI) return run_viterbi(m, d, PathOut{nullptr, 0}, nullptr, nullptr, m->d_stats.p);
+  if (mode == JH_MODE_VITERBI) {
+    // Viterbi training: the fast decoders (lane-per-sequence / checkpointed long path) write byte paths, k_viterbi_path_counts
+    // adds every sequence's weight along its path; models outside their scope keep the reference-order kernel with counts
+    if (m->opt.vit_train_fast && m->opt.fast && m->fast.usable && m->S <= 255 && !groups_active(m, d)) {
+      int r;
+      if ((r = m->d_vt_paths.reserve((size_t)d->n_res + 16)) || (r = m->d_vt_scores.reserve((size_t)d->n_seq))) return r;
+      if (!m->capturing) cudaEventRecord(m->evk0, s);
+      if ((r = run_viterbi(m, d, PathOut{m->d_vt_paths.p, 1}, nullptr, m->d_vt_scores.p, nullptr))) return r;
+      const int n_stats = (int)m->n_stats();
+      const size_t smem = (size_t)n_stats * sizeof(double);
+      const int in_smem = smem <= 160 * 1024;
+      auto kern = jhv::k_viterbi_path_counts;
+      if (in_smem && smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((d->n_seq + 7) / 8, (int64_t)m->sm_count * (in_smem && smem > 64 * 1024 ? 1 : 2)));
+      kern<<<(int)grid, 256, in_smem ? smem : 0, s>>>(m->fast.dev(), d->dev(), m->d_vt_paths.p, m->d_vt_scores.p, m->n_cond * m->a, in_smem, m->d_stats.p);
+      JH_LAUNCHED();
+      if (!m->capturing) cudaEventRecord(m->evk1, s);
+      m->ktimed = true;
+      JH_CUDA(cudaGetLastError());
+      return JH_OK;
+    }
+    if (!m->capturing) cudaEventRecord(m->evk0, s);
+    int r = run_viterbi(m, d, PathOut{nullptr, 0}, nullptr, nullptr, m->d_stats.p);
+    if (!m->capturing) cudaEventRecord(m->evk1, s);
+    m->ktimed = true;
+    return r;
+  }
   const bool sparse = prefer_sparse(m, d);
   if (m->opt.deterministic && (sparse || groups_active(m, d) || !(m->opt.fast && m->fast.usable))) {
     jh_set_error("deterministic mode covers the octet kernels only (plain first-order models with 5..32 states, many sequences)");

@@ -231,4 +231,50 @@ __global__ void __launch_bounds__(128) k_viterbi_lanes(VitTables V, OctData D, u
   }
 }
 
+// Viterbi training (HigherOrderHMM.viterbi with path == null, :617-708 + :723-726 of the E-step loop): the statistics are the
+// weight of every sequence added along its best path.  The paths come from the fast decoders above (byte per residue, 255 =
+// no state), so the E-step of Viterbi training is `decode + count` instead of the reference-order kernel with its choice
+// matrix: one warp per sequence, lanes stride over the positions, counts go to a shared-memory copy of the statistics block
+// when it fits (fp64 atomics on shared memory; a global table of a few hundred hot cells would serialise in the L2).
+// stats: [transition | emission | score] as in kernels_mma.cuh.
+__global__ void __launch_bounds__(256) k_viterbi_path_counts(jhf::FastDev F, DevData D, const uint8_t *paths, const double *scores, int n_cond_a,
+                                                             int in_smem, double *stats) {
+  extern __shared__ double sst[];
+  const int n_stats = F.n_child + n_cond_a, G = F.G;
+  double *const st_ = in_smem ? sst : stats;
+  if (in_smem) {
+    for (int i = threadIdx.x; i < n_stats; i += blockDim.x) sst[i] = 0;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  double score_sum = 0;
+  for (int64_t n = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5); n < D.n_seq; n += (int64_t)gridDim.x * wpc) {
+    const int64_t off = D.offsets[n];
+    const int L = (int)(D.offsets[n + 1] - off);
+    const double w = D.weights ? D.weights[n] : 1.0;
+    const uint8_t *x = D.codes + off, *p = paths + off;
+    if (lane == 0) score_sum += w * scores[n];
+    for (int l = lane; l < L; l += 32) {
+      const int s = p[l];
+      if (s == 255) continue;  // the trace stopped: nothing is counted from here on (all later states are 255 as well)
+      const int slot = l == 0 ? F.pistat[s] : F.tstat[(int)p[l - 1] * G + s];
+      if (slot >= 0) atomicAdd(&st_[slot], w);
+      if (l >= F.korder[s] && F.estat_tab[s] >= 0) {
+        int h = 0, pw = 1;
+        for (int k = 0; k <= F.Kmax && l - k >= 0; k++) {
+          h += pw * (int)__ldg(x + l - k);
+          pw *= F.a;
+        }
+        atomicAdd(&st_[F.n_child + F.estat_tab[s] + h % F.estat_mod[s]], w);
+      }
+    }
+  }
+  if (lane == 0 && score_sum != 0) atomicAdd(&stats[n_stats], score_sum);
+  if (in_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_stats; i += blockDim.x)
+      if (sst[i] != 0) atomicAdd(&stats[i], sst[i]);
+  }
+}
+
 }  // namespace jhv

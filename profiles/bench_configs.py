@@ -45,6 +45,7 @@ def run(name, hmm, data, what, reps=3):
           "decode_u8": lambda: eng.posterior_decode(nd, narrow=True),
           # the caller's path buffer reused (already touched pages: no first-touch faults inside the call)
           "viterbi_u8_reuse": lambda: eng.viterbi(nd, narrow=True, out=_buf(nd.n_res)),
+          "vit_estep": lambda: eng.estep(nd, mode=_native.MODE_VITERBI, fetch=False),  # E-step of Viterbi training
           "train": lambda: hmm.train(data)}[what]  # the whole HigherOrderHMM.train call (data set resident; parameters read back)
     if not name.startswith("full_"):
         fn()  # warm-up
@@ -54,7 +55,7 @@ def run(name, hmm, data, what, reps=3):
         fn()
         _native.check(_native.lib().jh_synchronize())
         wall = (time.perf_counter() - t0) * 1e3
-        ms.append((eng.last_main_kernel_ms() if what == "estep" else wall if what == "train" else eng.last_kernel_ms(), wall))
+        ms.append((eng.last_main_kernel_ms() if what in ("estep", "vit_estep") else wall if what == "train" else eng.last_kernel_ms(), wall))
     k = float(np.median([m[0] for m in ms]))
     print(json.dumps({"config": name, "op": what, "states": S, "n_seq": data.getNumberOfElements(), "residues": res, "kernel_ms": round(k, 3),
                       "call_ms": round(float(np.median([m[1] for m in ms])), 3), "residues_states_per_s": res * S / (k * 1e-3),
@@ -70,6 +71,7 @@ run("cfg1_decode_u8_s2_k1_100k", lambda: ergodic_hmm(2, 1), lambda: make_data(10
 run("cfg1_viterbi_u8_s2_k1_100k", lambda: ergodic_hmm(2, 1), lambda: make_data(100_000, 1000), "viterbi_u8")
 run("cfg2_viterbi_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "viterbi")
 run("cfg2_bw_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "estep")
+run("cfg2_viterbi_training_estep_s8_k2", lambda: ergodic_hmm(8, 2), lambda: make_data(n(1_000_000), 1000), "vit_estep")
 run("cfg3_bw_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(1_000_000), 1000), "estep")
 run("cfg3_loglik_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(1_000_000), 1000), "loglik")
 run("cfg3_decode_s32_k3", lambda: ergodic_hmm(32, 3, ess=4.0), lambda: make_data(n(200_000), 1000), "decode")

@@ -191,6 +191,32 @@ def test_viterbi_training_matches_oracle(nat, oracle_lib):
     np.testing.assert_allclose(hmm.last_objectives[0], robj, rtol=1e-12)
 
 
+@pytest.mark.parametrize("route", [1, 0], ids=["decode_and_count", "reference_order_kernel"])
+@pytest.mark.parametrize("name", ["erg_s2_k1", "erg_s3_k0_map", "erg_s8_k2", "erg_s32_k3", "sparse", "banded_s40", "sunflower_41", "order2_s3"])
+def test_viterbi_training_estep_both_routes(nat, oracle_lib, name, route):
+    """E-step of Viterbi training (weights added along the best paths): the fast decoders + k_viterbi_path_counts
+    (vit_train_fast = 1: every model the scaled tables cover) and the reference-order kernel with counts, weighted and
+    unweighted, ragged data incl. sequences shorter than the emission order — counts equal the oracle's exactly."""
+    hmm = MODELS[name]()
+    om = oracle_lib.OracleModel(hmm.ir())
+    rng = np.random.default_rng(31)
+    lens = np.concatenate([rng.integers(1, 120, 60), [1, 2, 3, 257, 300]])
+    data = dataset_of([random_dna(rng, int(L)) for L in lens])
+    w = np.round(rng.random(lens.size) * 4 + 0.5, 3)
+    eng, nd = hmm._engine(), hmm._data(data)
+    eng.set_option("vit_train_fast", route)
+    for weights in (None, w):
+        nd.set_weights(weights)
+        ts, es, sc = eng.estep(nd, mode=nat.MODE_VITERBI)
+        rts, res, rsc = om.estep(data.codes, data.offsets, weights, mode=0)
+        np.testing.assert_allclose(ts, rts, rtol=1e-13, atol=1e-12)  # sums of the same weights in another order
+        np.testing.assert_allclose(es, res, rtol=1e-13, atol=1e-12)
+        assert sc == pytest.approx(rsc, rel=1e-12)
+    nd.set_weights(None)
+    obj = eng.baum_welch(nd, nat.MODE_VITERBI, nat.TERM_ITERATIONS, 4, 0.0)
+    np.testing.assert_allclose(obj, om.train(data.codes, data.offsets, mode=0, max_iter=4), rtol=1e-12)
+
+
 @pytest.mark.parametrize("name", ["erg_s2_k1", "erg_s5_k2", "sparse", "order2_s3", "erg_s32_k3"])
 def test_posterior_matrix_and_decoding(nat, oracle_lib, fast, name):
     hmm = MODELS[name]()
