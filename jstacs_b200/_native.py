@@ -15,7 +15,8 @@ TERM_ITERATIONS, TERM_SMALL_DIFFERENCE = 0, 1
 ABI_VERSION = 2
 COMM_ID_BYTES = 128
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libjstacs_hmm_b200.so")
+# JSTACS_HMM_LIB: another build of the same library (A/B measurements of two builds in one process environment)
+LIB_PATH = os.environ.get("JSTACS_HMM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libjstacs_hmm_b200.so")
 
 _P_I32 = C.POINTER(C.c_int32)
 _P_F64 = C.POINTER(C.c_double)
