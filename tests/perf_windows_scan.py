@@ -1,14 +1,15 @@
 """The NHMMer call pattern (projects/xanthogenomes/NHMMer.java:225-244): a profile HMM with silent states — the PLAN7 model
 parsed from the reference's repeats.hmm (tests/golden/profile_repeats.json, 105 states) — scores EVERY window of a fixed
 width along a sequence, hmm.getLogProbFor(seq, i, i + w - 1) for all i, here as one jh_loglik_windows call.
-usage: python profiles/windows_scan.py [sequence length] [window width]"""
+usage: python tests/perf_windows_scan.py [sequence length] [window width]
+(lives under tests/ because it checks a sample of the windows against the oracle, which only tests may load)"""
 import json
 import os
 import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 
 import __graft_entry__ as g
