@@ -1,1 +1,4 @@
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "meets_in_the_middle or deterministic_estep or viterbi_training_estep or test_banded_models_whole_sequence_passes" > gpurun_out/r3B_memcheck.log 2>&1; echo rc=$?; grep -c "Invalid\|out of bounds\|misaligned" gpurun_out/r3B_memcheck.log; tail -6 gpurun_out/r3B_memcheck.log | cut -c1-250
+# scratch: the command file handed to gpurun by profiles/gpurun_retry.sh (last used for the final validation of round 2)
+python -m pytest tests -q -m gpu
+python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py
