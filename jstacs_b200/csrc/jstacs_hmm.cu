@@ -2964,7 +2964,9 @@ static int estep_device(jh_model *m, jh_dataset *d, int mode) {
       const int in_smem = smem <= 160 * 1024;
       auto kern = jhv::k_viterbi_path_counts;
       if (in_smem && smem > 48 * 1024) JH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((d->n_seq + 7) / 8, (int64_t)m->sm_count * (in_smem && smem > 64 * 1024 ? 1 : 2)));
+      // latency bound (shared-memory atomics, path bytes): as many warps per SM as the statistics copies leave room for
+      const int64_t per_sm = in_smem ? std::max<int64_t>(1, std::min<int64_t>(6, (int64_t)(200 * 1024) / std::max<size_t>(smem, 1))) : 6;
+      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((d->n_seq + 7) / 8, (int64_t)m->sm_count * per_sm));
       kern<<<(int)grid, 256, in_smem ? smem : 0, s>>>(m->fast.dev(), d->dev(), m->d_vt_paths.p, m->d_vt_scores.p, m->n_cond * m->a, in_smem, m->d_stats.p);
       JH_LAUNCHED();
       if (!m->capturing) cudaEventRecord(m->evk1, s);

@@ -1,4 +1,2 @@
-# scratch: the command file handed to gpurun by profiles/gpurun_retry.sh (last used for the final validation of round 2)
-python -m pytest tests -q -m gpu
-python -c "import __graft_entry__ as g; g.smoke()"
-python bench.py
+python -m pytest tests/test_gpu_parity.py -q -m gpu -x -k "viterbi_training" 2>&1 | tail -1
+python profiles/bench_configs.py 1.0 cfg2_viterbi_training_estep_s8_k2 2>/dev/null | cut -c1-200
